@@ -1,0 +1,269 @@
+/* oracle/pv_oracle.c: TEST INFRASTRUCTURE ONLY -- see pv_oracle.h.
+ *
+ * Every function cites the reference lines (relative to /root/reference/src/flan) it restates.
+ * Float operation order is kept exactly as the reference writes it; build with -ffp-contract=off.
+ *
+ * Third-party arithmetic: the reference calls FFTW3f (fftwf_plan_dft_r2c_1d / c2r_1d,
+ * FFTHelper.cpp:21-24,41,47), which is not vendored and not installed. Its published semantics
+ * (unnormalised forward e^{-2 pi i kn/N}; unnormalised c2r that ignores Im of bins 0 and N/2) are
+ * restated with a radix-2 FFT evaluated in double and rounded once to float -- operation for
+ * operation the same transform as oracle/ref_shim/fftw_standin.cpp backend 0, so that this file and
+ * the verbatim reference build agree bit for bit.
+ */
+#define _GNU_SOURCE
+#include "pv_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---------- double-precision FFT stand-in for FFTW (power-of-two sizes) ---------- */
+
+typedef struct { double re, im; } cpx_t;
+
+typedef struct
+	{
+	int n;
+	cpx_t * tw;     /* exp(-2 pi i k / n), k < n/2 */
+	int * rev;
+	cpx_t * work;
+	} fft_t;
+
+static int fft_init( fft_t * f, int n )
+	{
+	if( n < 2 || ( n & ( n - 1 ) ) != 0 ) return -1;
+	f->n = n;
+	f->tw = (cpx_t *) malloc( sizeof( cpx_t ) * ( n / 2 ) );
+	f->rev = (int *) malloc( sizeof( int ) * n );
+	f->work = (cpx_t *) malloc( sizeof( cpx_t ) * n );
+	const long double two_pi = 6.283185307179586476925286766559005768L;
+	for( int k = 0; k < n / 2; ++k )
+		{
+		const long double a = -two_pi * (long double) k / (long double) n;
+		f->tw[k].re = (double) cosl( a );
+		f->tw[k].im = (double) sinl( a );
+		}
+	int bits = 0;
+	while( ( 1 << bits ) < n ) ++bits;
+	for( int i = 0; i < n; ++i )
+		{
+		int r = 0;
+		for( int b = 0; b < bits; ++b ) if( i & ( 1 << b ) ) r |= 1 << ( bits - 1 - b );
+		f->rev[i] = r;
+		}
+	return 0;
+	}
+
+static void fft_free( fft_t * f ) { free( f->tw ); free( f->rev ); free( f->work ); }
+
+static void fft_run( fft_t * f, int sign )
+	{
+	const int n = f->n;
+	cpx_t * w = f->work;
+	for( int i = 0; i < n; ++i )
+		if( i < f->rev[i] ) { cpx_t t = w[i]; w[i] = w[f->rev[i]]; w[f->rev[i]] = t; }
+	for( int len = 2; len <= n; len <<= 1 )
+		{
+		const int half = len / 2, step = n / len;
+		for( int i = 0; i < n; i += len )
+			for( int j = 0; j < half; ++j )
+				{
+				cpx_t t = f->tw[j * step];
+				if( sign > 0 ) t.im = -t.im;
+				const cpx_t u = w[i + j];
+				const cpx_t x = w[i + j + half];
+				cpx_t v;
+				v.re = x.re * t.re - x.im * t.im;
+				v.im = x.re * t.im + x.im * t.re;
+				w[i + j].re = u.re + v.re;           w[i + j].im = u.im + v.im;
+				w[i + j + half].re = u.re - v.re;    w[i + j + half].im = u.im - v.im;
+				}
+		}
+	}
+
+/* ---------- constants: defines.h:44-45 ---------- */
+
+static float pvo_pi( void )  { return acosf( -1.0f ); }
+static float pvo_pi2( void ) { return pvo_pi() * 2.0f; }
+
+int64_t pvo_num_frames( int64_t n, int hop )
+	{
+	/* AudioPV.cpp:17: std::ceil( get_num_frames() / hopSize ) + 1 with an INTEGER quotient. */
+	return n / hop + 1;
+	}
+
+int pvo_hop_from_rates( float sample_rate, float analysis_rate )
+	{
+	/* PVBuffer.cpp:381-384: Frame get_hop_size() { return get_sample_rate() / get_analysis_rate(); } */
+	return (int)( sample_rate / analysis_rate );
+	}
+
+void pvo_hann( int window_size, float * out )
+	{
+	/* WindowFunctions.cpp:8: const float pi = std::acos( -1.0f );
+	 * WindowFunctions.cpp:12: return 0.5f * ( 1.0f - cos( 2.0f * pi * x ) );
+	 * With g++ the unqualified cos is ::cos(double): the argument is a float product promoted to
+	 * double, and the subtraction / multiply run in double before the return narrows to float.
+	 * AudioPV.cpp:33: x = float( i ) / float( window_size - 1 ). */
+	const float pi = acosf( -1.0f );
+	for( int i = 0; i < window_size; ++i )
+		{
+		const float x = (float) i / (float)( window_size - 1 );
+		const float arg = 2.0f * pi * x;
+		out[i] = (float)( 0.5 * ( 1.0 - cos( (double) arg ) ) );
+		}
+	}
+
+void pvo_mid_side( const float * in, int64_t n, float * out )
+	{
+	/* AudioConversions.cpp:42-49 */
+	const float sqrt2 = sqrtf( 2.0f );
+	for( int64_t i = 0; i < n; ++i )
+		{
+		const float l = in[i], r = in[n + i];
+		out[i]     = ( l + r ) / sqrt2;
+		out[n + i] = ( l - r ) / sqrt2;
+		}
+	}
+
+/* phase_vocoder.cpp:5-53 */
+static void pvo_phase_vocoder( double * phase_buffer, float re, float im, float bin_frequency,
+                               float analysis_rate, float sample_rate, float * m_out, float * f_out )
+	{
+	const float pi2 = pvo_pi2();
+	const int use_wrapping = analysis_rate < sample_rate;                 /* :37 */
+	const float phase = atan2f( im, re );                                 /* :43 std::arg */
+	const float phase_diff = (float)( (double) phase - *phase_buffer );   /* :44 float - double -> float */
+	*phase_buffer = phase;                                                /* :45 */
+	const float expected_phase_diff = bin_frequency / analysis_rate * pi2;/* :47 */
+	const float delta_phase = phase_diff - expected_phase_diff;           /* :48 */
+	float wrapped = delta_phase;
+	if( use_wrapping )
+		{
+		const float q = delta_phase / pi2;                                /* :40 x / pi2 */
+		const float r = roundf( q );
+		const float pr = pi2 * r;
+		wrapped = delta_phase - pr;                                       /* :40 */
+		}
+	const float t = wrapped * analysis_rate;                              /* :50 left to right */
+	const float delta_frequency = t / pi2;
+	*m_out = hypotf( re, im );                                            /* :52 std::abs */
+	*f_out = bin_frequency + delta_frequency;                             /* :52 */
+	}
+
+int pvo_convert_to_pv( const float * audio, int C, int64_t n, float sample_rate,
+                       int window_size, int hop, int dft_size,
+                       int64_t frame_begin, int64_t frame_end, float * pv_out )
+	{
+	if( C < 0 || n < 0 || hop <= 0 || window_size <= 0 || dft_size < window_size ) return -1;
+	const int num_bins = dft_size / 2 + 1;                                /* :15 */
+	const int64_t num_hops = pvo_num_frames( n, hop );                    /* :17 */
+	if( frame_begin < 0 || frame_end > num_hops || frame_begin > frame_end ) return -1;
+	const float analysis_rate = sample_rate / hop;                        /* :25 float / int */
+
+	float * hann = (float *) malloc( sizeof( float ) * window_size );
+	pvo_hann( window_size, hann );                                        /* :30-34 */
+
+	fft_t fft;
+	if( fft_init( &fft, dft_size ) != 0 ) { free( hann ); return -1; }
+	double * phase_buffer = (double *) malloc( sizeof( double ) * num_bins );   /* :37 */
+	float * bin_frequency = (float *) malloc( sizeof( float ) * num_bins );
+	for( int b = 0; b < num_bins; ++b )
+		bin_frequency[b] = (float) b * sample_rate / (float) dft_size;    /* PVBuffer.cpp:443-446 */
+
+	const int64_t rows = frame_end - frame_begin;
+	for( int c = 0; c < C; ++c )                                          /* :41 */
+		{
+		const float * x = audio + (int64_t) c * n;
+		for( int b = 0; b < num_bins; ++b ) phase_buffer[b] = 0.0;        /* :44 */
+		/* frame_begin-1 is run only to obtain the phase the serial loop would carry. */
+		const int64_t first = frame_begin > 0 ? frame_begin - 1 : 0;
+		for( int64_t pv_frame = first; pv_frame < frame_end; ++pv_frame ) /* :47 */
+			{
+			const int64_t start = (int64_t) hop * pv_frame - window_size / 2;   /* :52 */
+			for( int i = 0; i < window_size; ++i )                        /* :61-62 */
+				{
+				const int64_t s = start + i;
+				const float v = ( s < 0 || n <= s ) ? 0.0f : x[s];        /* :54-58 */
+				fft.work[i].re = (double)( v * hann[i] );
+				fft.work[i].im = 0.0;
+				}
+			for( int i = window_size; i < dft_size; ++i ) { fft.work[i].re = 0.0; fft.work[i].im = 0.0; }   /* :65 */
+			fft_run( &fft, -1 );                                          /* :67 */
+			for( int b = 0; b < num_bins; ++b )                           /* :69-73 */
+				{
+				const float re = (float) fft.work[b].re, im = (float) fft.work[b].im;
+				float m, f;
+				pvo_phase_vocoder( &phase_buffer[b], re, im, bin_frequency[b], analysis_rate, sample_rate, &m, &f );
+				if( pv_frame >= frame_begin )
+					{
+					float * o = pv_out + 2 * ( ( (int64_t) c * rows + ( pv_frame - frame_begin ) ) * num_bins + b );
+					o[0] = m; o[1] = f;
+					}
+				}
+			}
+		}
+	free( bin_frequency ); free( phase_buffer ); fft_free( &fft ); free( hann );
+	return 0;
+	}
+
+int pvo_convert_to_audio( const float * pv, int C, int64_t F, int B, float sample_rate,
+                          float analysis_rate, int window_size, float * audio_out )
+	{
+	if( C < 0 || F < 0 || B < 2 || window_size <= 0 ) return -1;
+	const float pi2 = pvo_pi2();
+	const int dft_size = ( B - 1 ) * 2;                                   /* PVBuffer.cpp:356-359 */
+	const int hop = pvo_hop_from_rates( sample_rate, analysis_rate );
+	if( hop <= 0 || window_size > dft_size ) return -1;
+	const int64_t out_n = F * hop;                                        /* :93 */
+	memset( audio_out, 0, sizeof( float ) * (size_t) C * out_n );         /* :95 zero-filled buffer */
+
+	float * hann = (float *) malloc( sizeof( float ) * window_size );
+	pvo_hann( window_size, hann );
+	const float window_scale = 2.67f / ( dft_size * window_size / hop );  /* :99 int arithmetic in the parenthesis */
+	for( int i = 0; i < window_size; ++i ) hann[i] = hann[i] * window_scale;   /* :102 */
+
+	fft_t fft;
+	if( fft_init( &fft, dft_size ) != 0 ) { free( hann ); return -1; }
+	double * phase_buffer = (double *) malloc( sizeof( double ) * B );    /* :105 */
+
+	for( int c = 0; c < C; ++c )                                          /* :108 */
+		{
+		float * out = audio_out + (int64_t) c * out_n;
+		for( int b = 0; b < B; ++b ) phase_buffer[b] = 0.0;               /* :111 */
+		for( int64_t pv_frame = 0; pv_frame < F; ++pv_frame )             /* :113 */
+			{
+			const float * row = pv + 2 * ( ( (int64_t) c * F + pv_frame ) * B );
+			/* :117-120 + phase_vocoder.cpp:55-61; then Hermitian extension as FFTW c2r reads it
+			 * (imaginary parts of bins 0 and N/2 ignored). */
+			for( int b = 0; b < B; ++b )
+				{
+				const float m = row[2 * b], f = row[2 * b + 1];
+				const float phase_diff = f / analysis_rate * pi2;         /* phase_vocoder.cpp:57 */
+				phase_buffer[b] += phase_diff;                            /* :58 */
+				if( phase_buffer[b] > pi2 ) phase_buffer[b] = fmod( phase_buffer[b], (double) pi2 );   /* :59 */
+				const float theta = (float) phase_buffer[b];
+				const float re = m * cosf( theta ), im = m * sinf( theta );   /* :60 std::polar */
+				if( b == 0 || b == dft_size / 2 ) { fft.work[b].re = re; fft.work[b].im = 0.0; }
+				else
+					{
+					fft.work[b].re = re;             fft.work[b].im = im;
+					fft.work[dft_size - b].re = re;  fft.work[dft_size - b].im = -(double) im;
+					}
+				}
+			fft_run( &fft, +1 );                                          /* :122 */
+			const int64_t start = (int64_t) hop * pv_frame - window_size / 2;   /* :125 */
+			const int64_t end = start + window_size;
+			const int64_t sb = start > 0 ? start : 0;                     /* :127 */
+			const int64_t eb = end < out_n ? end : out_n;                 /* :128 */
+			for( int64_t i = sb - start; i < eb - start; ++i )            /* :133-134 */
+				{
+				const float y = (float) fft.work[i].re;
+				const float p = y * hann[i];
+				out[start + i] = out[start + i] + p;
+				}
+			}
+		}
+	free( phase_buffer ); fft_free( &fft ); free( hann );
+	return 0;
+	}
