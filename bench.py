@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- PV frames/sec (analysis + resynthesis) of the B200 phase-vocoder engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference's own CPU path (oracle/_ref)
+
+Workload (BASELINE.json configs[1]): stereo 48 kHz, 10 minutes of seeded noise + chirp per GPU, window 4096,
+hop 256, dft 4096 -> 112 501 frames x 2 channels x 2049 bins per GPU (3.69 GB of PV data, far larger than the
+126 MB L2, so no cache flush is needed between steps). A step is one pass of the hot path over that batch:
+Audio::convert_to_PV followed by PV::convert_to_audio, inputs resident in HBM. With N > 1 the signal is N times
+as long and frame-range sharded (weak scaling): each rank transforms its contiguous frame range; resynthesis
+exchanges the per-bin phase state (all_gather) and the window-hop overlap-add halo (send/recv) over NCCL.
+
+One JSON line on stdout (rank 0). `value` = frames of all ranks / max-over-ranks device time (CUDA events).
+`e2e` = the same step driven from pinned HOST buffers: H2D of the audio, both transforms, D2H of the result.
+`roofline` = algorithmic bytes of the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json.
+`cpu_baseline` = the reference's own sources (oracle/_ref, vendored pffft as the FFTW stand-in), one thread as
+written, on a bounded sample of the same signal.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SR, W, HOP, N_DFT, CH = 48000.0, 4096, 256, 4096, 2
+SECONDS_PER_GPU = 600
+WORKLOAD = "cfg2: stereo 48 kHz 10 min noise+chirp per GPU, window 4096 hop 256 dft 4096, convert_to_PV + convert_to_audio"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seconds", type=float, default=SECONDS_PER_GPU, help="signal length per GPU (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _poll(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+            if out:
+                f = [s.strip() for s in out[0].split(",")]
+                self.samples.append({"sm": float(f[1]), "max": float(f[2]), "power": float(f[3]),
+                                     "hw_slowdown": f[4], "hw_thermal": f[5], "sw_thermal": f[6], "sw_power_cap": f[7]})
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self.stop.is_set():
+            self._poll()
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=15)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(s["sm"] for s in self.samples)
+        reasons = []
+        for key, name in (("hw_slowdown", "hw_slowdown"), ("hw_thermal", "hw_thermal_slowdown"),
+                          ("sw_thermal", "sw_thermal_slowdown"), ("sw_power_cap", "sw_power_cap")):
+            if any(s[key].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0]["max"], "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(s["power"] for s in self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own sources (oracle/_ref)
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(seconds, threads, steps, warmup):
+    """Round trips of `seconds` of the workload signal per thread, `threads` host threads. Returns frames/s."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import RefLib
+    from flan_b200.signals import noise_chirp
+    if not RefLib.available():
+        raise RuntimeError("oracle/_ref/libflan_ref.so missing (built by __graft_entry__.build() where /root/reference exists)")
+    ref = RefLib(1)      # vendored pffft as the FFTW stand-in: the reference's float-SIMD speed class
+    n = int(SR * seconds)
+    chunks = [np.stack([noise_chirp(n, SR, 1234 + i)]) for i in range(threads)]
+    frames_per_chunk = n // HOP + 1
+
+    def work(i):
+        ref.bench(chunks[i], SR, W, HOP, N_DFT, 1)
+
+    def step():
+        th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return frames_per_chunk * threads * steps / dt, dt / steps, frames_per_chunk * threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = args.steps if args.steps is not None else 3
+    warmup = args.warmup if args.warmup is not None else 1
+    cores = os.cpu_count() or 1
+    seconds = 30.0
+    try:
+        fps, step_s, frames = cpu_reference_run(seconds, cores, steps, warmup)
+    except Exception as e:  # the oracle always exists; this is a broken checkout
+        print(json.dumps({"impl": "reference", "unavailable": str(e)}))
+        return
+    sample = "%d host threads x one mono %g s chunk of the cfg2 signal each per step (%d frames/step), reference " \
+             "AudioPV.cpp compiled verbatim, FFTW stand-in = vendored pffft" % (cores, seconds, frames)
+    line = {
+        "impl": "reference",
+        "metric": "PV frames/sec (analysis+resynth)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flan_b200.engine import Engine
+    from flan_b200.signals import noise_chirp
+    from flan_b200.sharding import frame_shard, sharded_resynthesis
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps = args.steps if args.steps is not None else 10
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = Engine(local_rank)
+    dev = eng.device
+
+    n_total = int(SR * args.seconds) * world
+    sh = frame_shard(n_total, HOP, W, world, rank)
+    B = N_DFT // 2 + 1
+    ar = eng.analysis_rate(SR, HOP)
+    n_local = sh.audio_hi - sh.audio_lo
+    host_audio = torch.empty((CH, n_local), dtype=torch.float32).pin_memory()
+    for c in range(CH):
+        host_audio[c].copy_(torch.from_numpy(noise_chirp(n_local, SR, 1234 + c + 100 * rank)))
+    x = host_audio.to(dev, non_blocking=True)
+    pv = torch.empty((CH, sh.frames, B, 2), dtype=torch.float32, device=dev)
+    out_len = sh.span_hi - sh.span_lo
+    y = torch.empty((CH, out_len), dtype=torch.float32, device=dev)
+    host_out = torch.empty((CH, out_len), dtype=torch.float32).pin_memory()
+
+    def allgather(state):
+        if world == 1:
+            return state.unsqueeze(0)
+        bufs = torch.empty((world,) + tuple(state.shape), dtype=state.dtype, device=dev)
+        dist.all_gather_into_tensor(bufs, state.contiguous())
+        return bufs
+
+    def step(xin):
+        if world == 1:
+            eng.convert_to_pv(xin, SR, W, HOP, N_DFT, out=pv)
+            eng.convert_to_audio(pv, SR, ar, W, out=y)
+            return y
+        eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
+        o, _ = sharded_resynthesis(eng, dist, sh, pv, SR, ar, allgather,
+                                   lambda t, dst: dist.isend(t, dst), lambda t, src: dist.recv(t, src))
+        return o
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step(x)
+    barrier()
+
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream -----------------------
+    eng.set_timing(True)
+    for k in eng.KERNEL_KINDS:
+        eng.kernel_time(k)
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step(x)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    ktimes = {k: eng.kernel_time(k) for k in eng.KERNEL_KINDS}
+    eng.set_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_rank = CH * sh.frames
+    frames_all = torch.tensor([frames_rank], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(frames_all, op=dist.ReduceOp.SUM)
+    frames_all = float(frames_all.item())
+    value = frames_all * steps / (ms_max * 1e-3)
+
+    # ---- end to end: pinned host audio in, pinned host audio out, every step --------------------------------
+    def e2e_step():
+        xin = host_audio.to(dev, non_blocking=True)
+        o = step(xin)
+        host_out.copy_(o, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = frames_all * steps / float(te.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        an_ms, an_n = ktimes["analysis"]
+        sy_ms, sy_n = ktimes["synthesis"]
+        seg_ms, seg_n = ktimes["phase_seg"]
+        scan_ms, scan_n = ktimes["phase_scan"]
+        an_bytes = 4.0 * CH * n_local + 8.0 * CH * sh.frames * B          # per launch: audio read + PV written
+        sy_bytes = 8.0 * CH * sh.frames * B + 4.0 * CH * out_len          # per launch: PV read + audio written
+        kern = []
+        if an_n:
+            kern.append(("pv_analysis_kernel<4096>", an_bytes, an_ms / an_n))
+        if sy_n:
+            kern.append(("pv_synthesis_kernel<4096>", sy_bytes, sy_ms / sy_n))
+        dom = max(kern, key=lambda k: k[2]) if kern else None
+        roofline = None
+        if dom:
+            ach = dom[1] / (dom[2] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1],
+                        "ms_per_launch": dom[2]}
+        per_kernel = {}
+        for name, byts, m in kern:
+            per_kernel[name] = {"ms_per_launch": m, "achieved_gbs": byts / (m * 1e-3) / 1e9, "frac": byts / (m * 1e-3) / 1e9 / peak}
+        if seg_n:
+            per_kernel["pv_phase_seg_kernel"] = {"ms_per_launch": seg_ms / seg_n}
+        if scan_n:
+            per_kernel["pv_phase_scan_kernel"] = {"ms_per_launch": scan_ms / scan_n}
+        # the whole round trip against its compulsory traffic 2 * (4h + 8B) bytes per frame
+        rt_bytes = (an_bytes + sy_bytes) * steps
+        step_gbs = rt_bytes / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "PV frames/sec (analysis+resynth)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "channels": CH, "frames_per_gpu": sh.frames, "bins": B,
+                       "seconds_per_gpu": args.seconds, "sharding": "none" if world == 1 else "contiguous frame ranges, dp%d" % world,
+                       "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush"},
+            "legs": {"analysis_frames_per_s": frames_rank / (an_ms / an_n * 1e-3) if an_n else None,
+                     "resynthesis_frames_per_s": frames_rank / ((sy_ms + seg_ms + scan_ms) / sy_n * 1e-3) if sy_n else None,
+                     "audio_samples_per_s": value * HOP,
+                     "round_trip_hbm_gbs": step_gbs, "round_trip_frac_of_peak": step_gbs / peak},
+            "roofline": roofline, "kernels": per_kernel,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n_local),
+                    "d2h_bytes_per_step": int(4 * CH * out_len)},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                secs = 60.0
+                fps, step_s, frames = cpu_reference_run(secs, 1, 1, 0)
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                        "sample": "one mono %g s chunk of the cfg2 signal (%d frames), round trip, reference sources "
+                                                  "compiled verbatim, FFTW stand-in = vendored pffft, 1 thread as the reference runs" % (secs, frames)}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

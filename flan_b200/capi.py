@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI in include/flan_b200.h (libflan_b200.so).
+
+There is no fallback: if the CUDA library is missing or no device is usable this raises.
+"""
+import ctypes
+import os
+
+from . import build
+
+_i64 = ctypes.c_int64
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+_f = ctypes.c_float
+
+OK, INVALID, UNSUPPORTED, CUDA, CANCELLED, NOMEM = range(6)
+
+# every symbol include/flan_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("flan_b200_device_count", _int, []),
+    ("flan_b200_create", _int, [_int, ctypes.POINTER(_vp)]),
+    ("flan_b200_destroy", None, [_vp]),
+    ("flan_b200_last_error", ctypes.c_char_p, [_vp]),
+    ("flan_b200_set_stream", _int, [_vp, _vp]),
+    ("flan_b200_synchronize", _int, [_vp]),
+    ("flan_b200_sm_count", _int, [_vp]),
+    ("flan_b200_launch_count", _i64, [_vp]),
+    ("flan_b200_set_timing", _int, [_vp, _int]),
+    ("flan_b200_kernel_time", _int, [_vp, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
+    ("flan_b200_malloc", _int, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    ("flan_b200_free", _int, [_vp, _vp]),
+    ("flan_b200_upload", _int, [_vp, _vp, _vp, ctypes.c_size_t]),
+    ("flan_b200_download", _int, [_vp, _vp, _vp, ctypes.c_size_t]),
+    ("flan_b200_num_frames", _i64, [_i64, _int]),
+    ("flan_b200_hop_from_rates", _int, [_f, _f]),
+    ("flan_b200_analysis_rate", _f, [_f, _int]),
+    ("flan_b200_convert_to_pv", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _vp, _vp]),
+    ("flan_b200_convert_to_pv_range", _int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _f, _int, _int, _int, _i64, _i64, _vp, _i64]),
+    ("flan_b200_convert_to_audio", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _vp, _vp, ctypes.POINTER(_int)]),
+    ("flan_b200_phase_summary", _int, [_vp, _vp, _i64, _int, _i64, _i64, _int, _f, _f, _int, _vp]),
+    ("flan_b200_phase_carry", _int, [_vp, _vp, _int, _int, _int, _vp]),
+    ("flan_b200_convert_to_audio_range", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _vp, _i64, _i64, _i64]),
+    ("flan_b200_add", _int, [_vp, _vp, _vp, _i64]),
+    ("flan_b200_mid_side", _int, [_vp, _vp, _vp, _i64]),
+    ("flan_b200_convert_to_pv_host", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _int, _vp, _vp]),
+    ("flan_b200_convert_to_audio_host", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _int, _vp, _vp, ctypes.POINTER(_int)]),
+]
+
+_lib = None
+
+
+class FlanB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("flan_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """Load libflan_b200.so (built in-tree by flan_b200.build). Raises if it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = build.lib_path()
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s is missing: run `python -m flan_b200.build` (nvcc). flan_b200 has no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Context:
+    """Owns a flan_b200_ctx bound to one CUDA device."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.flan_b200_create(device, ctypes.byref(h))
+        if rc != OK:
+            raise FlanB200Error(rc, self.lib.flan_b200_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.flan_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != OK:
+            raise FlanB200Error(rc, self.lib.flan_b200_last_error(self.h).decode())
+
+    def call(self, name, *args):
+        self.check(getattr(self.lib, name)(self.h, *args))

@@ -1,0 +1,192 @@
+// flan_b200/csrc/emu/pv_emu.cpp -- CPU thread emulator of the kernel bodies in pv_body.cuh.
+//
+// TEST HARNESS, not a product path: nothing in libflan_b200.so links or calls this. It runs the very
+// same CTA body source the GPU runs, one std::thread per CUDA thread with std::barrier standing in for
+// __syncthreads, so that index math, shared-memory layouts and barrier placement can be validated
+// against the oracle in a container without a GPU (tests/test_emulator.py). libm replaces the CUDA
+// math library, so results agree with the device to rounding, not bit for bit.
+#include "../pv_body.cuh"
+#include "../pv_tables.h"
+
+#include <atomic>
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+using namespace pvk;
+
+namespace {
+
+struct HostEnv
+	{
+	int tid;
+	std::barrier<> * bar;
+	void sync() { bar->arrive_and_wait(); }
+	float ldg( const float * p ) { return *p; }
+	float2 ldg2( const float2 * p ) { return *p; }
+	float2 ldcs2( const float2 * p ) { return *p; }
+	void st_stream2( float2 * p, float2 v ) { *p = v; }
+	void st_stream( float * p, float v ) { *p = v; }
+	void red_add( float * p, float v ) { std::atomic_ref<float>( *p ).fetch_add( v ); }
+	void sincos( float x, float * s, float * c ) { *s = sinf( x ); *c = cosf( x ); }
+	void cp_async4( float * dst, const float * src, bool valid ) { *dst = valid ? *src : 0.0f; }
+	void cp_async_commit() {}
+	void cp_async_wait_all() {}
+	};
+
+template<int N, class Body> void run_cta( Body && body )
+	{
+	constexpr int T = N / 16;
+	std::vector<float> ring( N );
+	std::vector<float2> x0( N / 2 ), x1( N / 2 );
+	std::barrier<> bar( T );
+	std::vector<std::thread> th;
+	for( int t = 0; t < T; ++t )
+		th.emplace_back( [&, t]
+			{
+			HostEnv env{ t, &bar };
+			body( env, ring.data(), x0.data(), x1.data() );
+			} );
+	for( auto & x : th ) x.join();
+	}
+
+template<int N> void analysis_n( const AnalysisArgs & a, int64_t blocks )
+	{
+	for( int64_t b = 0; b < blocks; ++b )
+		run_cta<N>( [&]( HostEnv & env, float * ring, float2 * x0, float2 * x1 ) { analysis_cta<N>( a, b, env, ring, x0, x1 ); } );
+	}
+
+template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
+	{
+	for( int64_t b = 0; b < blocks; ++b )
+		run_cta<N>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1 ) { synthesis_cta<N>( a, b, env, ola, x0, x1 ); } );
+	}
+
+} // namespace
+
+extern "C" {
+
+// Same contract as flan_b200_convert_to_pv_range, on host memory. seg_len <= 0 picks the product's choice for `sms` SMs.
+int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_offset, int C, int64_t n_total,
+                     float sr, int W, int hop, int N, int64_t frame_begin, int64_t frame_end, int seg_len, int sms,
+                     float * pv_rows, int64_t pv_channel_stride )
+	{
+	HostTables tb;
+	if( !build_tables( N, W, hop, sr, sr / hop, tb ) ) return 1;
+	const int64_t frames = frame_end - frame_begin;
+	if( seg_len <= 0 ) seg_len = choose_seg_len( frames, C, sms, W, hop );
+	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	AnalysisArgs a{};
+	a.audio = audio; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;
+	a.pv = (float2 *) pv_rows; a.pv_channel_stride = pv_channel_stride;
+	a.frame_begin = frame_begin; a.frame_end = frame_end; a.seg_len = seg_len; a.segs_per_channel = segs;
+	a.W = W; a.hop = hop; a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
+	a.win = tb.win_analysis.data(); a.expected = tb.expected.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.k = tb.k;
+	const int64_t blocks = (int64_t) C * segs;
+	switch( N )
+		{
+		case 256: analysis_n<256>( a, blocks ); break;
+		case 512: analysis_n<512>( a, blocks ); break;
+		case 1024: analysis_n<1024>( a, blocks ); break;
+		case 2048: analysis_n<2048>( a, blocks ); break;
+		case 4096: analysis_n<4096>( a, blocks ); break;
+		case 8192: analysis_n<8192>( a, blocks ); break;
+		default: return 2;
+		}
+	return 0;
+	}
+
+// Same contract as flan_b200_convert_to_audio_range (carry_in / carry_out: [C][B] PhaseSeg, may be null).
+int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, int64_t frame_begin, int64_t frame_end,
+                      int64_t frames_total, int B, float sr, float ar, int W, int seg_len, int sms,
+                      const PhaseSeg * carry_in, PhaseSeg * carry_out,
+                      float * out, int64_t out_stride, int64_t out_offset, int64_t out_len, int * nan_flag )
+	{
+	const int N = ( B - 1 ) * 2;
+	const int hop = (int)( sr / ar );
+	HostTables tb;
+	if( !build_tables( N, W, hop, sr, ar, tb ) ) return 1;
+	const int64_t frames = frame_end - frame_begin;
+	if( seg_len <= 0 ) seg_len = choose_seg_len( frames, C, sms, W, hop );
+	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	std::vector<PhaseSeg> seg( (size_t) C * segs * B );
+	std::vector<double> acc( (size_t) C * segs * B );
+	int flag = 0;
+	for( int c = 0; c < C; ++c )
+		for( int s = 0; s < segs; ++s )
+			for( int b = 0; b < B; ++b )
+				{
+				const int64_t fa = frame_begin + (int64_t) s * seg_len;
+				const int64_t fb = fa + seg_len < frame_end ? fa + seg_len : frame_end;
+				const float2 * col = (const float2 *) pv_rows + (int64_t) c * pv_channel_stride + ( fa - frame_begin ) * (int64_t) B + b;
+				seg[( (size_t) c * segs + s ) * B + b] = phase_segment_summary( col, (int64_t) B, fb - fa, tb.k, tb.P, tb.rcpP, flag,
+					[]( const float2 * p ) { return *p; } );
+				}
+	for( int c = 0; c < C; ++c )
+		for( int b = 0; b < B; ++b )
+			{
+			PhaseSeg st; st.sum.q = st.sum.r = st.mx.q = st.mx.r = 0.0;
+			if( carry_in ) st = carry_in[(size_t) c * B + b];
+			for( int s = 0; s < segs; ++s )
+				{
+				acc[( (size_t) c * segs + s ) * B + b] = phase_state_value( st, tb.P );
+				phase_state_combine( st, seg[( (size_t) c * segs + s ) * B + b], tb.P, tb.rcpP );
+				}
+			if( carry_out ) carry_out[(size_t) c * B + b] = st;
+			}
+	if( nan_flag ) *nan_flag = flag;
+	if( !out ) return 0;
+	for( int c = 0; c < C; ++c ) std::memset( out + (int64_t) c * out_stride, 0, sizeof( float ) * (size_t) out_len );
+	SynthArgs a{};
+	a.pv = (const float2 *) pv_rows; a.pv_channel_stride = pv_channel_stride;
+	a.frame_begin = frame_begin; a.frame_end = frame_end;
+	a.out = out; a.out_stride = out_stride; a.out_offset = out_offset;
+	const int64_t total = frames_total * hop;
+	a.out_lo = out_offset > 0 ? out_offset : 0;
+	a.out_hi = out_offset + out_len < total ? out_offset + out_len : total;
+	a.acc_start = acc.data(); a.seg_len = seg_len; a.segs_per_channel = segs;
+	a.W = W; a.hop = hop; a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
+	a.win = tb.win_synthesis.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.k = tb.k; a.P = tb.P; a.rcpP = tb.rcpP;
+	const int64_t blocks = (int64_t) C * segs;
+	switch( N )
+		{
+		case 256: synthesis_n<256>( a, blocks ); break;
+		case 512: synthesis_n<512>( a, blocks ); break;
+		case 1024: synthesis_n<1024>( a, blocks ); break;
+		case 2048: synthesis_n<2048>( a, blocks ); break;
+		case 4096: synthesis_n<4096>( a, blocks ); break;
+		case 8192: synthesis_n<8192>( a, blocks ); break;
+		default: return 2;
+		}
+	return 0;
+	}
+
+// Host tables, for tests of the plan arithmetic.
+int pv_emu_tables( int N, int W, int hop, float sr, float ar, float * win_a, float * win_s, float * expected )
+	{
+	HostTables tb;
+	if( !build_tables( N, W, hop, sr, ar, tb ) ) return 1;
+	std::memcpy( win_a, tb.win_analysis.data(), sizeof( float ) * W );
+	std::memcpy( win_s, tb.win_synthesis.data(), sizeof( float ) * W );
+	std::memcpy( expected, tb.expected.data(), sizeof( float ) * ( N / 2 + 1 ) );
+	return 0;
+	}
+
+// div_const against IEEE division on `count` floats starting at bit pattern `first`; returns mismatches.
+int64_t pv_emu_div_const_mismatches( float c, uint32_t first, int64_t count )
+	{
+	const float rc = 1.0f / c;
+	int64_t bad = 0;
+	for( int64_t i = 0; i < count; ++i )
+		{
+		uint32_t u = first + (uint32_t) i; float x; std::memcpy( &x, &u, 4 );
+		if( !( fabsf( x ) < 3.0e38f ) ) continue;
+		if( div_const( x, c, rc ) != x / c ) ++bad;
+		}
+	return bad;
+	}
+
+}

@@ -1,0 +1,452 @@
+// flan_b200/csrc/pv_body.cuh
+//
+// CTA bodies of the analysis (Audio::convert_to_PV, reference Conversions/AudioPV.cpp:12-78) and
+// resynthesis (PV::convert_to_audio, AudioPV.cpp:86-139) kernels, written against an Env so that the
+// identical source runs on the device (pv_kernels.cu) and in the CPU thread emulator (emu/pv_emu.cpp).
+//
+// Work decomposition (both directions): a CTA owns one contiguous SEGMENT of frames of one channel and
+// walks it in frame order. A frame of N-point real FFT is computed by T = N/16 threads, 8 complex
+// points each (the real transform is a packed N/2-point complex FFT). Walking in order lets
+//   * analysis keep the previous frame's phase of "its" bins in registers (the serial dependency of
+//     AudioPV.cpp:47/phase_vocoder.cpp:44-45), at the cost of one warm-up FFT per segment, and reuse
+//     the sliding window from a shared-memory ring so each input sample is fetched from HBM once;
+//   * resynthesis keep the fp64 phase accumulators (phase_vocoder.cpp:58-59) in registers and the
+//     overlap-add in a shared-memory ring that is flushed hop by hop, so every output sample is
+//     written once, contributions added in increasing frame order like AudioPV.cpp:133-134.
+// Window coefficients, twiddles and bin constants for a thread's fixed positions stay in registers or
+// L1 across the walk.
+#pragma once
+
+#include "pv_core.cuh"
+
+namespace pvk {
+
+// ------------------------------------------------------------------------------------------------
+// FFT pass chain over the ping-pong exchange buffers x0/x1 (M float2 each).
+// Pass 0 (radix 8, no twiddles) is issued by the caller's prologue; this runs passes 1..last.
+// ------------------------------------------------------------------------------------------------
+template<int M, int p, bool STORE_LAST, class Env>
+PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env )
+	{
+	using P = FftPlan<M>;
+	if constexpr( p < P::num_passes )
+		{
+		constexpr int Rp = P::radix( p - 1 ), NSp = P::ns( p - 1 );     // producer of our input
+		constexpr int R = P::radix( p ), NS = P::ns( p );
+		float2 * in  = ( ( p - 1 ) % 2 == 0 ) ? x0 : x1;
+		float2 * out = ( p % 2 == 0 ) ? x0 : x1;
+		fft_load<M, Rp, NSp>( t, v, in );
+		fft_butterflies<M, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
+		if constexpr( p < P::num_passes - 1 || STORE_LAST )
+			{
+			fft_store<M, R, NS>( t, v, out );
+			env.sync();
+			}
+		fft_pass_chain<M, p + 1, STORE_LAST>( t, v, x0, x1, tw, env );
+		}
+	}
+
+// Buffer that holds the natural-order output of the last pass when STORE_LAST is set.
+template<int M> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
+	{
+	return ( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Analysis
+// ------------------------------------------------------------------------------------------------
+struct AnalysisArgs
+	{
+	const float * audio;        // local buffer; channel c starts at audio + c * audio_stride
+	int64_t audio_stride;       // elements between channels of the local buffer
+	int64_t audio_offset;       // absolute sample index held at local position 0 (frame-range shards)
+	int64_t n_total;            // samples per channel of the whole signal; reads outside [0,n_total) are 0
+	float2 * pv;                // rows of (m,f): pv + c * pv_channel_stride + (frame - frame_begin) * B
+	int64_t pv_channel_stride;
+	int64_t frame_begin, frame_end;   // absolute frames produced by this launch
+	int seg_len;                // frames per CTA
+	int segs_per_channel;
+	int W, hop;
+	int aligned2;               // hop and W/2 even: ring reads as float2
+	const float * win;          // [W] Hann, reference expression evaluated on the host
+	const float * expected;     // [B] expected_phase_diff per bin (phase_vocoder.cpp:47), host-evaluated
+	const float2 * post_tw;     // [N/4+1] e^{-2 pi i k/N}
+	const float2 * pass_tw;     // concatenated per-pass twiddles
+	PvConsts k;
+	};
+
+template<int N, class Env>
+PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float * ring, float2 * x0, float2 * x1 )
+	{
+	constexpr int M = N / 2, T = M / 8;
+	using P = FftPlan<M>;
+	const int t = env.tid;
+	const int c = (int)( block / a.segs_per_channel );
+	const int seg = (int)( block % a.segs_per_channel );
+	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
+	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
+	if( fa >= fb ) return;
+
+	const float * xch = a.audio + (int64_t) c * a.audio_stride;
+	const int W = a.W, hop = a.hop;
+	const int half = W / 2;
+
+	// per-thread constants for its fixed window positions and bins
+	float w[16];
+#pragma unroll
+	for( int s = 0; s < 8; ++s )
+		{
+		const int i0 = 2 * ( t + s * T );
+		w[2 * s]     = ( i0 < W )     ? env.ldg( a.win + i0 ) : 0.0f;
+		w[2 * s + 1] = ( i0 + 1 < W ) ? env.ldg( a.win + i0 + 1 ) : 0.0f;
+		}
+	float prev[9], expd[9];
+#pragma unroll
+	for( int u = 0; u < 4; ++u )
+		{
+		const int k = t + u * T;
+		prev[2 * u] = 0.0f; prev[2 * u + 1] = 0.0f;
+		expd[2 * u] = env.ldg( a.expected + k );
+		expd[2 * u + 1] = env.ldg( a.expected + ( M - k ) );
+		}
+	prev[8] = 0.0f;
+	expd[8] = env.ldg( a.expected + M / 2 );
+
+	// Stage samples [lo,hi) (absolute indices) into the ring; zero outside the signal (AudioPV.cpp:54-58).
+	auto stage = [&]( int64_t lo, int64_t hi )
+		{
+		for( int64_t s = lo + t; s < hi; s += T )
+			{
+			const bool valid = ( s >= 0 && s < a.n_total );
+			env.cp_async4( ring + ( s & ( N - 1 ) ), valid ? ( xch + ( s - a.audio_offset ) ) : xch, valid );
+			}
+		env.cp_async_commit();
+		};
+
+	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
+	// that does not start at frame 0 recomputes it with one warm-up FFT.
+	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
+	stage( (int64_t) hop * first - half, (int64_t) hop * first - half + W );
+
+	for( int64_t f = first; f < fb; ++f )
+		{
+		const int64_t start = (int64_t) hop * f - half;                 // AudioPV.cpp:52
+		env.cp_async_wait_all();
+		env.sync();
+
+		// pass 0: windowed load (AudioPV.cpp:61-62; zero padding :65) + radix-8
+		float2 v[8];
+		if( a.aligned2 )
+			{
+#pragma unroll
+			for( int s = 0; s < 8; ++s )
+				{
+				const int i0 = 2 * ( t + s * T );
+				float2 r = *reinterpret_cast<const float2 *>( ring + ( ( start + i0 ) & ( N - 1 ) ) );
+				v[s].x = ( i0 < W )     ? mul_rn( r.x, w[2 * s] ) : 0.0f;
+				v[s].y = ( i0 + 1 < W ) ? mul_rn( r.y, w[2 * s + 1] ) : 0.0f;
+				}
+			}
+		else
+			{
+#pragma unroll
+			for( int s = 0; s < 8; ++s )
+				{
+				const int i0 = 2 * ( t + s * T );
+				const float r0 = ring[( start + i0 ) & ( N - 1 )];
+				const float r1 = ring[( start + i0 + 1 ) & ( N - 1 )];
+				v[s].x = ( i0 < W )     ? mul_rn( r0, w[2 * s] ) : 0.0f;
+				v[s].y = ( i0 + 1 < W ) ? mul_rn( r1, w[2 * s + 1] ) : 0.0f;
+				}
+			}
+		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
+		fft_store<M, 8, 1>( t, v, x0 );
+		env.sync();
+
+		// every thread has consumed frame f's window: the next frame's new samples may land in the ring
+		if( f + 1 < fb )
+			{
+			const int64_t nlo = (int64_t) hop * ( f + 1 ) - half;
+			const int64_t plo = start + W;                              // end of the current window
+			stage( nlo > plo ? nlo : plo, nlo + W );
+			}
+
+		fft_pass_chain<M, 1, true>( t, v, x0, x1, a.pass_tw, env );
+		const float2 * z = fft_result_buffer<M>( x0, x1 );
+
+		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73)
+		const bool emit = ( f >= fa );
+		float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t)( M + 1 );
+#pragma unroll
+		for( int u = 0; u < 4; ++u )
+			{
+			const int k = t + u * T;
+			float2 xk, xm;
+			if( k == 0 )
+				{
+				const float2 z0 = z[0];
+				xk.x = z0.x + z0.y; xk.y = 0.0f;        // DC
+				xm.x = z0.x - z0.y; xm.y = 0.0f;        // Nyquist
+				}
+			else
+				{
+				const float2 zk = z[k], zm = z[M - k];
+				const float2 tw = env.ldg2( a.post_tw + k );
+				float2 A, Bq;
+				A.x = zk.x + zm.x; A.y = zk.y - zm.y;
+				Bq.x = zk.y + zm.y; Bq.y = zm.x - zk.x;         // -i * (zk - conj(zm))
+				const float2 Pq = cmul( Bq, tw );
+				xk.x = 0.5f * ( A.x + Pq.x ); xk.y = 0.5f * ( A.y + Pq.y );
+				xm.x = 0.5f * ( A.x - Pq.x ); xm.y = -0.5f * ( A.y - Pq.y );
+				}
+			if( emit )
+				{
+				const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], bin_frequency_of( k, a.k ), expd[2 * u], a.k );
+				const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], bin_frequency_of( M - k, a.k ), expd[2 * u + 1], a.k );
+				env.st_stream2( row + k, mk );
+				env.st_stream2( row + ( M - k ), mm );
+				}
+			else
+				{
+				prev[2 * u] = atan2f( xk.y, xk.x );
+				prev[2 * u + 1] = atan2f( xm.y, xm.x );
+				}
+			}
+		if( t == 0 )
+			{
+			const float2 zh = z[M / 2];
+			if( emit )
+				env.st_stream2( row + M / 2, phase_vocoder_bin( zh.x, -zh.y, prev[8], bin_frequency_of( M / 2, a.k ), expd[8], a.k ) );
+			else
+				prev[8] = atan2f( -zh.y, zh.x );
+			}
+		}
+	env.cp_async_wait_all();
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Resynthesis: phase-scan helpers
+// ------------------------------------------------------------------------------------------------
+
+// Segment summary of one bin over frames [fa,fb): total phase increment and its max prefix, in split
+// form (see PhaseSum). `flag` is raised on NaN/Inf, the is_nan_or_inf() pre-scan of AudioPV.cpp:88.
+template<class Ld>
+PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, int64_t rows, const PvConsts & k,
+                                      double P, double rcpP, int & flag, Ld && ld )
+	{
+	PhaseSeg s; s.sum.q = 0.0; s.sum.r = 0.0; s.mx.q = 0.0; s.mx.r = 0.0;
+	for( int64_t i = 0; i < rows; ++i )
+		{
+		const float2 mf = ld( col + i * row_stride );
+		if( !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f ) ) flag = 1;
+		s.sum.r += (double) phase_increment( mf.y, k );
+		phase_sum_normalize( s.sum, P, rcpP );
+		if( phase_sum_less( s.mx, s.sum ) ) s.mx = s.sum;
+		}
+	return s;
+	}
+
+// state <- state (+) seg : running (sum, max prefix) over segments in frame order.
+PV_HD void phase_state_combine( PhaseSeg & st, const PhaseSeg & seg, double P, double rcpP )
+	{
+	PhaseSum cand; cand.q = st.sum.q + seg.mx.q; cand.r = st.sum.r + seg.mx.r;
+	phase_sum_normalize( cand, P, rcpP );
+	if( phase_sum_less( st.mx, cand ) ) st.mx = cand;
+	st.sum.q += seg.sum.q; st.sum.r += seg.sum.r;
+	phase_sum_normalize( st.sum, P, rcpP );
+	}
+
+// The reference's accumulator value for running state st: S - P * max(0, floor(maxprefix / P)).
+PV_HD double phase_state_value( const PhaseSeg & st, double P )
+	{
+	return fma( st.sum.q - st.mx.q, P, st.sum.r );
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Resynthesis
+// ------------------------------------------------------------------------------------------------
+struct SynthArgs
+	{
+	const float2 * pv;          // rows: pv + c * pv_channel_stride + (frame - frame_begin) * B
+	int64_t pv_channel_stride;
+	int64_t frame_begin, frame_end;
+	float * out;                // local span; sample s of channel c at out + c * out_stride + (s - out_offset)
+	int64_t out_stride;
+	int64_t out_offset;
+	int64_t out_lo, out_hi;     // absolute samples that exist in the local span (others are dropped: AudioPV.cpp:127-128)
+	const double * acc_start;   // [C][segs_per_channel][B] accumulator value entering each segment
+	int seg_len;
+	int segs_per_channel;
+	int W, hop;
+	int aligned2;
+	const float * win;          // [W] Hann * window_scale, host-evaluated (AudioPV.cpp:99-102)
+	const float2 * post_tw;
+	const float2 * pass_tw;
+	PvConsts k;
+	double P, rcpP;             // double(pi2) and its reciprocal
+	};
+
+template<int N, class Env>
+PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float * ola, float2 * x0, float2 * x1 )
+	{
+	constexpr int M = N / 2, T = M / 8, B = M + 1;
+	using P = FftPlan<M>;
+	const int t = env.tid;
+	const int c = (int)( block / a.segs_per_channel );
+	const int seg = (int)( block % a.segs_per_channel );
+	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
+	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
+	if( fa >= fb ) return;
+
+	const int W = a.W, hop = a.hop;
+	const int half = W / 2;
+	const int fin = ( hop < W ) ? hop : W;          // samples finalised per frame
+
+	float w[16];
+#pragma unroll
+	for( int s = 0; s < 8; ++s )
+		{
+		const int i0 = 2 * ( t + s * T );
+		w[2 * s]     = ( i0 < W )     ? env.ldg( a.win + i0 ) : 0.0f;
+		w[2 * s + 1] = ( i0 + 1 < W ) ? env.ldg( a.win + i0 + 1 ) : 0.0f;
+		}
+	double acc[9];
+	const double * acc0 = a.acc_start + ( (int64_t) c * a.segs_per_channel + seg ) * B;
+#pragma unroll
+	for( int u = 0; u < 4; ++u )
+		{
+		const int k = t + u * T;
+		acc[2 * u] = acc0[k];
+		acc[2 * u + 1] = acc0[M - k];
+		}
+	acc[8] = acc0[M / 2];
+
+	for( int i = t; i < N; i += T ) ola[i] = 0.0f;
+
+	float * och = a.out + (int64_t) c * a.out_stride;
+	// Samples whose every contributing frame lies in this segment are stored; the W-hop samples shared with
+	// the previous / next segment receive exactly two partial sums and are combined with red.add (a + b is
+	// commutative, so the result does not depend on arrival order).
+	const int64_t interior_lo = (int64_t) hop * fa + half - hop;
+	const int64_t interior_hi = (int64_t) hop * fb - half;
+	auto flush = [&]( int64_t lo, int64_t hi )
+		{
+		for( int64_t s = lo + t; s < hi; s += T )
+			{
+			const float val = ola[s & ( N - 1 )];
+			ola[s & ( N - 1 )] = 0.0f;
+			if( s >= a.out_lo && s < a.out_hi )
+				{
+				float * dst = och + ( s - a.out_offset );
+				if( s >= interior_lo && s < interior_hi ) env.st_stream( dst, val );
+				else env.red_add( dst, val );
+				}
+			}
+		};
+
+	auto polar = [&]( float2 mf, double & ph ) -> float2
+		{
+		phase_accumulate( ph, phase_increment( mf.y, a.k ), a.P, a.rcpP );      // phase_vocoder.cpp:57-59
+		const float theta = (float) ph;
+		float sn, cs;
+		env.sincos( theta, &sn, &cs );
+		float2 r; r.x = mul_rn( mf.x, cs ); r.y = mul_rn( mf.x, sn );           // :60 std::polar
+		return r;
+		};
+
+	for( int64_t f = fa; f < fb; ++f )
+		{
+		const int64_t start = (int64_t) hop * f - half;                          // AudioPV.cpp:125
+		const float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t) B;
+
+		// bins -> packed half-size spectrum Z'[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/N} (X[k] - conj X[M-k]),
+		// stored with re/im swapped so the forward pass chain computes the inverse transform.
+#pragma unroll
+		for( int u = 0; u < 4; ++u )
+			{
+			const int k = t + u * T;
+			const float2 xk = polar( env.ldcs2( row + k ), acc[2 * u] );
+			const float2 xm = polar( env.ldcs2( row + ( M - k ) ), acc[2 * u + 1] );
+			if( k == 0 )
+				{
+				// imaginary parts of bins 0 and N/2 are ignored by a c2r transform
+				float2 z; z.x = xk.x + xm.x; z.y = xk.x - xm.x;
+				float2 zs; zs.x = z.y; zs.y = z.x;
+				x1[0] = zs;
+				}
+			else
+				{
+				const float2 tw = env.ldg2( a.post_tw + k );
+				float2 A, Bv, Q;
+				A.x = xk.x + xm.x;  A.y = xk.y - xm.y;
+				Bv.x = xk.x - xm.x; Bv.y = xk.y + xm.y;
+				Q.x = Bv.x * tw.x + Bv.y * tw.y;                 // Bv * conj(tw)
+				Q.y = Bv.y * tw.x - Bv.x * tw.y;
+				float2 zk, zm;
+				zk.y = A.x - Q.y; zk.x = A.y + Q.x;              // swapped (im, re) of Z'[k]
+				zm.y = A.x + Q.y; zm.x = Q.x - A.y;              // swapped (im, re) of Z'[M-k]
+				x1[k] = zk;
+				x1[M - k] = zm;
+				}
+			}
+		if( t == 0 )
+			{
+			const float2 xh = polar( env.ldcs2( row + M / 2 ), acc[8] );
+			float2 zs; zs.y = 2.0f * xh.x; zs.x = -2.0f * xh.y;   // Z'[M/2] = 2 conj X[M/2], swapped
+			x1[M / 2] = zs;
+			}
+		env.sync();
+
+		float2 v[8];
+		fft_load<M, 8, 64>( t, v, x1 );                           // natural order (identity swizzle)
+		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
+		fft_store<M, 8, 1>( t, v, x0 );
+		env.sync();
+		fft_pass_chain<M, 1, false>( t, v, x0, x1, a.pass_tw, env );
+
+		// v[s] = swapped z[n], n = t + s*T: y[2n] = v.y, y[2n+1] = v.x. Windowed overlap-add (AudioPV.cpp:133-134).
+		if( a.aligned2 )
+			{
+#pragma unroll
+			for( int s = 0; s < 8; ++s )
+				{
+				const int i0 = 2 * ( t + s * T );
+				if( i0 < W )
+					{
+					float2 * slot = reinterpret_cast<float2 *>( ola + ( ( start + i0 ) & ( N - 1 ) ) );
+					float2 cur = *slot;
+					cur.x = add_rn( cur.x, mul_rn( v[s].y, w[2 * s] ) );
+					if( i0 + 1 < W ) cur.y = add_rn( cur.y, mul_rn( v[s].x, w[2 * s + 1] ) );
+					*slot = cur;
+					}
+				}
+			}
+		else
+			{
+#pragma unroll
+			for( int s = 0; s < 8; ++s )
+				{
+				const int i0 = 2 * ( t + s * T );
+				if( i0 < W )
+					{
+					float * p0 = ola + ( ( start + i0 ) & ( N - 1 ) );
+					*p0 = add_rn( *p0, mul_rn( v[s].y, w[2 * s] ) );
+					}
+				if( i0 + 1 < W )
+					{
+					float * p1 = ola + ( ( start + i0 + 1 ) & ( N - 1 ) );
+					*p1 = add_rn( *p1, mul_rn( v[s].x, w[2 * s + 1] ) );
+					}
+				}
+			}
+		env.sync();
+		// no later frame of this segment reaches [start, start+fin) again; the barriers of the next
+		// frame order this zeroing before its overlap-add
+		flush( start, start + fin );
+		}
+	// remainder of the last window
+	const int64_t last_start = (int64_t) hop * ( fb - 1 ) - half;
+	flush( last_start + fin, last_start + W );
+	}
+
+} // namespace pvk

@@ -1,0 +1,546 @@
+// flan_b200/csrc/pv_capi.cu -- implementation of the C ABI declared in include/flan_b200.h.
+//
+// Host-side orchestration only: plan (constant table) cache, scratch workspace, launch geometry and
+// error mapping. All arithmetic of the path runs in the kernels of pv_kernels.cu; there is no CPU
+// fallback here -- every entry point fails with FLAN_B200_CUDA when no device is usable.
+#include "../../include/flan_b200.h"
+
+#include "pv_launch.h"
+#include "pv_tables.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace pvk;
+
+static_assert( sizeof( flan_b200_phase_state ) == sizeof( PhaseSeg ), "phase state layout" );
+
+namespace {
+
+struct DevicePlan
+	{
+	HostTables host;
+	float * win_analysis = nullptr;
+	float * win_synthesis = nullptr;
+	float * expected = nullptr;
+	float2 * post_tw = nullptr;
+	float2 * pass_tw = nullptr;
+	};
+
+thread_local std::string g_create_error;
+
+} // namespace
+
+struct flan_b200_ctx
+	{
+	int device = 0;
+	int sms = 0;
+	cudaStream_t stream = nullptr;
+	std::string error;
+	std::mutex mutex;       // plan cache + workspace; launches on one ctx are serialised by its stream
+	std::map<std::tuple<int, int, int, uint32_t, uint32_t>, std::unique_ptr<DevicePlan>> plans;
+	void * workspace = nullptr;
+	size_t workspace_bytes = 0;
+	int * d_flag = nullptr;
+	int64_t launches = 0;
+	bool timing = false;
+	struct Timed { int kind; cudaEvent_t start, stop; };
+	std::vector<Timed> timed;
+	};
+
+namespace {
+
+int fail( flan_b200_ctx * ctx, int code, const std::string & msg )
+	{
+	if( ctx ) ctx->error = msg;
+	return code;
+	}
+
+int cuda_fail( flan_b200_ctx * ctx, cudaError_t e, const char * what )
+	{
+	return fail( ctx, e == cudaErrorMemoryAllocation ? FLAN_B200_NOMEM : FLAN_B200_CUDA,
+	             std::string( what ) + ": " + cudaGetErrorString( e ) );
+	}
+
+#define CK( call, what ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) return cuda_fail( ctx, e_, what ); } while( 0 )
+
+uint32_t fbits( float f ) { uint32_t u; std::memcpy( &u, &f, 4 ); return u; }
+
+template<class T> cudaError_t upload_vec( const std::vector<T> & v, T ** d, cudaStream_t st )
+	{
+	cudaError_t e = cudaMalloc( (void **) d, sizeof( T ) * ( v.empty() ? 1 : v.size() ) );
+	if( e != cudaSuccess ) return e;
+	if( v.empty() ) return cudaSuccess;
+	// pageable source: the copy is staged before the call returns, so `v` may die afterwards
+	return cudaMemcpyAsync( *d, v.data(), sizeof( T ) * v.size(), cudaMemcpyHostToDevice, st );
+	}
+
+int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, DevicePlan ** out )
+	{
+	if( !dft_size_supported( N ) )
+		return fail( ctx, FLAN_B200_UNSUPPORTED, "dft_size must be a power of two in [256, 8192], got " + std::to_string( N ) );
+	if( W < 2 || W > N || hop < 1 || (int64_t) N * W / hop < 1 )
+		return fail( ctx, FLAN_B200_INVALID, "need 2 <= window_size <= dft_size and 1 <= hop <= dft_size*window_size" );
+	if( !( sr > 0.0f ) || !( ar > 0.0f ) )
+		return fail( ctx, FLAN_B200_INVALID, "sample_rate and analysis_rate must be positive" );
+	std::lock_guard<std::mutex> lock( ctx->mutex );
+	const auto key = std::make_tuple( N, W, hop, fbits( sr ), fbits( ar ) );
+	auto it = ctx->plans.find( key );
+	if( it != ctx->plans.end() ) { *out = it->second.get(); return FLAN_B200_OK; }
+	auto plan = std::make_unique<DevicePlan>();
+	if( !build_tables( N, W, hop, sr, ar, plan->host ) )
+		return fail( ctx, FLAN_B200_INVALID, "could not build plan tables" );
+	CK( upload_vec( plan->host.win_analysis, &plan->win_analysis, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.win_synthesis, &plan->win_synthesis, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.expected, &plan->expected, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.post_tw, &plan->post_tw, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
+	*out = plan.get();
+	ctx->plans[key] = std::move( plan );
+	return FLAN_B200_OK;
+	}
+
+int get_workspace( flan_b200_ctx * ctx, size_t bytes, void ** out )
+	{
+	std::lock_guard<std::mutex> lock( ctx->mutex );
+	if( bytes > ctx->workspace_bytes )
+		{
+		if( ctx->workspace )
+			{
+			CK( cudaStreamSynchronize( ctx->stream ), "workspace sync" );
+			cudaFree( ctx->workspace );
+			ctx->workspace = nullptr; ctx->workspace_bytes = 0;
+			}
+		CK( cudaMalloc( &ctx->workspace, bytes ), "workspace alloc" );
+		ctx->workspace_bytes = bytes;
+		}
+	*out = ctx->workspace;
+	return FLAN_B200_OK;
+	}
+
+// Brackets one kernel launch with events when timing is on (bench.py's per-kernel roofline).
+struct LaunchTimer
+	{
+	flan_b200_ctx * ctx; int kind; cudaEvent_t start = nullptr, stop = nullptr;
+	LaunchTimer( flan_b200_ctx * c, int k ) : ctx( c ), kind( k )
+		{
+		if( !ctx->timing ) return;
+		if( cudaEventCreate( &start ) != cudaSuccess || cudaEventCreate( &stop ) != cudaSuccess ) { start = stop = nullptr; return; }
+		cudaEventRecord( start, ctx->stream );
+		}
+	~LaunchTimer()
+		{
+		ctx->launches++;
+		if( !start ) return;
+		cudaEventRecord( stop, ctx->stream );
+		ctx->timed.push_back( { kind, start, stop } );
+		}
+	};
+
+bool cancelled( const volatile int * cancel ) { return cancel && *cancel; }
+
+size_t align_up( size_t v, size_t a ) { return ( v + a - 1 ) / a * a; }
+
+// Shared by the whole-signal and the frame-range forms of resynthesis.
+int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride, int C,
+                 int64_t frame_begin, int64_t frame_end, int64_t frames_total, int B,
+                 float sr, float ar, int W, const PhaseSeg * d_carry_in, PhaseSeg * d_carry_out,
+                 float * d_out, int64_t out_stride, int64_t out_offset, int64_t out_len,
+                 bool summary_only, const volatile int * cancel )
+	{
+	if( C < 1 || B < 2 || frame_begin < 0 || frame_end < frame_begin || frames_total < frame_end )
+		return fail( ctx, FLAN_B200_INVALID, "bad channel / bin / frame-range arguments" );
+	const int N = ( B - 1 ) * 2;                                        // PVBuffer.cpp:356-359
+	const int hop = flan_b200_hop_from_rates( sr, ar );
+	DevicePlan * plan = nullptr;
+	int rc = get_plan( ctx, N, W, hop, sr, ar, &plan );
+	if( rc ) return rc;
+	const int64_t frames = frame_end - frame_begin;
+	if( frames == 0 ) return FLAN_B200_OK;
+	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop );
+	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
+	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
+	void * ws = nullptr;
+	rc = get_workspace( ctx, seg_bytes + acc_bytes, &ws );
+	if( rc ) return rc;
+	PhaseSeg * d_seg = (PhaseSeg *) ws;
+	double * d_acc = (double *)( (char *) ws + seg_bytes );
+
+	PhaseSegArgs sa{};
+	sa.pv = (const float2 *) d_pv_rows; sa.pv_channel_stride = pv_channel_stride;
+	sa.frame_begin = frame_begin; sa.frame_end = frame_end;
+	sa.seg_len = seg_len; sa.segs_per_channel = segs; sa.B = B;
+	sa.seg_out = d_seg; sa.nan_flag = ctx->d_flag;
+	sa.k = plan->host.k; sa.P = plan->host.P; sa.rcpP = plan->host.rcpP;
+	{ LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->stream ), "phase summary launch" ); }
+
+	PhaseScanArgs sc{};
+	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
+	sc.carry_in = d_carry_in; sc.carry_out = d_carry_out;
+	sc.acc_start = summary_only ? nullptr : d_acc;
+	sc.P = plan->host.P; sc.rcpP = plan->host.rcpP;
+	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); }
+	if( summary_only ) return FLAN_B200_OK;
+	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+
+	for( int c = 0; c < C; ++c )
+		CK( cudaMemsetAsync( d_out + (int64_t) c * out_stride, 0, sizeof( float ) * (size_t) out_len, ctx->stream ), "output clear" );
+
+	SynthArgs a{};
+	a.pv = (const float2 *) d_pv_rows; a.pv_channel_stride = pv_channel_stride;
+	a.frame_begin = frame_begin; a.frame_end = frame_end;
+	a.out = d_out; a.out_stride = out_stride; a.out_offset = out_offset;
+	const int64_t total = frames_total * hop;                           // AudioPV.cpp:93
+	a.out_lo = out_offset > 0 ? out_offset : 0;
+	a.out_hi = ( out_offset + out_len < total ) ? out_offset + out_len : total;
+	a.acc_start = d_acc;
+	a.seg_len = seg_len; a.segs_per_channel = segs;
+	a.W = W; a.hop = hop;
+	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
+	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
+	{ LaunchTimer lt( ctx, 3 ); CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream ), "synthesis launch" ); }
+	return FLAN_B200_OK;
+	}
+
+} // namespace
+
+extern "C" {
+
+int flan_b200_device_count( void )
+	{
+	int n = 0;
+	if( cudaGetDeviceCount( &n ) != cudaSuccess ) return 0;
+	return n;
+	}
+
+int flan_b200_create( int device, flan_b200_ctx ** out )
+	{
+	if( !out ) return FLAN_B200_INVALID;
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount( &n );
+	if( e != cudaSuccess || n < 1 )
+		{
+		g_create_error = std::string( "no CUDA device: " ) + ( e != cudaSuccess ? cudaGetErrorString( e ) : "device count is 0" )
+		               + " (flan_b200 has no CPU fallback)";
+		return FLAN_B200_CUDA;
+		}
+	if( device < 0 || device >= n ) { g_create_error = "device index out of range"; return FLAN_B200_INVALID; }
+	e = cudaSetDevice( device );
+	if( e != cudaSuccess ) { g_create_error = cudaGetErrorString( e ); return FLAN_B200_CUDA; }
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties( &prop, device );
+	if( e != cudaSuccess ) { g_create_error = cudaGetErrorString( e ); return FLAN_B200_CUDA; }
+	if( prop.major < 10 )
+		{
+		g_create_error = "flan_b200 kernels are built for sm_100a only; device is sm_" + std::to_string( prop.major * 10 + prop.minor );
+		return FLAN_B200_CUDA;
+		}
+	auto * ctx = new flan_b200_ctx;
+	ctx->device = device;
+	ctx->sms = prop.multiProcessorCount;
+	e = cudaMalloc( (void **) &ctx->d_flag, sizeof( int ) );
+	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flag, 0, sizeof( int ) );
+	if( e != cudaSuccess ) { g_create_error = cudaGetErrorString( e ); delete ctx; return FLAN_B200_CUDA; }
+	*out = ctx;
+	return FLAN_B200_OK;
+	}
+
+void flan_b200_destroy( flan_b200_ctx * ctx )
+	{
+	if( !ctx ) return;
+	cudaSetDevice( ctx->device );
+	cudaStreamSynchronize( ctx->stream );
+	for( auto & kv : ctx->plans )
+		{
+		DevicePlan * p = kv.second.get();
+		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected );
+		cudaFree( p->post_tw ); cudaFree( p->pass_tw );
+		}
+	if( ctx->workspace ) cudaFree( ctx->workspace );
+	cudaFree( ctx->d_flag );
+	delete ctx;
+	}
+
+const char * flan_b200_last_error( const flan_b200_ctx * ctx )
+	{
+	return ctx ? ctx->error.c_str() : g_create_error.c_str();
+	}
+
+int flan_b200_set_stream( flan_b200_ctx * ctx, void * cuda_stream )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	ctx->stream = (cudaStream_t) cuda_stream;
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_synchronize( flan_b200_ctx * ctx )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	CK( cudaStreamSynchronize( ctx->stream ), "synchronize" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_sm_count( const flan_b200_ctx * ctx ) { return ctx ? ctx->sms : 0; }
+int64_t flan_b200_launch_count( const flan_b200_ctx * ctx ) { return ctx ? ctx->launches : 0; }
+
+int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	ctx->timing = enabled != 0;
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches )
+	{
+	if( !ctx || !total_ms || !launches ) return FLAN_B200_INVALID;
+	CK( cudaStreamSynchronize( ctx->stream ), "timing sync" );
+	double ms = 0.0; int64_t n = 0;
+	std::vector<flan_b200_ctx::Timed> keep;
+	for( auto & t : ctx->timed )
+		{
+		if( t.kind != kind ) { keep.push_back( t ); continue; }
+		float f = 0.0f;
+		if( cudaEventElapsedTime( &f, t.start, t.stop ) == cudaSuccess ) { ms += f; ++n; }
+		cudaEventDestroy( t.start ); cudaEventDestroy( t.stop );
+		}
+	ctx->timed.swap( keep );
+	*total_ms = ms; *launches = n;
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_malloc( flan_b200_ctx * ctx, size_t bytes, void ** d_out )
+	{
+	if( !ctx || !d_out ) return FLAN_B200_INVALID;
+	CK( cudaSetDevice( ctx->device ), "set device" );
+	CK( cudaMalloc( d_out, bytes ? bytes : 1 ), "device alloc" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_free( flan_b200_ctx * ctx, void * d_ptr )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	CK( cudaFree( d_ptr ), "device free" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_upload( flan_b200_ctx * ctx, void * d_dst, const void * h_src, size_t bytes )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	CK( cudaMemcpyAsync( d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream ), "upload" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_download( flan_b200_ctx * ctx, void * h_dst, const void * d_src, size_t bytes )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	CK( cudaMemcpyAsync( h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream ), "download" );
+	return FLAN_B200_OK;
+	}
+
+int64_t flan_b200_num_frames( int64_t n, int hop )
+	{
+	if( hop < 1 ) return 0;
+	return n / hop + 1;                                 // AudioPV.cpp:17
+	}
+
+int flan_b200_hop_from_rates( float sample_rate, float analysis_rate )
+	{
+	return (int)( sample_rate / analysis_rate );        // PVBuffer.cpp:381-384
+	}
+
+float flan_b200_analysis_rate( float sample_rate, int hop )
+	{
+	return sample_rate / hop;                           // AudioPV.cpp:25
+	}
+
+int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_local, int64_t audio_stride,
+                                   int64_t audio_offset, int64_t audio_len, int C, int64_t n_total,
+                                   float sr, int W, int hop, int N,
+                                   int64_t frame_begin, int64_t frame_end,
+                                   float * d_pv_rows, int64_t pv_channel_stride )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( C < 1 || n_total < 0 || hop < 1 )
+		return fail( ctx, FLAN_B200_INVALID, "bad channel count, length or hop" );
+	const int64_t F = flan_b200_num_frames( n_total, hop );
+	if( frame_begin < 0 || frame_end < frame_begin || frame_end > F )
+		return fail( ctx, FLAN_B200_INVALID, "frame range outside [0, n/hop + 1]" );
+	DevicePlan * plan = nullptr;
+	int rc = get_plan( ctx, N, W, hop, sr, flan_b200_analysis_rate( sr, hop ), &plan );
+	if( rc ) return rc;
+	const int64_t frames = frame_end - frame_begin;
+	if( frames == 0 ) return FLAN_B200_OK;
+	// the shard must hold every in-signal sample its frames (and the warm-up frame) read
+	int64_t need_lo = (int64_t) hop * ( frame_begin > 0 ? frame_begin - 1 : 0 ) - W / 2;
+	int64_t need_hi = (int64_t) hop * ( frame_end - 1 ) - W / 2 + W;
+	if( need_lo < 0 ) need_lo = 0;
+	if( need_hi > n_total ) need_hi = n_total;
+	if( need_hi > need_lo && ( audio_offset > need_lo || audio_offset + audio_len < need_hi ) )
+		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
+
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop );
+	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	AnalysisArgs a{};
+	a.audio = d_audio_local; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;
+	a.pv = (float2 *) d_pv_rows; a.pv_channel_stride = pv_channel_stride;
+	a.frame_begin = frame_begin; a.frame_end = frame_end;
+	a.seg_len = seg_len; a.segs_per_channel = segs;
+	a.W = W; a.hop = hop;
+	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
+	a.win = plan->win_analysis; a.expected = plan->expected; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	a.k = plan->host.k;
+	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream ), "analysis launch" ); }
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_convert_to_pv( flan_b200_ctx * ctx, const float * d_audio, int C, int64_t n,
+                             float sr, int W, int hop, int N, float * d_pv, const volatile int * cancel )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop must be >= 1" );
+	const int64_t F = flan_b200_num_frames( n, hop );
+	int rc = flan_b200_convert_to_pv_range( ctx, d_audio, n, 0, n, C, n, sr, W, hop, N, 0, F, d_pv, F * ( N / 2 + 1 ) );
+	if( rc ) return rc;
+	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, int B,
+                                float sr, float ar, int W, float * d_audio_out,
+                                const volatile int * cancel, int * nan_or_inf )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( !( ar > 0.0f ) || !( sr > 0.0f ) ) return fail( ctx, FLAN_B200_INVALID, "rates must be positive" );
+	const int hop = flan_b200_hop_from_rates( sr, ar );
+	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "analysis_rate above sample_rate gives hop 0" );
+	const int64_t out_n = F * hop;
+	if( nan_or_inf ) CK( cudaMemsetAsync( ctx->d_flag, 0, sizeof( int ), ctx->stream ), "flag clear" );
+	int rc = synth_range( ctx, d_pv, F * B, C, 0, F, F, B, sr, ar, W, nullptr, nullptr,
+	                      d_audio_out, out_n, 0, out_n, false, cancel );
+	if( rc ) return rc;
+	if( nan_or_inf )
+		{
+		CK( cudaMemcpyAsync( nan_or_inf, ctx->d_flag, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ), "flag read" );
+		CK( cudaStreamSynchronize( ctx->stream ), "flag sync" );
+		}
+	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_phase_summary( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                             int C, int64_t frame_begin, int64_t frame_end, int B,
+                             float sr, float ar, int W, flan_b200_phase_state * d_state_out )
+	{
+	if( !ctx || !d_state_out ) return FLAN_B200_INVALID;
+	if( frame_end == frame_begin )
+		{
+		CK( cudaMemsetAsync( d_state_out, 0, sizeof( PhaseSeg ) * (size_t) C * B, ctx->stream ), "state clear" );
+		return FLAN_B200_OK;
+		}
+	return synth_range( ctx, d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frame_end, B, sr, ar, W,
+	                    nullptr, (PhaseSeg *) d_state_out, nullptr, 0, 0, 0, true, nullptr );
+	}
+
+int flan_b200_phase_carry( flan_b200_ctx * ctx, const flan_b200_phase_state * d_all, int rank,
+                           int C, int B, flan_b200_phase_state * d_carry_out )
+	{
+	if( !ctx || rank < 0 || C < 1 || B < 1 ) return FLAN_B200_INVALID;
+	const double P = (double)( std::acos( -1.0f ) * 2.0f );
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_phase_carry( (const PhaseSeg *) d_all, rank, (int64_t) C * B, (PhaseSeg *) d_carry_out, P, 1.0 / P, ctx->stream ), "phase carry launch" ); }
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                                      int C, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
+                                      int B, float sr, float ar, int W,
+                                      const flan_b200_phase_state * d_carry_in,
+                                      float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( !( ar > 0.0f ) || !( sr > 0.0f ) || flan_b200_hop_from_rates( sr, ar ) < 1 )
+		return fail( ctx, FLAN_B200_INVALID, "bad rates" );
+	return synth_range( ctx, d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frames_total, B, sr, ar, W,
+	                    (const PhaseSeg *) d_carry_in, nullptr, d_out_local, out_stride, out_offset, out_len, false, nullptr );
+	}
+
+int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( n <= 0 ) return FLAN_B200_OK;
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_add( d_out, d_add, n, ctx->sms, ctx->stream ), "add launch" ); }
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_mid_side( flan_b200_ctx * ctx, const float * d_in, float * d_out, int64_t n )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( n <= 0 ) return FLAN_B200_OK;
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_mid_side( d_in, d_out, n, ctx->sms, ctx->stream ), "mid/side launch" ); }
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_convert_to_pv_host( flan_b200_ctx * ctx, const float * h_audio, int C, int64_t n,
+                                  float sr, int W, int hop, int N, int mid_side,
+                                  float * h_pv, const volatile int * cancel )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( hop < 1 || C < 1 || n < 0 ) return fail( ctx, FLAN_B200_INVALID, "bad shape" );
+	if( mid_side && C != 2 ) return fail( ctx, FLAN_B200_INVALID, "mid/side needs exactly two channels (AudioPV.cpp:82)" );
+	const int64_t F = flan_b200_num_frames( n, hop );
+	const size_t audio_bytes = sizeof( float ) * (size_t) C * n;
+	const size_t pv_bytes = sizeof( float ) * 2 * (size_t) C * F * ( N / 2 + 1 );
+	float * d_audio = nullptr, * d_ms = nullptr, * d_pv = nullptr;
+	int rc = flan_b200_malloc( ctx, audio_bytes, (void **) &d_audio );
+	if( !rc && mid_side ) rc = flan_b200_malloc( ctx, audio_bytes, (void **) &d_ms );
+	if( !rc ) rc = flan_b200_malloc( ctx, pv_bytes, (void **) &d_pv );
+	if( !rc ) rc = flan_b200_upload( ctx, d_audio, h_audio, audio_bytes );
+	if( !rc && mid_side ) rc = flan_b200_mid_side( ctx, d_audio, d_ms, n );
+	if( !rc ) rc = flan_b200_convert_to_pv( ctx, mid_side ? d_ms : d_audio, C, n, sr, W, hop, N, d_pv, cancel );
+	if( !rc ) rc = flan_b200_download( ctx, h_pv, d_pv, pv_bytes );
+	cudaError_t e = cudaStreamSynchronize( ctx->stream );
+	cudaFree( d_audio ); cudaFree( d_ms ); cudaFree( d_pv );
+	if( !rc && e != cudaSuccess ) return cuda_fail( ctx, e, "convert_to_pv_host" );
+	return rc;
+	}
+
+int flan_b200_convert_to_audio_host( flan_b200_ctx * ctx, const float * h_pv, int C, int64_t F, int B,
+                                     float sr, float ar, int W, int left_right,
+                                     float * h_audio_out, const volatile int * cancel, int * nan_or_inf )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( C < 1 || F < 0 || B < 2 || !( ar > 0.0f ) ) return fail( ctx, FLAN_B200_INVALID, "bad shape" );
+	if( left_right && C != 2 ) return fail( ctx, FLAN_B200_INVALID, "left/right needs exactly two channels (AudioPV.cpp:143)" );
+	const int hop = flan_b200_hop_from_rates( sr, ar );
+	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop < 1" );
+	const int64_t out_n = F * hop;
+	const size_t pv_bytes = sizeof( float ) * 2 * (size_t) C * F * B;
+	const size_t audio_bytes = sizeof( float ) * (size_t) C * out_n;
+	float * d_pv = nullptr, * d_audio = nullptr, * d_lr = nullptr;
+	int rc = flan_b200_malloc( ctx, pv_bytes, (void **) &d_pv );
+	if( !rc ) rc = flan_b200_malloc( ctx, audio_bytes, (void **) &d_audio );
+	if( !rc && left_right ) rc = flan_b200_malloc( ctx, audio_bytes, (void **) &d_lr );
+	if( !rc ) rc = flan_b200_upload( ctx, d_pv, h_pv, pv_bytes );
+	if( !rc ) rc = flan_b200_convert_to_audio( ctx, d_pv, C, F, B, sr, ar, W, d_audio, cancel, nan_or_inf );
+	if( !rc && left_right ) rc = flan_b200_mid_side( ctx, d_audio, d_lr, out_n );
+	if( !rc ) rc = flan_b200_download( ctx, h_audio_out, left_right ? d_lr : d_audio, audio_bytes );
+	cudaError_t e = cudaStreamSynchronize( ctx->stream );
+	cudaFree( d_pv ); cudaFree( d_audio ); cudaFree( d_lr );
+	if( !rc && e != cudaSuccess ) return cuda_fail( ctx, e, "convert_to_audio_host" );
+	return rc;
+	}
+
+} // extern "C"

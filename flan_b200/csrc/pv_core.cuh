@@ -1,0 +1,344 @@
+// flan_b200/csrc/pv_core.cuh
+//
+// Per-thread building blocks of the phase-vocoder kernels: radix-8/4/2 Stockham FFT passes over a
+// shared-memory exchange buffer, the real-FFT pack/unpack, and the float32 op sequences of the
+// reference's phase_vocoder() / inverse_phase_vocoder() (reference src/flan/phase_vocoder.cpp:5-61).
+//
+// Everything here is __host__ __device__ and written against an `Env` (thread id, barrier, shared
+// memory, async copy) so that the SAME source runs as a CUDA kernel body (pv_kernels.cu) and under
+// the CPU thread emulator (emu/pv_emu.cpp, one std::thread per CUDA thread, std::barrier for
+// __syncthreads). The emulator exists so index math, swizzles and barrier placement can be checked
+// in a container with no GPU; it is a test harness, not a product path.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define PV_HD __host__ __device__ __forceinline__
+#else
+#define PV_HD inline
+#endif
+
+namespace pvk {
+
+// ---------------------------------------------------------------------------------------------
+// Exactly rounded float ops. nvcc contracts a*b+c into FMA by default; the reference is compiled
+// without contraction, so every op of the phase-vocoder arithmetic goes through these.
+// (The host build of this header is compiled with -ffp-contract=off.)
+// ---------------------------------------------------------------------------------------------
+PV_HD float mul_rn( float a, float b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fmul_rn( a, b );
+#else
+	return a * b;
+#endif
+	}
+PV_HD float add_rn( float a, float b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fadd_rn( a, b );
+#else
+	return a + b;
+#endif
+	}
+PV_HD float sub_rn( float a, float b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fsub_rn( a, b );
+#else
+	return a - b;
+#endif
+	}
+PV_HD float fma_rn( float a, float b, float c )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fmaf_rn( a, b, c );
+#else
+	return fmaf( a, b, c );
+#endif
+	}
+
+// x / c for a loop-invariant divisor c with rc = RN(1/c): reciprocal multiply plus one FMA residual
+// correction (Markstein). Checked exhaustively against IEEE division for every float x in
+// [2^-100, 2^40] and c in { pi2, 187.5, 344.53125, 750, 375, ... } (tests/test_host_math.py samples
+// it again): identical quotients. Three instructions instead of the ~10 of a generic IEEE divide.
+PV_HD float div_const( float x, float c, float rc )
+	{
+	const float q0 = mul_rn( x, rc );
+	const float e = fma_rn( -q0, c, x );
+	return fma_rn( e, rc, q0 );
+	}
+
+// std::round(float): half away from zero (phase_vocoder.cpp:40).
+PV_HD float round_half_away( float x )
+	{
+	return roundf( x );
+	}
+
+// ---------------------------------------------------------------------------------------------
+// Complex helpers (float2 = re, im)
+// ---------------------------------------------------------------------------------------------
+PV_HD float2 cmul( float2 a, float2 w )
+	{
+	float2 r;
+	r.x = a.x * w.x - a.y * w.y;
+	r.y = a.x * w.y + a.y * w.x;
+	return r;
+	}
+
+// Forward 8-point DFT in place (e^{-2 pi i nk/8}); a[k] <- sum_n a[n] w^{nk}. `a` has stride S between
+// elements so a radix-8 butterfly can act on a strided subset of the thread's 8 registers.
+template<int S>
+PV_HD void dft8( float2 * a )
+	{
+	const float h = 0.70710678118654752440f;
+	float2 b0, b1, b2, b3, b4, b5, b6, b7;
+	b0.x = a[0*S].x + a[4*S].x; b0.y = a[0*S].y + a[4*S].y;
+	b4.x = a[0*S].x - a[4*S].x; b4.y = a[0*S].y - a[4*S].y;
+	b1.x = a[1*S].x + a[5*S].x; b1.y = a[1*S].y + a[5*S].y;
+	b5.x = a[1*S].x - a[5*S].x; b5.y = a[1*S].y - a[5*S].y;
+	b2.x = a[2*S].x + a[6*S].x; b2.y = a[2*S].y + a[6*S].y;
+	b6.x = a[2*S].x - a[6*S].x; b6.y = a[2*S].y - a[6*S].y;
+	b3.x = a[3*S].x + a[7*S].x; b3.y = a[3*S].y + a[7*S].y;
+	b7.x = a[3*S].x - a[7*S].x; b7.y = a[3*S].y - a[7*S].y;
+	// b5 *= (1-i)/sqrt2 ; b6 *= -i ; b7 *= (-1-i)/sqrt2
+	float2 t;
+	t.x = ( b5.x + b5.y ) * h; t.y = ( b5.y - b5.x ) * h; b5 = t;
+	t.x = b6.y; t.y = -b6.x; b6 = t;
+	t.x = ( b7.y - b7.x ) * h; t.y = -( b7.x + b7.y ) * h; b7 = t;
+	// even outputs: DFT4 of b0..b3
+	float2 c0, c1, c2, c3;
+	c0.x = b0.x + b2.x; c0.y = b0.y + b2.y;
+	c2.x = b0.x - b2.x; c2.y = b0.y - b2.y;
+	c1.x = b1.x + b3.x; c1.y = b1.y + b3.y;
+	c3.x = b1.y - b3.y; c3.y = -( b1.x - b3.x );      // -i * (b1 - b3)
+	a[0*S].x = c0.x + c1.x; a[0*S].y = c0.y + c1.y;
+	a[4*S].x = c0.x - c1.x; a[4*S].y = c0.y - c1.y;
+	a[2*S].x = c2.x + c3.x; a[2*S].y = c2.y + c3.y;
+	a[6*S].x = c2.x - c3.x; a[6*S].y = c2.y - c3.y;
+	// odd outputs: DFT4 of b4..b7
+	c0.x = b4.x + b6.x; c0.y = b4.y + b6.y;
+	c2.x = b4.x - b6.x; c2.y = b4.y - b6.y;
+	c1.x = b5.x + b7.x; c1.y = b5.y + b7.y;
+	c3.x = b5.y - b7.y; c3.y = -( b5.x - b7.x );
+	a[1*S].x = c0.x + c1.x; a[1*S].y = c0.y + c1.y;
+	a[5*S].x = c0.x - c1.x; a[5*S].y = c0.y - c1.y;
+	a[3*S].x = c2.x + c3.x; a[3*S].y = c2.y + c3.y;
+	a[7*S].x = c2.x - c3.x; a[7*S].y = c2.y - c3.y;
+	}
+
+template<int S>
+PV_HD void dft4( float2 * a )
+	{
+	float2 c0, c1, c2, c3;
+	c0.x = a[0*S].x + a[2*S].x; c0.y = a[0*S].y + a[2*S].y;
+	c2.x = a[0*S].x - a[2*S].x; c2.y = a[0*S].y - a[2*S].y;
+	c1.x = a[1*S].x + a[3*S].x; c1.y = a[1*S].y + a[3*S].y;
+	c3.x = a[1*S].y - a[3*S].y; c3.y = -( a[1*S].x - a[3*S].x );
+	a[0*S].x = c0.x + c1.x; a[0*S].y = c0.y + c1.y;
+	a[2*S].x = c0.x - c1.x; a[2*S].y = c0.y - c1.y;
+	a[1*S].x = c2.x + c3.x; a[1*S].y = c2.y + c3.y;
+	a[3*S].x = c2.x - c3.x; a[3*S].y = c2.y - c3.y;
+	}
+
+template<int S>
+PV_HD void dft2( float2 * a )
+	{
+	float2 u = a[0], v = a[S];
+	a[0].x = u.x + v.x; a[0].y = u.y + v.y;
+	a[S].x = u.x - v.x; a[S].y = u.y - v.y;
+	}
+
+// ---------------------------------------------------------------------------------------------
+// FFT plan for a complex transform of M points held 8 per thread by T = M/8 threads.
+// Passes are Stockham autosort: pass p has radix R_p and Ns_p = product of the earlier radices.
+//   thread t holds, before and after every pass, the elements at logical index  t + s*T, s = 0..7
+//   butterfly u (u < 8/R) of thread t is jj = t + u*T and acts on registers s = u + r*(8/R)
+//   it writes element r to logical index  (jj / Ns)*Ns*R + (jj % Ns) + r*Ns
+// M = 8^a * {1,2,4}: radix-8 passes first (the first needs no twiddles), the small radix last.
+// ---------------------------------------------------------------------------------------------
+template<int M> struct FftPlan
+	{
+	static_assert( M >= 128 && M <= 4096 && ( M & ( M - 1 ) ) == 0, "complex FFT size must be 128..4096" );
+	static constexpr int T = M / 8;
+	static constexpr int log2M = ( M == 128 ) ? 7 : ( M == 256 ) ? 8 : ( M == 512 ) ? 9 : ( M == 1024 ) ? 10 : ( M == 2048 ) ? 11 : 12;
+	static constexpr int num_r8 = log2M / 3;                  // radix-8 passes
+	static constexpr int last_r = 1 << ( log2M % 3 );         // 1 (none), 2 or 4
+	static constexpr int num_passes = num_r8 + ( last_r > 1 ? 1 : 0 );
+	static constexpr int radix( int p ) { return p < num_r8 ? 8 : last_r; }
+	static constexpr int ns( int p ) { int n = 1; for( int i = 0; i < p; ++i ) n *= radix( i ); return n; }
+	// offset (in float2) of pass p's twiddle table inside the concatenated table; pass 0 has none.
+	static constexpr int tw_offset( int p ) { int o = 0; for( int i = 1; i < p; ++i ) o += ( radix( i ) - 1 ) * ns( i ); return o; }
+	static constexpr int tw_total = tw_offset( num_passes );
+	};
+
+// Shared-memory exchange layouts (float2 elements, 64-bit accesses are served per half-warp, so 16
+// consecutive lanes must hit 16 distinct values of index mod 16):
+//   after the Ns=1 radix-8 pass lanes write index 8*jj + r     -> xor bits [6:4] into bits [2:0]
+//   after the Ns=8 pass lanes write 8R*(jj/8) + jj%8 + 8r      -> xor bit log2(8R) into bit 3
+//   after passes with Ns >= 16 lanes write consecutive indices -> identity
+// The matching reads are 16 consecutive, aligned indices, which any of these xors only permutes.
+template<int NS, int R> PV_HD int swz( int idx )
+	{
+	if( NS == 1 ) return idx ^ ( ( idx >> 4 ) & 7 );
+	if( NS == 8 ) return idx ^ ( ( ( idx >> ( R == 8 ? 6 : R == 4 ? 5 : 4 ) ) & 1 ) << 3 );
+	return idx;
+	}
+
+// One butterfly pass on the thread's 8 registers: twiddle (skipped when NS == 1), DFT_R.
+template<int M, int R, int NS, class TwLoad>
+PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw )
+	{
+	constexpr int T = M / 8;
+	constexpr int U = 8 / R;            // butterflies per thread; register stride between butterfly elements
+#pragma unroll
+	for( int u = 0; u < U; ++u )
+		{
+		if( NS > 1 )
+			{
+			const int jm = ( t + u * T ) & ( NS - 1 );
+#pragma unroll
+			for( int r = 1; r < R; ++r )
+				v[u + r * U] = cmul( v[u + r * U], ldtw( tw + ( r - 1 ) * NS + jm ) );
+			}
+		if( R == 8 ) dft8<U>( v + u );
+		if( R == 4 ) dft4<U>( v + u );
+		if( R == 2 ) dft2<U>( v + u );
+		}
+	}
+
+// Scatter the pass's outputs to the exchange buffer (swizzled for this pass's write pattern).
+template<int M, int R, int NS>
+PV_HD void fft_store( int t, const float2 * v, float2 * xout )
+	{
+	constexpr int T = M / 8;
+	constexpr int U = 8 / R;
+#pragma unroll
+	for( int u = 0; u < U; ++u )
+		{
+		const int jj = t + u * T;
+		const int base = ( jj / NS ) * NS * R + ( jj & ( NS - 1 ) );
+#pragma unroll
+		for( int r = 0; r < R; ++r )
+			xout[swz<NS, R>( base + r * NS )] = v[u + r * U];
+		}
+	}
+
+// Gather the 8 elements t + s*T written by the pass with (R, NS).
+template<int M, int R, int NS>
+PV_HD void fft_load( int t, float2 * v, const float2 * xin )
+	{
+	constexpr int T = M / 8;
+#pragma unroll
+	for( int s = 0; s < 8; ++s )
+		v[s] = xin[swz<NS, R>( t + s * T )];
+	}
+
+// ---------------------------------------------------------------------------------------------
+// Phase-vocoder arithmetic
+// ---------------------------------------------------------------------------------------------
+struct PvConsts
+	{
+	float sample_rate;       // PVBuffer::Format::sample_rate
+	float analysis_rate;     // float(sr) / hop                       AudioPV.cpp:25
+	float rcp_analysis_rate; // RN(1 / analysis_rate)
+	float pi2;               // acosf(-1) * 2.0f                      defines.h:44-45
+	float rcp_pi2;           // RN(1 / pi2)
+	float bin_scale;         // 1 / dft_size (exact: power of two)    PVBuffer.cpp:443-446
+	int use_wrapping;        // analysis_rate < sample_rate           phase_vocoder.cpp:37
+	};
+
+// |z| as the reference's std::abs(complex<float>) = hypotf. For operands in the normal range the
+// fused sum of squares + IEEE sqrt differs from hypotf by at most 1 ulp; out-of-range operands take
+// the scaled path so nothing overflows or flushes to zero.
+PV_HD float cabs_f( float re, float im )
+	{
+	const float ax = fabsf( re ), ay = fabsf( im );
+	const float mx = fmaxf( ax, ay );
+	if( mx > 1.0e-18f && mx < 1.0e18f )
+		return sqrtf( fmaf( re, re, im * im ) );
+	return hypotf( re, im );
+	}
+
+// phase_vocoder(), reference phase_vocoder.cpp:5-53, in its float32 operation order.
+// `prev_phase` is the previous frame's arg() of this bin (the reference stores it in a double; it
+// only ever holds a float value). Divisions by the loop constants use div_const (bit-identical).
+PV_HD float2 phase_vocoder_bin( float re, float im, float & prev_phase, float bin_frequency,
+                                float expected_phase_diff, const PvConsts & k )
+	{
+	const float phase = atan2f( im, re );                                   // :43 std::arg
+	const float phase_diff = sub_rn( phase, prev_phase );                   // :44
+	prev_phase = phase;                                                     // :45
+	const float delta = sub_rn( phase_diff, expected_phase_diff );          // :48
+	float wrapped = delta;
+	if( k.use_wrapping )                                                    // :49, wrap() :38-41
+		{
+		const float q = div_const( delta, k.pi2, k.rcp_pi2 );
+		const float r = round_half_away( q );
+		wrapped = sub_rn( delta, mul_rn( k.pi2, r ) );
+		}
+	const float df = div_const( mul_rn( wrapped, k.analysis_rate ), k.pi2, k.rcp_pi2 );   // :50
+	float2 mf;
+	mf.x = cabs_f( re, im );                                                // :52 std::abs
+	mf.y = add_rn( bin_frequency, df );                                     // :52
+	return mf;
+	}
+
+// PVBuffer::bin_to_frequency, PVBuffer.cpp:443-446: b * float(sr) / float(dft). dft is a power of two,
+// so the division is an exact scaling.
+PV_HD float bin_frequency_of( int b, const PvConsts & k )
+	{
+	return mul_rn( mul_rn( (float) b, k.sample_rate ), k.bin_scale );
+	}
+
+// inverse_phase_vocoder(), reference phase_vocoder.cpp:55-61: float increment, double accumulator,
+// wrap only when the accumulator exceeds double(pi2), modulus double(pi2) (not 2*pi).
+PV_HD float phase_increment( float f, const PvConsts & k )
+	{
+	return mul_rn( div_const( f, k.analysis_rate, k.rcp_analysis_rate ), k.pi2 );   // :57
+	}
+
+// fmod(x, P) for x > P > 0 (exact, like libm's).
+PV_HD double fmod_pos( double x, double P, double rcpP )
+	{
+	double n = floor( x * rcpP );
+	double r = fma( -n, P, x );
+	if( r < 0.0 ) r += P;
+	if( r >= P ) r -= P;
+	return r;
+	}
+
+PV_HD void phase_accumulate( double & acc, float inc, double P, double rcpP )
+	{
+	acc += (double) inc;                                                    // :58
+	if( acc > P ) acc = fmod_pos( acc, P, rcpP );                           // :59
+	}
+
+// Running phase sum in the split form S = q*P + r, r in [0,P), q integral (held in a double): the
+// reference's accumulator equals S - P*max(0, floor(max prefix of S / P)) ("phase scan"),
+// so segment summaries (sum, max prefix) compose associatively.
+struct PhaseSum { double q, r; };
+
+PV_HD void phase_sum_normalize( PhaseSum & s, double P, double rcpP )
+	{
+	if( s.r >= P || s.r < 0.0 )
+		{
+		double n = floor( s.r * rcpP );
+		double r = fma( -n, P, s.r );
+		if( r < 0.0 ) { r += P; n -= 1.0; }
+		if( r >= P ) { r -= P; n += 1.0; }
+		s.r = r; s.q += n;
+		}
+	}
+
+PV_HD bool phase_sum_less( const PhaseSum & a, const PhaseSum & b )
+	{
+	return a.q < b.q || ( a.q == b.q && a.r < b.r );
+	}
+
+struct PhaseSeg { PhaseSum sum, mx; };   // total and max prefix (the empty prefix counts as 0)
+
+} // namespace pvk

@@ -1,0 +1,222 @@
+// flan_b200/csrc/pv_kernels.cu -- sm_100a kernels of the phase-vocoder engine and their launchers.
+//
+//   pv_analysis_kernel<N>    Audio::convert_to_PV     (reference Conversions/AudioPV.cpp:12-78)
+//   pv_phase_seg_kernel      per-segment phase-sum summaries     (phase_vocoder.cpp:57-59, scan form)
+//   pv_phase_scan_kernel     exclusive scan of the summaries over segments -> accumulator per segment
+//   pv_synthesis_kernel<N>   PV::convert_to_audio     (AudioPV.cpp:86-139)
+//   pv_mid_side_kernel       Audio::convert_to_mid_side (Audio/AudioConversions.cpp:32-51)
+//
+// The CTA bodies live in pv_body.cuh (shared with the CPU thread emulator); this file supplies the
+// device Env (barrier, cp.async staging, cache-hinted loads/stores, red.add) and the launch geometry.
+#include "pv_body.cuh"
+#include "pv_launch.h"
+
+#include <cuda_runtime.h>
+
+namespace pvk {
+
+struct DeviceEnv
+	{
+	int tid;
+	__device__ __forceinline__ void sync() { __syncthreads(); }
+	__device__ __forceinline__ float ldg( const float * p ) { return __ldg( p ); }
+	__device__ __forceinline__ float2 ldg2( const float2 * p ) { return __ldg( p ); }
+	__device__ __forceinline__ float2 ldcs2( const float2 * p ) { return __ldcs( p ); }
+	__device__ __forceinline__ void st_stream2( float2 * p, float2 v ) { __stcs( p, v ); }
+	__device__ __forceinline__ void st_stream( float * p, float v ) { __stcs( p, v ); }
+	__device__ __forceinline__ void red_add( float * p, float v ) { atomicAdd( p, v ); }
+	__device__ __forceinline__ void sincos( float x, float * s, float * c ) { sincosf( x, s, c ); }
+	// 4-byte asynchronous global->shared copy (LDGSTS); src-size 0 zero-fills the destination.
+	__device__ __forceinline__ void cp_async4( float * dst, const float * src, bool valid )
+		{
+		const unsigned d = (unsigned) __cvta_generic_to_shared( dst );
+		const int sz = valid ? 4 : 0;
+		asm volatile( "cp.async.ca.shared.global [%0], [%1], 4, %2;\n" :: "r"( d ), "l"( src ), "r"( sz ) : "memory" );
+		}
+	__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;\n" ::: "memory" ); }
+	__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;\n" ::: "memory" ); }
+	};
+
+template<int N>
+__global__ void __launch_bounds__( N / 16 ) pv_analysis_kernel( const AnalysisArgs a )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+	float * ring = reinterpret_cast<float *>( smem_raw );
+	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
+	float2 * x1 = x0 + N / 2;
+	DeviceEnv env; env.tid = threadIdx.x;
+	analysis_cta<N>( a, (int64_t) blockIdx.x, env, ring, x0, x1 );
+	}
+
+template<int N>
+__global__ void __launch_bounds__( N / 16 ) pv_synthesis_kernel( const SynthArgs a )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+	float * ola = reinterpret_cast<float *>( smem_raw );
+	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
+	float2 * x1 = x0 + N / 2;
+	DeviceEnv env; env.tid = threadIdx.x;
+	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1 );
+	}
+
+// One thread per (channel, segment, bin): summary of the segment's phase increments.
+__global__ void __launch_bounds__( 256 ) pv_phase_seg_kernel( const PhaseSegArgs a )
+	{
+	const int bchunks = ( a.B + 255 ) / 256;
+	const int64_t blk = blockIdx.x;
+	const int b = (int)( blk % bchunks ) * 256 + threadIdx.x;
+	const int seg = (int)( ( blk / bchunks ) % a.segs_per_channel );
+	const int c = (int)( blk / ( (int64_t) bchunks * a.segs_per_channel ) );
+	if( b >= a.B ) return;
+	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
+	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
+	const float2 * col = a.pv + (int64_t) c * a.pv_channel_stride + ( fa - a.frame_begin ) * (int64_t) a.B + b;
+	int flag = 0;
+	const PhaseSeg s = phase_segment_summary( col, (int64_t) a.B, fb - fa, a.k, a.P, a.rcpP, flag,
+		[]( const float2 * p ) { return __ldg( p ); } );
+	PhaseSeg * dst = a.seg_out + ( (int64_t) c * a.segs_per_channel + seg ) * a.B + b;
+	*dst = s;
+	if( flag ) *a.nan_flag = 1;
+	}
+
+// One thread per (channel, bin): serial walk over the segments (a few thousand at most), writing the
+// accumulator value that enters each segment. carry_in/carry_out chain frame-range shards across GPUs.
+__global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanArgs a )
+	{
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	const int c = blockIdx.y;
+	if( b >= a.B ) return;
+	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
+	if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
+	const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
+	double * dst = a.acc_start ? a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b : nullptr;
+	for( int s = 0; s < a.segs_per_channel; ++s )
+		{
+		if( dst ) dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
+		phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+		}
+	if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = st;
+	}
+
+// carry[r] = summaries[0] (+) ... (+) summaries[r-1], for this rank r.
+__global__ void __launch_bounds__( 128 ) pv_phase_carry_kernel( const PhaseSeg * all, int rank, int64_t per_rank, PhaseSeg * carry, double P, double rcpP )
+	{
+	const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if( i >= per_rank ) return;
+	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
+	for( int r = 0; r < rank; ++r ) phase_state_combine( st, all[(int64_t) r * per_rank + i], P, rcpP );
+	carry[i] = st;
+	}
+
+// Audio::convert_to_mid_side (AudioConversions.cpp:42-49): (L +- R) / sqrt(2.0f), IEEE division.
+__global__ void __launch_bounds__( 256 ) pv_mid_side_kernel( const float * in, float * out, int64_t n )
+	{
+	const float sqrt2 = 1.41421356237309504880f;
+	for( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x )
+		{
+		const float l = in[i], r = in[n + i];
+		out[i]     = __fdiv_rn( __fadd_rn( l, r ), sqrt2 );
+		out[n + i] = __fdiv_rn( __fsub_rn( l, r ), sqrt2 );
+		}
+	}
+
+// out[i] += add[i] (overlap-add halo received from a neighbouring frame-range shard)
+__global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float * add, int64_t n )
+	{
+	for( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x )
+		out[i] = __fadd_rn( out[i], add[i] );
+	}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * ( N / 2 );
+	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	pv_analysis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	return cudaGetLastError();
+	}
+
+template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * ( N / 2 );
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	pv_synthesis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	return cudaGetLastError();
+	}
+
+bool dft_size_supported( int N )
+	{
+	return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192;
+	}
+
+cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	switch( N )
+		{
+		case 256:  return launch_analysis_n<256>( a, blocks, st );
+		case 512:  return launch_analysis_n<512>( a, blocks, st );
+		case 1024: return launch_analysis_n<1024>( a, blocks, st );
+		case 2048: return launch_analysis_n<2048>( a, blocks, st );
+		case 4096: return launch_analysis_n<4096>( a, blocks, st );
+		case 8192: return launch_analysis_n<8192>( a, blocks, st );
+		default:   return cudaErrorInvalidValue;
+		}
+	}
+
+cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	switch( N )
+		{
+		case 256:  return launch_synthesis_n<256>( a, blocks, st );
+		case 512:  return launch_synthesis_n<512>( a, blocks, st );
+		case 1024: return launch_synthesis_n<1024>( a, blocks, st );
+		case 2048: return launch_synthesis_n<2048>( a, blocks, st );
+		case 4096: return launch_synthesis_n<4096>( a, blocks, st );
+		case 8192: return launch_synthesis_n<8192>( a, blocks, st );
+		default:   return cudaErrorInvalidValue;
+		}
+	}
+
+cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st )
+	{
+	const int64_t blocks = (int64_t)( ( a.B + 255 ) / 256 ) * a.segs_per_channel * C;
+	pv_phase_seg_kernel<<<(unsigned) blocks, 256, 0, st>>>( a );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
+	{
+	dim3 grid( ( a.B + 127 ) / 128, C );
+	pv_phase_scan_kernel<<<grid, 128, 0, st>>>( a );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_phase_carry( const PhaseSeg * all, int rank, int64_t per_rank, PhaseSeg * carry, double P, double rcpP, cudaStream_t st )
+	{
+	pv_phase_carry_kernel<<<(unsigned)( ( per_rank + 127 ) / 128 ), 128, 0, st>>>( all, rank, per_rank, carry, P, rcpP );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_mid_side( const float * in, float * out, int64_t n, int sms, cudaStream_t st )
+	{
+	int64_t blocks = ( n + 255 ) / 256;
+	if( blocks > (int64_t) sms * 16 ) blocks = (int64_t) sms * 16;
+	if( blocks < 1 ) blocks = 1;
+	pv_mid_side_kernel<<<(unsigned) blocks, 256, 0, st>>>( in, out, n );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_add( float * out, const float * add, int64_t n, int sms, cudaStream_t st )
+	{
+	int64_t blocks = ( n + 255 ) / 256;
+	if( blocks > (int64_t) sms * 16 ) blocks = (int64_t) sms * 16;
+	if( blocks < 1 ) blocks = 1;
+	pv_add_kernel<<<(unsigned) blocks, 256, 0, st>>>( out, add, n );
+	return cudaGetLastError();
+	}
+
+} // namespace pvk

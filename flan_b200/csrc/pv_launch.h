@@ -1,0 +1,40 @@
+// flan_b200/csrc/pv_launch.h -- host-visible launch interface of pv_kernels.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include "pv_body.cuh"
+
+namespace pvk {
+
+struct PhaseSegArgs
+	{
+	const float2 * pv;
+	int64_t pv_channel_stride;
+	int64_t frame_begin, frame_end;
+	int seg_len, segs_per_channel, B;
+	PhaseSeg * seg_out;         // [C][segs_per_channel][B]
+	int * nan_flag;             // set to 1 when a NaN/Inf magnitude or frequency is seen (AudioPV.cpp:88)
+	PvConsts k;
+	double P, rcpP;
+	};
+
+struct PhaseScanArgs
+	{
+	const PhaseSeg * seg;       // [C][segs_per_channel][B]
+	int segs_per_channel, B;
+	const PhaseSeg * carry_in;  // [C][B] or null (state before the first local frame)
+	PhaseSeg * carry_out;       // [C][B] or null (state after the last local frame)
+	double * acc_start;         // [C][segs_per_channel][B] or null
+	double P, rcpP;
+	};
+
+bool dft_size_supported( int N );
+cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st );
+cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st );
+cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st );
+cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st );
+cudaError_t launch_phase_carry( const PhaseSeg * all, int rank, int64_t per_rank, PhaseSeg * carry, double P, double rcpP, cudaStream_t st );
+cudaError_t launch_mid_side( const float * in, float * out, int64_t n, int sms, cudaStream_t st );
+cudaError_t launch_add( float * out, const float * add, int64_t n, int sms, cudaStream_t st );
+
+} // namespace pvk

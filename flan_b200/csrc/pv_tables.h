@@ -1,0 +1,129 @@
+// flan_b200/csrc/pv_tables.h -- host-side constant tables of one (dft, window, hop, rates) plan.
+//
+// Window, per-bin constants and window_scale are evaluated on the HOST with the reference's own
+// expressions (g++ semantics, -ffp-contract=off) and uploaded, so no libm / compiler divergence can
+// leak into device code. Shared by the C ABI (pv_capi.cu) and the CPU
+// thread emulator (emu/pv_emu.cpp).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "pv_body.cuh"
+
+namespace pvk {
+
+struct HostTables
+	{
+	int N = 0, W = 0, hop = 0;
+	std::vector<float> win_analysis;    // Windows::hann( i / (W-1) )                         AudioPV.cpp:30-34
+	std::vector<float> win_synthesis;   // hann * window_scale                               AudioPV.cpp:98-103
+	std::vector<float> expected;        // bin_frequency / analysis_rate * pi2, per bin      phase_vocoder.cpp:47
+	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
+	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated
+	PvConsts k{};
+	double P = 0.0, rcpP = 0.0;
+	};
+
+// WindowFunctions.cpp:8-13: pi = std::acos(-1.0f); 0.5f * (1.0f - cos(2.0f * pi * x)). With g++ the
+// unqualified cos is ::cos(double): float product promoted, arithmetic in double, narrowed on return.
+inline float hann_reference( float x )
+	{
+	const float pi = std::acos( -1.0f );
+	const float arg = 2.0f * pi * x;
+	return (float)( 0.5 * ( 1.0 - ::cos( (double) arg ) ) );
+	}
+
+template<int M> inline void append_pass_twiddles( std::vector<float2> & out )
+	{
+	using P = FftPlan<M>;
+	const long double two_pi = 6.283185307179586476925286766559005768L;
+	for( int p = 1; p < P::num_passes; ++p )
+		{
+		const int R = P::radix( p ), NS = P::ns( p );
+		for( int r = 1; r < R; ++r )
+			for( int jm = 0; jm < NS; ++jm )
+				{
+				const long double a = -two_pi * (long double) r * (long double) jm / (long double)( NS * R );
+				float2 w; w.x = (float) cosl( a ); w.y = (float) sinl( a );
+				out.push_back( w );
+				}
+		}
+	}
+
+inline bool build_tables( int N, int W, int hop, float sample_rate, float analysis_rate, HostTables & t )
+	{
+	if( W < 1 || W > N || hop < 1 ) return false;
+	t.N = N; t.W = W; t.hop = hop;
+	const int M = N / 2, B = M + 1;
+
+	t.k.sample_rate = sample_rate;
+	t.k.analysis_rate = analysis_rate;
+	t.k.rcp_analysis_rate = 1.0f / analysis_rate;
+	const float pi = std::acos( -1.0f );            // defines.h:44
+	t.k.pi2 = pi * 2.0f;                            // defines.h:45
+	t.k.rcp_pi2 = 1.0f / t.k.pi2;
+	t.k.bin_scale = 1.0f / (float) N;               // exact: N is a power of two
+	t.k.use_wrapping = analysis_rate < sample_rate; // phase_vocoder.cpp:37
+	t.P = (double) t.k.pi2;
+	t.rcpP = 1.0 / t.P;
+
+	t.win_analysis.resize( W );
+	t.win_synthesis.resize( W );
+	// AudioPV.cpp:99: 2.67f / ( get_dft_size() * get_window_size() / get_hop_size() ), int arithmetic inside
+	const int denom = N * W / hop;
+	const float window_scale = 2.67f / denom;
+	for( int i = 0; i < W; ++i )
+		{
+		const float h = hann_reference( float( i ) / float( W - 1 ) );
+		t.win_analysis[i] = h;
+		t.win_synthesis[i] = h * window_scale;      // AudioPV.cpp:102
+		}
+
+	t.expected.resize( B );
+	for( int b = 0; b < B; ++b )
+		{
+		const float binf = (float) b * sample_rate / (float) N;     // PVBuffer.cpp:443-446
+		t.expected[b] = binf / analysis_rate * t.k.pi2;             // phase_vocoder.cpp:47
+		}
+
+	const long double two_pi = 6.283185307179586476925286766559005768L;
+	t.post_tw.resize( M / 2 + 1 );
+	for( int k = 0; k <= M / 2; ++k )
+		{
+		const long double a = -two_pi * (long double) k / (long double) N;
+		t.post_tw[k].x = (float) cosl( a );
+		t.post_tw[k].y = (float) sinl( a );
+		}
+
+	t.pass_tw.clear();
+	switch( M )
+		{
+		case 128:  append_pass_twiddles<128>( t.pass_tw ); break;
+		case 256:  append_pass_twiddles<256>( t.pass_tw ); break;
+		case 512:  append_pass_twiddles<512>( t.pass_tw ); break;
+		case 1024: append_pass_twiddles<1024>( t.pass_tw ); break;
+		case 2048: append_pass_twiddles<2048>( t.pass_tw ); break;
+		case 4096: append_pass_twiddles<4096>( t.pass_tw ); break;
+		default: return false;
+		}
+	return true;
+	}
+
+// Frames per CTA. Long enough that the warm-up FFT (analysis) and the shared overlap regions
+// (resynthesis: a sample may be shared by at most two segments, which needs seg_len*hop >= W-hop) are
+// amortised; short enough that the grid covers the SMs several times over.
+inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop )
+	{
+	const int64_t min_len = ( W + hop - 1 ) / hop;           // >= W/hop
+	int64_t target_ctas = (int64_t) sms * 8;
+	int64_t len = ( frames * channels + target_ctas - 1 ) / target_ctas;
+	if( len > 64 ) len = 64;
+	if( len < min_len ) len = min_len;
+	if( len < 4 ) len = 4;
+	if( len > frames ) len = frames > 0 ? frames : 1;
+	return (int) len;
+	}
+
+} // namespace pvk

@@ -1,0 +1,162 @@
+"""Thin Python driver over the C ABI for the tests and bench.py.
+
+torch is plumbing here: it owns device memory and the CUDA stream the kernels are enqueued on; all
+arithmetic happens in libflan_b200.so. Method names follow the reference's (Audio::convert_to_PV,
+PV::convert_to_audio, Audio::convert_to_mid_side; src/flan/Conversions/AudioPV.cpp).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("flan_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.ctx = capi.Context(device)
+        self.lib = self.ctx.lib
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _bind_stream(self):
+        self.ctx.call("flan_b200_set_stream", ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+
+    @staticmethod
+    def _chk(t, dtype=torch.float32):
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), "need a contiguous CUDA %s tensor" % dtype
+        return ctypes.c_void_p(t.data_ptr())
+
+    def num_frames(self, n, hop):
+        return int(self.lib.flan_b200_num_frames(n, hop))
+
+    def analysis_rate(self, sr, hop):
+        return float(self.lib.flan_b200_analysis_rate(sr, hop))
+
+    def hop_from_rates(self, sr, ar):
+        return int(self.lib.flan_b200_hop_from_rates(sr, ar))
+
+    def launch_count(self):
+        return int(self.lib.flan_b200_launch_count(self.ctx.h))
+
+    KERNEL_KINDS = {"analysis": 0, "phase_seg": 1, "phase_scan": 2, "synthesis": 3, "aux": 4}
+
+    def set_timing(self, enabled):
+        self.ctx.call("flan_b200_set_timing", int(enabled))
+
+    def kernel_time(self, kind):
+        """(total_ms, launches) of one kernel kind since the last query (synchronises the stream)."""
+        ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+        self._bind_stream()
+        self.ctx.call("flan_b200_kernel_time", self.KERNEL_KINDS[kind], ctypes.byref(ms), ctypes.byref(n))
+        return ms.value, n.value
+
+    def synchronize(self):
+        self.ctx.call("flan_b200_synchronize")
+
+    # -- Audio::convert_to_PV --------------------------------------------------------------------
+    def convert_to_pv(self, audio, sr, W, hop, N, out=None):
+        """audio: cuda float32 [C, n] -> pv: cuda float32 [C, F, N/2+1, 2] of (m, f)."""
+        C, n = audio.shape
+        F = self.num_frames(n, hop)
+        if out is None:
+            out = torch.empty((C, F, N // 2 + 1, 2), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_pv", self._chk(audio), C, n, sr, W, hop, N, self._chk(out), None)
+        return out
+
+    def convert_to_pv_range(self, audio_local, audio_offset, n_total, sr, W, hop, N, frame_begin, frame_end, out=None):
+        C, n_local = audio_local.shape
+        rows = frame_end - frame_begin
+        B = N // 2 + 1
+        if out is None:
+            out = torch.empty((C, rows, B, 2), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_pv_range", self._chk(audio_local), n_local, audio_offset, n_local, C, n_total,
+                      sr, W, hop, N, frame_begin, frame_end, self._chk(out), rows * B)
+        return out
+
+    # -- PV::convert_to_audio --------------------------------------------------------------------
+    def convert_to_audio(self, pv, sr, ar, W, out=None, check_nan=False):
+        C, F, B, _ = pv.shape
+        hop = self.hop_from_rates(sr, ar)
+        if out is None:
+            out = torch.empty((C, F * hop), dtype=torch.float32, device=self.device)
+        flag = ctypes.c_int(0)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_audio", self._chk(pv), C, F, B, sr, ar, W, self._chk(out), None,
+                      ctypes.byref(flag) if check_nan else None)
+        return (out, bool(flag.value)) if check_nan else out
+
+    def phase_summary(self, pv_rows, frame_begin, sr, ar, W):
+        C, rows, B, _ = pv_rows.shape
+        state = torch.empty((C, B, 4), dtype=torch.float64, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_phase_summary", self._chk(pv_rows), rows * B, C, frame_begin, frame_begin + rows, B,
+                      sr, ar, W, self._chk(state, torch.float64))
+        return state
+
+    def phase_carry(self, all_states, rank):
+        R, C, B, _ = all_states.shape
+        carry = torch.empty((C, B, 4), dtype=torch.float64, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_phase_carry", self._chk(all_states, torch.float64), rank, C, B, self._chk(carry, torch.float64))
+        return carry
+
+    def convert_to_audio_range(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len, out=None):
+        C, rows, B, _ = pv_rows.shape
+        if out is None:
+            out = torch.empty((C, out_len), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_audio_range", self._chk(pv_rows), rows * B, C, frame_begin, frame_begin + rows,
+                      frames_total, B, sr, ar, W, None if carry is None else self._chk(carry, torch.float64),
+                      self._chk(out), out_len, out_offset, out_len)
+        return out
+
+    def add(self, dst, src):
+        assert dst.numel() == src.numel()
+        self._bind_stream()
+        self.ctx.call("flan_b200_add", self._chk(dst), self._chk(src), dst.numel())
+
+    def empty_like_audio(self, C, n):
+        return torch.empty((C, n), dtype=torch.float32, device=self.device)
+
+    def add_into(self, dst_view, src):
+        """dst_view[c, :] += src[c, :] for a (possibly strided-by-channel) view of an audio tensor."""
+        for c in range(dst_view.shape[0]):
+            self.add(dst_view[c], src[c])
+
+    # -- Audio::convert_to_mid_side ---------------------------------------------------------------
+    def mid_side(self, audio):
+        assert audio.shape[0] == 2
+        out = torch.empty_like(audio)
+        self._bind_stream()
+        self.ctx.call("flan_b200_mid_side", self._chk(audio), self._chk(out), audio.shape[1])
+        return out
+
+    # -- host-buffer forms (the call the reference-facing C++ layer makes) -------------------------
+    def convert_to_pv_host(self, audio_np, sr, W, hop, N, mid_side=False, out=None):
+        audio_np = np.ascontiguousarray(audio_np, np.float32)
+        C, n = audio_np.shape
+        F = self.num_frames(n, hop)
+        if out is None:
+            out = np.empty((C, F, N // 2 + 1, 2), np.float32)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_pv_host", ctypes.c_void_p(audio_np.ctypes.data), C, n, sr, W, hop, N,
+                      int(mid_side), ctypes.c_void_p(out.ctypes.data), None)
+        return out
+
+    def convert_to_audio_host(self, pv_np, sr, ar, W, left_right=False, out=None):
+        pv_np = np.ascontiguousarray(pv_np, np.float32)
+        C, F, B, _ = pv_np.shape
+        hop = self.hop_from_rates(sr, ar)
+        if out is None:
+            out = np.empty((C, F * hop), np.float32)
+        flag = ctypes.c_int(0)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_audio_host", ctypes.c_void_p(pv_np.ctypes.data), C, F, B, sr, ar, W,
+                      int(left_right), ctypes.c_void_p(out.ctypes.data), None, ctypes.byref(flag))
+        return out, bool(flag.value)

@@ -1,0 +1,94 @@
+"""Frame-range sharding of one signal across ranks (BASELINE.json config 3).
+
+Pure index arithmetic plus the exchange schedule; the transforms themselves are the C ABI's *_range
+entry points (or, in the CPU tests, the thread emulator). One process per GPU; torch.distributed carries
+  * analysis: nothing, if each rank holds its frame range's samples plus a halo of W/2 + hop on the left
+    (the extra hop lets it recompute the phase of frame f0-1) and W/2 on the right;
+  * resynthesis: an all_gather of the per-bin phase state (C x B x 32 bytes per rank) and one
+    send/recv per shard boundary of the W - hop overlap-add samples that two shards share.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class FrameShard:
+    rank: int
+    world: int
+    n: int              # samples per channel of the whole signal
+    hop: int
+    W: int
+    frames_total: int   # F = n // hop + 1                     (AudioPV.cpp:17)
+    f0: int             # first frame of this rank
+    f1: int             # one past the last frame
+    audio_lo: int       # samples [audio_lo, audio_hi) must be resident for analysis
+    audio_hi: int
+    span_lo: int        # output samples [span_lo, span_hi) receive contributions from this rank's frames
+    span_hi: int
+    own_lo: int         # output samples [own_lo, own_hi) are final on this rank after the halo exchange
+    own_hi: int
+
+    @property
+    def frames(self):
+        return self.f1 - self.f0
+
+    @property
+    def out_total(self):
+        return self.frames_total * self.hop          # AudioPV.cpp:93
+
+
+def frame_shard(n, hop, W, world, rank):
+    F = n // hop + 1
+    per = (F + world - 1) // world
+    f0 = min(F, rank * per)
+    f1 = min(F, f0 + per)
+    half = W // 2
+    total = F * hop
+    if f1 > f0:
+        first = f0 - 1 if f0 > 0 else 0
+        audio_lo = max(0, hop * first - half)
+        audio_hi = min(n, hop * (f1 - 1) - half + W)
+        audio_hi = max(audio_hi, audio_lo)
+        span_lo = max(0, hop * f0 - half)
+        span_hi = min(total, hop * (f1 - 1) - half + W)
+        own_lo = 0 if f0 == 0 else min(total, hop * f0 - half + (W - hop))
+        own_hi = total if f1 == F else min(total, hop * f1 - half + (W - hop))
+    else:
+        audio_lo = audio_hi = span_lo = span_hi = own_lo = own_hi = 0
+    return FrameShard(rank, world, n, hop, W, F, f0, f1, audio_lo, audio_hi, span_lo, span_hi, own_lo, own_hi)
+
+
+def head_overlap(shard):
+    """Samples [lo, hi) of this rank's span that belong to the previous rank (partial sums to send left)."""
+    if shard.f0 == 0 or shard.frames == 0:
+        return (0, 0)
+    return (shard.span_lo, min(shard.own_lo, shard.span_hi))
+
+
+def sharded_resynthesis(engine, dist, shard, pv_rows, sr, ar, allgather, send, recv):
+    """Resynthesise this rank's frames and finish the samples it owns.
+
+    engine: flan_b200.engine.Engine (or the emulator adapter of the CPU tests) -- same method names.
+    allgather(state) -> stacked [world, C, B, 4]; send(tensor, dst) / recv(tensor, src) move one halo.
+    Returns (local_out, lo) where local_out[:, own_lo-lo : own_hi-lo] is final.
+    """
+    state = engine.phase_summary(pv_rows, shard.f0, sr, ar, shard.W)
+    carry = engine.phase_carry(allgather(state), shard.rank)
+    lo, hi = shard.span_lo, shard.span_hi
+    out = engine.convert_to_audio_range(pv_rows, shard.f0, shard.frames_total, sr, ar, shard.W, carry, lo, hi - lo)
+    # lower-frame contributions first (AudioPV.cpp:133-134): the owner adds the right neighbour's partial sums
+    h_lo, h_hi = head_overlap(shard)
+    reqs = []
+    if h_hi > h_lo and shard.rank > 0:
+        reqs.append(send(out[:, h_lo - lo:h_hi - lo].contiguous(), shard.rank - 1))
+    if shard.rank + 1 < shard.world:
+        nxt = frame_shard(shard.n, shard.hop, shard.W, shard.world, shard.rank + 1)
+        n_lo, n_hi = head_overlap(nxt)
+        if n_hi > n_lo:
+            buf = engine.empty_like_audio(out.shape[0], n_hi - n_lo)
+            recv(buf, shard.rank + 1)
+            tail = out[:, n_lo - lo:n_hi - lo]
+            engine.add_into(tail, buf)
+    for r in reqs:
+        if r is not None:
+            r.wait()
+    return out, lo

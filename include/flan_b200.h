@@ -1,0 +1,146 @@
+/* include/flan_b200.h -- C ABI of the B200 phase-vocoder engine (libflan_b200.so).
+ *
+ * The reference (loganmcbroom/Flan) has no plugin or FFI seam for this path: the boundary is the C++
+ * member call itself,
+ *     PV    flan::Audio::convert_to_PV( Frame window, Frame hop, Frame dft, std::atomic<bool>& ) const
+ *                                                   (src/flan/Audio/Audio.h:158-163, Conversions/AudioPV.cpp:12-78)
+ *     Audio flan::PV::convert_to_audio( std::atomic<bool>& ) const
+ *                                                   (src/flan/PV/PV.h:88-90,     Conversions/AudioPV.cpp:86-139)
+ * plus the stereo wrappers convert_to_ms_PV / convert_to_lr_audio (AudioPV.cpp:80-84,141-145).
+ * The entry points below are what a Flan build binds in place of the bodies of those four functions
+ * (and of FFTHelper's FFTW plans, src/flan/FFTHelper.cpp:16-48); flan_b200/host/ holds the C++ side
+ * (flan::Audio / flan::PV with the reference's signatures) and INTEGRATION.md the patch a maintainer
+ * would apply. Plain pointers and sizes only; no C++ or torch types cross this line.
+ *
+ * Conventions
+ *   - Layouts are the reference's: audio is planar float[C][n] (AudioBuffer.cpp:479-482); PV data is
+ *     MF{float m; float f;} [C][F][B], B = dft/2+1 (PVBuffer.cpp:526-529). All offsets are 64-bit.
+ *   - "d_" pointers are device memory on the context's GPU; "h_" pointers are host memory.
+ *   - Device-pointer calls are asynchronous on the context's stream (flan_b200_set_stream) unless noted.
+ *   - Every call returns FLAN_B200_OK or an error code; flan_b200_last_error() gives the text. The C++
+ *     layer maps any failure to the reference's "print and return a null object" (AudioPV.cpp:82,143).
+ *   - There is no CPU fallback: without a CUDA device flan_b200_create() fails.
+ *   - dft sizes: powers of two from 256 to 8192, window <= dft, hop >= 1. Other sizes return
+ *     FLAN_B200_UNSUPPORTED (the reference only guarantees powers of two, Audio.h:151-153).
+ */
+#ifndef FLAN_B200_H
+#define FLAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLAN_B200_OK           0
+#define FLAN_B200_INVALID      1   /* bad argument */
+#define FLAN_B200_UNSUPPORTED  2   /* dft size outside the supported set */
+#define FLAN_B200_CUDA         3   /* CUDA runtime error */
+#define FLAN_B200_CANCELLED    4   /* cancel flag was raised (flan_CANCEL_POINT, defines.h:52-62) */
+#define FLAN_B200_NOMEM        5
+
+typedef struct flan_b200_ctx flan_b200_ctx;
+
+/* Running-phase state of one (channel, bin) in split form: sum = q*P + r and its maximum prefix
+ * (P = double(pi2)); see DESIGN.md "phase scan". Exchanged between frame-range shards. 32 bytes. */
+typedef struct { double sum_q, sum_r, max_q, max_r; } flan_b200_phase_state;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  flan_b200_device_count( void );
+int  flan_b200_create( int device, flan_b200_ctx ** out );
+void flan_b200_destroy( flan_b200_ctx * ctx );
+const char * flan_b200_last_error( const flan_b200_ctx * ctx );   /* ctx may be NULL: error of the last failed create */
+int  flan_b200_set_stream( flan_b200_ctx * ctx, void * cuda_stream );   /* cudaStream_t; NULL = legacy default stream */
+int  flan_b200_synchronize( flan_b200_ctx * ctx );
+int  flan_b200_sm_count( const flan_b200_ctx * ctx );
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
+
+/* Per-kernel device timing for bench.py's roofline line: when enabled, every kernel launch is bracketed by
+ * CUDA events on the context's stream. flan_b200_kernel_time synchronises the stream, returns the summed
+ * duration and launch count of one kernel kind since the last call for that kind, and resets it.
+ * kinds: 0 analysis, 1 phase segment summary, 2 phase scan, 3 resynthesis, 4 mid/side + add + carry. */
+int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled );
+int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches );
+
+/* ---- device buffers (storage behind flan::AudioBuffer / flan::PVBuffer) ---------------------- */
+int flan_b200_malloc( flan_b200_ctx * ctx, size_t bytes, void ** d_out );
+int flan_b200_free( flan_b200_ctx * ctx, void * d_ptr );
+int flan_b200_upload( flan_b200_ctx * ctx, void * d_dst, const void * h_src, size_t bytes );     /* async on the stream */
+int flan_b200_download( flan_b200_ctx * ctx, void * h_dst, const void * d_src, size_t bytes );   /* async on the stream */
+
+/* ---- shapes (reference arithmetic) ---------------------------------------------------------- */
+/* F = n / hop + 1 with an integer quotient (AudioPV.cpp:17). */
+int64_t flan_b200_num_frames( int64_t n, int hop );
+/* hop = int( sample_rate / analysis_rate ) (PVBuffer::get_hop_size, PVBuffer.cpp:381-384). */
+int flan_b200_hop_from_rates( float sample_rate, float analysis_rate );
+/* analysis_rate = float(sample_rate) / hop (AudioPV.cpp:25). */
+float flan_b200_analysis_rate( float sample_rate, int hop );
+
+/* ---- Audio::convert_to_PV (AudioPV.cpp:12-78) ----------------------------------------------- */
+/* d_audio: float[C][n]; d_pv: MF[C][F][dft/2+1], F = flan_b200_num_frames(n, hop).
+ * cancel (may be NULL) is the host-side flag of flan_CANCEL_ARG, polled between launches. */
+int flan_b200_convert_to_pv( flan_b200_ctx * ctx, const float * d_audio, int channels, int64_t n,
+                             float sample_rate, int window_size, int hop, int dft_size,
+                             float * d_pv, const volatile int * cancel );
+
+/* Frame-range shard of the same transform: produce frames [frame_begin, frame_end) of every channel.
+ * d_audio_local holds, per channel (stride audio_stride elements), samples [audio_offset, audio_offset +
+ * audio_len) of the signal and must cover [hop*(frame_begin-1) - window/2, hop*(frame_end-1) + window/2)
+ * clipped to [0, n_total) -- i.e. a left halo of window/2 + hop and a right halo of window/2 samples.
+ * d_pv_rows: row 0 of channel c is frame frame_begin; channels are pv_channel_stride MF elements apart. */
+int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_local, int64_t audio_stride,
+                                   int64_t audio_offset, int64_t audio_len, int channels, int64_t n_total,
+                                   float sample_rate, int window_size, int hop, int dft_size,
+                                   int64_t frame_begin, int64_t frame_end,
+                                   float * d_pv_rows, int64_t pv_channel_stride );
+
+/* ---- PV::convert_to_audio (AudioPV.cpp:86-139) ---------------------------------------------- */
+/* d_pv: MF[C][F][B]; d_audio_out: float[C][F*hop], hop = flan_b200_hop_from_rates(sr, analysis_rate).
+ * *nan_or_inf (may be NULL, host memory, written after an internal stream sync only if non-NULL)
+ * reports the is_nan_or_inf() pre-scan of AudioPV.cpp:88; like the reference, conversion continues. */
+int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins,
+                                float sample_rate, float analysis_rate, int window_size,
+                                float * d_audio_out, const volatile int * cancel, int * nan_or_inf );
+
+/* Frame-range shard, step 1: phase state accumulated over the local frames [frame_begin, frame_end),
+ * per (channel, bin): d_state_out[C][B]. Ranks all-gather these. */
+int flan_b200_phase_summary( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                             int channels, int64_t frame_begin, int64_t frame_end, int bins,
+                             float sample_rate, float analysis_rate, int window_size,
+                             flan_b200_phase_state * d_state_out );
+/* Step 2: state entering rank `rank` = combination of the gathered states of ranks 0..rank-1.
+ * d_all: [ranks][C][B] in rank order; d_carry_out: [C][B]. */
+int flan_b200_phase_carry( flan_b200_ctx * ctx, const flan_b200_phase_state * d_all, int rank,
+                           int channels, int bins, flan_b200_phase_state * d_carry_out );
+/* Step 3: resynthesise the local frames. d_out_local (ZEROED by this call) holds, per channel (stride
+ * out_stride), samples [out_offset, out_offset + out_len) of the output; frames write the part of
+ * [hop*frame_begin - window/2, hop*(frame_end-1) + window/2) that lies inside it and inside
+ * [0, frames_total*hop). The first and last window-hop samples of that span are partial sums that the
+ * caller adds to the neighbouring shard's (flan_b200_add). d_carry_in may be NULL (rank 0). */
+int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                                      int channels, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
+                                      int bins, float sample_rate, float analysis_rate, int window_size,
+                                      const flan_b200_phase_state * d_carry_in,
+                                      float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len );
+/* d_out[i] += d_add[i], i < n (overlap-add halo received from a neighbour). */
+int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n );
+
+/* ---- Audio::convert_to_mid_side / convert_to_left_right (AudioConversions.cpp:32-56) --------- */
+/* d_in, d_out: float[2][n]; the transform is its own inverse up to rounding. */
+int flan_b200_mid_side( flan_b200_ctx * ctx, const float * d_in, float * d_out, int64_t n );
+
+/* ---- host-buffer forms (what flan::Audio::convert_to_PV / flan::PV::convert_to_audio call when the
+ *      buffers live in std::vector): upload, transform, download, synchronise. ------------------- */
+int flan_b200_convert_to_pv_host( flan_b200_ctx * ctx, const float * h_audio, int channels, int64_t n,
+                                  float sample_rate, int window_size, int hop, int dft_size, int mid_side,
+                                  float * h_pv, const volatile int * cancel );
+int flan_b200_convert_to_audio_host( flan_b200_ctx * ctx, const float * h_pv, int channels, int64_t frames, int bins,
+                                     float sample_rate, float analysis_rate, int window_size, int left_right,
+                                     float * h_audio_out, const volatile int * cancel, int * nan_or_inf );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

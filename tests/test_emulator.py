@@ -1,0 +1,140 @@
+"""CPU checks of the kernels' logic: the CTA bodies of flan_b200/csrc/pv_body.cuh run under the host thread
+emulator (same source as the CUDA kernels, libm instead of the CUDA math library) against the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from emu_lib import Emu
+from flan_b200.signals import noise_chirp, sine_sweep
+from flan_b200.sharding import frame_shard
+from parity import assert_analysis_parity, assert_synthesis_parity
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from flan_b200 import build
+    build.build_emulator()
+    return Emu()
+
+
+SHAPES = [(256, 16, 256, 20), (512, 32, 512, 17), (1024, 64, 1024, 16), (2048, 128, 2048, 7), (4096, 256, 4096, 5),
+          (8192, 512, 8192, 3), (256, 64, 1024, 0), (1000, 100, 1024, 0), (2048, 128, 4096, 0), (512, 512, 512, 0),
+          (300, 7, 512, 0)]
+
+
+@pytest.mark.parametrize("W,h,N,seg", SHAPES)
+@pytest.mark.parametrize("kind", ["noise", "sweep"])
+def test_emulated_analysis_matches_oracle(emu, oracle, W, h, N, seg, kind):
+    sr = 48000.0
+    n = 6000 if h >= 16 else 1500
+    x = np.stack([noise_chirp(n, sr, 5) if kind == "noise" else sine_sweep(n, sr)])
+    pv = emu.analysis(x, sr, W, h, N, seg_len=seg)
+    assert_analysis_parity(pv, oracle.convert_to_pv(x, sr, W, h, N), sr, h, N)
+
+
+@pytest.mark.parametrize("W,h,N,seg", SHAPES)
+def test_emulated_synthesis_matches_oracle(emu, oracle, W, h, N, seg):
+    sr = 48000.0
+    n = 6000 if h >= 16 else 1500
+    x = np.stack([noise_chirp(n, sr, 6), sine_sweep(n, sr)])
+    pv = oracle.convert_to_pv(x, sr, W, h, N)
+    ar = oracle.analysis_rate(sr, h)
+    seg_len = max(seg, (W + h - 1) // h) if seg else 0
+    out, _, flag = emu.synthesis(pv, sr, ar, W, seg_len=seg_len)
+    assert flag == 0
+    assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_emulator_against_golden(emu, path):
+    g = np.load(path)
+    sr, W, h, N = float(g["sr"]), int(g["W"]), int(g["hop"]), int(g["N"])
+    assert_analysis_parity(emu.analysis(g["audio_in"], sr, W, h, N), g["pv"], sr, h, N)
+    out, _, _ = emu.synthesis(g["pv"], sr, float(g["analysis_rate"]), W)
+    assert_synthesis_parity(out, g["audio_out"])
+
+
+def test_emulated_segmenting_is_invisible(emu):
+    # the same frames, cut into different segment lengths, must give identical bits (warm-up FFT = carried phase)
+    sr, W, h, N = 44100.0, 512, 32, 512
+    x = np.stack([noise_chirp(5000, sr, 11)])
+    a = emu.analysis(x, sr, W, h, N, seg_len=1000)
+    b = emu.analysis(x, sr, W, h, N, seg_len=16)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_negative_frequency_phase_representative(emu, oracle):
+    # bins driven to long negative-phase excursions: the reference never wraps a negative accumulator
+    # (phase_vocoder.cpp:59), so segment starts must carry the same unreduced representative.
+    sr, W, h, N = 48000.0, 256, 16, 256
+    F, B = 400, N // 2 + 1
+    rng = np.random.default_rng(3)
+    pv = np.zeros((1, F, B, 2), np.float32)
+    pv[..., 0] = rng.random((1, F, B), dtype=np.float32)
+    binf = np.arange(B) * sr / N
+    pv[..., 1] = (binf[None, None, :] + rng.normal(0, 900, (1, F, B))).astype(np.float32)
+    pv[0, :, 0:3, 1] = -np.abs(pv[0, :, 0:3, 1]) - 500.0        # persistently negative
+    pv[0, 100:, 5, 1] = -2000.0
+    ar = oracle.analysis_rate(sr, h)
+    out, _, _ = emu.synthesis(pv, sr, ar, W, seg_len=16)
+    assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+
+
+def test_nan_flag(emu, oracle):
+    sr, W, h, N = 48000.0, 256, 32, 256
+    pv = oracle.convert_to_pv(np.stack([noise_chirp(2000, sr, 1)]), sr, W, h, N)
+    pv[0, 10, 7, 1] = np.inf
+    _, _, flag = emu.synthesis(pv, sr, oracle.analysis_rate(sr, h), W, synth=False)
+    assert flag == 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_frame_range_shards(emu, oracle, world):
+    # frame-range shards with halos reproduce the unsharded transform (serial emulation of the ranks)
+    sr, W, h, N = 48000.0, 512, 32, 512
+    n = 7000
+    x = np.stack([noise_chirp(n, sr, 21), sine_sweep(n, sr)])
+    ref_pv = oracle.convert_to_pv(x, sr, W, h, N)
+    ar = oracle.analysis_rate(sr, h)
+    ref_audio = oracle.convert_to_audio(ref_pv, sr, ar, W)
+    full = emu.analysis(x, sr, W, h, N)
+    shards = [frame_shard(n, h, W, world, r) for r in range(world)]
+    carry = None
+    total = np.zeros_like(ref_audio)
+    for s in shards:
+        local = np.ascontiguousarray(x[:, s.audio_lo:s.audio_hi])
+        pv = emu.analysis(local, sr, W, h, N, s.f0, s.f1, audio_offset=s.audio_lo, n_total=n)
+        assert np.array_equal(pv.view(np.uint32), full[:, s.f0:s.f1].view(np.uint32))
+        out, carry, _ = emu.synthesis(ref_pv[:, s.f0:s.f1], sr, ar, W, frame_begin=s.f0, frames_total=s.frames_total,
+                                      carry_in=carry, want_carry=True, out_offset=s.span_lo,
+                                      out_len=s.span_hi - s.span_lo)
+        total[:, s.span_lo:s.span_hi] += out
+    assert_synthesis_parity(total, ref_audio)
+
+
+def test_host_tables_match_reference_expressions(emu, oracle):
+    for (N, W, h, sr) in [(2048, 2048, 128, 44100.0), (4096, 4096, 256, 48000.0), (1024, 1000, 100, 22050.0)]:
+        ar = oracle.analysis_rate(sr, h)
+        wa, ws, ex = emu.tables(N, W, h, sr, ar)
+        hann = oracle.hann(W)
+        assert np.array_equal(wa.view(np.uint32), hann.view(np.uint32))
+        scale = np.float32(2.67) / np.float32((N * W) // h)
+        assert np.array_equal(ws.view(np.uint32), (hann * scale).astype(np.float32).view(np.uint32))
+        pi2 = np.float32(np.float32(np.arccos(np.float32(-1))) * np.float32(2))
+        binf = (np.arange(N // 2 + 1, dtype=np.float32) * np.float32(sr) / np.float32(N)).astype(np.float32)
+        assert np.array_equal(ex.view(np.uint32), (binf / ar * pi2).astype(np.float32).view(np.uint32))
+
+
+def test_div_const_is_ieee_division(emu):
+    # sampled re-run of the exhaustive check quoted in pv_core.cuh (every float in [2^-100, 2^40], 13 divisors)
+    pi2 = float(np.float32(np.float32(np.arccos(np.float32(-1))) * np.float32(2)))
+    rng = np.random.default_rng(0)
+    for c in (pi2, 187.5, 344.53125, 750.0, 93.75, 48000.0 / 100, 22050.0 / 100):
+        for _ in range(8):
+            first = int(rng.integers(np.float32(1e-25).view(np.uint32), np.float32(1e12).view(np.uint32)))
+            assert emu.div_const_mismatches(c, first, 500000) == 0
+            assert emu.div_const_mismatches(c, first | 0x80000000, 500000) == 0
