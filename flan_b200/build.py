@@ -64,9 +64,41 @@ def build_emulator(force=False):
     return emu_path()
 
 
+HOST = os.path.join(HERE, "host")
+
+
+def host_path():
+    return os.path.join(LIB, "libflan_b200_host.so")
+
+
+def api_test_path():
+    return os.path.join(LIB, "libflan_api_test.so")
+
+
+def build_host(force=False):
+    """The C++ side of the boundary (flan::Audio / flan::PV over the C ABI) and the API test driver."""
+    build_library(force)
+    os.makedirs(LIB, exist_ok=True)
+    root = os.path.dirname(HERE)
+    srcs = [os.path.join(HOST, "src", n) for n in ("b200_storage.cpp", "AudioBuffer.cpp", "PVBuffer.cpp", "AudioPV.cpp")]
+    hdrs = []
+    for d, _, files in os.walk(os.path.join(HOST, "include")):
+        hdrs += [os.path.join(d, f) for f in files]
+    inc = ["-I" + os.path.join(HOST, "include"), "-I" + os.path.join(root, "include")]
+    common = ["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-Wall"] + inc
+    link = ["-L" + LIB, "-Wl,-rpath,$ORIGIN"]
+    if force or _newer(host_path(), srcs + hdrs + [lib_path()]):
+        subprocess.run(common + ["-o", host_path()] + srcs + link + ["-lflan_b200"], check=True)
+    drv = os.path.join(root, "tests", "cpp", "flan_api_driver.cpp")
+    if force or _newer(api_test_path(), [drv, host_path()] + hdrs):
+        subprocess.run(common + ["-o", api_test_path(), drv] + link + ["-lflan_b200_host", "-lflan_b200"], check=True)
+    return host_path()
+
+
 def build_all(force=False):
     build_library(force)
     build_emulator(force)
+    build_host(force)
 
 
 if __name__ == "__main__":

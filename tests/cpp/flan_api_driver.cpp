@@ -1,0 +1,61 @@
+// tests/cpp/flan_api_driver.cpp -- user code written against the reference's C++ API (the shape of the reference's
+// own tests/flanTest.cpp:39-44: audio.convert_to_PV(...).<PV op>.convert_to_audio()), compiled against the B200
+// build's headers. Exposed through extern "C" so pytest can feed it numpy buffers and compare with the oracle.
+#include "flan/Audio/Audio.h"
+#include "flan/PV/PV.h"
+
+#include <cstring>
+
+using namespace flan;
+
+extern "C" {
+
+// Returns frames, or -1 if the API returned a null PV. mode: 0 convert_to_PV, 1 convert_to_ms_PV
+int api_convert_to_pv( const float * audio, int C, int n, float sr, int W, int hop, int N, int mode, float * pv_out, float * ar_out )
+	{
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	PV pv = mode ? a.convert_to_ms_PV( W, hop, N ) : a.convert_to_PV( W, hop, N );
+	if( pv.is_null() ) return -1;
+	*ar_out = pv.get_analysis_rate();
+	std::memcpy( pv_out, pv.get_buffer().data(), sizeof( MF ) * pv.get_buffer().size() );
+	return pv.get_num_frames();
+	}
+
+// Device-resident chain: analysis, an in-place host edit of one MF through the reference-style accessor (to exercise
+// the dirty tracking), resynthesis. Returns output frames or -1.
+int api_round_trip( const float * audio, int C, int n, float sr, int W, int hop, int N, int touch, int lr, float * audio_out )
+	{
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	PV pv = a.convert_to_PV( W, hop, N );
+	if( pv.is_null() ) return -1;
+	if( touch ) pv.get_MF( 0, 1, 3 ).m *= 2.0f;
+	Audio out = lr ? pv.convert_to_lr_audio() : pv.convert_to_audio();
+	if( out.is_null() ) return -1;
+	std::memcpy( audio_out, out.get_buffer().data(), sizeof( float ) * out.get_buffer().size() );
+	return out.get_num_frames();
+	}
+
+// PV given on the host (e.g. loaded or edited by user code) -> audio.
+int api_convert_to_audio( const float * pv, int C, int F, int B, float sr, float ar, int W, float * audio_out )
+	{
+	PVBuffer::Format f;
+	f.num_channels = C; f.num_frames = F; f.num_bins = B; f.sample_rate = sr; f.analysis_rate = ar; f.window_size = W;
+	PV p( ( PVBuffer( f ) ) );
+	std::memcpy( p.get_buffer().data(), pv, sizeof( MF ) * size_t( C ) * F * B );
+	Audio out = p.convert_to_audio();
+	if( out.is_null() ) return -1;
+	std::memcpy( audio_out, out.get_buffer().data(), sizeof( float ) * out.get_buffer().size() );
+	return out.get_num_frames();
+	}
+
+// Cancellation protocol: a raised canceller yields a null object (AudioPV.cpp:49,115).
+int api_cancelled_is_null( void )
+	{
+	std::atomic<bool> cancel( true );
+	AudioBuffer::Format f; f.num_channels = 1; f.num_frames = 4096; f.sample_rate = 48000;
+	Audio a = Audio::create_from_format( f );
+	PV pv = a.convert_to_PV( 256, 32, 256, cancel );
+	return pv.is_null() ? 1 : 0;
+	}
+
+}
