@@ -29,17 +29,14 @@ struct HostEnv
 	void st_stream2( float2 * p, float2 v ) { *p = v; }
 	void st_stream( float * p, float v ) { *p = v; }
 	void red_add( float * p, float v ) { std::atomic_ref<float>( *p ).fetch_add( v ); }
-	void sincos( float x, float * s, float * c ) { *s = sinf( x ); *c = cosf( x ); }
-	void cp_async4( float * dst, const float * src, bool valid ) { *dst = valid ? *src : 0.0f; }
-	void cp_async_commit() {}
-	void cp_async_wait_all() {}
+	void prefetch( const void * ) {}
 	};
 
 template<int N, class Body> void run_cta( Body && body )
 	{
 	constexpr int T = N / 16;
 	std::vector<float> ring( N );
-	std::vector<float2> x0( N / 2 ), x1( N / 2 );
+	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size );
 	std::barrier<> bar( T );
 	std::vector<std::thread> th;
 	for( int t = 0; t < T; ++t )
@@ -54,7 +51,7 @@ template<int N, class Body> void run_cta( Body && body )
 template<int N> void analysis_n( const AnalysisArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N>( [&]( HostEnv & env, float * ring, float2 * x0, float2 * x1 ) { analysis_cta<N>( a, b, env, ring, x0, x1 ); } );
+		run_cta<N>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1 ) { analysis_cta<N>( a, b, env, x0, x1 ); } );
 	}
 
 template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
@@ -81,8 +78,9 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.audio = audio; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;
 	a.pv = (float2 *) pv_rows; a.pv_channel_stride = pv_channel_stride;
 	a.frame_begin = frame_begin; a.frame_end = frame_end; a.seg_len = seg_len; a.segs_per_channel = segs;
-	a.W = W; a.hop = hop; a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
-	a.win = tb.win_analysis.data(); a.expected = tb.expected.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.W = W; a.hop = hop;
+	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 ) && ( (uintptr_t) audio % 8 == 0 );
+	a.win = tb.win_analysis.data(); a.expected = tb.expected.data(); a.binf = tb.binf.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;
 	switch( N )

@@ -8,13 +8,13 @@
 // walks it in frame order. A frame of N-point real FFT is computed by T = N/16 threads, 8 complex
 // points each (the real transform is a packed N/2-point complex FFT). Walking in order lets
 //   * analysis keep the previous frame's phase of "its" bins in registers (the serial dependency of
-//     AudioPV.cpp:47/phase_vocoder.cpp:44-45), at the cost of one warm-up FFT per segment, and reuse
-//     the sliding window from a shared-memory ring so each input sample is fetched from HBM once;
+//     AudioPV.cpp:47/phase_vocoder.cpp:44-45), at the cost of one warm-up FFT per segment; consecutive
+//     windows overlap by W-hop samples, which stay in L1, so each input sample leaves HBM once;
 //   * resynthesis keep the fp64 phase accumulators (phase_vocoder.cpp:58-59) in registers and the
 //     overlap-add in a shared-memory ring that is flushed hop by hop, so every output sample is
 //     written once, contributions added in increasing frame order like AudioPV.cpp:133-134.
-// Window coefficients, twiddles and bin constants for a thread's fixed positions stay in registers or
-// L1 across the walk.
+// Window coefficients and bin constants for a thread's fixed positions stay in registers across the walk;
+// every shared-memory access is "per-thread base + immediate" (see xpad in pv_core.cuh).
 #pragma once
 
 #include "pv_core.cuh"
@@ -22,8 +22,8 @@
 namespace pvk {
 
 // ------------------------------------------------------------------------------------------------
-// FFT pass chain over the ping-pong exchange buffers x0/x1 (M float2 each).
-// Pass 0 (radix 8, no twiddles) is issued by the caller's prologue; this runs passes 1..last.
+// FFT pass chain over the ping-pong exchange buffers x0/x1 (XBuf<M>::size float2 each).
+// Pass 0 (radix 8, no twiddles) is issued by the caller; this runs passes 1..last.
 // ------------------------------------------------------------------------------------------------
 template<int M, int p, bool STORE_LAST, class Env>
 PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env )
@@ -31,11 +31,11 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 	using P = FftPlan<M>;
 	if constexpr( p < P::num_passes )
 		{
-		constexpr int Rp = P::radix( p - 1 ), NSp = P::ns( p - 1 );     // producer of our input
+		constexpr int NSp = P::ns( p - 1 );     // layout our input was written in
 		constexpr int R = P::radix( p ), NS = P::ns( p );
 		float2 * in  = ( ( p - 1 ) % 2 == 0 ) ? x0 : x1;
 		float2 * out = ( p % 2 == 0 ) ? x0 : x1;
-		fft_load<M, Rp, NSp>( t, v, in );
+		fft_load<M, NSp>( t, v, in );
 		fft_butterflies<M, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
 		if constexpr( p < P::num_passes - 1 || STORE_LAST )
 			{
@@ -46,7 +46,7 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 		}
 	}
 
-// Buffer that holds the natural-order output of the last pass when STORE_LAST is set.
+// Buffer that holds the natural-order output of the last pass when STORE_LAST is set (its Ns >= 64: no padding).
 template<int M> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
 	{
 	return ( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
@@ -67,19 +67,19 @@ struct AnalysisArgs
 	int seg_len;                // frames per CTA
 	int segs_per_channel;
 	int W, hop;
-	int aligned2;               // hop and W/2 even: ring reads as float2
+	int aligned2;               // every in-signal window of every channel starts on an 8-byte boundary
 	const float * win;          // [W] Hann, reference expression evaluated on the host
 	const float * expected;     // [B] expected_phase_diff per bin (phase_vocoder.cpp:47), host-evaluated
+	const float * binf;         // [B] bin_to_frequency(b) (PVBuffer.cpp:443-446), host-evaluated
 	const float2 * post_tw;     // [N/4+1] e^{-2 pi i k/N}
 	const float2 * pass_tw;     // concatenated per-pass twiddles
 	PvConsts k;
 	};
 
 template<int N, class Env>
-PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float * ring, float2 * x0, float2 * x1 )
+PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1 )
 	{
 	constexpr int M = N / 2, T = M / 8;
-	using P = FftPlan<M>;
 	const int t = env.tid;
 	const int c = (int)( block / a.segs_per_channel );
 	const int seg = (int)( block % a.segs_per_channel );
@@ -91,15 +91,18 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 	const int W = a.W, hop = a.hop;
 	const int half = W / 2;
 
-	// per-thread constants for its fixed window positions and bins
+	// Per-thread constants for its fixed window positions and bins. The window carries a factor 1/2 (exact) that
+	// the real-FFT unpack would otherwise apply per bin: 0.5*(x*w) == x*(0.5*w) bit for bit.
 	float w[16];
 #pragma unroll
 	for( int s = 0; s < 8; ++s )
 		{
 		const int i0 = 2 * ( t + s * T );
-		w[2 * s]     = ( i0 < W )     ? env.ldg( a.win + i0 ) : 0.0f;
-		w[2 * s + 1] = ( i0 + 1 < W ) ? env.ldg( a.win + i0 + 1 ) : 0.0f;
+		w[2 * s]     = ( i0 < W )     ? 0.5f * env.ldg( a.win + i0 ) : 0.0f;
+		w[2 * s + 1] = ( i0 + 1 < W ) ? 0.5f * env.ldg( a.win + i0 + 1 ) : 0.0f;
 		}
+	// Bins of this thread: slot u holds k = t + u*T and its mirror M-k (k = 0: DC and Nyquist); bin M/2 is the
+	// ninth bin of thread T/2.
 	float prev[9], expd[9];
 #pragma unroll
 	for( int u = 0; u < 4; ++u )
@@ -112,39 +115,26 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 	prev[8] = 0.0f;
 	expd[8] = env.ldg( a.expected + M / 2 );
 
-	// Stage samples [lo,hi) (absolute indices) into the ring; zero outside the signal (AudioPV.cpp:54-58).
-	auto stage = [&]( int64_t lo, int64_t hi )
-		{
-		for( int64_t s = lo + t; s < hi; s += T )
-			{
-			const bool valid = ( s >= 0 && s < a.n_total );
-			env.cp_async4( ring + ( s & ( N - 1 ) ), valid ? ( xch + ( s - a.audio_offset ) ) : xch, valid );
-			}
-		env.cp_async_commit();
-		};
-
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
 	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
-	stage( (int64_t) hop * first - half, (int64_t) hop * first - half + W );
+	const bool full_window = ( W == N ) && a.aligned2;
 
 	for( int64_t f = first; f < fb; ++f )
 		{
 		const int64_t start = (int64_t) hop * f - half;                 // AudioPV.cpp:52
-		env.cp_async_wait_all();
-		env.sync();
-
-		// pass 0: windowed load (AudioPV.cpp:61-62; zero padding :65) + radix-8
+		const float * src = xch + ( start - a.audio_offset ) + 2 * t;   // this thread's first sample pair
 		float2 v[8];
-		if( a.aligned2 )
+		// pass 0: windowed load (AudioPV.cpp:54-62; zero padding :65) + radix-8. Windows overlap by W-hop samples:
+		// all but the newest hop are L1 hits.
+		if( full_window && start >= 0 && start + W <= a.n_total )
 			{
 #pragma unroll
 			for( int s = 0; s < 8; ++s )
 				{
-				const int i0 = 2 * ( t + s * T );
-				float2 r = *reinterpret_cast<const float2 *>( ring + ( ( start + i0 ) & ( N - 1 ) ) );
-				v[s].x = ( i0 < W )     ? mul_rn( r.x, w[2 * s] ) : 0.0f;
-				v[s].y = ( i0 + 1 < W ) ? mul_rn( r.y, w[2 * s + 1] ) : 0.0f;
+				const float2 r = env.ldg2( reinterpret_cast<const float2 *>( src + 2 * s * T ) );
+				v[s].x = mul_rn( r.x, w[2 * s] );
+				v[s].y = mul_rn( r.y, w[2 * s + 1] );
 				}
 			}
 		else
@@ -153,26 +143,26 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			for( int s = 0; s < 8; ++s )
 				{
 				const int i0 = 2 * ( t + s * T );
-				const float r0 = ring[( start + i0 ) & ( N - 1 )];
-				const float r1 = ring[( start + i0 + 1 ) & ( N - 1 )];
-				v[s].x = ( i0 < W )     ? mul_rn( r0, w[2 * s] ) : 0.0f;
-				v[s].y = ( i0 + 1 < W ) ? mul_rn( r1, w[2 * s + 1] ) : 0.0f;
+				const int64_t p0 = start + i0, p1 = p0 + 1;
+				const float r0 = ( i0 < W && p0 >= 0 && p0 < a.n_total )     ? env.ldg( src + 2 * s * T ) : 0.0f;
+				const float r1 = ( i0 + 1 < W && p1 >= 0 && p1 < a.n_total ) ? env.ldg( src + 2 * s * T + 1 ) : 0.0f;
+				v[s].x = mul_rn( r0, w[2 * s] );
+				v[s].y = mul_rn( r1, w[2 * s + 1] );
 				}
 			}
 		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
 		fft_store<M, 8, 1>( t, v, x0 );
 		env.sync();
 
-		// every thread has consumed frame f's window: the next frame's new samples may land in the ring
+		// pull the next frame's newest samples towards L1 while this frame computes
 		if( f + 1 < fb )
 			{
-			const int64_t nlo = (int64_t) hop * ( f + 1 ) - half;
-			const int64_t plo = start + W;                              // end of the current window
-			stage( nlo > plo ? nlo : plo, nlo + W );
+			const int64_t p = start + W + (int64_t) t * 32;
+			if( t * 32 < hop && p >= 0 && p < a.n_total ) env.prefetch( xch + ( p - a.audio_offset ) );
 			}
 
 		fft_pass_chain<M, 1, true>( t, v, x0, x1, a.pass_tw, env );
-		const float2 * z = fft_result_buffer<M>( x0, x1 );
+		const float2 * z = fft_result_buffer<M>( x0, x1 );         // Z/2 in natural order
 
 		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73)
 		const bool emit = ( f >= fa );
@@ -182,11 +172,11 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			{
 			const int k = t + u * T;
 			float2 xk, xm;
-			if( k == 0 )
+			if( u == 0 && t == 0 )
 				{
 				const float2 z0 = z[0];
-				xk.x = z0.x + z0.y; xk.y = 0.0f;        // DC
-				xm.x = z0.x - z0.y; xm.y = 0.0f;        // Nyquist
+				xk.x = 2.0f * ( z0.x + z0.y ); xk.y = 0.0f;       // DC
+				xm.x = 2.0f * ( z0.x - z0.y ); xm.y = 0.0f;       // Nyquist
 				}
 			else
 				{
@@ -194,34 +184,36 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				const float2 tw = env.ldg2( a.post_tw + k );
 				float2 A, Bq;
 				A.x = zk.x + zm.x; A.y = zk.y - zm.y;
-				Bq.x = zk.y + zm.y; Bq.y = zm.x - zk.x;         // -i * (zk - conj(zm))
+				Bq.x = zk.y + zm.y; Bq.y = zm.x - zk.x;           // -i * (zk - conj(zm))
 				const float2 Pq = cmul( Bq, tw );
-				xk.x = 0.5f * ( A.x + Pq.x ); xk.y = 0.5f * ( A.y + Pq.y );
-				xm.x = 0.5f * ( A.x - Pq.x ); xm.y = -0.5f * ( A.y - Pq.y );
+				xk.x = A.x + Pq.x; xk.y = A.y + Pq.y;
+				xm.x = A.x - Pq.x; xm.y = Pq.y - A.y;
 				}
 			if( emit )
 				{
-				const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], bin_frequency_of( k, a.k ), expd[2 * u], a.k );
-				const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], bin_frequency_of( M - k, a.k ), expd[2 * u + 1], a.k );
+				const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], env.ldg( a.binf + k ), expd[2 * u], a.k );
+				const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], env.ldg( a.binf + ( M - k ) ), expd[2 * u + 1], a.k );
 				env.st_stream2( row + k, mk );
 				env.st_stream2( row + ( M - k ), mm );
 				}
 			else
 				{
-				prev[2 * u] = atan2f( xk.y, xk.x );
-				prev[2 * u + 1] = atan2f( xm.y, xm.x );
+				prev[2 * u] = atan2_pv( xk.y, xk.x );
+				prev[2 * u + 1] = atan2_pv( xm.y, xm.x );
 				}
 			}
-		if( t == 0 )
+		if( t == T / 2 )
 			{
-			const float2 zh = z[M / 2];
+			const float2 zh = z[M / 2];                           // X[M/2] = conj(Z[M/2])
+			const float re = 2.0f * zh.x, im = -2.0f * zh.y;
 			if( emit )
-				env.st_stream2( row + M / 2, phase_vocoder_bin( zh.x, -zh.y, prev[8], bin_frequency_of( M / 2, a.k ), expd[8], a.k ) );
+				env.st_stream2( row + M / 2, phase_vocoder_bin( re, im, prev[8], env.ldg( a.binf + M / 2 ), expd[8], a.k ) );
 			else
-				prev[8] = atan2f( -zh.y, zh.x );
+				prev[8] = atan2_pv( im, re );
 			}
+		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
+		if( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) env.sync();
 		}
-	env.cp_async_wait_all();
 	}
 
 // ------------------------------------------------------------------------------------------------
@@ -290,7 +282,6 @@ template<int N, class Env>
 PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float * ola, float2 * x0, float2 * x1 )
 	{
 	constexpr int M = N / 2, T = M / 8, B = M + 1;
-	using P = FftPlan<M>;
 	const int t = env.tid;
 	const int c = (int)( block / a.segs_per_channel );
 	const int seg = (int)( block % a.segs_per_channel );
@@ -333,8 +324,9 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		{
 		for( int64_t s = lo + t; s < hi; s += T )
 			{
-			const float val = ola[s & ( N - 1 )];
-			ola[s & ( N - 1 )] = 0.0f;
+			const int slot = (int) s & ( N - 1 );
+			const float val = ola[slot];
+			ola[slot] = 0.0f;
 			if( s >= a.out_lo && s < a.out_hi )
 				{
 				float * dst = och + ( s - a.out_offset );
@@ -349,7 +341,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		phase_accumulate( ph, phase_increment( mf.y, a.k ), a.P, a.rcpP );      // phase_vocoder.cpp:57-59
 		const float theta = (float) ph;
 		float sn, cs;
-		env.sincos( theta, &sn, &cs );
+		sincos_pv( theta, &sn, &cs );
 		float2 r; r.x = mul_rn( mf.x, cs ); r.y = mul_rn( mf.x, sn );           // :60 std::polar
 		return r;
 		};
@@ -367,11 +359,10 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 			const int k = t + u * T;
 			const float2 xk = polar( env.ldcs2( row + k ), acc[2 * u] );
 			const float2 xm = polar( env.ldcs2( row + ( M - k ) ), acc[2 * u + 1] );
-			if( k == 0 )
+			if( u == 0 && t == 0 )
 				{
 				// imaginary parts of bins 0 and N/2 are ignored by a c2r transform
-				float2 z; z.x = xk.x + xm.x; z.y = xk.x - xm.x;
-				float2 zs; zs.x = z.y; zs.y = z.x;
+				float2 zs; zs.x = xk.x - xm.x; zs.y = xk.x + xm.x;
 				x1[0] = zs;
 				}
 			else
@@ -389,7 +380,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 				x1[M - k] = zm;
 				}
 			}
-		if( t == 0 )
+		if( t == T / 2 )
 			{
 			const float2 xh = polar( env.ldcs2( row + M / 2 ), acc[8] );
 			float2 zs; zs.y = 2.0f * xh.x; zs.x = -2.0f * xh.y;   // Z'[M/2] = 2 conj X[M/2], swapped
@@ -397,14 +388,19 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 			}
 		env.sync();
 
+		// pull the next frame's row towards L1 while this frame computes (one 128-byte line per thread)
+		if( f + 1 < fb )
+			for( int i = t * 16; i < B; i += T * 16 ) env.prefetch( row + B + i );
+
 		float2 v[8];
-		fft_load<M, 8, 64>( t, v, x1 );                           // natural order (identity swizzle)
+		fft_load<M, 64>( t, v, x1 );                              // natural order
 		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
 		fft_store<M, 8, 1>( t, v, x0 );
 		env.sync();
 		fft_pass_chain<M, 1, false>( t, v, x0, x1, a.pass_tw, env );
 
 		// v[s] = swapped z[n], n = t + s*T: y[2n] = v.y, y[2n+1] = v.x. Windowed overlap-add (AudioPV.cpp:133-134).
+		const int rs = (int) start & ( N - 1 );
 		if( a.aligned2 )
 			{
 #pragma unroll
@@ -413,7 +409,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 				const int i0 = 2 * ( t + s * T );
 				if( i0 < W )
 					{
-					float2 * slot = reinterpret_cast<float2 *>( ola + ( ( start + i0 ) & ( N - 1 ) ) );
+					float2 * slot = reinterpret_cast<float2 *>( ola + ( ( rs + i0 ) & ( N - 1 ) ) );
 					float2 cur = *slot;
 					cur.x = add_rn( cur.x, mul_rn( v[s].y, w[2 * s] ) );
 					if( i0 + 1 < W ) cur.y = add_rn( cur.y, mul_rn( v[s].x, w[2 * s + 1] ) );
@@ -429,12 +425,12 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 				const int i0 = 2 * ( t + s * T );
 				if( i0 < W )
 					{
-					float * p0 = ola + ( ( start + i0 ) & ( N - 1 ) );
+					float * p0 = ola + ( ( rs + i0 ) & ( N - 1 ) );
 					*p0 = add_rn( *p0, mul_rn( v[s].y, w[2 * s] ) );
 					}
 				if( i0 + 1 < W )
 					{
-					float * p1 = ola + ( ( start + i0 + 1 ) & ( N - 1 ) );
+					float * p1 = ola + ( ( rs + i0 + 1 ) & ( N - 1 ) );
 					*p1 = add_rn( *p1, mul_rn( v[s].x, w[2 * s + 1] ) );
 					}
 				}

@@ -31,6 +31,7 @@ struct DevicePlan
 	float * win_analysis = nullptr;
 	float * win_synthesis = nullptr;
 	float * expected = nullptr;
+	float * binf = nullptr;
 	float2 * post_tw = nullptr;
 	float2 * pass_tw = nullptr;
 	};
@@ -101,6 +102,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	CK( upload_vec( plan->host.win_analysis, &plan->win_analysis, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.win_synthesis, &plan->win_synthesis, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.expected, &plan->expected, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.binf, &plan->binf, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.post_tw, &plan->post_tw, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
 	*out = plan.get();
@@ -171,11 +173,16 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
 	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
+	int group_len = 32;
+	while( ( segs + group_len - 1 ) / group_len > 65535 ) group_len *= 2;
+	const int groups = ( segs + group_len - 1 ) / group_len;
+	const size_t grp_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * groups * B, 256 );
 	void * ws = nullptr;
-	rc = get_workspace( ctx, seg_bytes + acc_bytes, &ws );
+	rc = get_workspace( ctx, seg_bytes + acc_bytes + grp_bytes, &ws );
 	if( rc ) return rc;
 	PhaseSeg * d_seg = (PhaseSeg *) ws;
 	double * d_acc = (double *)( (char *) ws + seg_bytes );
+	PhaseSeg * d_grp = (PhaseSeg *)( (char *) ws + seg_bytes + acc_bytes );
 
 	PhaseSegArgs sa{};
 	sa.pv = (const float2 *) d_pv_rows; sa.pv_channel_stride = pv_channel_stride;
@@ -187,10 +194,11 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 
 	PhaseScanArgs sc{};
 	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
+	sc.group_len = group_len; sc.groups = groups; sc.group = d_grp;
 	sc.carry_in = d_carry_in; sc.carry_out = d_carry_out;
 	sc.acc_start = summary_only ? nullptr : d_acc;
 	sc.P = plan->host.P; sc.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); }
+	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); ctx->launches += summary_only ? 1 : 2; }
 	if( summary_only ) return FLAN_B200_OK;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
@@ -266,7 +274,7 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 	for( auto & kv : ctx->plans )
 		{
 		DevicePlan * p = kv.second.get();
-		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected );
+		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected ); cudaFree( p->binf );
 		cudaFree( p->post_tw ); cudaFree( p->pass_tw );
 		}
 	if( ctx->workspace ) cudaFree( ctx->workspace );
@@ -399,8 +407,9 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	a.frame_begin = frame_begin; a.frame_end = frame_end;
 	a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop;
-	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
-	a.win = plan->win_analysis; a.expected = plan->expected; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 )
+	          && ( (uintptr_t) d_audio_local % 8 == 0 );
+	a.win = plan->win_analysis; a.expected = plan->expected; a.binf = plan->binf; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
 	a.k = plan->host.k;
 	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream ), "analysis launch" ); }
 	return FLAN_B200_OK;

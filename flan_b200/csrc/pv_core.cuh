@@ -175,18 +175,22 @@ template<int M> struct FftPlan
 	static constexpr int tw_total = tw_offset( num_passes );
 	};
 
-// Shared-memory exchange layouts (float2 elements, 64-bit accesses are served per half-warp, so 16
-// consecutive lanes must hit 16 distinct values of index mod 16):
-//   after the Ns=1 radix-8 pass lanes write index 8*jj + r     -> xor bits [6:4] into bits [2:0]
-//   after the Ns=8 pass lanes write 8R*(jj/8) + jj%8 + 8r      -> xor bit log2(8R) into bit 3
-//   after passes with Ns >= 16 lanes write consecutive indices -> identity
-// The matching reads are 16 consecutive, aligned indices, which any of these xors only permutes.
-template<int NS, int R> PV_HD int swz( int idx )
+// Shared-memory exchange layouts (float2 elements; 64-bit accesses are served per half-warp, so 16 consecutive
+// lanes must hit 16 distinct values of index mod 16). Padding, not XOR, so that every access of a thread is
+// "per-thread base + compile-time constant" and the base is loop-invariant over the frame walk:
+//   after the Ns=1 radix-8 pass lanes write 8*jj + r          -> pad(i) = i + i/16      (8t + t/2 + r)
+//   after the Ns=8 radix-8 pass lanes write 64*(jj/8)+jj%8+8r -> pad(i) = i + 8*(i/64)  (72J + j + 8r)
+//   after passes with Ns >= 64 lanes write consecutive indices -> identity
+// The matching reads t + s*T are 16 consecutive, aligned indices: pad only shifts them as a block.
+template<int NS> PV_HD int xpad( int i )
 	{
-	if( NS == 1 ) return idx ^ ( ( idx >> 4 ) & 7 );
-	if( NS == 8 ) return idx ^ ( ( ( idx >> ( R == 8 ? 6 : R == 4 ? 5 : 4 ) ) & 1 ) << 3 );
-	return idx;
+	if( NS == 1 ) return i + ( i >> 4 );
+	if( NS == 8 ) return i + ( ( i >> 6 ) << 3 );
+	return i;
 	}
+
+// Exchange buffer length (float2) that covers the largest padded index.
+template<int M> struct XBuf { static constexpr int size = M + M / 8; };
 
 // One butterfly pass on the thread's 8 registers: twiddle (skipped when NS == 1), DFT_R.
 template<int M, int R, int NS, class TwLoad>
@@ -210,7 +214,8 @@ PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw
 		}
 	}
 
-// Scatter the pass's outputs to the exchange buffer (swizzled for this pass's write pattern).
+// Scatter the pass's outputs: element r of butterfly u goes to pad(expand(jj_u)) + r*NS (the pad of a butterfly's
+// base does not depend on r for any of the three layouts).
 template<int M, int R, int NS>
 PV_HD void fft_store( int t, const float2 * v, float2 * xout )
 	{
@@ -220,21 +225,22 @@ PV_HD void fft_store( int t, const float2 * v, float2 * xout )
 	for( int u = 0; u < U; ++u )
 		{
 		const int jj = t + u * T;
-		const int base = ( jj / NS ) * NS * R + ( jj & ( NS - 1 ) );
+		const int base = xpad<NS>( ( jj / NS ) * NS * R + ( jj & ( NS - 1 ) ) );
 #pragma unroll
 		for( int r = 0; r < R; ++r )
-			xout[swz<NS, R>( base + r * NS )] = v[u + r * U];
+			xout[base + r * NS] = v[u + r * U];
 		}
 	}
 
-// Gather the 8 elements t + s*T written by the pass with (R, NS).
-template<int M, int R, int NS>
+// Gather the 8 elements t + s*T written by the pass with NS: pad(t + s*T) = pad(t) + pad(s*T).
+template<int M, int NS>
 PV_HD void fft_load( int t, float2 * v, const float2 * xin )
 	{
 	constexpr int T = M / 8;
+	const float2 * base = xin + xpad<NS>( t );
 #pragma unroll
 	for( int s = 0; s < 8; ++s )
-		v[s] = xin[swz<NS, R>( t + s * T )];
+		v[s] = base[xpad<NS>( s * T )];
 	}
 
 // ---------------------------------------------------------------------------------------------
@@ -251,15 +257,57 @@ struct PvConsts
 	int use_wrapping;        // analysis_rate < sample_rate           phase_vocoder.cpp:37
 	};
 
-// |z| as the reference's std::abs(complex<float>) = hypotf. For operands in the normal range the
-// fused sum of squares + IEEE sqrt differs from hypotf by at most 1 ulp; out-of-range operands take
-// the scaled path so nothing overflows or flushes to zero.
-PV_HD float cabs_f( float re, float im )
+PV_HD float rcp_approx( float x )
 	{
-	const float ax = fabsf( re ), ay = fabsf( im );
-	const float mx = fmaxf( ax, ay );
+#if defined(__CUDA_ARCH__)
+	float r; asm( "rcp.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r;
+#else
+	return 1.0f / x;
+#endif
+	}
+PV_HD float sqrt_approx( float x )
+	{
+#if defined(__CUDA_ARCH__)
+	float r; asm( "sqrt.approx.ftz.f32 %0, %1;" : "=f"( r ) : "f"( x ) ); return r;
+#else
+	return sqrtf( x );
+#endif
+	}
+
+// std::arg(complex<float>) = atan2f(im, re) (phase_vocoder.cpp:43). Octant reduction to r = min/max in [0,1], a
+// degree-7 minimax polynomial in r^2 (|error| < 1.2e-7 rad evaluated in float, i.e. the rounding of the result), then
+// the quadrant fix-ups; ~20 instructions against ~46 for the CUDA library's atan2f. The results at the axes are the
+// correctly rounded pi/2 and pi, and a zero spectrum gives phase 0 as FFTW's exact zeros do in the reference.
+PV_HD float atan2_pv( float y, float x )
+	{
+	const float ax = fabsf( x ), ay = fabsf( y );
+	const float mx = fmaxf( fmaxf( ax, ay ), 1.0e-37f );
+	const float mn = fminf( ax, ay );
+	const float r = mn * rcp_approx( mx );
+	const float s = r * r;
+	float p = -0.00405455008149147f;
+	p = fmaf( p, s, 0.021862896159291267f );
+	p = fmaf( p, s, -0.055912237614393234f );
+	p = fmaf( p, s, 0.09642190486192703f );
+	p = fmaf( p, s, -0.1390862762928009f );
+	p = fmaf( p, s, 0.19946564733982086f );
+	p = fmaf( p, s, -0.33329859375953674f );
+	p = fmaf( p, s, 0.9999993443489075f );
+	float a = p * r;
+	if( ay > ax ) a = 1.57079637050628662109375f - a;
+	if( x < 0.0f ) a = 3.1415927410125732421875f - a;
+	return copysignf( a, y );
+	}
+
+// std::abs(complex<float>) = hypotf (phase_vocoder.cpp:52). In the normal range a fused sum of squares and a
+// 1-ulp square root stay within a few ulp of hypotf (tolerance 1e-4 relative); operands whose squares would
+// overflow or flush to zero take the library path, exact zeros return 0.
+PV_HD float cabs_pv( float re, float im )
+	{
+	const float mx = fmaxf( fabsf( re ), fabsf( im ) );
 	if( mx > 1.0e-18f && mx < 1.0e18f )
-		return sqrtf( fmaf( re, re, im * im ) );
+		return sqrt_approx( fmaf( re, re, im * im ) );
+	if( mx == 0.0f ) return 0.0f;
 	return hypotf( re, im );
 	}
 
@@ -269,7 +317,7 @@ PV_HD float cabs_f( float re, float im )
 PV_HD float2 phase_vocoder_bin( float re, float im, float & prev_phase, float bin_frequency,
                                 float expected_phase_diff, const PvConsts & k )
 	{
-	const float phase = atan2f( im, re );                                   // :43 std::arg
+	const float phase = atan2_pv( im, re );                                 // :43 std::arg
 	const float phase_diff = sub_rn( phase, prev_phase );                   // :44
 	prev_phase = phase;                                                     // :45
 	const float delta = sub_rn( phase_diff, expected_phase_diff );          // :48
@@ -282,7 +330,7 @@ PV_HD float2 phase_vocoder_bin( float re, float im, float & prev_phase, float bi
 		}
 	const float df = div_const( mul_rn( wrapped, k.analysis_rate ), k.pi2, k.rcp_pi2 );   // :50
 	float2 mf;
-	mf.x = cabs_f( re, im );                                                // :52 std::abs
+	mf.x = cabs_pv( re, im );                                               // :52 std::abs
 	mf.y = add_rn( bin_frequency, df );                                     // :52
 	return mf;
 	}
@@ -299,6 +347,37 @@ PV_HD float bin_frequency_of( int b, const PvConsts & k )
 PV_HD float phase_increment( float f, const PvConsts & k )
 	{
 	return mul_rn( div_const( f, k.analysis_rate, k.rcp_analysis_rate ), k.pi2 );   // :57
+	}
+
+// sinf / cosf of the accumulated phase (std::polar, phase_vocoder.cpp:60). The accumulator lives in [0, 2pi] except
+// during negative excursions, so: 3-term Cody-Waite reduction by pi/2, the classic minimax kernels on [-pi/4, pi/4]
+// (|error| ~1 ulp), quadrant swap. Arguments beyond the range where the reduction is exact use the library.
+PV_HD void sincos_pv( float x, float * sn, float * cs )
+	{
+	if( !( fabsf( x ) < 32768.0f ) )
+		{
+#if defined(__CUDA_ARCH__)
+		sincosf( x, sn, cs );
+#else
+		*sn = sinf( x ); *cs = cosf( x );
+#endif
+		return;
+		}
+	const float j = rintf( x * 0.636619772367581343f );
+	float r = fmaf( j, -1.57079601287841796875f, x );
+	r = fmaf( j, -3.1391647326017846353352069854736328125e-7f, r );
+	r = fmaf( j, -5.390302529957764765544681040410068817436695098876953125e-15f, r );
+	const int q = (int) j;
+	const float s = r * r;
+	float ps = fmaf( fmaf( -1.9515295891e-4f, s, 8.3321608736e-3f ), s, -1.6666654611e-1f );
+	ps = fmaf( ps * s, r, r );
+	float pc = fmaf( fmaf( 2.443315711809948e-5f, s, -1.388731625493765e-3f ), s, 4.166664568298827e-2f );
+	pc = fmaf( pc * s, s, fmaf( -0.5f, s, 1.0f ) );
+	float a = ( q & 1 ) ? pc : ps;
+	float b = ( q & 1 ) ? ps : pc;
+	if( q & 2 ) a = -a;
+	if( ( q + 1 ) & 2 ) b = -b;
+	*sn = a; *cs = b;
 	}
 
 // fmod(x, P) for x > P > 0 (exact, like libm's).

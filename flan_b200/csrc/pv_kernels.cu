@@ -25,27 +25,17 @@ struct DeviceEnv
 	__device__ __forceinline__ void st_stream2( float2 * p, float2 v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void st_stream( float * p, float v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void red_add( float * p, float v ) { atomicAdd( p, v ); }
-	__device__ __forceinline__ void sincos( float x, float * s, float * c ) { sincosf( x, s, c ); }
-	// 4-byte asynchronous global->shared copy (LDGSTS); src-size 0 zero-fills the destination.
-	__device__ __forceinline__ void cp_async4( float * dst, const float * src, bool valid )
-		{
-		const unsigned d = (unsigned) __cvta_generic_to_shared( dst );
-		const int sz = valid ? 4 : 0;
-		asm volatile( "cp.async.ca.shared.global [%0], [%1], 4, %2;\n" :: "r"( d ), "l"( src ), "r"( sz ) : "memory" );
-		}
-	__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;\n" ::: "memory" ); }
-	__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;\n" ::: "memory" ); }
+	__device__ __forceinline__ void prefetch( const void * p ) { asm volatile( "prefetch.global.L2 [%0];" :: "l"( p ) ); }
 	};
 
 template<int N>
 __global__ void __launch_bounds__( N / 16 ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
-	float * ring = reinterpret_cast<float *>( smem_raw );
-	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
-	float2 * x1 = x0 + N / 2;
+	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
+	float2 * x1 = x0 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	analysis_cta<N>( a, (int64_t) blockIdx.x, env, ring, x0, x1 );
+	analysis_cta<N>( a, (int64_t) blockIdx.x, env, x0, x1 );
 	}
 
 template<int N>
@@ -54,7 +44,7 @@ __global__ void __launch_bounds__( N / 16 ) pv_synthesis_kernel( const SynthArgs
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float * ola = reinterpret_cast<float *>( smem_raw );
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
-	float2 * x1 = x0 + N / 2;
+	float2 * x1 = x0 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
 	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1 );
 	}
@@ -81,21 +71,47 @@ __global__ void __launch_bounds__( 256 ) pv_phase_seg_kernel( const PhaseSegArgs
 
 // One thread per (channel, bin): serial walk over the segments (a few thousand at most), writing the
 // accumulator value that enters each segment. carry_in/carry_out chain frame-range shards across GPUs.
-__global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanArgs a )
+// The scan over segments runs in three short phases so that its serial depth is group_len + groups + group_len
+// instead of segs_per_channel (the combine is associative):
+//   mode 0  reduce each group of consecutive segments to one state          thread per (channel, group, bin)
+//   mode 1  exclusive scan of the group states (carry_in / carry_out here)  thread per (channel, bin)
+//   mode 2  re-walk each group from its prefix, writing acc_start           thread per (channel, group, bin)
+__global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanArgs a, int mode )
 	{
 	const int b = blockIdx.x * blockDim.x + threadIdx.x;
-	const int c = blockIdx.y;
+	const int g = blockIdx.y;
+	const int c = blockIdx.z;
 	if( b >= a.B ) return;
 	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
-	if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
-	const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
-	double * dst = a.acc_start ? a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b : nullptr;
-	for( int s = 0; s < a.segs_per_channel; ++s )
+	PhaseSeg * grp = a.group + (int64_t) c * a.groups * a.B + b;
+	if( mode == 1 )
 		{
-		if( dst ) dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
+		if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
+		for( int i = 0; i < a.groups; ++i )
+			{
+			const PhaseSeg tmp = grp[(int64_t) i * a.B];
+			grp[(int64_t) i * a.B] = st;
+			phase_state_combine( st, tmp, a.P, a.rcpP );
+			}
+		if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = st;
+		return;
+		}
+	const int s0 = g * a.group_len;
+	const int s1 = ( s0 + a.group_len < a.segs_per_channel ) ? s0 + a.group_len : a.segs_per_channel;
+	const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
+	if( mode == 0 )
+		{
+		for( int s = s0; s < s1; ++s ) phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+		grp[(int64_t) g * a.B] = st;
+		return;
+		}
+	st = grp[(int64_t) g * a.B];
+	double * dst = a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b;
+	for( int s = s0; s < s1; ++s )
+		{
+		dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
 		phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
 		}
-	if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = st;
 	}
 
 // carry[r] = summaries[0] (+) ... (+) summaries[r-1], for this rank r.
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * ( N / 2 );
+	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size;
 	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	pv_analysis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
@@ -141,7 +157,7 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 
 template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * ( N / 2 );
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size;
 	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	pv_synthesis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
@@ -190,8 +206,10 @@ cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st )
 
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 	{
-	dim3 grid( ( a.B + 127 ) / 128, C );
-	pv_phase_scan_kernel<<<grid, 128, 0, st>>>( a );
+	const dim3 wide( ( a.B + 127 ) / 128, a.groups, C ), narrow( ( a.B + 127 ) / 128, 1, C );
+	pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
+	pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
+	if( a.acc_start ) pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 2 );
 	return cudaGetLastError();
 	}
 

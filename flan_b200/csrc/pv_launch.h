@@ -22,6 +22,8 @@ struct PhaseScanArgs
 	{
 	const PhaseSeg * seg;       // [C][segs_per_channel][B]
 	int segs_per_channel, B;
+	int group_len, groups;      // segments per scan group, ceil(segs_per_channel / group_len) <= 65535
+	PhaseSeg * group;           // [C][groups][B] scratch
 	const PhaseSeg * carry_in;  // [C][B] or null (state before the first local frame)
 	PhaseSeg * carry_out;       // [C][B] or null (state after the last local frame)
 	double * acc_start;         // [C][segs_per_channel][B] or null

@@ -20,6 +20,7 @@ struct HostTables
 	std::vector<float> win_analysis;    // Windows::hann( i / (W-1) )                         AudioPV.cpp:30-34
 	std::vector<float> win_synthesis;   // hann * window_scale                               AudioPV.cpp:98-103
 	std::vector<float> expected;        // bin_frequency / analysis_rate * pi2, per bin      phase_vocoder.cpp:47
+	std::vector<float> binf;            // bin_to_frequency(b) = b * float(sr) / float(dft)   PVBuffer.cpp:443-446
 	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
 	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated
 	PvConsts k{};
@@ -82,9 +83,11 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		}
 
 	t.expected.resize( B );
+	t.binf.resize( B );
 	for( int b = 0; b < B; ++b )
 		{
 		const float binf = (float) b * sample_rate / (float) N;     // PVBuffer.cpp:443-446
+		t.binf[b] = binf;
 		t.expected[b] = binf / analysis_rate * t.k.pi2;             // phase_vocoder.cpp:47
 		}
 
