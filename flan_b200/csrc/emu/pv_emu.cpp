@@ -80,7 +80,7 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.frame_begin = frame_begin; a.frame_end = frame_end; a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 ) && ( (uintptr_t) audio % 8 == 0 );
-	a.win = tb.win_analysis.data(); a.expected = tb.expected.data(); a.binf = tb.binf.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;
 	switch( N )

@@ -69,8 +69,8 @@ struct AnalysisArgs
 	int W, hop;
 	int aligned2;               // every in-signal window of every channel starts on an 8-byte boundary
 	const float * win;          // [W] Hann, reference expression evaluated on the host
-	const float * expected;     // [B] expected_phase_diff per bin (phase_vocoder.cpp:47), host-evaluated
-	const float * binf;         // [B] bin_to_frequency(b) (PVBuffer.cpp:443-446), host-evaluated
+	const float2 * binc;        // [B] (bin_to_frequency(b), expected_phase_diff(b)), host-evaluated
+	                            //     (PVBuffer.cpp:443-446, phase_vocoder.cpp:47)
 	const float2 * post_tw;     // [N/4+1] e^{-2 pi i k/N}
 	const float2 * pass_tw;     // concatenated per-pass twiddles
 	PvConsts k;
@@ -103,17 +103,9 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		}
 	// Bins of this thread: slot u holds k = t + u*T and its mirror M-k (k = 0: DC and Nyquist); bin M/2 is the
 	// ninth bin of thread T/2.
-	float prev[9], expd[9];
+	float prev[9];
 #pragma unroll
-	for( int u = 0; u < 4; ++u )
-		{
-		const int k = t + u * T;
-		prev[2 * u] = 0.0f; prev[2 * u + 1] = 0.0f;
-		expd[2 * u] = env.ldg( a.expected + k );
-		expd[2 * u + 1] = env.ldg( a.expected + ( M - k ) );
-		}
-	prev[8] = 0.0f;
-	expd[8] = env.ldg( a.expected + M / 2 );
+	for( int u = 0; u < 9; ++u ) prev[u] = 0.0f;
 
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
@@ -164,7 +156,8 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		fft_pass_chain<M, 1, true>( t, v, x0, x1, a.pass_tw, env );
 		const float2 * z = fft_result_buffer<M>( x0, x1 );         // Z/2 in natural order
 
-		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73)
+		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73). The warm-up frame runs the same code with its stores
+		// predicated off: only the phases it leaves in prev[] matter.
 		const bool emit = ( f >= fa );
 		float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t)( M + 1 );
 #pragma unroll
@@ -189,27 +182,21 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				xk.x = A.x + Pq.x; xk.y = A.y + Pq.y;
 				xm.x = A.x - Pq.x; xm.y = Pq.y - A.y;
 				}
+			const float2 ck = env.ldg2( a.binc + k ), cm = env.ldg2( a.binc + ( M - k ) );
+			const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], ck.x, ck.y, a.k );
+			const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], cm.x, cm.y, a.k );
 			if( emit )
 				{
-				const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], env.ldg( a.binf + k ), expd[2 * u], a.k );
-				const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], env.ldg( a.binf + ( M - k ) ), expd[2 * u + 1], a.k );
 				env.st_stream2( row + k, mk );
 				env.st_stream2( row + ( M - k ), mm );
-				}
-			else
-				{
-				prev[2 * u] = atan2_pv( xk.y, xk.x );
-				prev[2 * u + 1] = atan2_pv( xm.y, xm.x );
 				}
 			}
 		if( t == T / 2 )
 			{
 			const float2 zh = z[M / 2];                           // X[M/2] = conj(Z[M/2])
-			const float re = 2.0f * zh.x, im = -2.0f * zh.y;
-			if( emit )
-				env.st_stream2( row + M / 2, phase_vocoder_bin( re, im, prev[8], env.ldg( a.binf + M / 2 ), expd[8], a.k ) );
-			else
-				prev[8] = atan2_pv( im, re );
+			const float2 ch = env.ldg2( a.binc + M / 2 );
+			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev[8], ch.x, ch.y, a.k );
+			if( emit ) env.st_stream2( row + M / 2, mh );
 			}
 		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
 		if( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) env.sync();

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -31,7 +32,7 @@ struct DevicePlan
 	float * win_analysis = nullptr;
 	float * win_synthesis = nullptr;
 	float * expected = nullptr;
-	float * binf = nullptr;
+	float2 * binc = nullptr;
 	float2 * post_tw = nullptr;
 	float2 * pass_tw = nullptr;
 	};
@@ -53,6 +54,7 @@ struct flan_b200_ctx
 	int * d_flag = nullptr;
 	int64_t launches = 0;
 	bool timing = false;
+	int tps_analysis = 768, tps_synthesis = 768;    // register-allocation variant (resident threads per SM)
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
 	};
@@ -102,7 +104,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	CK( upload_vec( plan->host.win_analysis, &plan->win_analysis, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.win_synthesis, &plan->win_synthesis, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.expected, &plan->expected, ctx->stream ), "plan upload" );
-	CK( upload_vec( plan->host.binf, &plan->binf, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.binc, &plan->binc, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.post_tw, &plan->post_tw, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
 	*out = plan.get();
@@ -218,7 +220,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
 	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
 	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 3 ); CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream ), "synthesis launch" ); }
+	{ LaunchTimer lt( ctx, 3 ); CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, ctx->tps_synthesis ), "synthesis launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -258,6 +260,8 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 		}
 	auto * ctx = new flan_b200_ctx;
 	ctx->device = device;
+	if( const char * e = std::getenv( "FLAN_B200_TPS_ANALYSIS" ) ) ctx->tps_analysis = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) ctx->tps_synthesis = std::atoi( e );
 	ctx->sms = prop.multiProcessorCount;
 	e = cudaMalloc( (void **) &ctx->d_flag, sizeof( int ) );
 	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flag, 0, sizeof( int ) );
@@ -274,7 +278,7 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 	for( auto & kv : ctx->plans )
 		{
 		DevicePlan * p = kv.second.get();
-		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected ); cudaFree( p->binf );
+		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected ); cudaFree( p->binc );
 		cudaFree( p->post_tw ); cudaFree( p->pass_tw );
 		}
 	if( ctx->workspace ) cudaFree( ctx->workspace );
@@ -409,9 +413,9 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 )
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
-	a.win = plan->win_analysis; a.expected = plan->expected; a.binf = plan->binf; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	a.win = plan->win_analysis; a.binc = plan->binc; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
 	a.k = plan->host.k;
-	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream ), "analysis launch" ); }
+	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, ctx->tps_analysis ), "analysis launch" ); }
 	return FLAN_B200_OK;
 	}
 

@@ -274,16 +274,20 @@ PV_HD float sqrt_approx( float x )
 #endif
 	}
 
-// std::arg(complex<float>) = atan2f(im, re) (phase_vocoder.cpp:43). Octant reduction to r = min/max in [0,1], a
-// degree-7 minimax polynomial in r^2 (|error| < 1.2e-7 rad evaluated in float, i.e. the rounding of the result), then
-// the quadrant fix-ups; ~20 instructions against ~46 for the CUDA library's atan2f. The results at the axes are the
-// correctly rounded pi/2 and pi, and a zero spectrum gives phase 0 as FFTW's exact zeros do in the reference.
-PV_HD float atan2_pv( float y, float x )
+// std::arg and std::abs of one spectrum value (phase_vocoder.cpp:43,52: atan2f and hypotf), sharing the octant
+// reduction r = min/max in [0,1]:
+//   phase: degree-7 minimax polynomial in r^2 (|error| < 1.2e-7 rad evaluated in float, i.e. the rounding of the
+//          result) and the quadrant fix-ups; at the axes the results are the correctly rounded pi/2 and pi, and a zero
+//          spectrum gives phase 0 as FFTW's exact zeros do in the reference;
+//   magnitude: max * sqrt(1 + r^2), which can neither overflow nor flush to zero and is within ~4 ulp of hypotf
+//          (tolerance 1e-4 relative); exact zeros give 0.
+// ~23 instructions for both against ~60 for the CUDA library's atan2f + hypotf.
+PV_HD float polar_pv( float re, float im, float & phase )
 	{
-	const float ax = fabsf( x ), ay = fabsf( y );
-	const float mx = fmaxf( fmaxf( ax, ay ), 1.0e-37f );
+	const float ax = fabsf( re ), ay = fabsf( im );
+	const float mx = fmaxf( ax, ay );
 	const float mn = fminf( ax, ay );
-	const float r = mn * rcp_approx( mx );
+	const float r = mn * rcp_approx( fmaxf( mx, 1.0e-37f ) );
 	const float s = r * r;
 	float p = -0.00405455008149147f;
 	p = fmaf( p, s, 0.021862896159291267f );
@@ -295,20 +299,17 @@ PV_HD float atan2_pv( float y, float x )
 	p = fmaf( p, s, 0.9999993443489075f );
 	float a = p * r;
 	if( ay > ax ) a = 1.57079637050628662109375f - a;
-	if( x < 0.0f ) a = 3.1415927410125732421875f - a;
-	return copysignf( a, y );
+	if( re < 0.0f ) a = 3.1415927410125732421875f - a;
+	phase = copysignf( a, im );
+	return mx * sqrt_approx( fmaf( r, r, 1.0f ) );
 	}
 
-// std::abs(complex<float>) = hypotf (phase_vocoder.cpp:52). In the normal range a fused sum of squares and a
-// 1-ulp square root stay within a few ulp of hypotf (tolerance 1e-4 relative); operands whose squares would
-// overflow or flush to zero take the library path, exact zeros return 0.
-PV_HD float cabs_pv( float re, float im )
+// std::round(float), half away from zero (phase_vocoder.cpp:40), as trunc(x + copysign(0.5, x)): exact for every
+// float except |x| = 0.5 - 2^-25, where the addition itself rounds up (the result then differs by one whole turn of
+// the wrap, i.e. f by exactly analysis_rate).
+PV_HD float round_half_away_fast( float x )
 	{
-	const float mx = fmaxf( fabsf( re ), fabsf( im ) );
-	if( mx > 1.0e-18f && mx < 1.0e18f )
-		return sqrt_approx( fmaf( re, re, im * im ) );
-	if( mx == 0.0f ) return 0.0f;
-	return hypotf( re, im );
+	return truncf( x + copysignf( 0.5f, x ) );
 	}
 
 // phase_vocoder(), reference phase_vocoder.cpp:5-53, in its float32 operation order.
@@ -317,20 +318,16 @@ PV_HD float cabs_pv( float re, float im )
 PV_HD float2 phase_vocoder_bin( float re, float im, float & prev_phase, float bin_frequency,
                                 float expected_phase_diff, const PvConsts & k )
 	{
-	const float phase = atan2_pv( im, re );                                 // :43 std::arg
+	float phase;
+	float2 mf;
+	mf.x = polar_pv( re, im, phase );                                       // :43 std::arg, :52 std::abs
 	const float phase_diff = sub_rn( phase, prev_phase );                   // :44
 	prev_phase = phase;                                                     // :45
 	const float delta = sub_rn( phase_diff, expected_phase_diff );          // :48
-	float wrapped = delta;
-	if( k.use_wrapping )                                                    // :49, wrap() :38-41
-		{
-		const float q = div_const( delta, k.pi2, k.rcp_pi2 );
-		const float r = round_half_away( q );
-		wrapped = sub_rn( delta, mul_rn( k.pi2, r ) );
-		}
+	const float q = div_const( delta, k.pi2, k.rcp_pi2 );                   // wrap() :38-41
+	const float r = round_half_away_fast( q );
+	const float wrapped = k.use_wrapping ? sub_rn( delta, mul_rn( k.pi2, r ) ) : delta;    // :49
 	const float df = div_const( mul_rn( wrapped, k.analysis_rate ), k.pi2, k.rcp_pi2 );   // :50
-	float2 mf;
-	mf.x = cabs_pv( re, im );                                               // :52 std::abs
 	mf.y = add_rn( bin_frequency, df );                                     // :52
 	return mf;
 	}

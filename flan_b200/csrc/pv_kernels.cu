@@ -28,8 +28,11 @@ struct DeviceEnv
 	__device__ __forceinline__ void prefetch( const void * p ) { asm volatile( "prefetch.global.L2 [%0];" :: "l"( p ) ); }
 	};
 
-template<int N>
-__global__ void __launch_bounds__( N / 16 ) pv_analysis_kernel( const AnalysisArgs a )
+// TPS = resident threads per SM the register allocation is sized for (512 -> 128, 768 -> 85, 1024 -> 64 registers).
+constexpr int min_blocks( int N, int TPS ) { return TPS / ( N / 16 ) > 32 ? 32 : ( TPS / ( N / 16 ) > 0 ? TPS / ( N / 16 ) : 1 ); }
+
+template<int N, int TPS>
+__global__ void __launch_bounds__( N / 16, min_blocks( N, TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
@@ -38,8 +41,8 @@ __global__ void __launch_bounds__( N / 16 ) pv_analysis_kernel( const AnalysisAr
 	analysis_cta<N>( a, (int64_t) blockIdx.x, env, x0, x1 );
 	}
 
-template<int N>
-__global__ void __launch_bounds__( N / 16 ) pv_synthesis_kernel( const SynthArgs a )
+template<int N, int TPS>
+__global__ void __launch_bounds__( N / 16, min_blocks( N, TPS ) ) pv_synthesis_kernel( const SynthArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float * ola = reinterpret_cast<float *>( smem_raw );
@@ -146,22 +149,34 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size;
-	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	pv_analysis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	pv_analysis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
+template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps )
+	{
+	if( tps >= 1024 ) return launch_analysis_nt<N, 1024>( a, blocks, st );
+	if( tps >= 768 ) return launch_analysis_nt<N, 768>( a, blocks, st );
+	return launch_analysis_nt<N, 512>( a, blocks, st );
+	}
 
-template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size;
-	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	pv_synthesis_kernel<N><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	pv_synthesis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
+	}
+template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps )
+	{
+	if( tps >= 1024 ) return launch_synthesis_nt<N, 1024>( a, blocks, st );
+	if( tps >= 768 ) return launch_synthesis_nt<N, 768>( a, blocks, st );
+	return launch_synthesis_nt<N, 512>( a, blocks, st );
 	}
 
 bool dft_size_supported( int N )
@@ -169,30 +184,30 @@ bool dft_size_supported( int N )
 	return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192;
 	}
 
-cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps )
 	{
 	switch( N )
 		{
-		case 256:  return launch_analysis_n<256>( a, blocks, st );
-		case 512:  return launch_analysis_n<512>( a, blocks, st );
-		case 1024: return launch_analysis_n<1024>( a, blocks, st );
-		case 2048: return launch_analysis_n<2048>( a, blocks, st );
-		case 4096: return launch_analysis_n<4096>( a, blocks, st );
-		case 8192: return launch_analysis_n<8192>( a, blocks, st );
+		case 256:  return launch_analysis_n<256>( a, blocks, st, tps );
+		case 512:  return launch_analysis_n<512>( a, blocks, st, tps );
+		case 1024: return launch_analysis_n<1024>( a, blocks, st, tps );
+		case 2048: return launch_analysis_n<2048>( a, blocks, st, tps );
+		case 4096: return launch_analysis_n<4096>( a, blocks, st, tps );
+		case 8192: return launch_analysis_n<8192>( a, blocks, st, tps );
 		default:   return cudaErrorInvalidValue;
 		}
 	}
 
-cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st )
+cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps )
 	{
 	switch( N )
 		{
-		case 256:  return launch_synthesis_n<256>( a, blocks, st );
-		case 512:  return launch_synthesis_n<512>( a, blocks, st );
-		case 1024: return launch_synthesis_n<1024>( a, blocks, st );
-		case 2048: return launch_synthesis_n<2048>( a, blocks, st );
-		case 4096: return launch_synthesis_n<4096>( a, blocks, st );
-		case 8192: return launch_synthesis_n<8192>( a, blocks, st );
+		case 256:  return launch_synthesis_n<256>( a, blocks, st, tps );
+		case 512:  return launch_synthesis_n<512>( a, blocks, st, tps );
+		case 1024: return launch_synthesis_n<1024>( a, blocks, st, tps );
+		case 2048: return launch_synthesis_n<2048>( a, blocks, st, tps );
+		case 4096: return launch_synthesis_n<4096>( a, blocks, st, tps );
+		case 8192: return launch_synthesis_n<8192>( a, blocks, st, tps );
 		default:   return cudaErrorInvalidValue;
 		}
 	}

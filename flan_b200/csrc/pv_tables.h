@@ -21,6 +21,7 @@ struct HostTables
 	std::vector<float> win_synthesis;   // hann * window_scale                               AudioPV.cpp:98-103
 	std::vector<float> expected;        // bin_frequency / analysis_rate * pi2, per bin      phase_vocoder.cpp:47
 	std::vector<float> binf;            // bin_to_frequency(b) = b * float(sr) / float(dft)   PVBuffer.cpp:443-446
+	std::vector<float2> binc;           // (binf, expected) interleaved, as the analysis kernel reads them
 	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
 	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated
 	PvConsts k{};
@@ -90,6 +91,8 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		t.binf[b] = binf;
 		t.expected[b] = binf / analysis_rate * t.k.pi2;             // phase_vocoder.cpp:47
 		}
+	t.binc.resize( B );
+	for( int b = 0; b < B; ++b ) { t.binc[b].x = t.binf[b]; t.binc[b].y = t.expected[b]; }
 
 	const long double two_pi = 6.283185307179586476925286766559005768L;
 	t.post_tw.resize( M / 2 + 1 );
