@@ -30,20 +30,23 @@ struct HostEnv
 	void st_stream( float * p, float v ) { *p = v; }
 	void red_add( float * p, float v ) { std::atomic_ref<float>( *p ).fetch_add( v ); }
 	void prefetch( const void * ) {}
+	void cp_async8( float2 * dst, const float2 * src ) { *dst = *src; }
+	void cp_async_commit() {}
+	void cp_async_wait_all() {}
 	};
 
 template<int N, class Body> void run_cta( Body && body )
 	{
 	constexpr int T = N / 16;
 	std::vector<float> ring( N );
-	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size );
+	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size ), rowbuf( N / 2 + 2 );
 	std::barrier<> bar( T );
 	std::vector<std::thread> th;
 	for( int t = 0; t < T; ++t )
 		th.emplace_back( [&, t]
 			{
 			HostEnv env{ t, &bar };
-			body( env, ring.data(), x0.data(), x1.data() );
+			body( env, ring.data(), x0.data(), x1.data(), rowbuf.data() );
 			} );
 	for( auto & x : th ) x.join();
 	}
@@ -51,13 +54,13 @@ template<int N, class Body> void run_cta( Body && body )
 template<int N> void analysis_n( const AnalysisArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1 ) { analysis_cta<N>( a, b, env, x0, x1 ); } );
+		run_cta<N>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N>( a, b, env, x0, x1 ); } );
 	}
 
 template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1 ) { synthesis_cta<N>( a, b, env, ola, x0, x1 ); } );
+		run_cta<N>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta<N>( a, b, env, ola, x0, x1, rowbuf ); } );
 	}
 
 } // namespace

@@ -266,7 +266,7 @@ struct SynthArgs
 	};
 
 template<int N, class Env>
-PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float * ola, float2 * x0, float2 * x1 )
+PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf )
 	{
 	constexpr int M = N / 2, T = M / 8, B = M + 1;
 	const int t = env.tid;
@@ -300,6 +300,19 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 	acc[8] = acc0[M / 2];
 
 	for( int i = t; i < N; i += T ) ola[i] = 0.0f;
+
+	// The (m,f) row of the NEXT frame is staged into shared memory with 8-byte cp.async while the current frame
+	// computes, so the HBM latency of the streaming read never sits on the critical path.
+	const float2 * pv_ch = a.pv + (int64_t) c * a.pv_channel_stride;
+	auto stage_row = [&]( int64_t f )
+		{
+		const float2 * src = pv_ch + ( f - a.frame_begin ) * (int64_t) B;
+		for( int i = t; i < B; i += T ) env.cp_async8( rowbuf + i, src + i );
+		env.cp_async_commit();
+		};
+	stage_row( fa );
+	env.cp_async_wait_all();
+	env.sync();
 
 	float * och = a.out + (int64_t) c * a.out_stride;
 	// Samples whose every contributing frame lies in this segment are stored; the W-hop samples shared with
@@ -336,7 +349,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 	for( int64_t f = fa; f < fb; ++f )
 		{
 		const int64_t start = (int64_t) hop * f - half;                          // AudioPV.cpp:125
-		const float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t) B;
+		const float2 * row = rowbuf;
 
 		// bins -> packed half-size spectrum Z'[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/N} (X[k] - conj X[M-k]),
 		// stored with re/im swapped so the forward pass chain computes the inverse transform.
@@ -344,8 +357,8 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		for( int u = 0; u < 4; ++u )
 			{
 			const int k = t + u * T;
-			const float2 xk = polar( env.ldcs2( row + k ), acc[2 * u] );
-			const float2 xm = polar( env.ldcs2( row + ( M - k ) ), acc[2 * u + 1] );
+			const float2 xk = polar( row[k], acc[2 * u] );
+			const float2 xm = polar( row[M - k], acc[2 * u + 1] );
 			if( u == 0 && t == 0 )
 				{
 				// imaginary parts of bins 0 and N/2 are ignored by a c2r transform
@@ -369,15 +382,14 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 			}
 		if( t == T / 2 )
 			{
-			const float2 xh = polar( env.ldcs2( row + M / 2 ), acc[8] );
+			const float2 xh = polar( row[M / 2], acc[8] );
 			float2 zs; zs.y = 2.0f * xh.x; zs.x = -2.0f * xh.y;   // Z'[M/2] = 2 conj X[M/2], swapped
 			x1[M / 2] = zs;
 			}
 		env.sync();
 
-		// pull the next frame's row towards L1 while this frame computes (one 128-byte line per thread)
-		if( f + 1 < fb )
-			for( int i = t * 16; i < B; i += T * 16 ) env.prefetch( row + B + i );
+		// every thread has consumed its bins of this row: start fetching the next one
+		if( f + 1 < fb ) stage_row( f + 1 );
 
 		float2 v[8];
 		fft_load<M, 64>( t, v, x1 );                              // natural order
@@ -422,6 +434,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 					}
 				}
 			}
+		env.cp_async_wait_all();       // the next row has had the whole pass chain to arrive; the barrier publishes it
 		env.sync();
 		// no later frame of this segment reaches [start, start+fin) again; the barriers of the next
 		// frame order this zeroing before its overlap-add

@@ -25,6 +25,14 @@ struct DeviceEnv
 	__device__ __forceinline__ void st_stream2( float2 * p, float2 v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void st_stream( float * p, float v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void red_add( float * p, float v ) { atomicAdd( p, v ); }
+	// 8-byte asynchronous global->shared copy (LDGSTS), completion tracked per thread by commit / wait groups
+	__device__ __forceinline__ void cp_async8( float2 * dst, const float2 * src )
+		{
+		const unsigned d = (unsigned) __cvta_generic_to_shared( dst );
+		asm volatile( "cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"( d ), "l"( src ) : "memory" );
+		}
+	__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;\n" ::: "memory" ); }
+	__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;\n" ::: "memory" ); }
 	__device__ __forceinline__ void prefetch( const void * p ) { asm volatile( "prefetch.global.L2 [%0];" :: "l"( p ) ); }
 	};
 
@@ -48,8 +56,9 @@ __global__ void __launch_bounds__( N / 16, min_blocks( N, TPS ) ) pv_synthesis_k
 	float * ola = reinterpret_cast<float *>( smem_raw );
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
 	float2 * x1 = x0 + XBuf<N / 2>::size;
+	float2 * rowbuf = x1 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1 );
+	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1, rowbuf );
 	}
 
 // One thread per (channel, segment, bin): summary of the segment's phase increments.
@@ -166,7 +175,7 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 
 template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size;
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 );
 	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	pv_synthesis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
