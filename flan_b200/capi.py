@@ -59,7 +59,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = build.lib_path()
+    path = os.environ.get("FLAN_B200_LIB") or build.lib_path()      # override: experiment builds only
     if not os.path.exists(path):
         raise FileNotFoundError(
             "%s is missing: run `python -m flan_b200.build` (nvcc). flan_b200 has no CPU fallback." % path)

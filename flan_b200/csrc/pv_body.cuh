@@ -214,14 +214,23 @@ PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, in
                                       double P, double rcpP, int & flag, Ld && ld )
 	{
 	PhaseSeg s; s.sum.q = 0.0; s.sum.r = 0.0; s.mx.q = 0.0; s.mx.r = 0.0;
-	for( int64_t i = 0; i < rows; ++i )
+	auto step = [&]( float2 mf )
 		{
-		const float2 mf = ld( col + i * row_stride );
 		if( !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f ) ) flag = 1;
 		s.sum.r += (double) phase_increment( mf.y, k );
 		phase_sum_normalize( s.sum, P, rcpP );
 		if( phase_sum_less( s.mx, s.sum ) ) s.mx = s.sum;
+		};
+	int64_t i = 0;
+	for( ; i + 8 <= rows; i += 8 )          // eight independent row loads in flight per thread
+		{
+		float2 mf[8];
+#pragma unroll
+		for( int j = 0; j < 8; ++j ) mf[j] = ld( col + ( i + j ) * row_stride );
+#pragma unroll
+		for( int j = 0; j < 8; ++j ) step( mf[j] );
 		}
+	for( ; i < rows; ++i ) step( ld( col + i * row_stride ) );
 	return s;
 	}
 

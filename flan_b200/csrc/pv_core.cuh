@@ -348,18 +348,29 @@ PV_HD float phase_increment( float f, const PvConsts & k )
 
 // sinf / cosf of the accumulated phase (std::polar, phase_vocoder.cpp:60). The accumulator lives in [0, 2pi] except
 // during negative excursions, so: 3-term Cody-Waite reduction by pi/2, the classic minimax kernels on [-pi/4, pi/4]
-// (|error| ~1 ulp), quadrant swap. Arguments beyond the range where the reduction is exact use the library.
+// (|error| ~1 ulp), quadrant swap. Arguments beyond the range where the reduction is exact use the library, out of
+// line so that its Payne-Hanek path is not replicated per bin.
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void sincos_library( float x, float * sn, float * cs ) { sincosf( x, sn, cs ); }
+#endif
 PV_HD void sincos_pv( float x, float * sn, float * cs )
 	{
 	if( !( fabsf( x ) < 32768.0f ) )
 		{
 #if defined(__CUDA_ARCH__)
-		sincosf( x, sn, cs );
+		sincos_library( x, sn, cs );
 #else
 		*sn = sinf( x ); *cs = cosf( x );
 #endif
 		return;
 		}
+#if defined(__CUDA_ARCH__) && defined(PV_MUFU_SINCOS)
+	// range-reduce to [-pi, pi] with the true 2*pi (split constant), then the SFU approximations (|error| ~5e-7)
+	const float k = rintf( x * 0.15915494309189535f );
+	float r = fmaf( k, -6.28318548202514648f, x );
+	r = fmaf( k, 1.74845553146951715e-7f, r );
+	*sn = __sinf( r ); *cs = __cosf( r );
+#else
 	const float j = rintf( x * 0.636619772367581343f );
 	float r = fmaf( j, -1.57079601287841796875f, x );
 	r = fmaf( j, -3.1391647326017846353352069854736328125e-7f, r );
@@ -375,6 +386,7 @@ PV_HD void sincos_pv( float x, float * sn, float * cs )
 	if( q & 2 ) a = -a;
 	if( ( q + 1 ) & 2 ) b = -b;
 	*sn = a; *cs = b;
+#endif
 	}
 
 // fmod(x, P) for x > P > 0 (exact, like libm's).
