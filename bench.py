@@ -27,6 +27,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = 1
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import numpy as np  # noqa: E402
 
@@ -151,7 +156,7 @@ def run_reference(args):
     try:
         fps, step_s, frames = cpu_reference_run(seconds, cores, steps, warmup)
     except Exception as e:  # the oracle always exists; this is a broken checkout
-        print(json.dumps({"impl": "reference", "unavailable": str(e)}))
+        emit({"impl": "reference", "unavailable": str(e)})
         return
     sample = "%d host threads x one mono %g s chunk of the cfg2 signal each per step (%d frames/step), reference " \
              "AudioPV.cpp compiled verbatim, FFTW stand-in = vendored pffft" % (cores, seconds, frames)
@@ -165,7 +170,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -332,13 +337,17 @@ def run_ours(args):
                                                   "compiled verbatim, FFTW stand-in = vendored pffft, 1 thread as the reference runs" % (secs, frames)}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # Only the JSON line may reach stdout: libraries (NCCL prints its version there) are diverted to stderr.
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

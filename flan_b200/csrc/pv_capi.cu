@@ -54,6 +54,8 @@ struct flan_b200_ctx
 	int * d_flag = nullptr;
 	int64_t launches = 0;
 	bool timing = false;
+	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
+	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0; uint32_t sr = 0, ar = 0; bool valid = false; } seg_key;
 	int tps_analysis = 768, tps_synthesis = 768;    // register-allocation variant (resident threads per SM)
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
@@ -158,7 +160,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
                  int64_t frame_begin, int64_t frame_end, int64_t frames_total, int B,
                  float sr, float ar, int W, const PhaseSeg * d_carry_in, PhaseSeg * d_carry_out,
                  float * d_out, int64_t out_stride, int64_t out_offset, int64_t out_len,
-                 bool summary_only, const volatile int * cancel )
+                 bool summary_only, const volatile int * cancel, bool reuse_summary = false )
 	{
 	if( C < 1 || B < 2 || frame_begin < 0 || frame_end < frame_begin || frames_total < frame_end )
 		return fail( ctx, FLAN_B200_INVALID, "bad channel / bin / frame-range arguments" );
@@ -186,13 +188,21 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	double * d_acc = (double *)( (char *) ws + seg_bytes );
 	PhaseSeg * d_grp = (PhaseSeg *)( (char *) ws + seg_bytes + acc_bytes );
 
+	flan_b200_ctx::SegKey key;
+	key.pv = d_pv_rows; key.stride = pv_channel_stride; key.fb = frame_begin; key.fe = frame_end;
+	key.C = C; key.B = B; key.W = W; key.sr = fbits( sr ); key.ar = fbits( ar ); key.valid = true;
+	const flan_b200_ctx::SegKey & old = ctx->seg_key;
+	const bool have_summaries = reuse_summary && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
+	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.sr == key.sr && old.ar == key.ar;
+	ctx->seg_key = key;
+
 	PhaseSegArgs sa{};
 	sa.pv = (const float2 *) d_pv_rows; sa.pv_channel_stride = pv_channel_stride;
 	sa.frame_begin = frame_begin; sa.frame_end = frame_end;
 	sa.seg_len = seg_len; sa.segs_per_channel = segs; sa.B = B;
 	sa.seg_out = d_seg; sa.nan_flag = ctx->d_flag;
 	sa.k = plan->host.k; sa.P = plan->host.P; sa.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->stream ), "phase summary launch" ); }
+	if( !have_summaries ) { LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->stream ), "phase summary launch" ); }
 
 	PhaseScanArgs sc{};
 	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
@@ -415,6 +425,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
 	a.win = plan->win_analysis; a.binc = plan->binc; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
 	a.k = plan->host.k;
+	ctx->seg_key.valid = false;
 	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, ctx->tps_analysis ), "analysis launch" ); }
 	return FLAN_B200_OK;
 	}
@@ -480,14 +491,15 @@ int flan_b200_phase_carry( flan_b200_ctx * ctx, const flan_b200_phase_state * d_
 int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
                                       int C, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
                                       int B, float sr, float ar, int W,
-                                      const flan_b200_phase_state * d_carry_in,
+                                      const flan_b200_phase_state * d_carry_in, int reuse_summary,
                                       float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len )
 	{
 	if( !ctx ) return FLAN_B200_INVALID;
 	if( !( ar > 0.0f ) || !( sr > 0.0f ) || flan_b200_hop_from_rates( sr, ar ) < 1 )
 		return fail( ctx, FLAN_B200_INVALID, "bad rates" );
 	return synth_range( ctx, d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frames_total, B, sr, ar, W,
-	                    (const PhaseSeg *) d_carry_in, nullptr, d_out_local, out_stride, out_offset, out_len, false, nullptr );
+	                    (const PhaseSeg *) d_carry_in, nullptr, d_out_local, out_stride, out_offset, out_len, false, nullptr,
+	                    reuse_summary != 0 );
 	}
 
 int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n )

@@ -106,14 +106,15 @@ class Engine:
         self.ctx.call("flan_b200_phase_carry", self._chk(all_states, torch.float64), rank, C, B, self._chk(carry, torch.float64))
         return carry
 
-    def convert_to_audio_range(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len, out=None):
+    def convert_to_audio_range(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len, out=None,
+                               reuse_summary=False):
         C, rows, B, _ = pv_rows.shape
         if out is None:
             out = torch.empty((C, out_len), dtype=torch.float32, device=self.device)
         self._bind_stream()
         self.ctx.call("flan_b200_convert_to_audio_range", self._chk(pv_rows), rows * B, C, frame_begin, frame_begin + rows,
                       frames_total, B, sr, ar, W, None if carry is None else self._chk(carry, torch.float64),
-                      self._chk(out), out_len, out_offset, out_len)
+                      int(reuse_summary), self._chk(out), out_len, out_offset, out_len)
         return out
 
     def add(self, dst, src):

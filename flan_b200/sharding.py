@@ -74,7 +74,9 @@ def sharded_resynthesis(engine, dist, shard, pv_rows, sr, ar, allgather, send, r
     state = engine.phase_summary(pv_rows, shard.f0, sr, ar, shard.W)
     carry = engine.phase_carry(allgather(state), shard.rank)
     lo, hi = shard.span_lo, shard.span_hi
-    out = engine.convert_to_audio_range(pv_rows, shard.f0, shard.frames_total, sr, ar, shard.W, carry, lo, hi - lo)
+    # the rows are untouched since phase_summary: its per-segment summaries are reused, the PV is read once more only
+    out = engine.convert_to_audio_range(pv_rows, shard.f0, shard.frames_total, sr, ar, shard.W, carry, lo, hi - lo,
+                                        reuse_summary=True)
     # lower-frame contributions first (AudioPV.cpp:133-134): the owner adds the right neighbour's partial sums
     h_lo, h_hi = head_overlap(shard)
     reqs = []

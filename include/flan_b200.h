@@ -118,11 +118,14 @@ int flan_b200_phase_carry( flan_b200_ctx * ctx, const flan_b200_phase_state * d_
  * out_stride), samples [out_offset, out_offset + out_len) of the output; frames write the part of
  * [hop*frame_begin - window/2, hop*(frame_end-1) + window/2) that lies inside it and inside
  * [0, frames_total*hop). The first and last window-hop samples of that span are partial sums that the
- * caller adds to the neighbouring shard's (flan_b200_add). d_carry_in may be NULL (rank 0). */
+ * caller adds to the neighbouring shard's (flan_b200_add). d_carry_in may be NULL (rank 0).
+ * reuse_summary != 0 promises that the PV rows are unchanged since the flan_b200_phase_summary call that immediately
+ * preceded on this context with the same rows / range / rates: its per-segment summaries (still in the context's
+ * scratch) are reused instead of reading the PV data a second time. The promise is checked against the arguments. */
 int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
                                       int channels, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
                                       int bins, float sample_rate, float analysis_rate, int window_size,
-                                      const flan_b200_phase_state * d_carry_in,
+                                      const flan_b200_phase_state * d_carry_in, int reuse_summary,
                                       float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len );
 /* d_out[i] += d_add[i], i < n (overlap-add halo received from a neighbour). */
 int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n );

@@ -39,7 +39,8 @@ class EmuEngine:
             st[..., 0], st[..., 1] = sq, sr_
         return torch.from_numpy(st)
 
-    def convert_to_audio_range(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len):
+    def convert_to_audio_range(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len,
+                               reuse_summary=False):
         out, _, _ = self.emu.synthesis(pv_rows.numpy(), sr, ar, W, frame_begin=frame_begin, frames_total=frames_total,
                                        carry_in=None if carry is None else np.ascontiguousarray(carry.numpy()),
                                        out_offset=out_offset, out_len=out_len, sms=2)

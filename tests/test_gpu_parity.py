@@ -258,3 +258,20 @@ def test_full_size_cfg5_clip(eng, oracle):
 def test_full_size_cfg3_ten_minutes(eng, oracle):
     x, sr, W, h, N = make_config("cfg3", 600)       # 96 kHz, W=8192: 10 of the 60 minutes (1 h = 22 GB PV, see bench)
     _full_size_checks(eng, dev(x), sr, W, h, N, oracle)
+
+
+def test_summary_reuse_is_bit_identical(eng):
+    import torch
+    x, sr, W, h, N = make_config("cfg5", 1.5)
+    pv = eng.convert_to_pv(dev(x), sr, W, h, N)
+    ar = eng.analysis_rate(sr, h)
+    F = pv.shape[1]
+    plain = eng.convert_to_audio_range(pv, 0, F, sr, ar, W, None, 0, F * h)
+    eng.phase_summary(pv, 0, sr, ar, W)
+    reused = eng.convert_to_audio_range(pv, 0, F, sr, ar, W, None, 0, F * h, reuse_summary=True)
+    assert torch.equal(plain, reused)
+    # a promise that does not match the preceding call is ignored, not trusted
+    eng.phase_summary(pv[:, :100].contiguous(), 0, sr, ar, W)
+    again = eng.convert_to_audio_range(pv, 0, F, sr, ar, W, None, 0, F * h, reuse_summary=True)
+    assert torch.equal(plain, again)
+    assert torch.equal(plain, eng.convert_to_audio(pv, sr, ar, W))
