@@ -207,19 +207,21 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 // Resynthesis: phase-scan helpers
 // ------------------------------------------------------------------------------------------------
 
-// Segment summary of one bin over frames [fa,fb): total phase increment and its max prefix, in split
-// form (see PhaseSum). `flag` is raised on NaN/Inf, the is_nan_or_inf() pre-scan of AudioPV.cpp:88.
+// Segment summary of one bin over frames [fa,fb): total phase increment and its max prefix. Within a segment (a few
+// thousand radians at most) the running sum is a plain double -- absolute error ~1e-12 rad -- and only the two
+// results are converted to the split form (see PhaseSum). `flag` is raised on NaN/Inf, the is_nan_or_inf() pre-scan
+// of AudioPV.cpp:88.
 template<class Ld>
 PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, int64_t rows, const PvConsts & k,
                                       double P, double rcpP, int & flag, Ld && ld )
 	{
-	PhaseSeg s; s.sum.q = 0.0; s.sum.r = 0.0; s.mx.q = 0.0; s.mx.r = 0.0;
+	double sum = 0.0, mx = 0.0;
+	bool bad = false;
 	auto step = [&]( float2 mf )
 		{
-		if( !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f ) ) flag = 1;
-		s.sum.r += (double) phase_increment( mf.y, k );
-		phase_sum_normalize( s.sum, P, rcpP );
-		if( phase_sum_less( s.mx, s.sum ) ) s.mx = s.sum;
+		bad = bad || !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f );
+		sum += (double) phase_increment( mf.y, k );
+		mx = ( sum > mx ) ? sum : mx;
 		};
 	int64_t i = 0;
 	for( ; i + 8 <= rows; i += 8 )          // eight independent row loads in flight per thread
@@ -231,6 +233,10 @@ PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, in
 		for( int j = 0; j < 8; ++j ) step( mf[j] );
 		}
 	for( ; i < rows; ++i ) step( ld( col + i * row_stride ) );
+	if( bad ) flag = 1;
+	PhaseSeg s;
+	phase_sum_from_double( sum, P, rcpP, s.sum.q, s.sum.r );
+	phase_sum_from_double( mx, P, rcpP, s.mx.q, s.mx.r );
 	return s;
 	}
 
@@ -331,6 +337,19 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 	const int64_t interior_hi = (int64_t) hop * fb - half;
 	auto flush = [&]( int64_t lo, int64_t hi )
 		{
+		if( lo >= interior_lo && hi <= interior_hi && lo >= a.out_lo && hi <= a.out_hi )
+			{
+			// whole range final and inside the local span (every frame but the first and last W/hop of a segment)
+			float * dst = och + ( lo - a.out_offset );
+			const int rs0 = (int) lo & ( N - 1 );
+			for( int i = t; i < (int)( hi - lo ); i += T )
+				{
+				const int slot = ( rs0 + i ) & ( N - 1 );
+				env.st_stream( dst + i, ola[slot] );
+				ola[slot] = 0.0f;
+				}
+			return;
+			}
 		for( int64_t s = lo + t; s < hi; s += T )
 			{
 			const int slot = (int) s & ( N - 1 );

@@ -399,10 +399,26 @@ PV_HD double fmod_pos( double x, double P, double rcpP )
 	return r;
 	}
 
+// Branch-free: the wrap is computed for every bin (nearly all of them wrap every frame: the expected phase advance
+// of bin b is b*2*pi*hop/dft) and selected by the reference's condition, so negative accumulators stay unwrapped.
 PV_HD void phase_accumulate( double & acc, float inc, double P, double rcpP )
 	{
-	acc += (double) inc;                                                    // :58
-	if( acc > P ) acc = fmod_pos( acc, P, rcpP );                           // :59
+	const double x = acc + (double) inc;                                    // :58
+	const double n = floor( x * rcpP );
+	double r = fma( -n, P, x );
+	r = ( r < 0.0 ) ? r + P : r;
+	r = ( r >= P ) ? r - P : r;
+	acc = ( x > P ) ? r : x;                                                // :59
+	}
+
+// Split form of a plain double sum (|s| far below 2^53 * P).
+PV_HD void phase_sum_from_double( double s, double P, double rcpP, double & q, double & r )
+	{
+	double n = floor( s * rcpP );
+	double rem = fma( -n, P, s );
+	if( rem < 0.0 ) { rem += P; n -= 1.0; }
+	if( rem >= P ) { rem -= P; n += 1.0; }
+	q = n; r = rem;
 	}
 
 // Running phase sum in the split form S = q*P + r, r in [0,P), q integral (held in a double): the
