@@ -56,30 +56,68 @@ def parse():
 # clocks
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons sampled every few ms DURING the timed region (NVML; nvidia-smi as fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
         self.samples = []
         self.stop = threading.Event()
         self.th = None
-
-    def _poll(self):
+        self.nvml = None
+        self.handle = None
         try:
-            out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
-            if out:
-                f = [s.strip() for s in out[0].split(",")]
-                self.samples.append({"sm": float(f[1]), "max": float(f[2]), "power": float(f[3]),
-                                     "hw_slowdown": f[4], "hw_thermal": f[5], "sw_thermal": f[6], "sw_power_cap": f[7]})
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
         except Exception:
-            pass
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                pass
+        return index
+
+    def _poll_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        self.samples.append({"sm": float(sm), "max": float(mx), "power": pw, "reasons": int(rs)})
+
+    def _poll_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().splitlines()
+        if out:
+            f = [x.strip() for x in out[0].split(",")]
+            rs = 0
+            for bit, val in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):
+                if val.lower().startswith("active"):
+                    rs |= bit
+            self.samples.append({"sm": float(f[0]), "max": float(f[1]), "power": float(f[2]), "reasons": rs})
 
     def _run(self):
         while not self.stop.is_set():
-            self._poll()
-            self.stop.wait(0.1)
+            try:
+                if self.nvml:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
+            except Exception:
+                pass
+            self.stop.wait(0.004)
 
     def __enter__(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -92,15 +130,15 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(s["sm"] for s in self.samples)
-        reasons = []
-        for key, name in (("hw_slowdown", "hw_slowdown"), ("hw_thermal", "hw_thermal_slowdown"),
-                          ("sw_thermal", "sw_thermal_slowdown"), ("sw_power_cap", "sw_power_cap")):
-            if any(s[key].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
+        sm = sorted(x["sm"] for x in self.samples)
+        bits = 0
+        for x in self.samples:
+            bits |= x["reasons"]
+        reasons = [name for bit, name in self.REASONS.items() if bits & bit]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0]["max"], "reasons": reasons,
-                "samples": len(self.samples), "power_w_max": max(s["power"] for s in self.samples)}
+                "samples": len(self.samples), "power_w_max": max(x["power"] for x in self.samples),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peak():
@@ -186,7 +224,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    steps = args.steps if args.steps is not None else 10
+    steps = args.steps if args.steps is not None else 20
     warmup = max(3, args.warmup if args.warmup is not None else 3)
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -215,11 +253,12 @@ def run_ours(args):
         dist.all_gather_into_tensor(bufs, state.contiguous())
         return bufs
 
-    def step(xin):
+    def step(xin, yout=None):
         if world == 1:
+            yout = y if yout is None else yout
             eng.convert_to_pv(xin, SR, W, HOP, N_DFT, out=pv)
-            eng.convert_to_audio(pv, SR, ar, W, out=y)
-            return y
+            eng.convert_to_audio(pv, SR, ar, W, out=yout)
+            return yout
         eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
         o, _ = sharded_resynthesis(eng, dist, sh, pv, SR, ar, allgather,
                                    lambda t, dst: dist.isend(t, dst), lambda t, src: dist.recv(t, src))
@@ -264,16 +303,41 @@ def run_ours(args):
     value = frames_all * steps / (ms_max * 1e-3)
 
     # ---- end to end: pinned host audio in, pinned host audio out, every step --------------------------------
-    def e2e_step():
-        xin = host_audio.to(dev, non_blocking=True)
-        o = step(xin)
-        host_out.copy_(o, non_blocking=True)
+    # Every step uploads its input from pinned host memory and downloads its result to pinned host memory. As a
+    # user converting a batch of files would, the copies run on their own streams with double-buffered device
+    # buffers, so step i+1's upload and step i-1's download overlap step i's kernels (PCIe is full duplex).
+    s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_comp = torch.cuda.current_stream(dev)
+    x_bufs = [torch.empty_like(x) for _ in range(2)]
+    y_bufs = [torch.empty((CH, out_len), dtype=torch.float32, device=dev) for _ in range(2)]
+    host_outs = [torch.empty((CH, out_len), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ev_h2d = [torch.cuda.Event() for _ in range(2)]
+    ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_d2h = [torch.cuda.Event() for _ in range(2)]
+    keep = [None, None]
 
-    e2e_step()
+    def e2e_step(i):
+        b = i % 2
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_comp[b])          # the kernels that read x_bufs[b] two steps ago are done
+            x_bufs[b].copy_(host_audio, non_blocking=True)
+            ev_h2d[b].record(s_h2d)
+        s_comp.wait_event(ev_h2d[b])
+        s_comp.wait_event(ev_d2h[b])              # y_bufs[b] has been downloaded
+        o = step(x_bufs[b], y_bufs[b])
+        ev_comp[b].record(s_comp)
+        keep[b] = o
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_comp[b])
+            host_outs[b].copy_(o, non_blocking=True)
+            ev_d2h[b].record(s_d2h)
+
+    for i in range(2):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        e2e_step()
+    for i in range(steps):
+        e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -296,11 +360,16 @@ def run_ours(args):
             kern.append(("pv_synthesis_kernel<4096>", sy_bytes, sy_ms / sy_n))
         dom = max(kern, key=lambda k: k[2]) if kern else None
         roofline = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel on the same workload (ncu)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        except Exception:
+            traffic = {}
         if dom:
             ach = dom[1] / (dom[2] * 1e-3) / 1e9
+            tr = traffic.get(dom[0], {}) if (world == 1 and args.seconds == SECONDS_PER_GPU) else {}
             roofline = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1],
-                        "ms_per_launch": dom[2]}
+                        "traffic": tr.get("dram_bytes_per_launch"), "traffic_capture": tr.get("capture"),
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[1], "ms_per_launch": dom[2]}
         per_kernel = {}
         for name, byts, m in kern:
             per_kernel[name] = {"ms_per_launch": m, "achieved_gbs": byts / (m * 1e-3) / 1e9, "frac": byts / (m * 1e-3) / 1e9 / peak}
@@ -324,7 +393,9 @@ def run_ours(args):
                      "round_trip_hbm_gbs": step_gbs, "round_trip_frac_of_peak": step_gbs / peak},
             "roofline": roofline, "kernels": per_kernel,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n_local),
-                    "d2h_bytes_per_step": int(4 * CH * out_len)},
+                    "d2h_bytes_per_step": int(4 * CH * out_len),
+                    "how": "pinned host -> device upload, convert_to_PV, convert_to_audio, device -> pinned host download every "
+                           "step; copies on their own streams, double-buffered, overlapping the neighbouring steps' kernels"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
