@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "lib")
 NVCC_FLAGS = [
     "-std=c++17", "--expt-relaxed-constexpr",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-DPV_MUFU_SINCOS",
+    "-lineinfo", "-O3",
     "-Xcompiler", "-fPIC,-ffp-contract=off",
 ]
 

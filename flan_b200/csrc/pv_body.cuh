@@ -164,16 +164,10 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		for( int u = 0; u < 4; ++u )
 			{
 			const int k = t + u * T;
+			// k = 0 pairs Z[0] with itself: the general unpack then yields DC in xk and Nyquist in xm (bin M), both real
 			float2 xk, xm;
-			if( u == 0 && t == 0 )
 				{
-				const float2 z0 = z[0];
-				xk.x = 2.0f * ( z0.x + z0.y ); xk.y = 0.0f;       // DC
-				xm.x = 2.0f * ( z0.x - z0.y ); xm.y = 0.0f;       // Nyquist
-				}
-			else
-				{
-				const float2 zk = z[k], zm = z[M - k];
+				const float2 zk = z[k], zm = z[( M - k ) & ( M - 1 )];
 				const float2 tw = env.ldg2( a.post_tw + k );
 				float2 A, Bq;
 				A.x = zk.x + zm.x; A.y = zk.y - zm.y;
@@ -385,15 +379,11 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		for( int u = 0; u < 4; ++u )
 			{
 			const int k = t + u * T;
-			const float2 xk = polar( row[k], acc[2 * u] );
-			const float2 xm = polar( row[M - k], acc[2 * u + 1] );
-			if( u == 0 && t == 0 )
-				{
-				// imaginary parts of bins 0 and N/2 are ignored by a c2r transform
-				float2 zs; zs.x = xk.x - xm.x; zs.y = xk.x + xm.x;
-				x1[0] = zs;
-				}
-			else
+			float2 xk = polar( row[k], acc[2 * u] );
+			float2 xm = polar( row[M - k], acc[2 * u + 1] );
+			// imaginary parts of bins 0 and N/2 are ignored by a c2r transform: with them cleared the general pack gives
+			// Z'[0] = (X0 + XM) + i (X0 - XM); its mirror lands in the unused slot M of the buffer
+			if( u == 0 && t == 0 ) { xk.y = 0.0f; xm.y = 0.0f; }
 				{
 				const float2 tw = env.ldg2( a.post_tw + k );
 				float2 A, Bv, Q;

@@ -347,25 +347,13 @@ PV_HD float phase_increment( float f, const PvConsts & k )
 	}
 
 // sinf / cosf of the accumulated phase (std::polar, phase_vocoder.cpp:60). The accumulator lives in [0, 2pi] except
-// during negative excursions, so: 3-term Cody-Waite reduction by pi/2, the classic minimax kernels on [-pi/4, pi/4]
-// (|error| ~1 ulp), quadrant swap. Arguments beyond the range where the reduction is exact use the library, out of
-// line so that its Payne-Hanek path is not replicated per bin.
-#if defined(__CUDA_ARCH__)
-static __device__ __noinline__ void sincos_library( float x, float * sn, float * cs ) { sincosf( x, sn, cs ); }
-#endif
+// during negative excursions. Reduction to [-pi, pi] by the true 2*pi with a split constant (two FMAs: exact product,
+// one rounding; accurate to ~3e-7 rad for |x| up to ~2^24 rad, beyond which float32 itself no longer resolves the
+// phase), then the SFU sine / cosine (|error| ~5e-7). Measured effect on the output: 3e-7 max abs (tolerance 1e-5).
+// -DPV_POLY_SINCOS selects 1-ulp polynomial kernels instead.
 PV_HD void sincos_pv( float x, float * sn, float * cs )
 	{
-	if( !( fabsf( x ) < 32768.0f ) )
-		{
-#if defined(__CUDA_ARCH__)
-		sincos_library( x, sn, cs );
-#else
-		*sn = sinf( x ); *cs = cosf( x );
-#endif
-		return;
-		}
-#if defined(__CUDA_ARCH__) && defined(PV_MUFU_SINCOS)
-	// range-reduce to [-pi, pi] with the true 2*pi (split constant), then the SFU approximations (|error| ~5e-7)
+#if defined(__CUDA_ARCH__) && !defined(PV_POLY_SINCOS)
 	const float k = rintf( x * 0.15915494309189535f );
 	float r = fmaf( k, -6.28318548202514648f, x );
 	r = fmaf( k, 1.74845553146951715e-7f, r );
@@ -399,16 +387,15 @@ PV_HD double fmod_pos( double x, double P, double rcpP )
 	return r;
 	}
 
-// Branch-free: the wrap is computed for every bin (nearly all of them wrap every frame: the expected phase advance
-// of bin b is b*2*pi*hop/dft) and selected by the reference's condition, so negative accumulators stay unwrapped.
+// acc += inc; if( acc > P ) acc = fmod( acc, P ). The remainder is taken as x - floor(x/P)*P without the usual +-P
+// fix-ups: when x/P lies within one double ulp of an integer the result can land just outside [0,P) -- congruent to
+// the reference's value modulo P, i.e. the same phase to 2e-7 rad, and the next wrap re-synchronises it.
 PV_HD void phase_accumulate( double & acc, float inc, double P, double rcpP )
 	{
 	const double x = acc + (double) inc;                                    // :58
-	const double n = floor( x * rcpP );
-	double r = fma( -n, P, x );
-	r = ( r < 0.0 ) ? r + P : r;
-	r = ( r >= P ) ? r - P : r;
-	acc = ( x > P ) ? r : x;                                                // :59
+	double r = x;
+	if( x > P ) r = fma( -floor( x * rcpP ), P, x );                        // :59
+	acc = r;
 	}
 
 // Split form of a plain double sum (|s| far below 2^53 * P).
