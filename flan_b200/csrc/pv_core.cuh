@@ -89,67 +89,81 @@ PV_HD float2 cmul( float2 a, float2 w )
 	return r;
 	}
 
+// Packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 act on an aligned register pair, i.e. on one complex
+// value, in ONE issue slot at the FP32 pipe's full FLOP rate). The kernels are issue-bound, so complex adds and
+// lane-wise products go through these; negation is an operand modifier and costs nothing.
+PV_HD float2 add2( float2 a, float2 b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fadd2_rn( a, b );
+#else
+	float2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r;
+#endif
+	}
+PV_HD float2 sub2( float2 a, float2 b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fadd2_rn( a, make_float2( -b.x, -b.y ) );
+#else
+	float2 r; r.x = a.x - b.x; r.y = a.y - b.y; return r;
+#endif
+	}
+PV_HD float2 mul2( float2 a, float2 b )
+	{
+#if defined(__CUDA_ARCH__)
+	return __fmul2_rn( a, b );
+#else
+	float2 r; r.x = a.x * b.x; r.y = a.y * b.y; return r;
+#endif
+	}
+PV_HD float2 fma2( float2 a, float2 b, float2 c )
+	{
+#if defined(__CUDA_ARCH__)
+	return __ffma2_rn( a, b, c );
+#else
+	float2 r; r.x = fmaf( a.x, b.x, c.x ); r.y = fmaf( a.y, b.y, c.y ); return r;
+#endif
+	}
+PV_HD float2 splat2( float s ) { float2 r; r.x = s; r.y = s; return r; }
+// -i * (a - b): the rotation is done by the subtraction itself (two scalar ops, no register shuffling)
+PV_HD float2 rotsub( float2 a, float2 b ) { float2 r; r.x = a.y - b.y; r.y = b.x - a.x; return r; }
+
 // Forward 8-point DFT in place (e^{-2 pi i nk/8}); a[k] <- sum_n a[n] w^{nk}. `a` has stride S between
 // elements so a radix-8 butterfly can act on a strided subset of the thread's 8 registers.
+// 21 FADD2 + 10 FADD + 2 FMUL2 issue slots (52 scalar operations).
 template<int S>
 PV_HD void dft8( float2 * a )
 	{
 	const float h = 0.70710678118654752440f;
-	float2 b0, b1, b2, b3, b4, b5, b6, b7;
-	b0.x = a[0*S].x + a[4*S].x; b0.y = a[0*S].y + a[4*S].y;
-	b4.x = a[0*S].x - a[4*S].x; b4.y = a[0*S].y - a[4*S].y;
-	b1.x = a[1*S].x + a[5*S].x; b1.y = a[1*S].y + a[5*S].y;
-	b5.x = a[1*S].x - a[5*S].x; b5.y = a[1*S].y - a[5*S].y;
-	b2.x = a[2*S].x + a[6*S].x; b2.y = a[2*S].y + a[6*S].y;
-	b6.x = a[2*S].x - a[6*S].x; b6.y = a[2*S].y - a[6*S].y;
-	b3.x = a[3*S].x + a[7*S].x; b3.y = a[3*S].y + a[7*S].y;
-	b7.x = a[3*S].x - a[7*S].x; b7.y = a[3*S].y - a[7*S].y;
-	// b5 *= (1-i)/sqrt2 ; b6 *= -i ; b7 *= (-1-i)/sqrt2
+	const float2 b0 = add2( a[0*S], a[4*S] ); float2 b4 = sub2( a[0*S], a[4*S] );
+	const float2 b1 = add2( a[1*S], a[5*S] ); float2 b5 = sub2( a[1*S], a[5*S] );
+	const float2 b2 = add2( a[2*S], a[6*S] ); const float2 b6 = rotsub( a[2*S], a[6*S] );   // (a2 - a6) * -i
+	const float2 b3 = add2( a[3*S], a[7*S] ); float2 b7 = sub2( a[3*S], a[7*S] );
+	// b5 *= (1-i)/sqrt2 ; b7 *= (-1-i)/sqrt2
 	float2 t;
-	t.x = ( b5.x + b5.y ) * h; t.y = ( b5.y - b5.x ) * h; b5 = t;
-	t.x = b6.y; t.y = -b6.x; b6 = t;
-	t.x = ( b7.y - b7.x ) * h; t.y = -( b7.x + b7.y ) * h; b7 = t;
+	t.x = b5.x + b5.y; t.y = b5.y - b5.x; b5 = mul2( t, splat2( h ) );
+	t.x = b7.y - b7.x; t.y = -( b7.x + b7.y ); b7 = mul2( t, splat2( h ) );
 	// even outputs: DFT4 of b0..b3
-	float2 c0, c1, c2, c3;
-	c0.x = b0.x + b2.x; c0.y = b0.y + b2.y;
-	c2.x = b0.x - b2.x; c2.y = b0.y - b2.y;
-	c1.x = b1.x + b3.x; c1.y = b1.y + b3.y;
-	c3.x = b1.y - b3.y; c3.y = -( b1.x - b3.x );      // -i * (b1 - b3)
-	a[0*S].x = c0.x + c1.x; a[0*S].y = c0.y + c1.y;
-	a[4*S].x = c0.x - c1.x; a[4*S].y = c0.y - c1.y;
-	a[2*S].x = c2.x + c3.x; a[2*S].y = c2.y + c3.y;
-	a[6*S].x = c2.x - c3.x; a[6*S].y = c2.y - c3.y;
-	// odd outputs: DFT4 of b4..b7
-	c0.x = b4.x + b6.x; c0.y = b4.y + b6.y;
-	c2.x = b4.x - b6.x; c2.y = b4.y - b6.y;
-	c1.x = b5.x + b7.x; c1.y = b5.y + b7.y;
-	c3.x = b5.y - b7.y; c3.y = -( b5.x - b7.x );
-	a[1*S].x = c0.x + c1.x; a[1*S].y = c0.y + c1.y;
-	a[5*S].x = c0.x - c1.x; a[5*S].y = c0.y - c1.y;
-	a[3*S].x = c2.x + c3.x; a[3*S].y = c2.y + c3.y;
-	a[7*S].x = c2.x - c3.x; a[7*S].y = c2.y - c3.y;
+	float2 c0 = add2( b0, b2 ), c2 = sub2( b0, b2 ), c1 = add2( b1, b3 ), c3 = rotsub( b1, b3 );
+	a[0*S] = add2( c0, c1 ); a[4*S] = sub2( c0, c1 ); a[2*S] = add2( c2, c3 ); a[6*S] = sub2( c2, c3 );
+	// odd outputs: DFT4 of b4, b5, b6, b7 (already twiddled)
+	c0 = add2( b4, b6 ); c2 = sub2( b4, b6 ); c1 = add2( b5, b7 ); c3 = rotsub( b5, b7 );
+	a[1*S] = add2( c0, c1 ); a[5*S] = sub2( c0, c1 ); a[3*S] = add2( c2, c3 ); a[7*S] = sub2( c2, c3 );
 	}
 
 template<int S>
 PV_HD void dft4( float2 * a )
 	{
-	float2 c0, c1, c2, c3;
-	c0.x = a[0*S].x + a[2*S].x; c0.y = a[0*S].y + a[2*S].y;
-	c2.x = a[0*S].x - a[2*S].x; c2.y = a[0*S].y - a[2*S].y;
-	c1.x = a[1*S].x + a[3*S].x; c1.y = a[1*S].y + a[3*S].y;
-	c3.x = a[1*S].y - a[3*S].y; c3.y = -( a[1*S].x - a[3*S].x );
-	a[0*S].x = c0.x + c1.x; a[0*S].y = c0.y + c1.y;
-	a[2*S].x = c0.x - c1.x; a[2*S].y = c0.y - c1.y;
-	a[1*S].x = c2.x + c3.x; a[1*S].y = c2.y + c3.y;
-	a[3*S].x = c2.x - c3.x; a[3*S].y = c2.y - c3.y;
+	const float2 c0 = add2( a[0*S], a[2*S] ), c2 = sub2( a[0*S], a[2*S] );
+	const float2 c1 = add2( a[1*S], a[3*S] ), c3 = rotsub( a[1*S], a[3*S] );
+	a[0*S] = add2( c0, c1 ); a[2*S] = sub2( c0, c1 ); a[1*S] = add2( c2, c3 ); a[3*S] = sub2( c2, c3 );
 	}
 
 template<int S>
 PV_HD void dft2( float2 * a )
 	{
-	float2 u = a[0], v = a[S];
-	a[0].x = u.x + v.x; a[0].y = u.y + v.y;
-	a[S].x = u.x - v.x; a[S].y = u.y - v.y;
+	const float2 u = a[0], v = a[S];
+	a[0] = add2( u, v ); a[S] = sub2( u, v );
 	}
 
 // ---------------------------------------------------------------------------------------------
