@@ -37,9 +37,17 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 		float2 * out = ( p % 2 == 0 ) ? x0 : x1;
 		fft_load<M, NSp>( t, v, in );
 		fft_butterflies<M, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
-		if constexpr( p < P::num_passes - 1 || STORE_LAST )
+		if constexpr( p < P::num_passes - 1 )
 			{
 			fft_store<M, R, NS>( t, v, out );
+			env.sync();
+			}
+		else if constexpr( STORE_LAST )
+			{
+			// Last pass: its outputs are in natural order, v[s] = Z[t + s*T]. The real-FFT unpack pairs Z[k] with
+			// Z[M-k]: the lower half (s < 4) stays in this thread's registers, only the upper half is published.
+#pragma unroll
+			for( int s = 4; s < 8; ++s ) out[t + s * ( M / 8 )] = v[s];
 			env.sync();
 			}
 		fft_pass_chain<M, p + 1, STORE_LAST>( t, v, x0, x1, tw, env );
@@ -153,7 +161,9 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			if( t * 32 < hop && p >= 0 && p < a.n_total ) env.prefetch( xch + ( p - a.audio_offset ) );
 			}
 
+#ifndef PV_ABL_NOFFT
 		fft_pass_chain<M, 1, true>( t, v, x0, x1, a.pass_tw, env );
+#endif
 		const float2 * z = fft_result_buffer<M>( x0, x1 );         // Z/2 in natural order
 
 		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73). The warm-up frame runs the same code with its stores
@@ -167,7 +177,9 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			// k = 0 pairs Z[0] with itself: the general unpack then yields DC in xk and Nyquist in xm (bin M), both real
 			float2 xk, xm;
 				{
-				const float2 zk = z[k], zm = z[( M - k ) & ( M - 1 )];
+				const float2 zk = v[u];
+				float2 zm = z[( u == 0 && t == 0 ) ? M / 2 : M - k];
+				if( u == 0 && t == 0 ) zm = v[0];
 				const float2 tw = env.ldg2( a.post_tw + k );
 				float2 A, Bq;
 				A.x = zk.x + zm.x; A.y = zk.y - zm.y;
@@ -177,8 +189,12 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				xm.x = A.x - Pq.x; xm.y = Pq.y - A.y;
 				}
 			const float2 ck = env.ldg2( a.binc + k ), cm = env.ldg2( a.binc + ( M - k ) );
+#ifndef PV_ABL_NOEPI
 			const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], ck.x, ck.y, a.k );
 			const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], cm.x, cm.y, a.k );
+#else
+			const float2 mk = add2( xk, ck ), mm = add2( xm, cm );      // ablation build only
+#endif
 			if( emit )
 				{
 				env.st_stream2( row + k, mk );
@@ -375,6 +391,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 
 		// bins -> packed half-size spectrum Z'[k] = (X[k] + conj X[M-k]) + i e^{+2 pi i k/N} (X[k] - conj X[M-k]),
 		// stored with re/im swapped so the forward pass chain computes the inverse transform.
+		float2 v[8];
 #pragma unroll
 		for( int u = 0; u < 4; ++u )
 			{
@@ -394,8 +411,8 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 				float2 zk, zm;
 				zk.y = A.x - Q.y; zk.x = A.y + Q.x;              // swapped (im, re) of Z'[k]
 				zm.y = A.x + Q.y; zm.x = Q.x - A.y;              // swapped (im, re) of Z'[M-k]
-				x1[k] = zk;
-				x1[M - k] = zm;
+				v[u] = zk;                 // Z'[t + u*T] is this thread's own pass-0 input
+				x1[M - k] = zm;            // the mirror side belongs to thread T - t
 				}
 			}
 		if( t == T / 2 )
@@ -409,8 +426,8 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		// every thread has consumed its bins of this row: start fetching the next one
 		if( f + 1 < fb ) stage_row( f + 1 );
 
-		float2 v[8];
-		fft_load<M, 64>( t, v, x1 );                              // natural order
+#pragma unroll
+		for( int s = 4; s < 8; ++s ) v[s] = x1[t + s * T];          // upper half of Z' from the mirror threads
 		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
 		fft_store<M, 8, 1>( t, v, x0 );
 		env.sync();

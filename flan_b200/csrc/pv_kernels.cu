@@ -18,7 +18,12 @@ namespace pvk {
 struct DeviceEnv
 	{
 	int tid;
-	__device__ __forceinline__ void sync() { __syncthreads(); }
+	__device__ __forceinline__ void sync()
+		{
+#ifndef PV_ABL_NOSYNC
+		__syncthreads();
+#endif
+		}
 	__device__ __forceinline__ float ldg( const float * p ) { return __ldg( p ); }
 	__device__ __forceinline__ float2 ldg2( const float2 * p ) { return __ldg( p ); }
 	__device__ __forceinline__ float2 ldcs2( const float2 * p ) { return __ldcs( p ); }
