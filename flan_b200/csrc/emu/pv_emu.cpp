@@ -35,9 +35,9 @@ struct HostEnv
 	void cp_async_wait_all() {}
 	};
 
-template<int N, class Body> void run_cta( Body && body )
+template<int N, int PT, class Body> void run_cta( Body && body )
 	{
-	constexpr int T = N / 16;
+	constexpr int T = N / ( 2 * PT );
 	std::vector<float> ring( N );
 	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size ), rowbuf( N / 2 + 2 );
 	std::barrier<> bar( T );
@@ -51,16 +51,16 @@ template<int N, class Body> void run_cta( Body && body )
 	for( auto & x : th ) x.join();
 	}
 
-template<int N> void analysis_n( const AnalysisArgs & a, int64_t blocks )
+template<int N, int PT> void analysis_n( const AnalysisArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N>( a, b, env, x0, x1 ); } );
+		run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT>( a, b, env, x0, x1 ); } );
 	}
 
 template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta<N>( a, b, env, ola, x0, x1, rowbuf ); } );
+		run_cta<N, 8>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta<N>( a, b, env, ola, x0, x1, rowbuf ); } );
 	}
 
 } // namespace
@@ -70,8 +70,9 @@ extern "C" {
 // Same contract as flan_b200_convert_to_pv_range, on host memory. seg_len <= 0 picks the product's choice for `sms` SMs.
 int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_offset, int C, int64_t n_total,
                      float sr, int W, int hop, int N, int64_t frame_begin, int64_t frame_end, int seg_len, int sms,
-                     float * pv_rows, int64_t pv_channel_stride )
+                     float * pv_rows, int64_t pv_channel_stride, int points_per_thread )
 	{
+	const bool pt16 = points_per_thread == 16 && N >= 512;
 	HostTables tb;
 	if( !build_tables( N, W, hop, sr, sr / hop, tb ) ) return 1;
 	const int64_t frames = frame_end - frame_begin;
@@ -83,17 +84,18 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.frame_begin = frame_begin; a.frame_end = frame_end; a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 ) && ( (uintptr_t) audio % 8 == 0 );
-	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.post_tw = tb.post_tw.data();
+	a.pass_tw = pt16 ? tb.pass_tw16.data() : tb.pass_tw.data();
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;
 	switch( N )
 		{
-		case 256: analysis_n<256>( a, blocks ); break;
-		case 512: analysis_n<512>( a, blocks ); break;
-		case 1024: analysis_n<1024>( a, blocks ); break;
-		case 2048: analysis_n<2048>( a, blocks ); break;
-		case 4096: analysis_n<4096>( a, blocks ); break;
-		case 8192: analysis_n<8192>( a, blocks ); break;
+		case 256: analysis_n<256, 8>( a, blocks ); break;
+		case 512: if( pt16 ) analysis_n<512, 16>( a, blocks ); else analysis_n<512, 8>( a, blocks ); break;
+		case 1024: if( pt16 ) analysis_n<1024, 16>( a, blocks ); else analysis_n<1024, 8>( a, blocks ); break;
+		case 2048: if( pt16 ) analysis_n<2048, 16>( a, blocks ); else analysis_n<2048, 8>( a, blocks ); break;
+		case 4096: if( pt16 ) analysis_n<4096, 16>( a, blocks ); else analysis_n<4096, 8>( a, blocks ); break;
+		case 8192: if( pt16 ) analysis_n<8192, 16>( a, blocks ); else analysis_n<8192, 8>( a, blocks ); break;
 		default: return 2;
 		}
 	return 0;

@@ -25,39 +25,39 @@ namespace pvk {
 // FFT pass chain over the ping-pong exchange buffers x0/x1 (XBuf<M>::size float2 each).
 // Pass 0 (radix 8, no twiddles) is issued by the caller; this runs passes 1..last.
 // ------------------------------------------------------------------------------------------------
-template<int M, int p, bool STORE_LAST, class Env>
+template<int M, int PT, int p, bool STORE_LAST, class Env>
 PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env )
 	{
-	using P = FftPlan<M>;
+	using P = FftPlan<M, PT>;
 	if constexpr( p < P::num_passes )
 		{
 		constexpr int NSp = P::ns( p - 1 );     // layout our input was written in
 		constexpr int R = P::radix( p ), NS = P::ns( p );
 		float2 * in  = ( ( p - 1 ) % 2 == 0 ) ? x0 : x1;
 		float2 * out = ( p % 2 == 0 ) ? x0 : x1;
-		fft_load<M, NSp>( t, v, in );
-		fft_butterflies<M, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
+		fft_load<M, PT, NSp>( t, v, in );
+		fft_butterflies<M, PT, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
 		if constexpr( p < P::num_passes - 1 )
 			{
-			fft_store<M, R, NS>( t, v, out );
+			fft_store<M, PT, R, NS>( t, v, out );
 			env.sync();
 			}
 		else if constexpr( STORE_LAST )
 			{
 			// Last pass: its outputs are in natural order, v[s] = Z[t + s*T]. The real-FFT unpack pairs Z[k] with
-			// Z[M-k]: the lower half (s < 4) stays in this thread's registers, only the upper half is published.
+			// Z[M-k]: the lower half (s < PT/2) stays in this thread's registers, only the upper half is published.
 #pragma unroll
-			for( int s = 4; s < 8; ++s ) out[t + s * ( M / 8 )] = v[s];
+			for( int s = PT / 2; s < PT; ++s ) out[t + s * ( M / PT )] = v[s];
 			env.sync();
 			}
-		fft_pass_chain<M, p + 1, STORE_LAST>( t, v, x0, x1, tw, env );
+		fft_pass_chain<M, PT, p + 1, STORE_LAST>( t, v, x0, x1, tw, env );
 		}
 	}
 
-// Buffer that holds the natural-order output of the last pass when STORE_LAST is set (its Ns >= 64: no padding).
-template<int M> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
+// Buffer that receives the natural-order output of the last pass when STORE_LAST is set (its Ns >= 16: no padding).
+template<int M, int PT> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
 	{
-	return ( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
+	return ( ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
 	}
 
 // ------------------------------------------------------------------------------------------------
@@ -84,10 +84,10 @@ struct AnalysisArgs
 	PvConsts k;
 	};
 
-template<int N, class Env>
+template<int N, int PT, class Env>
 PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1 )
 	{
-	constexpr int M = N / 2, T = M / 8;
+	constexpr int M = N / 2, T = M / PT, H = PT / 2;      // H pairs of bins (k, M-k) per thread
 	const int t = env.tid;
 	const int c = (int)( block / a.segs_per_channel );
 	const int seg = (int)( block % a.segs_per_channel );
@@ -101,19 +101,19 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 
 	// Per-thread constants for its fixed window positions and bins. The window carries a factor 1/2 (exact) that
 	// the real-FFT unpack would otherwise apply per bin: 0.5*(x*w) == x*(0.5*w) bit for bit.
-	float w[16];
+	float w[2 * PT];
 #pragma unroll
-	for( int s = 0; s < 8; ++s )
+	for( int s = 0; s < PT; ++s )
 		{
 		const int i0 = 2 * ( t + s * T );
 		w[2 * s]     = ( i0 < W )     ? 0.5f * env.ldg( a.win + i0 ) : 0.0f;
 		w[2 * s + 1] = ( i0 + 1 < W ) ? 0.5f * env.ldg( a.win + i0 + 1 ) : 0.0f;
 		}
 	// Bins of this thread: slot u holds k = t + u*T and its mirror M-k (k = 0: DC and Nyquist); bin M/2 is the
-	// ninth bin of thread T/2.
-	float prev[9];
+	// extra bin of thread T/2.
+	float prev[PT + 1];
 #pragma unroll
-	for( int u = 0; u < 9; ++u ) prev[u] = 0.0f;
+	for( int u = 0; u < PT + 1; ++u ) prev[u] = 0.0f;
 
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
@@ -124,23 +124,23 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		{
 		const int64_t start = (int64_t) hop * f - half;                 // AudioPV.cpp:52
 		const float * src = xch + ( start - a.audio_offset ) + 2 * t;   // this thread's first sample pair
-		float2 v[8];
-		// pass 0: windowed load (AudioPV.cpp:54-62; zero padding :65) + radix-8. Windows overlap by W-hop samples:
+		float2 v[PT];
+		// pass 0: windowed load (AudioPV.cpp:54-62; zero padding :65) + radix-PT. Windows overlap by W-hop samples:
 		// all but the newest hop are L1 hits.
 		if( full_window && start >= 0 && start + W <= a.n_total )
 			{
 #pragma unroll
-			for( int s = 0; s < 8; ++s )
+			for( int s = 0; s < PT; ++s )
 				{
 				const float2 r = env.ldg2( reinterpret_cast<const float2 *>( src + 2 * s * T ) );
-				v[s].x = mul_rn( r.x, w[2 * s] );
-				v[s].y = mul_rn( r.y, w[2 * s + 1] );
+				float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
+				v[s] = mul2( r, ww );
 				}
 			}
 		else
 			{
 #pragma unroll
-			for( int s = 0; s < 8; ++s )
+			for( int s = 0; s < PT; ++s )
 				{
 				const int i0 = 2 * ( t + s * T );
 				const int64_t p0 = start + i0, p1 = p0 + 1;
@@ -150,8 +150,8 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				v[s].y = mul_rn( r1, w[2 * s + 1] );
 				}
 			}
-		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
-		fft_store<M, 8, 1>( t, v, x0 );
+		fft_butterflies<M, PT, PT, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
+		fft_store<M, PT, PT, 1>( t, v, x0 );
 		env.sync();
 
 		// pull the next frame's newest samples towards L1 while this frame computes
@@ -162,16 +162,16 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			}
 
 #ifndef PV_ABL_NOFFT
-		fft_pass_chain<M, 1, true>( t, v, x0, x1, a.pass_tw, env );
+		fft_pass_chain<M, PT, 1, true>( t, v, x0, x1, a.pass_tw, env );
 #endif
-		const float2 * z = fft_result_buffer<M>( x0, x1 );         // Z/2 in natural order
+		const float2 * z = fft_result_buffer<M, PT>( x0, x1 );     // upper half of Z/2 in natural order
 
 		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73). The warm-up frame runs the same code with its stores
 		// predicated off: only the phases it leaves in prev[] matter.
 		const bool emit = ( f >= fa );
 		float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t)( M + 1 );
 #pragma unroll
-		for( int u = 0; u < 4; ++u )
+		for( int u = 0; u < H; ++u )
 			{
 			const int k = t + u * T;
 			// k = 0 pairs Z[0] with itself: the general unpack then yields DC in xk and Nyquist in xm (bin M), both real
@@ -205,11 +205,11 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			{
 			const float2 zh = z[M / 2];                           // X[M/2] = conj(Z[M/2])
 			const float2 ch = env.ldg2( a.binc + M / 2 );
-			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev[8], ch.x, ch.y, a.k );
+			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev[PT], ch.x, ch.y, a.k );
 			if( emit ) env.st_stream2( row + M / 2, mh );
 			}
 		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
-		if( ( FftPlan<M>::num_passes - 1 ) % 2 == 0 ) env.sync();
+		if( ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) env.sync();
 		}
 	}
 
@@ -376,12 +376,16 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 
 	auto polar = [&]( float2 mf, double & ph ) -> float2
 		{
+#ifndef PV_ABL_NOEPI
 		phase_accumulate( ph, phase_increment( mf.y, a.k ), a.P, a.rcpP );      // phase_vocoder.cpp:57-59
 		const float theta = (float) ph;
 		float sn, cs;
 		sincos_pv( theta, &sn, &cs );
 		float2 r; r.x = mul_rn( mf.x, cs ); r.y = mul_rn( mf.x, sn );           // :60 std::polar
 		return r;
+#else
+		return mf;                                                              // ablation build only
+#endif
 		};
 
 	for( int64_t f = fa; f < fb; ++f )
@@ -428,13 +432,18 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 
 #pragma unroll
 		for( int s = 4; s < 8; ++s ) v[s] = x1[t + s * T];          // upper half of Z' from the mirror threads
-		fft_butterflies<M, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
-		fft_store<M, 8, 1>( t, v, x0 );
+		fft_butterflies<M, 8, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
+		fft_store<M, 8, 8, 1>( t, v, x0 );
 		env.sync();
-		fft_pass_chain<M, 1, false>( t, v, x0, x1, a.pass_tw, env );
+#ifndef PV_ABL_NOFFT
+		fft_pass_chain<M, 8, 1, false>( t, v, x0, x1, a.pass_tw, env );
+#endif
 
 		// v[s] = swapped z[n], n = t + s*T: y[2n] = v.y, y[2n+1] = v.x. Windowed overlap-add (AudioPV.cpp:133-134).
 		const int rs = (int) start & ( N - 1 );
+#ifdef PV_ABL_NOOLA
+		if( v[0].x == 123.456f )                                              // ablation build only
+#endif
 		if( a.aligned2 )
 			{
 #pragma unroll

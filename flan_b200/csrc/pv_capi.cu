@@ -35,6 +35,7 @@ struct DevicePlan
 	float2 * binc = nullptr;
 	float2 * post_tw = nullptr;
 	float2 * pass_tw = nullptr;
+	float2 * pass_tw16 = nullptr;
 	};
 
 thread_local std::string g_create_error;
@@ -56,7 +57,11 @@ struct flan_b200_ctx
 	bool timing = false;
 	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
 	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0; uint32_t sr = 0, ar = 0; bool valid = false; } seg_key;
-	int tps_analysis = 768, tps_synthesis = 768;    // register-allocation variant (resident threads per SM)
+	// Launch policy (overridable for experiments with FLAN_B200_TPS_* / FLAN_B200_PT_ANALYSIS): complex points per
+	// thread of the analysis FFT (0 = by size: 16 from dft 4096 up, else 8) and the register-allocation variant
+	// (resident threads per SM the kernel is compiled for; 0 = 512 with 16 points per thread, else 768).
+	int tps_analysis = 0, tps_synthesis = 768;
+	int pt_analysis = 0;
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
 	};
@@ -109,6 +114,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	CK( upload_vec( plan->host.binc, &plan->binc, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.post_tw, &plan->post_tw, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.pass_tw16, &plan->pass_tw16, ctx->stream ), "plan upload" );
 	*out = plan.get();
 	ctx->plans[key] = std::move( plan );
 	return FLAN_B200_OK;
@@ -272,6 +278,7 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	ctx->device = device;
 	if( const char * e = std::getenv( "FLAN_B200_TPS_ANALYSIS" ) ) ctx->tps_analysis = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) ctx->tps_synthesis = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_PT_ANALYSIS" ) ) ctx->pt_analysis = std::atoi( e );
 	ctx->sms = prop.multiProcessorCount;
 	e = cudaMalloc( (void **) &ctx->d_flag, sizeof( int ) );
 	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flag, 0, sizeof( int ) );
@@ -289,7 +296,7 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 		{
 		DevicePlan * p = kv.second.get();
 		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected ); cudaFree( p->binc );
-		cudaFree( p->post_tw ); cudaFree( p->pass_tw );
+		cudaFree( p->post_tw ); cudaFree( p->pass_tw ); cudaFree( p->pass_tw16 );
 		}
 	if( ctx->workspace ) cudaFree( ctx->workspace );
 	cudaFree( ctx->d_flag );
@@ -423,10 +430,14 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 )
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
-	a.win = plan->win_analysis; a.binc = plan->binc; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : 8 );
+	if( pt != 16 || N < 512 ) pt = 8;
+	const int tps_a = ctx->tps_analysis ? ctx->tps_analysis : ( pt == 16 ? 512 : 768 );
+	a.win = plan->win_analysis; a.binc = plan->binc; a.post_tw = plan->post_tw;
+	a.pass_tw = ( pt == 16 ) ? plan->pass_tw16 : plan->pass_tw;
 	a.k = plan->host.k;
 	ctx->seg_key.valid = false;
-	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, ctx->tps_analysis ), "analysis launch" ); }
+	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, tps_a, pt ), "analysis launch" ); }
 	return FLAN_B200_OK;
 	}
 

@@ -166,23 +166,61 @@ PV_HD void dft2( float2 * a )
 	a[0] = add2( u, v ); a[S] = sub2( u, v );
 	}
 
+// Multiply by the constant e^{-2 pi i K/16} = (c, s): (x c - y s, x s + y c) = x*(c,s) + y*(-s,c), two packed slots.
+PV_HD float2 cmul_const( float2 v, float c, float sn )
+	{
+	float2 cs; cs.x = c; cs.y = sn;
+	float2 sc; sc.x = -sn; sc.y = c;
+	return fma2( splat2( v.y ), sc, mul2( splat2( v.x ), cs ) );
+	}
+
+// Forward 16-point DFT in place as 4 x 4 (n = j + 4m, k' = k + 4m'): inner DFT4s over m, twiddles W16^{jk}, outer
+// DFT4s over j; the digit-reversed result is put back in natural order by register renaming.
+template<int S>
+PV_HD void dft16( float2 * a )
+	{
+#pragma unroll
+	for( int j = 0; j < 4; ++j ) dft4<4 * S>( a + j * S );          // a[(j + 4k)S] = y_j[k]
+	const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f, h = 0.70710678118654752440f;
+	a[( 1 + 4 * 1 ) * S] = cmul_const( a[( 1 + 4 * 1 ) * S], c1, -s1 );     // W^1
+	a[( 1 + 4 * 2 ) * S] = cmul_const( a[( 1 + 4 * 2 ) * S], h, -h );       // W^2
+	a[( 1 + 4 * 3 ) * S] = cmul_const( a[( 1 + 4 * 3 ) * S], s1, -c1 );     // W^3
+	a[( 2 + 4 * 1 ) * S] = cmul_const( a[( 2 + 4 * 1 ) * S], h, -h );       // W^2
+	a[( 2 + 4 * 2 ) * S] = cmul_const( a[( 2 + 4 * 2 ) * S], 0.0f, -1.0f ); // W^4 = -i
+	a[( 2 + 4 * 3 ) * S] = cmul_const( a[( 2 + 4 * 3 ) * S], -h, -h );      // W^6
+	a[( 3 + 4 * 1 ) * S] = cmul_const( a[( 3 + 4 * 1 ) * S], s1, -c1 );     // W^3
+	a[( 3 + 4 * 2 ) * S] = cmul_const( a[( 3 + 4 * 2 ) * S], -h, -h );      // W^6
+	a[( 3 + 4 * 3 ) * S] = cmul_const( a[( 3 + 4 * 3 ) * S], -c1, s1 );     // W^9
+#pragma unroll
+	for( int k = 0; k < 4; ++k ) dft4<S>( a + 4 * k * S );           // a[(4k + m')S] = X[k + 4m']
+	float2 o[16];
+#pragma unroll
+	for( int k = 0; k < 4; ++k )
+#pragma unroll
+		for( int m = 0; m < 4; ++m ) o[k + 4 * m] = a[( 4 * k + m ) * S];
+#pragma unroll
+	for( int i = 0; i < 16; ++i ) a[i * S] = o[i];
+	}
+
 // ---------------------------------------------------------------------------------------------
-// FFT plan for a complex transform of M points held 8 per thread by T = M/8 threads.
+// FFT plan for a complex transform of M points held PT (8 or 16) per thread by T = M/PT threads.
 // Passes are Stockham autosort: pass p has radix R_p and Ns_p = product of the earlier radices.
-//   thread t holds, before and after every pass, the elements at logical index  t + s*T, s = 0..7
-//   butterfly u (u < 8/R) of thread t is jj = t + u*T and acts on registers s = u + r*(8/R)
+//   thread t holds, before and after every pass, the elements at logical index  t + s*T, s = 0..PT-1
+//   butterfly u (u < PT/R) of thread t is jj = t + u*T and acts on registers s = u + r*(PT/R)
 //   it writes element r to logical index  (jj / Ns)*Ns*R + (jj % Ns) + r*Ns
-// M = 8^a * {1,2,4}: radix-8 passes first (the first needs no twiddles), the small radix last.
+// Radix-PT passes come first (the first needs no twiddles), the remainder 2^k last.
 // ---------------------------------------------------------------------------------------------
-template<int M> struct FftPlan
+template<int M, int PT = 8> struct FftPlan
 	{
 	static_assert( M >= 128 && M <= 4096 && ( M & ( M - 1 ) ) == 0, "complex FFT size must be 128..4096" );
-	static constexpr int T = M / 8;
+	static_assert( PT == 8 || PT == 16, "8 or 16 points per thread" );
+	static constexpr int T = M / PT;
 	static constexpr int log2M = ( M == 128 ) ? 7 : ( M == 256 ) ? 8 : ( M == 512 ) ? 9 : ( M == 1024 ) ? 10 : ( M == 2048 ) ? 11 : 12;
-	static constexpr int num_r8 = log2M / 3;                  // radix-8 passes
-	static constexpr int last_r = 1 << ( log2M % 3 );         // 1 (none), 2 or 4
-	static constexpr int num_passes = num_r8 + ( last_r > 1 ? 1 : 0 );
-	static constexpr int radix( int p ) { return p < num_r8 ? 8 : last_r; }
+	static constexpr int log2R = ( PT == 8 ) ? 3 : 4;
+	static constexpr int num_full = log2M / log2R;                // radix-PT passes
+	static constexpr int last_r = 1 << ( log2M % log2R );         // 1 (none), 2, 4 or 8
+	static constexpr int num_passes = num_full + ( last_r > 1 ? 1 : 0 );
+	static constexpr int radix( int p ) { return p < num_full ? PT : last_r; }
 	static constexpr int ns( int p ) { int n = 1; for( int i = 0; i < p; ++i ) n *= radix( i ); return n; }
 	// offset (in float2) of pass p's twiddle table inside the concatenated table; pass 0 has none.
 	static constexpr int tw_offset( int p ) { int o = 0; for( int i = 1; i < p; ++i ) o += ( radix( i ) - 1 ) * ns( i ); return o; }
@@ -192,9 +230,9 @@ template<int M> struct FftPlan
 // Shared-memory exchange layouts (float2 elements; 64-bit accesses are served per half-warp, so 16 consecutive
 // lanes must hit 16 distinct values of index mod 16). Padding, not XOR, so that every access of a thread is
 // "per-thread base + compile-time constant" and the base is loop-invariant over the frame walk:
-//   after the Ns=1 radix-8 pass lanes write 8*jj + r          -> pad(i) = i + i/16      (8t + t/2 + r)
+//   after the Ns=1 pass lanes write R*jj + r (R = 8 or 16)     -> pad(i) = i + i/16      (8t + t/2 + r | 17t + r)
 //   after the Ns=8 radix-8 pass lanes write 64*(jj/8)+jj%8+8r -> pad(i) = i + 8*(i/64)  (72J + j + 8r)
-//   after passes with Ns >= 64 lanes write consecutive indices -> identity
+//   after passes with Ns >= 16 lanes write consecutive indices -> identity
 // The matching reads t + s*T are 16 consecutive, aligned indices: pad only shifts them as a block.
 template<int NS> PV_HD int xpad( int i )
 	{
@@ -206,12 +244,12 @@ template<int NS> PV_HD int xpad( int i )
 // Exchange buffer length (float2) that covers the largest padded index.
 template<int M> struct XBuf { static constexpr int size = M + M / 8; };
 
-// One butterfly pass on the thread's 8 registers: twiddle (skipped when NS == 1), DFT_R.
-template<int M, int R, int NS, class TwLoad>
+// One butterfly pass on the thread's PT registers: twiddle (skipped when NS == 1), DFT_R.
+template<int M, int PT, int R, int NS, class TwLoad>
 PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw )
 	{
-	constexpr int T = M / 8;
-	constexpr int U = 8 / R;            // butterflies per thread; register stride between butterfly elements
+	constexpr int T = M / PT;
+	constexpr int U = PT / R;           // butterflies per thread; register stride between butterfly elements
 #pragma unroll
 	for( int u = 0; u < U; ++u )
 		{
@@ -222,6 +260,7 @@ PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw
 			for( int r = 1; r < R; ++r )
 				v[u + r * U] = cmul( v[u + r * U], ldtw( tw + ( r - 1 ) * NS + jm ) );
 			}
+		if( R == 16 ) dft16<U>( v + u );
 		if( R == 8 ) dft8<U>( v + u );
 		if( R == 4 ) dft4<U>( v + u );
 		if( R == 2 ) dft2<U>( v + u );
@@ -229,12 +268,12 @@ PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw
 	}
 
 // Scatter the pass's outputs: element r of butterfly u goes to pad(expand(jj_u)) + r*NS (the pad of a butterfly's
-// base does not depend on r for any of the three layouts).
-template<int M, int R, int NS>
+// base does not depend on r for any of the layouts).
+template<int M, int PT, int R, int NS>
 PV_HD void fft_store( int t, const float2 * v, float2 * xout )
 	{
-	constexpr int T = M / 8;
-	constexpr int U = 8 / R;
+	constexpr int T = M / PT;
+	constexpr int U = PT / R;
 #pragma unroll
 	for( int u = 0; u < U; ++u )
 		{
@@ -246,14 +285,14 @@ PV_HD void fft_store( int t, const float2 * v, float2 * xout )
 		}
 	}
 
-// Gather the 8 elements t + s*T written by the pass with NS: pad(t + s*T) = pad(t) + pad(s*T).
-template<int M, int NS>
+// Gather the PT elements t + s*T written by the pass with NS: pad(t + s*T) = pad(t) + pad(s*T).
+template<int M, int PT, int NS>
 PV_HD void fft_load( int t, float2 * v, const float2 * xin )
 	{
-	constexpr int T = M / 8;
+	constexpr int T = M / PT;
 	const float2 * base = xin + xpad<NS>( t );
 #pragma unroll
-	for( int s = 0; s < 8; ++s )
+	for( int s = 0; s < PT; ++s )
 		v[s] = base[xpad<NS>( s * T )];
 	}
 

@@ -42,20 +42,21 @@ struct DeviceEnv
 	};
 
 // TPS = resident threads per SM the register allocation is sized for (512 -> 128, 768 -> 85, 1024 -> 64 registers).
-constexpr int min_blocks( int N, int TPS ) { return TPS / ( N / 16 ) > 32 ? 32 : ( TPS / ( N / 16 ) > 0 ? TPS / ( N / 16 ) : 1 ); }
+constexpr int min_blocks( int threads, int TPS ) { return TPS / threads > 32 ? 32 : ( TPS / threads > 0 ? TPS / threads : 1 ); }
 
-template<int N, int TPS>
-__global__ void __launch_bounds__( N / 16, min_blocks( N, TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
+// PT = complex points per thread: 8 (radix-8 passes, N/16 threads per frame) or 16 (radix-16 passes, N/32 threads).
+template<int N, int PT, int TPS>
+__global__ void __launch_bounds__( N / ( 2 * PT ), min_blocks( N / ( 2 * PT ), TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
 	float2 * x1 = x0 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	analysis_cta<N>( a, (int64_t) blockIdx.x, env, x0, x1 );
+	analysis_cta<N, PT>( a, (int64_t) blockIdx.x, env, x0, x1 );
 	}
 
 template<int N, int TPS>
-__global__ void __launch_bounds__( N / 16, min_blocks( N, TPS ) ) pv_synthesis_kernel( const SynthArgs a )
+__global__ void __launch_bounds__( N / 16, min_blocks( N / 16, TPS ) ) pv_synthesis_kernel( const SynthArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float * ola = reinterpret_cast<float *>( smem_raw );
@@ -163,21 +164,28 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-template<int N, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int PT, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size;
-	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	pv_analysis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	pv_analysis_kernel<N, PT, TPS><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
 	return cudaGetLastError();
 	}
-template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps )
+template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps, int pt )
 	{
-	if( tps >= 1024 ) return launch_analysis_nt<N, 1024>( a, blocks, st );
-	if( tps >= 768 ) return launch_analysis_nt<N, 768>( a, blocks, st );
-	return launch_analysis_nt<N, 512>( a, blocks, st );
+	if constexpr( N >= 512 )
+		{
+		if( pt == 16 )
+			{
+			if( tps >= 768 ) return launch_analysis_nt<N, 16, 768>( a, blocks, st );
+			return launch_analysis_nt<N, 16, 512>( a, blocks, st );
+			}
+		}
+	if( tps >= 1024 ) return launch_analysis_nt<N, 8, 1024>( a, blocks, st );
+	if( tps >= 768 ) return launch_analysis_nt<N, 8, 768>( a, blocks, st );
+	return launch_analysis_nt<N, 8, 512>( a, blocks, st );
 	}
-
 template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 );
@@ -198,16 +206,16 @@ bool dft_size_supported( int N )
 	return N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192;
 	}
 
-cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps )
+cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps, int pt )
 	{
 	switch( N )
 		{
-		case 256:  return launch_analysis_n<256>( a, blocks, st, tps );
-		case 512:  return launch_analysis_n<512>( a, blocks, st, tps );
-		case 1024: return launch_analysis_n<1024>( a, blocks, st, tps );
-		case 2048: return launch_analysis_n<2048>( a, blocks, st, tps );
-		case 4096: return launch_analysis_n<4096>( a, blocks, st, tps );
-		case 8192: return launch_analysis_n<8192>( a, blocks, st, tps );
+		case 256:  return launch_analysis_n<256>( a, blocks, st, tps, pt );
+		case 512:  return launch_analysis_n<512>( a, blocks, st, tps, pt );
+		case 1024: return launch_analysis_n<1024>( a, blocks, st, tps, pt );
+		case 2048: return launch_analysis_n<2048>( a, blocks, st, tps, pt );
+		case 4096: return launch_analysis_n<4096>( a, blocks, st, tps, pt );
+		case 8192: return launch_analysis_n<8192>( a, blocks, st, tps, pt );
 		default:   return cudaErrorInvalidValue;
 		}
 	}

@@ -31,7 +31,7 @@ struct PhaseScanArgs
 	};
 
 bool dft_size_supported( int N );
-cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm );
+cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm, int points_per_thread );
 cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm );
 cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st );
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st );

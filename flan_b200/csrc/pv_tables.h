@@ -23,7 +23,8 @@ struct HostTables
 	std::vector<float> binf;            // bin_to_frequency(b) = b * float(sr) / float(dft)   PVBuffer.cpp:443-446
 	std::vector<float2> binc;           // (binf, expected) interleaved, as the analysis kernel reads them
 	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
-	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated
+	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated (8 points per thread plan)
+	std::vector<float2> pass_tw16;      // same for the 16-points-per-thread plan (dft >= 512)
 	PvConsts k{};
 	double P = 0.0, rcpP = 0.0;
 	};
@@ -37,9 +38,9 @@ inline float hann_reference( float x )
 	return (float)( 0.5 * ( 1.0 - ::cos( (double) arg ) ) );
 	}
 
-template<int M> inline void append_pass_twiddles( std::vector<float2> & out )
+template<int M, int PT> inline void append_pass_twiddles( std::vector<float2> & out )
 	{
-	using P = FftPlan<M>;
+	using P = FftPlan<M, PT>;
 	const long double two_pi = 6.283185307179586476925286766559005768L;
 	for( int p = 1; p < P::num_passes; ++p )
 		{
@@ -104,14 +105,15 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		}
 
 	t.pass_tw.clear();
+	t.pass_tw16.clear();
 	switch( M )
 		{
-		case 128:  append_pass_twiddles<128>( t.pass_tw ); break;
-		case 256:  append_pass_twiddles<256>( t.pass_tw ); break;
-		case 512:  append_pass_twiddles<512>( t.pass_tw ); break;
-		case 1024: append_pass_twiddles<1024>( t.pass_tw ); break;
-		case 2048: append_pass_twiddles<2048>( t.pass_tw ); break;
-		case 4096: append_pass_twiddles<4096>( t.pass_tw ); break;
+		case 128:  append_pass_twiddles<128, 8>( t.pass_tw ); break;
+		case 256:  append_pass_twiddles<256, 8>( t.pass_tw );   append_pass_twiddles<256, 16>( t.pass_tw16 ); break;
+		case 512:  append_pass_twiddles<512, 8>( t.pass_tw );   append_pass_twiddles<512, 16>( t.pass_tw16 ); break;
+		case 1024: append_pass_twiddles<1024, 8>( t.pass_tw );  append_pass_twiddles<1024, 16>( t.pass_tw16 ); break;
+		case 2048: append_pass_twiddles<2048, 8>( t.pass_tw );  append_pass_twiddles<2048, 16>( t.pass_tw16 ); break;
+		case 4096: append_pass_twiddles<4096, 8>( t.pass_tw );  append_pass_twiddles<4096, 16>( t.pass_tw16 ); break;
 		default: return false;
 		}
 	return true;

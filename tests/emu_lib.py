@@ -22,7 +22,7 @@ class Emu:
             build.build_emulator()
         L = ctypes.CDLL(path)
         L.pv_emu_analysis.argtypes = [_fp, _i64, _i64, ctypes.c_int, _i64, ctypes.c_float, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, _i64, _i64, ctypes.c_int, ctypes.c_int, _fp, _i64]
+                                      ctypes.c_int, _i64, _i64, ctypes.c_int, ctypes.c_int, _fp, _i64, ctypes.c_int]
         L.pv_emu_synthesis.argtypes = [_fp, _i64, ctypes.c_int, _i64, _i64, _i64, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, _fp, _i64, _i64, _i64, ctypes.POINTER(ctypes.c_int)]
@@ -32,7 +32,7 @@ class Emu:
         self.L = L
 
     def analysis(self, audio, sr, W, hop, N, frame_begin=0, frame_end=None, seg_len=0, sms=4,
-                 audio_offset=0, n_total=None):
+                 audio_offset=0, n_total=None, points_per_thread=8):
         audio = np.ascontiguousarray(audio, np.float32)
         C, n_local = audio.shape
         if n_total is None:
@@ -44,7 +44,7 @@ class Emu:
         B = N // 2 + 1
         pv = np.full((C, rows, B, 2), np.nan, np.float32)
         rc = self.L.pv_emu_analysis(_ptr(audio), n_local, audio_offset, C, n_total, sr, W, hop, N, frame_begin,
-                                    frame_end, seg_len, sms, _ptr(pv), rows * B)
+                                    frame_end, seg_len, sms, _ptr(pv), rows * B, points_per_thread)
         assert rc == 0, rc
         return pv
 
