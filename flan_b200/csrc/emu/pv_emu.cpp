@@ -25,6 +25,7 @@ struct HostEnv
 	void sync() { bar->arrive_and_wait(); }
 	float ldg( const float * p ) { return *p; }
 	float2 ldg2( const float2 * p ) { return *p; }
+	float4 ldg4( const float4 * p ) { return *p; }
 	float2 ldcs2( const float2 * p ) { return *p; }
 	void st_stream2( float2 * p, float2 v ) { *p = v; }
 	void st_stream( float * p, float v ) { *p = v; }
@@ -84,7 +85,7 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.frame_begin = frame_begin; a.frame_end = frame_end; a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 ) && ( (uintptr_t) audio % 8 == 0 );
-	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.post_tw = tb.post_tw.data();
+	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.binc4 = tb.binc4.data(); a.post_rot = tb.post_rot.data();
 	a.pass_tw = pt16 ? tb.pass_tw16.data() : tb.pass_tw.data();
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;

@@ -79,7 +79,8 @@ struct AnalysisArgs
 	const float * win;          // [W] Hann, reference expression evaluated on the host
 	const float2 * binc;        // [B] (bin_to_frequency(b), expected_phase_diff(b)), host-evaluated
 	                            //     (PVBuffer.cpp:443-446, phase_vocoder.cpp:47)
-	const float2 * post_tw;     // [N/4+1] e^{-2 pi i k/N}
+	const float4 * binc4;       // [N/4+1] the same constants per unpack pair: (binf[k], binf[M-k], expected[k], -expected[M-k])
+	const float2 * post_rot;    // [N/4+1] -i e^{-2 pi i k/N}
 	const float2 * pass_tw;     // concatenated per-pass twiddles
 	PvConsts k;
 	};
@@ -109,18 +110,27 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		w[2 * s]     = ( i0 < W )     ? 0.5f * env.ldg( a.win + i0 ) : 0.0f;
 		w[2 * s + 1] = ( i0 + 1 < W ) ? 0.5f * env.ldg( a.win + i0 + 1 ) : 0.0f;
 		}
-	// Bins of this thread: slot u holds k = t + u*T and its mirror M-k (k = 0: DC and Nyquist); bin M/2 is the
-	// extra bin of thread T/2.
-	float prev[PT + 1];
+	// Bins of this thread: slot u holds k = t + u*T and its mirror M-k (k = 0: DC and Nyquist), whose previous phases
+	// travel as one packed pair; bin M/2 is the extra bin of thread T/2.
+	float2 prev[H];
+	float prev_mid = 0.0f;
 #pragma unroll
-	for( int u = 0; u < PT + 1; ++u ) prev[u] = 0.0f;
+	for( int u = 0; u < H; ++u ) { prev[u].x = 0.0f; prev[u].y = 0.0f; }
 
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
 	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
 	const bool full_window = ( W == N ) && a.aligned2;
 
-	for( int64_t f = first; f < fb; ++f )
+	// Output row of frame f: bins k = t + u*T ascend from row_lo, their mirrors M-k descend from row_hi (per-thread
+	// bases advanced by one row per frame, so every store address is base + immediate). The warm-up frame's row lies
+	// before the first one and is never dereferenced.
+	const int64_t row0 = (int64_t) c * a.pv_channel_stride + ( first - a.frame_begin ) * (int64_t)( M + 1 );
+	float2 * row_lo = a.pv + ( row0 + t );
+	float2 * row_hi = a.pv + ( row0 + M - t );
+	float2 * row_mid = a.pv + ( row0 + M / 2 );
+
+	for( int64_t f = first; f < fb; ++f, row_lo += M + 1, row_hi += M + 1, row_mid += M + 1 )
 		{
 		const int64_t start = (int64_t) hop * f - half;                 // AudioPV.cpp:52
 		const float * src = xch + ( start - a.audio_offset ) + 2 * t;   // this thread's first sample pair
@@ -169,44 +179,46 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73). The warm-up frame runs the same code with its stores
 		// predicated off: only the phases it leaves in prev[] matter.
 		const bool emit = ( f >= fa );
-		float2 * row = a.pv + (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t)( M + 1 );
 #pragma unroll
 		for( int u = 0; u < H; ++u )
 			{
 			const int k = t + u * T;
-			// k = 0 pairs Z[0] with itself: the general unpack then yields DC in xk and Nyquist in xm (bin M), both real
-			float2 xk, xm;
-				{
-				const float2 zk = v[u];
-				float2 zm = z[( u == 0 && t == 0 ) ? M / 2 : M - k];
-				if( u == 0 && t == 0 ) zm = v[0];
-				const float2 tw = env.ldg2( a.post_tw + k );
-				float2 A, Bq;
-				A.x = zk.x + zm.x; A.y = zk.y - zm.y;
-				Bq.x = zk.y + zm.y; Bq.y = zm.x - zk.x;           // -i * (zk - conj(zm))
-				const float2 Pq = cmul( Bq, tw );
-				xk.x = A.x + Pq.x; xk.y = A.y + Pq.y;
-				xm.x = A.x - Pq.x; xm.y = Pq.y - A.y;
-				}
-			const float2 ck = env.ldg2( a.binc + k ), cm = env.ldg2( a.binc + ( M - k ) );
-#ifndef PV_ABL_NOEPI
-			const float2 mk = phase_vocoder_bin( xk.x, xk.y, prev[2 * u], ck.x, ck.y, a.k );
-			const float2 mm = phase_vocoder_bin( xm.x, xm.y, prev[2 * u + 1], cm.x, cm.y, a.k );
+			// X[k] = (Zk + conj Zm) + (-i w_k)(Zk - conj Zm),  conj X[M-k] = (Zk + conj Zm) - (-i w_k)(Zk - conj Zm), Zm = Z[M-k].
+			// k = 0 pairs Z[0] with itself and yields DC in X[k] and Nyquist (bin M) in X[M-k], both real.
+			const float2 zk = v[u];
+			float2 zm = z[( u == 0 && t == 0 ) ? M / 2 : M - k];
+			if( u == 0 && t == 0 ) zm = v[0];
+			const float2 A = add2( zk, pn2( zm ) );
+			const float2 D = add2( zk, np2( zm ) );
+#ifndef PV_ABL_NOTAB
+			const float2 Pq = cmul2( D, env.ldg2( a.post_rot + k ) );
+			const float2 xk = add2( A, Pq ), xmc = sub2( A, Pq );
+			const float4 cc = env.ldg4( a.binc4 + k );
 #else
-			const float2 mk = add2( xk, ck ), mm = add2( xm, cm );      // ablation build only
+			float2 wq; wq.x = 0.5f + k; wq.y = 0.25f;                        // ablation build only: no table traffic
+			const float2 Pq = cmul2( D, wq );
+			const float2 xk = add2( A, Pq ), xmc = sub2( A, Pq );
+			float4 cc; cc.x = k; cc.y = M - k; cc.z = 0.1f * k; cc.w = -0.1f * k;
+#endif
+			float2 binf, expd; binf.x = cc.x; binf.y = cc.y; expd.x = cc.z; expd.y = cc.w;
+			float2 mk, mm;
+#ifndef PV_ABL_NOEPI
+			phase_vocoder_pair( xk, xmc, prev[u], binf, expd, a.k, mk, mm );
+#else
+			mk = add2( xk, binf ); mm = add2( xmc, expd );               // ablation build only
 #endif
 			if( emit )
 				{
-				env.st_stream2( row + k, mk );
-				env.st_stream2( row + ( M - k ), mm );
+				env.st_stream2( row_lo + u * T, mk );
+				env.st_stream2( row_hi - u * T, mm );
 				}
 			}
 		if( t == T / 2 )
 			{
 			const float2 zh = z[M / 2];                           // X[M/2] = conj(Z[M/2])
 			const float2 ch = env.ldg2( a.binc + M / 2 );
-			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev[PT], ch.x, ch.y, a.k );
-			if( emit ) env.st_stream2( row + M / 2, mh );
+			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev_mid, ch.x, ch.y, a.k );
+			if( emit ) env.st_stream2( row_mid, mh );
 			}
 		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
 		if( ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) env.sync();

@@ -34,6 +34,8 @@ struct DevicePlan
 	float * expected = nullptr;
 	float2 * binc = nullptr;
 	float2 * post_tw = nullptr;
+	float2 * post_rot = nullptr;
+	float4 * binc4 = nullptr;
 	float2 * pass_tw = nullptr;
 	float2 * pass_tw16 = nullptr;
 	};
@@ -113,6 +115,8 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	CK( upload_vec( plan->host.expected, &plan->expected, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.binc, &plan->binc, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.post_tw, &plan->post_tw, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.post_rot, &plan->post_rot, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.binc4, &plan->binc4, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw16, &plan->pass_tw16, ctx->stream ), "plan upload" );
 	*out = plan.get();
@@ -296,7 +300,7 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 		{
 		DevicePlan * p = kv.second.get();
 		cudaFree( p->win_analysis ); cudaFree( p->win_synthesis ); cudaFree( p->expected ); cudaFree( p->binc );
-		cudaFree( p->post_tw ); cudaFree( p->pass_tw ); cudaFree( p->pass_tw16 );
+		cudaFree( p->post_tw ); cudaFree( p->post_rot ); cudaFree( p->binc4 ); cudaFree( p->pass_tw ); cudaFree( p->pass_tw16 );
 		}
 	if( ctx->workspace ) cudaFree( ctx->workspace );
 	cudaFree( ctx->d_flag );
@@ -433,7 +437,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : 8 );
 	if( pt != 16 || N < 512 ) pt = 8;
 	const int tps_a = ctx->tps_analysis ? ctx->tps_analysis : ( pt == 16 ? 512 : 768 );
-	a.win = plan->win_analysis; a.binc = plan->binc; a.post_tw = plan->post_tw;
+	a.win = plan->win_analysis; a.binc = plan->binc; a.binc4 = plan->binc4; a.post_rot = plan->post_rot;
 	a.pass_tw = ( pt == 16 ) ? plan->pass_tw16 : plan->pass_tw;
 	a.k = plan->host.k;
 	ctx->seg_key.valid = false;

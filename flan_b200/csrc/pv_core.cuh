@@ -125,6 +125,14 @@ PV_HD float2 fma2( float2 a, float2 b, float2 c )
 #endif
 	}
 PV_HD float2 splat2( float s ) { float2 r; r.x = s; r.y = s; return r; }
+// Operand forms the packed instructions take for free (SASS modifiers .LO_HI, .NP, -, and scalar broadcast .F32):
+PV_HD float2 swap2( float2 a ) { float2 r; r.x = a.y; r.y = a.x; return r; }     // (y, x)
+PV_HD float2 np2( float2 a ) { float2 r; r.x = -a.x; r.y = a.y; return r; }      // (-x, y)
+PV_HD float2 pn2( float2 a ) { float2 r; r.x = a.x; r.y = -a.y; return r; }      // (x, -y) = conj
+PV_HD float2 neg2( float2 a ) { float2 r; r.x = -a.x; r.y = -a.y; return r; }
+// a * w and a * conj(w) in two packed issue slots: (a.y, a.x) * w.y, then a * w.x -+ that.
+PV_HD float2 cmul2( float2 a, float2 w ) { return fma2( a, splat2( w.x ), np2( mul2( swap2( a ), splat2( w.y ) ) ) ); }
+PV_HD float2 cmulc2( float2 a, float2 w ) { return fma2( a, splat2( w.x ), pn2( mul2( swap2( a ), splat2( w.y ) ) ) ); }
 // -i * (a - b): the rotation is done by the subtraction itself (two scalar ops, no register shuffling)
 PV_HD float2 rotsub( float2 a, float2 b ) { float2 r; r.x = a.y - b.y; r.y = b.x - a.x; return r; }
 
@@ -166,12 +174,11 @@ PV_HD void dft2( float2 * a )
 	a[0] = add2( u, v ); a[S] = sub2( u, v );
 	}
 
-// Multiply by the constant e^{-2 pi i K/16} = (c, s): (x c - y s, x s + y c) = x*(c,s) + y*(-s,c), two packed slots.
+// Multiply by the constant e^{-2 pi i K/16} = (c, s): two packed slots, the constants ride as broadcast immediates.
 PV_HD float2 cmul_const( float2 v, float c, float sn )
 	{
-	float2 cs; cs.x = c; cs.y = sn;
-	float2 sc; sc.x = -sn; sc.y = c;
-	return fma2( splat2( v.y ), sc, mul2( splat2( v.x ), cs ) );
+	float2 w; w.x = c; w.y = sn;
+	return cmul2( v, w );
 	}
 
 // Forward 16-point DFT in place as 4 x 4 (n = j + 4m, k' = k + 4m'): inner DFT4s over m, twiddles W16^{jk}, outer
@@ -186,7 +193,7 @@ PV_HD void dft16( float2 * a )
 	a[( 1 + 4 * 2 ) * S] = cmul_const( a[( 1 + 4 * 2 ) * S], h, -h );       // W^2
 	a[( 1 + 4 * 3 ) * S] = cmul_const( a[( 1 + 4 * 3 ) * S], s1, -c1 );     // W^3
 	a[( 2 + 4 * 1 ) * S] = cmul_const( a[( 2 + 4 * 1 ) * S], h, -h );       // W^2
-	a[( 2 + 4 * 2 ) * S] = cmul_const( a[( 2 + 4 * 2 ) * S], 0.0f, -1.0f ); // W^4 = -i
+	{ const float2 q = a[( 2 + 4 * 2 ) * S]; float2 r; r.x = q.y; r.y = -q.x; a[( 2 + 4 * 2 ) * S] = r; }   // W^4 = -i
 	a[( 2 + 4 * 3 ) * S] = cmul_const( a[( 2 + 4 * 3 ) * S], -h, -h );      // W^6
 	a[( 3 + 4 * 1 ) * S] = cmul_const( a[( 3 + 4 * 1 ) * S], s1, -c1 );     // W^3
 	a[( 3 + 4 * 2 ) * S] = cmul_const( a[( 3 + 4 * 2 ) * S], -h, -h );      // W^6
@@ -258,7 +265,14 @@ PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw
 			const int jm = ( t + u * T ) & ( NS - 1 );
 #pragma unroll
 			for( int r = 1; r < R; ++r )
-				v[u + r * U] = cmul( v[u + r * U], ldtw( tw + ( r - 1 ) * NS + jm ) );
+				{
+#ifndef PV_ABL_NOTW
+				const float2 w = ldtw( tw + ( r - 1 ) * NS + jm );
+#else
+				float2 w; w.x = 0.5f + jm; w.y = 0.25f * r;                  // ablation build only: no table traffic
+#endif
+				v[u + r * U] = cmul2( v[u + r * U], w );
+				}
 			}
 		if( R == 16 ) dft16<U>( v + u );
 		if( R == 8 ) dft8<U>( v + u );
@@ -308,6 +322,7 @@ struct PvConsts
 	float rcp_pi2;           // RN(1 / pi2)
 	float bin_scale;         // 1 / dft_size (exact: power of two)    PVBuffer.cpp:443-446
 	int use_wrapping;        // analysis_rate < sample_rate           phase_vocoder.cpp:37
+	float wrap_pi2;          // use_wrapping ? pi2 : 0 (delta - 0*round == delta: the wrap without a branch)
 	};
 
 PV_HD float rcp_approx( float x )
@@ -383,6 +398,64 @@ PV_HD float2 phase_vocoder_bin( float re, float im, float & prev_phase, float bi
 	const float df = div_const( mul_rn( wrapped, k.analysis_rate ), k.pi2, k.rcp_pi2 );   // :50
 	mf.y = add_rn( bin_frequency, df );                                     // :52
 	return mf;
+	}
+
+// Packed x / c, lane-wise identical to div_const.
+PV_HD float2 div_const2( float2 x, float c, float rc )
+	{
+	const float2 q0 = mul2( x, splat2( rc ) );
+	const float2 e = fma2( q0, splat2( -c ), x );
+	return fma2( e, splat2( rc ), q0 );
+	}
+
+// phase_vocoder() for the two bins of a real-FFT unpack pair at once: xa = X[k], xbc = conj(X[M-k]) (the form the
+// unpack produces). Lane x of every packed value belongs to bin k, lane y to bin M-k, so each arithmetic step of
+// phase_vocoder.cpp:43-52 is ONE packed instruction for both bins (FADD2 / FMUL2 / FFMA2 round each lane exactly like
+// their scalar forms). Lane y works on the CONJUGATE throughout: its phase, phase difference, wrap and frequency
+// deviation are the exact negatives of bin M-k's (round-to-nearest, trunc and the half-away rounding are all odd
+// functions), so `prev.y` holds -phase, `expd.y` must be passed as -expected_phase_diff[M-k], and the last step
+// subtracts. Results are bit-identical to phase_vocoder_bin. binf = bin_to_frequency of (k, M-k). The last operation
+// of each output is scalar so that (m, f) of a bin land in an adjacent register pair for the 8-byte store.
+PV_HD void phase_vocoder_pair( float2 xa, float2 xbc, float2 & prev, float2 binf, float2 expd, const PvConsts & k,
+                               float2 & mf_a, float2 & mf_b )
+	{
+	const float axa = fabsf( xa.x ), aya = fabsf( xa.y ), axb = fabsf( xbc.x ), ayb = fabsf( xbc.y );
+	float2 mx, mn, rc;
+	mx.x = fmaxf( axa, aya ); mn.x = fminf( axa, aya );
+	mx.y = fmaxf( axb, ayb ); mn.y = fminf( axb, ayb );
+	rc.x = rcp_approx( fmaxf( mx.x, 1.0e-37f ) );
+	rc.y = rcp_approx( fmaxf( mx.y, 1.0e-37f ) );
+	const float2 r = mul2( mn, rc );
+	const float2 s = mul2( r, r );
+	float2 p = fma2( splat2( -0.00405455008149147f ), s, splat2( 0.021862896159291267f ) );
+	p = fma2( p, s, splat2( -0.055912237614393234f ) );
+	p = fma2( p, s, splat2( 0.09642190486192703f ) );
+	p = fma2( p, s, splat2( -0.1390862762928009f ) );
+	p = fma2( p, s, splat2( 0.19946564733982086f ) );
+	p = fma2( p, s, splat2( -0.33329859375953674f ) );
+	p = fma2( p, s, splat2( 0.9999993443489075f ) );
+	float2 a = mul2( p, r );
+	if( aya > axa ) a.x = 1.57079637050628662109375f - a.x;
+	if( xa.x < 0.0f ) a.x = 3.1415927410125732421875f - a.x;
+	if( ayb > axb ) a.y = 1.57079637050628662109375f - a.y;
+	if( xbc.x < 0.0f ) a.y = 3.1415927410125732421875f - a.y;
+	float2 phase;
+	phase.x = copysignf( a.x, xa.y );                                       // :43 std::arg of X[k]
+	phase.y = copysignf( a.y, xbc.y );                                      //     -arg of X[M-k]
+	const float2 q2 = fma2( r, r, splat2( 1.0f ) );
+	float2 sq; sq.x = sqrt_approx( q2.x ); sq.y = sqrt_approx( q2.y );
+
+	const float2 phase_diff = sub2( phase, prev );                          // :44
+	prev = phase;                                                           // :45
+	const float2 delta = sub2( phase_diff, expd );                          // :48
+	const float2 q = div_const2( delta, k.pi2, k.rcp_pi2 );                 // wrap() :38-41
+	float2 hf; hf.x = copysignf( 0.5f, q.x ); hf.y = copysignf( 0.5f, q.y );
+	const float2 qh = add2( q, hf );
+	float2 rr; rr.x = truncf( qh.x ); rr.y = truncf( qh.y );
+	const float2 wrapped = sub2( delta, mul2( splat2( k.wrap_pi2 ), rr ) ); // :49 (wrap_pi2 = 0 when wrapping is off)
+	const float2 df = div_const2( mul2( wrapped, splat2( k.analysis_rate ) ), k.pi2, k.rcp_pi2 );   // :50
+	mf_a.x = mul_rn( mx.x, sq.x ); mf_a.y = add_rn( binf.x, df.x );        // :52
+	mf_b.x = mul_rn( mx.y, sq.y ); mf_b.y = sub_rn( binf.y, df.y );
 	}
 
 // PVBuffer::bin_to_frequency, PVBuffer.cpp:443-446: b * float(sr) / float(dft). dft is a power of two,

@@ -13,6 +13,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace pvk {
 
 struct DeviceEnv
@@ -26,6 +28,7 @@ struct DeviceEnv
 		}
 	__device__ __forceinline__ float ldg( const float * p ) { return __ldg( p ); }
 	__device__ __forceinline__ float2 ldg2( const float2 * p ) { return __ldg( p ); }
+	__device__ __forceinline__ float4 ldg4( const float4 * p ) { return __ldg( p ); }
 	__device__ __forceinline__ float2 ldcs2( const float2 * p ) { return __ldcs( p ); }
 	__device__ __forceinline__ void st_stream2( float2 * p, float2 v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void st_stream( float * p, float v ) { __stcs( p, v ); }
@@ -164,9 +167,17 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// Development aid: FLAN_B200_SMEM_PAD=<bytes> inflates the dynamic shared memory request so that fewer CTAs fit per
+// SM (occupancy experiments). Unset in production.
+static size_t smem_pad()
+	{
+	static const size_t pad = [] { const char * e = std::getenv( "FLAN_B200_SMEM_PAD" ); return e ? (size_t) std::atol( e ) : (size_t) 0; }();
+	return pad;
+	}
+
 template<int N, int PT, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size;
+	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size + smem_pad();
 	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	pv_analysis_kernel<N, PT, TPS><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
@@ -179,6 +190,7 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 		if( pt == 16 )
 			{
 			if( tps >= 768 ) return launch_analysis_nt<N, 16, 768>( a, blocks, st );
+			if( tps >= 640 ) return launch_analysis_nt<N, 16, 640>( a, blocks, st );
 			return launch_analysis_nt<N, 16, 512>( a, blocks, st );
 			}
 		}
@@ -188,7 +200,7 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 	}
 template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 );
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
 	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	pv_synthesis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );

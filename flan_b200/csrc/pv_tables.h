@@ -23,6 +23,8 @@ struct HostTables
 	std::vector<float> binf;            // bin_to_frequency(b) = b * float(sr) / float(dft)   PVBuffer.cpp:443-446
 	std::vector<float2> binc;           // (binf, expected) interleaved, as the analysis kernel reads them
 	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
+	std::vector<float2> post_rot;       // -i e^{-2 pi i k / N} = (sin, -cos)(-2 pi k / N): the analysis unpack's multiplier
+	std::vector<float4> binc4;          // per unpack pair k = 0..N/4: (binf[k], binf[M-k], expected[k], -expected[M-k])
 	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated (8 points per thread plan)
 	std::vector<float2> pass_tw16;      // same for the 16-points-per-thread plan (dft >= 512)
 	PvConsts k{};
@@ -69,6 +71,7 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 	t.k.rcp_pi2 = 1.0f / t.k.pi2;
 	t.k.bin_scale = 1.0f / (float) N;               // exact: N is a power of two
 	t.k.use_wrapping = analysis_rate < sample_rate; // phase_vocoder.cpp:37
+	t.k.wrap_pi2 = t.k.use_wrapping ? t.k.pi2 : 0.0f;
 	t.P = (double) t.k.pi2;
 	t.rcpP = 1.0 / t.P;
 
@@ -102,6 +105,16 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		const long double a = -two_pi * (long double) k / (long double) N;
 		t.post_tw[k].x = (float) cosl( a );
 		t.post_tw[k].y = (float) sinl( a );
+		}
+
+	t.post_rot.resize( M / 2 + 1 );
+	t.binc4.resize( M / 2 + 1 );
+	for( int k = 0; k <= M / 2; ++k )
+		{
+		t.post_rot[k].x = t.post_tw[k].y;
+		t.post_rot[k].y = -t.post_tw[k].x;
+		t.binc4[k].x = t.binf[k];     t.binc4[k].y = t.binf[M - k];
+		t.binc4[k].z = t.expected[k]; t.binc4[k].w = -t.expected[M - k];   // lane y runs on the conjugate
 		}
 
 	t.pass_tw.clear();
