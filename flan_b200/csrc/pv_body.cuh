@@ -400,6 +400,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 #endif
 		};
 
+	const bool full_window = ( W == N ) && a.aligned2;
 	for( int64_t f = fa; f < fb; ++f )
 		{
 		const int64_t start = (int64_t) hop * f - half;                          // AudioPV.cpp:125
@@ -412,24 +413,23 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		for( int u = 0; u < 4; ++u )
 			{
 			const int k = t + u * T;
-			float2 xk = polar( row[k], acc[2 * u] );
-			float2 xm = polar( row[M - k], acc[2 * u + 1] );
+			float2 xk, xm;
+#ifndef PV_ABL_NOEPI
+			inverse_pv_pair( row[k], row[M - k], acc[2 * u], acc[2 * u + 1], a.k, a.P, a.rcpP, xk, xm );
+#else
+			xk = row[k]; xm = row[M - k];                                   // ablation build only
+#endif
 			// imaginary parts of bins 0 and N/2 are ignored by a c2r transform: with them cleared the general pack gives
 			// Z'[0] = (X0 + XM) + i (X0 - XM); its mirror lands in the unused slot M of the buffer
 			if( u == 0 && t == 0 ) { xk.y = 0.0f; xm.y = 0.0f; }
-				{
-				const float2 tw = env.ldg2( a.post_tw + k );
-				float2 A, Bv, Q;
-				A.x = xk.x + xm.x;  A.y = xk.y - xm.y;
-				Bv.x = xk.x - xm.x; Bv.y = xk.y + xm.y;
-				Q.x = Bv.x * tw.x + Bv.y * tw.y;                 // Bv * conj(tw)
-				Q.y = Bv.y * tw.x - Bv.x * tw.y;
-				float2 zk, zm;
-				zk.y = A.x - Q.y; zk.x = A.y + Q.x;              // swapped (im, re) of Z'[k]
-				zm.y = A.x + Q.y; zm.x = Q.x - A.y;              // swapped (im, re) of Z'[M-k]
-				v[u] = zk;                 // Z'[t + u*T] is this thread's own pass-0 input
-				x1[M - k] = zm;            // the mirror side belongs to thread T - t
-				}
+			// A = X[k] + conj X[M-k], Bv = X[k] - conj X[M-k], Q = Bv * conj(w_k); Z'[k] = A + iQ, Z'[M-k] = conj(A - iQ),
+			// both stored with (im, re) swapped.
+			const float2 tw = env.ldg2( a.post_tw + k );
+			const float2 A = add2( xk, pn2( xm ) );
+			const float2 Bv = add2( xk, np2( xm ) );
+			const float2 Q = cmulc2( Bv, tw );
+			v[u] = add2( swap2( A ), pn2( Q ) );            // Z'[t + u*T] is this thread's own pass-0 input
+			x1[M - k] = add2( np2( swap2( A ) ), Q );       // the mirror side belongs to thread T - t
 			}
 		if( t == T / 2 )
 			{
@@ -456,7 +456,19 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 #ifdef PV_ABL_NOOLA
 		if( v[0].x == 123.456f )                                              // ablation build only
 #endif
-		if( a.aligned2 )
+		if( full_window )
+			{
+			// whole window, even ring positions: out += y * w as one packed multiply and one packed add per sample pair
+			// (each lane rounds like the scalar mul_rn / add_rn: no contraction)
+#pragma unroll
+			for( int s = 0; s < 8; ++s )
+				{
+				float2 * slot = reinterpret_cast<float2 *>( ola + ( ( rs + 2 * ( t + s * T ) ) & ( N - 1 ) ) );
+				float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
+				*slot = add2( *slot, mul2( swap2( v[s] ), ww ) );
+				}
+			}
+		else if( a.aligned2 )
 			{
 #pragma unroll
 			for( int s = 0; s < 8; ++s )

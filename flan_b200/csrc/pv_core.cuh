@@ -503,6 +503,25 @@ PV_HD void sincos_pv( float x, float * sn, float * cs )
 #endif
 	}
 
+// inverse_phase_vocoder() (phase_vocoder.cpp:55-61) for the two bins of a pack pair at once: mfk = (m, f) of bin k,
+// mfm of bin M-k. The float steps (f / ar * pi2, the 2*pi reduction, m * (cos, sin)) are packed FP32x2 with lane x =
+// bin k, lane y = bin M-k; the fp64 accumulate stays scalar on the FP64 pipe. Lane-wise identical to
+// phase_increment + phase_accumulate + sincos_pv.
+PV_HD void sincos_pv2( float2 x, float2 & sn, float2 & cs )
+	{
+#if defined(__CUDA_ARCH__) && !defined(PV_POLY_SINCOS)
+	float2 kk = mul2( x, splat2( 0.15915494309189535f ) );
+	kk.x = rintf( kk.x ); kk.y = rintf( kk.y );
+	float2 r = fma2( kk, splat2( -6.28318548202514648f ), x );
+	r = fma2( kk, splat2( 1.74845553146951715e-7f ), r );
+	sn.x = __sinf( r.x ); cs.x = __cosf( r.x );
+	sn.y = __sinf( r.y ); cs.y = __cosf( r.y );
+#else
+	sincos_pv( x.x, &sn.x, &cs.x );
+	sincos_pv( x.y, &sn.y, &cs.y );
+#endif
+	}
+
 // fmod(x, P) for x > P > 0 (exact, like libm's).
 PV_HD double fmod_pos( double x, double P, double rcpP )
 	{
@@ -522,6 +541,21 @@ PV_HD void phase_accumulate( double & acc, float inc, double P, double rcpP )
 	double r = x;
 	if( x > P ) r = fma( -floor( x * rcpP ), P, x );                        // :59
 	acc = r;
+	}
+
+PV_HD void inverse_pv_pair( float2 mfk, float2 mfm, double & acck, double & accm, const PvConsts & k, double P, double rcpP,
+                            float2 & xk, float2 & xm )
+	{
+	float2 F; F.x = mfk.y; F.y = mfm.y;
+	const float2 inc = mul2( div_const2( F, k.analysis_rate, k.rcp_analysis_rate ), splat2( k.pi2 ) );     // :57
+	phase_accumulate( acck, inc.x, P, rcpP );                                                               // :58-59
+	phase_accumulate( accm, inc.y, P, rcpP );
+	float2 th; th.x = (float) acck; th.y = (float) accm;
+	float2 sn, cs;
+	sincos_pv2( th, sn, cs );
+	float2 ek, em; ek.x = cs.x; ek.y = sn.x; em.x = cs.y; em.y = sn.y;
+	xk = mul2( ek, splat2( mfk.x ) );                                                                       // :60 std::polar
+	xm = mul2( em, splat2( mfm.x ) );
 	}
 
 // Split form of a plain double sum (|s| far below 2^53 * P).
