@@ -267,3 +267,174 @@ int pvo_convert_to_audio( const float * pv, int C, int64_t F, int B, float sampl
 	free( phase_buffer ); fft_free( &fft ); free( hann );
 	return 0;
 	}
+
+/* ---------- PV-domain chain between analysis and resynthesis: PV::repitch / PV::stretch ---------- */
+
+/* Utility/Interpolator.cpp:15-105. sine (7) and sine2 (8) go through libm cos / sin. */
+static float pvo_interp( int id, float x )
+	{
+	switch( id )
+		{
+		case 1: return 0.5f;                                               /* midpoint   :15-21 */
+		case 2: return roundf( x );                                        /* nearest    :24-30 */
+		case 3: return 0.0f;                                               /* floor      :33-39 */
+		case 4: return 1.0f;                                               /* ceil       :42-48 */
+		case 5: return x * x * ( 3.0f - 2.0f * x );                        /* smoothstep :60-66 */
+		case 6: return x * x * x * ( x * ( x * 6.0f - 15.0f ) + 10.0f );   /* smootherstep :69-75 */
+		case 7: { const float pi = acosf( -1.0f ); return ( 1.0f - cosf( pi * x ) ) / 2.0f; }          /* :77-84 */
+		case 8: { const float pi = acosf( -1.0f ); return (float)( (double) sqrtf( 2.0f ) * sin( (double)( pi / 4.0f * x ) ) ); }   /* :86-92 */
+		case 9: return sqrtf( x );                                         /* sqrt       :95-101 */
+		default: return x;                                                 /* linear     :51-57 */
+		}
+	}
+
+static int clamp_int( int v, int lo, int hi ) { return v < lo ? lo : ( hi < v ? hi : v ); }
+
+/* modify_frequency_base, PV/PVModify.cpp:196-257. mod: [F][B] mapped bin positions in Hz (shared by all channels,
+ * indexed frame*B + bin, :217-219); in_mod: [C][F][B] the mapped frequency written into the output MFs. */
+static void pvo_modify_frequency_base( const float * pv, int C, int64_t F, int B, float sample_rate,
+                                       const float * mod, const float * in_mod, int interp, float * out )
+	{
+	const int dft = ( B - 1 ) * 2;                                         /* PVBuffer.cpp:356-359 */
+	const float bin_width = sample_rate / (float) dft;                     /* PVBuffer.cpp:438-441 */
+	memset( out, 0, sizeof( float ) * 2 * (size_t) C * (size_t) F * (size_t) B );      /* :204-205 */
+	for( int c = 0; c < C; ++c )                                           /* :207 */
+		for( int64_t frame = 0; frame < F; ++frame )                       /* :211 */
+			{
+			const float * in_row = pv + 2 * ( ( (int64_t) c * F + frame ) * B );
+			const float * im_row = in_mod + ( (int64_t) c * F + frame ) * B;
+			const float * mod_row = mod + frame * B;
+			float * out_row = out + 2 * ( ( (int64_t) c * F + frame ) * B );
+			for( int bin = 1; bin < B; ++bin )                             /* :214 */
+				{
+				const float loBin = mod_row[bin - 1] / bin_width;          /* :218 */
+				const float hiBin = mod_row[bin] / bin_width;              /* :219 */
+				const int forward = hiBin > loBin;                         /* :220 */
+				const int loBinRound = (int)( forward ? ceilf( loBin ) : floorf( loBin ) );   /* :222 */
+				const int hiBinRound = (int)( forward ? ceilf( hiBin ) : floorf( hiBin ) );   /* :223 */
+				const int start_bin = clamp_int( loBinRound, 0, B - 1 );   /* :224 */
+				const int end_bin = clamp_int( hiBinRound, 0, B - 1 );     /* :225 */
+				const float lo_m = in_row[2 * ( bin - 1 )], lo_f = im_row[bin - 1];    /* :227 */
+				const float hi_m = in_row[2 * bin], hi_f = im_row[bin];                /* :228 */
+				for( int y = start_bin; y != end_bin; forward ? ++y : --y )            /* :230 */
+					{
+					const float mix = pvo_interp( interp, ( (float) y - loBin ) / ( hiBin - loBin ) );  /* :232 */
+					const float w0 = ( 1.0f - mix ) * lo_m;                /* :234 */
+					const float w1 = mix * hi_m;                           /* :235 */
+					const float max_m = w0 < w1 ? lo_m : hi_m;             /* :237 */
+					const float max_f = w0 < w1 ? lo_f : hi_f;
+					if( max_m > out_row[2 * y] )                           /* :239 */
+						{
+						out_row[2 * y] = out_row[2 * y] + max_m;           /* :241 */
+						out_row[2 * y + 1] = max_f;                        /* :242 */
+						}
+					}
+				}
+			}
+	}
+
+/* PV::repitch, PV/PVModify.cpp:273-305. factor: [F][B] the sampled factor (PV/PV.h:31-35). */
+int pvo_repitch( const float * pv, int C, int64_t F, int B, float sample_rate, const float * factor, int interp, float * out )
+	{
+	if( C < 1 || F < 1 || B < 2 ) return -1;
+	const int dft = ( B - 1 ) * 2;
+	const float bin_width = sample_rate / (float) dft;
+	float * fs = (float *) malloc( sizeof( float ) * (size_t) F * B );
+	float * in_mod = (float *) malloc( sizeof( float ) * (size_t) C * F * B );
+	memcpy( fs, factor, sizeof( float ) * (size_t) F * B );
+	for( int64_t frame = 0; frame < F; ++frame )                           /* :278-280 */
+		for( int bin = 1; bin < B; ++bin )
+			fs[frame * B + bin] = fs[frame * B + bin] + fs[frame * B + bin - 1];
+	for( int64_t i = 0; i < F * B; ++i )                                   /* :283-284, PVBuffer.cpp:443-446 */
+		fs[i] = fs[i] * sample_rate / (float) dft;
+	const float top = (float)( B - 1 ) - 0.0001f;                          /* :293 */
+	for( int c = 0; c < C; ++c )                                           /* :289-302 */
+		for( int64_t frame = 0; frame < F; ++frame )
+			for( int bin = 0; bin < B; ++bin )
+				{
+				const float f = pv[2 * ( ( (int64_t) c * F + frame ) * B + bin ) + 1];
+				float fbin = f / bin_width;                                /* PVBuffer.cpp:438-441 */
+				fbin = fbin < 0.0f ? 0.0f : ( top < fbin ? top : fbin );   /* std::clamp */
+				const int lo = (int) floorf( fbin );                       /* :294 */
+				const int hi = lo + 1;                                     /* :295 */
+				const float lo_freq = fs[frame * B + lo];                  /* :296 */
+				const float hi_freq = fs[frame * B + hi];                  /* :297 */
+				const float r = fbin - (float) lo;                         /* :298 */
+				in_mod[( (int64_t) c * F + frame ) * B + bin] = lo_freq * ( 1.0f - r ) + hi_freq * r;   /* :299 */
+				}
+	pvo_modify_frequency_base( pv, C, F, B, sample_rate, fs, in_mod, interp, out );    /* :304 */
+	free( fs ); free( in_mod );
+	return 0;
+	}
+
+/* Output frame count of PV::stretch / PV::modify_time for a mod table in seconds: ceil( time_to_frame( max ) ),
+ * PV/PVModify.cpp:312-315, PVBuffer.cpp:428-431. */
+static int64_t pvo_time_frames( const float * mod, int64_t count, float sample_rate, int hop )
+	{
+	float mx = mod[0];
+	for( int64_t i = 1; i < count; ++i ) if( mx < mod[i] ) mx = mod[i];    /* std::max_element */
+	const float last = ceilf( mx * sample_rate / (float) hop );
+	return (int64_t)(int) last;
+	}
+
+/* modify_time_base, PV/PVModify.cpp:307-362. mod: [F][B] seconds. out: [C][out_frames][B], zero-filled here. */
+static void pvo_modify_time_base( const float * pv, int C, int64_t F, int B, float sample_rate, int hop,
+                                  const float * mod, int interp, int64_t out_frames, float * out )
+	{
+	memset( out, 0, sizeof( float ) * 2 * (size_t) C * (size_t) out_frames * (size_t) B );          /* :317-318 */
+	for( int c = 0; c < C; ++c )                                           /* :320 */
+		for( int bin = 0; bin < B; ++bin )                                 /* :326 */
+			for( int64_t frame = 1; frame < F; ++frame )                   /* :329 */
+				{
+				const float lFrame = mod[( frame - 1 ) * B + bin] * sample_rate / (float) hop;      /* :331 */
+				const float rFrame = mod[frame * B + bin] * sample_rate / (float) hop;              /* :332 */
+				const int forward = rFrame > lFrame;                       /* :333 */
+				const int start_frame = (int)( forward ? ceilf( lFrame ) : floorf( lFrame ) );      /* :335 */
+				const int end_frame = (int)( forward ? ceilf( rFrame ) : floorf( rFrame ) );        /* :336 */
+				const float * l = pv + 2 * ( ( (int64_t) c * F + frame - 1 ) * B + bin );           /* :338 */
+				const float * r = pv + 2 * ( ( (int64_t) c * F + frame ) * B + bin );               /* :339 */
+				for( int x = start_frame; x != end_frame; forward ? ++x : --x )                     /* :341 */
+					{
+					if( x < 0 || out_frames <= x ) continue;               /* :343 */
+					const float mix = pvo_interp( interp, ( (float) x - lFrame ) / ( rFrame - lFrame ) );   /* :345 */
+					const float w0 = ( 1.0f - mix ) * l[0];                /* :346 */
+					const float w1 = mix * r[0];                           /* :347 */
+					const float totalWeight = w0 + w1;                     /* :348 */
+					const float weightedFreqSum = w0 * l[1] + w1 * r[1];   /* :349 */
+					if( totalWeight == 0.0f ) break;                       /* :351-352: `return` leaves this frame pair */
+					float * o = out + 2 * ( ( (int64_t) c * out_frames + x ) * B + bin );
+					o[1] = ( o[1] * o[0] + weightedFreqSum ) / ( o[0] + totalWeight );              /* :354 */
+					o[0] = o[0] + totalWeight;                             /* :355 */
+					}
+				}
+	}
+
+/* PV::modify_time with a pre-sampled mod table in seconds (PV/PVModify.cpp:364-369). out == NULL: returns the
+ * output frame count only; otherwise out must hold [C][that many][B] MFs. */
+int64_t pvo_modify_time( const float * pv, int C, int64_t F, int B, float sample_rate, float analysis_rate,
+                         const float * mod_seconds, int interp, float * out )
+	{
+	if( C < 1 || F < 1 || B < 2 ) return -1;
+	const int hop = pvo_hop_from_rates( sample_rate, analysis_rate );
+	const int64_t out_frames = pvo_time_frames( mod_seconds, F * B, sample_rate, hop );
+	if( out && out_frames > 0 ) pvo_modify_time_base( pv, C, F, B, sample_rate, hop, mod_seconds, interp, out_frames, out );
+	return out_frames;
+	}
+
+/* PV::stretch, PV/PVModify.cpp:371-385. factor: [F][B]. Same out convention as pvo_modify_time. */
+int64_t pvo_stretch( const float * pv, int C, int64_t F, int B, float sample_rate, float analysis_rate,
+                     const float * factor, int interp, float * out )
+	{
+	if( C < 1 || F < 1 || B < 2 ) return -1;
+	const int hop = pvo_hop_from_rates( sample_rate, analysis_rate );
+	float * fs = (float *) malloc( sizeof( float ) * (size_t) F * B );
+	memcpy( fs, factor, sizeof( float ) * (size_t) F * B );
+	for( int bin = 0; bin < B; ++bin )                                     /* :376-378 */
+		for( int64_t frame = 1; frame < F; ++frame )
+			fs[frame * B + bin] = fs[frame * B + bin] + fs[( frame - 1 ) * B + bin];
+	const float rate = sample_rate / (float) hop;                          /* PVBuffer.cpp:433-436 */
+	for( int64_t i = 0; i < F * B; ++i ) fs[i] = fs[i] / rate;             /* :381-382 */
+	const int64_t out_frames = pvo_modify_time( pv, C, F, B, sample_rate, analysis_rate, fs, interp, out );   /* :384 */
+	free( fs );
+	return out_frames;
+	}

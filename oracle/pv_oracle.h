@@ -47,6 +47,17 @@ void pvo_mid_side( const float * in, int64_t n, float * out );
 /* PVBuffer::get_hop_size, PVBuffer.cpp:381-384. */
 int pvo_hop_from_rates( float sample_rate, float analysis_rate );
 
+/* ---- PV-domain chain: PV::repitch / PV::stretch / PV::modify_time, PV/PVModify.cpp:196-385 ----
+ * factor / mod tables are float[F][B], the reference's sample of its Function argument over the frame x bin grid
+ * (PV/PV.h:31-35). interp: 0 linear, 1 midpoint, 2 nearest, 3 floor, 4 ceil, 5 smoothstep, 6 smootherstep, 7 sine,
+ * 8 sine2, 9 sqrt (Utility/Interpolator.cpp). pv / out: interleaved (m,f) pairs. */
+int pvo_repitch( const float * pv, int C, int64_t F, int B, float sample_rate, const float * factor, int interp, float * out );
+/* Both return the output frame count; out == NULL computes only that, otherwise out is [C][count][B]. */
+int64_t pvo_stretch( const float * pv, int C, int64_t F, int B, float sample_rate, float analysis_rate,
+                     const float * factor, int interp, float * out );
+int64_t pvo_modify_time( const float * pv, int C, int64_t F, int B, float sample_rate, float analysis_rate,
+                         const float * mod_seconds, int interp, float * out );
+
 #ifdef __cplusplus
 }
 #endif

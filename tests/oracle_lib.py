@@ -42,6 +42,11 @@ class Oracle:
                                            ctypes.c_float, ctypes.c_int, _fp]
         L.pvo_mid_side.argtypes = [_fp, ctypes.c_int64, _fp]
         L.pvo_hop_from_rates.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.pvo_repitch.argtypes = [_fp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_float, _fp, ctypes.c_int, _fp]
+        for fn in (L.pvo_stretch, L.pvo_modify_time):
+            fn.restype = ctypes.c_int64
+            fn.argtypes = [_fp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp,
+                           ctypes.c_int, _fp]
         self.L = L
 
     def num_frames(self, n, hop):
@@ -83,6 +88,34 @@ class Oracle:
         out = np.empty_like(audio)
         self.L.pvo_mid_side(_ptr(audio), audio.shape[1], _ptr(out))
         return out
+
+    # PV-domain chain (PV/PVModify.cpp): factor / mod tables are float[F][B]
+    def repitch(self, pv, sr, factor, interp=0):
+        pv = np.ascontiguousarray(pv, np.float32)
+        factor = np.ascontiguousarray(factor, np.float32)
+        C, F, B, _ = pv.shape
+        assert factor.shape == (F, B)
+        out = np.empty_like(pv)
+        assert self.L.pvo_repitch(_ptr(pv), C, F, B, sr, _ptr(factor), interp, _ptr(out)) == 0
+        return out
+
+    def _time(self, fn, pv, sr, ar, table, interp):
+        pv = np.ascontiguousarray(pv, np.float32)
+        table = np.ascontiguousarray(table, np.float32)
+        C, F, B, _ = pv.shape
+        assert table.shape == (F, B)
+        frames = int(fn(_ptr(pv), C, F, B, sr, ar, _ptr(table), interp, None))
+        if frames <= 0:
+            return np.zeros((C, 0, B, 2), np.float32)
+        out = np.empty((C, frames, B, 2), np.float32)
+        assert fn(_ptr(pv), C, F, B, sr, ar, _ptr(table), interp, _ptr(out)) == frames
+        return out
+
+    def stretch(self, pv, sr, ar, factor, interp=0):
+        return self._time(self.L.pvo_stretch, pv, sr, ar, factor, interp)
+
+    def modify_time(self, pv, sr, ar, mod_seconds, interp=0):
+        return self._time(self.L.pvo_modify_time, pv, sr, ar, mod_seconds, interp)
 
 
 class RefLib:
@@ -143,3 +176,49 @@ class RefLib:
         C, n = audio.shape
         cs = ctypes.c_float()
         return self.L.flan_ref_bench(_ptr(audio), C, n, sr, W, hop, N, mode, ctypes.byref(cs))
+
+
+class RefModifyLib:
+    """The reference's own PV/PVModify.cpp (PV::repitch / stretch / modify_time), compiled verbatim with its real
+    Function / FunctionSample / Interpolator headers."""
+
+    @staticmethod
+    def path():
+        return os.path.join(ORACLE_DIR, "_ref", "libflan_ref_modify.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.path())
+
+    def __init__(self):
+        L = ctypes.CDLL(self.path())
+        i, f = ctypes.c_int, ctypes.c_float
+        L.flan_ref_repitch.argtypes = [_fp, i, i, i, f, f, i, _fp, i, _fp]
+        L.flan_ref_stretch.argtypes = [_fp, i, i, i, f, f, i, _fp, i, _fp, i]
+        L.flan_ref_modify_time.argtypes = [_fp, i, i, i, f, f, i, _fp, i, _fp, i]
+        self.L = L
+
+    def repitch(self, pv, sr, ar, W, factor, interp=0):
+        pv = np.ascontiguousarray(pv, np.float32)
+        factor = np.ascontiguousarray(factor, np.float32)
+        C, F, B, _ = pv.shape
+        out = np.empty_like(pv)
+        assert self.L.flan_ref_repitch(_ptr(pv), C, F, B, sr, ar, W, _ptr(factor), interp, _ptr(out)) == F
+        return out
+
+    def _time(self, fn, pv, sr, ar, W, table, interp):
+        pv = np.ascontiguousarray(pv, np.float32)
+        table = np.ascontiguousarray(table, np.float32)
+        C, F, B, _ = pv.shape
+        frames = fn(_ptr(pv), C, F, B, sr, ar, W, _ptr(table), interp, None, 0)
+        if frames <= 0:
+            return np.zeros((C, 0, B, 2), np.float32)
+        out = np.empty((C, frames, B, 2), np.float32)
+        assert fn(_ptr(pv), C, F, B, sr, ar, W, _ptr(table), interp, _ptr(out), frames) == frames
+        return out
+
+    def stretch(self, pv, sr, ar, W, factor, interp=0):
+        return self._time(self.L.flan_ref_stretch, pv, sr, ar, W, factor, interp)
+
+    def modify_time(self, pv, sr, ar, W, mod_seconds, interp=0):
+        return self._time(self.L.flan_ref_modify_time, pv, sr, ar, W, mod_seconds, interp)
