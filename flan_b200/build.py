@@ -41,25 +41,40 @@ def emu_path():
 
 def build_library(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
-    srcs = _sources("pv_kernels.cu", "pv_capi.cu")
-    deps = srcs + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_launch.h") + \
+    # (source, extra flags): the PV-domain kernels must reproduce the reference's float arithmetic bit for bit, so
+    # their translation unit is compiled without FMA contraction.
+    units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_modify.cu", ["-fmad=false"])]
+    srcs = _sources(*[u for u, _ in units])
+    deps = srcs + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_launch.h", "pv_modify.h", "pv_modify_body.cuh") + \
         [os.path.join(os.path.dirname(HERE), "include", "flan_b200.h")]
     if not force and not _newer(lib_path(), deps):
         return lib_path()
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", lib_path()] + srcs
-    subprocess.run(cmd, check=True)
+    objdir = os.path.join(LIB, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for (name, extra), src in zip(units, srcs):
+        obj = os.path.join(objdir, name + ".o")
+        objs.append(obj)
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.run(["nvcc", "-shared", "-o", lib_path()] + objs, check=True)
     return lib_path()
 
 
 def build_emulator(force=False):
     os.makedirs(LIB, exist_ok=True)
     src = os.path.join(CSRC, "emu", "pv_emu.cpp")
-    deps = [src] + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h")
+    src_modify = os.path.join(CSRC, "emu", "pv_modify_emu.cpp")
+    deps = [src, src_modify] + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_modify_body.cuh")
     if not force and not _newer(emu_path(), deps):
         return emu_path()
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-O2", "-ffp-contract=off", "-std=c++20", "-fPIC", "-shared", "-I" + cuda_inc,
-           "-o", emu_path(), src, "-lpthread"]
+           "-o", emu_path(), src, src_modify, "-lpthread"]
     subprocess.run(cmd, check=True)
     return emu_path()
 

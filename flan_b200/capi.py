@@ -41,6 +41,11 @@ SYMBOLS = [
     ("flan_b200_convert_to_audio_range", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _int, _vp, _i64, _i64, _i64]),
     ("flan_b200_add", _int, [_vp, _vp, _vp, _i64]),
     ("flan_b200_mid_side", _int, [_vp, _vp, _vp, _i64]),
+    ("flan_b200_repitch", _int, [_vp, _vp, _int, _i64, _int, _f, _vp, _i64, _int, _int, _vp]),
+    ("flan_b200_modify_frequency", _int, [_vp, _vp, _int, _i64, _int, _f, _vp, _i64, _int, _vp, _int, _vp]),
+    ("flan_b200_stretch_map", _int, [_vp, _vp, _i64, _int, _i64, _int, _f, _f, _vp]),
+    ("flan_b200_modify_time_frames", _int, [_vp, _vp, _i64, _int, _i64, _int, _f, _f, ctypes.POINTER(_i64)]),
+    ("flan_b200_modify_time", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _vp, _i64, _int, _int, _i64, _vp]),
     ("flan_b200_convert_to_pv_host", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _int, _vp, _vp]),
     ("flan_b200_convert_to_audio_host", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _int, _vp, _vp, ctypes.POINTER(_int)]),
 ]

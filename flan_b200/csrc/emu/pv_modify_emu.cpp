@@ -1,0 +1,118 @@
+// flan_b200/csrc/emu/pv_modify_emu.cpp -- CPU emulator of the PV-domain kernel bodies in pv_modify_body.cuh.
+//
+// TEST HARNESS, not a product path (nothing in libflan_b200.so links or calls this): it runs the same per-thread
+// phase functions the kernels of pv_modify.cu run, thread by thread between the barriers, with the host-side
+// orchestration of pv_capi.cu restated, so that the scatter logic, the monotonicity vote and the chunking can be
+// checked against the oracle in a container without a GPU (tests/test_emulator_modify.py). Threads of a phase are run
+// in DESCENDING thread order to make any accidental dependence on the order visible.
+#include "../pv_modify_body.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using namespace pvm;
+
+namespace {
+
+void repitch_rows( const RepitchArgs & a, int64_t rows, int nt )
+	{
+	std::vector<unsigned char> smem( RepitchRow::bytes( a.B ) );
+	RepitchRow s( smem.data(), a.B );
+	for( int64_t row = 0; row < rows; ++row )
+		{
+		for( int t = nt - 1; t >= 0; --t ) repitch_load( a, row, t, nt, s );
+		int flags = 0;
+		for( int t = nt - 1; t >= 0; --t ) flags |= repitch_map( a, t, nt, s );
+		for( int t = nt - 1; t >= 0; --t ) repitch_scatter( a, flags, t, nt, s );
+		for( int t = nt - 1; t >= 0; --t ) repitch_store( a, row, t, nt, s );
+		}
+	}
+
+bool strides_ok( int64_t fs, int bs, int B ) { return ( bs == 0 || bs == 1 ) && ( fs == 0 || fs == ( bs ? B : 1 ) ); }
+
+int64_t map_frames( const Table & mod, int64_t rows, int cols, float sr, int hop, bool & descends )
+	{
+	float mx = 0.0f; bool any = false; descends = false;
+	for( int64_t i = rows * cols - 1; i >= 0; --i )
+		{
+		float sec; bool d;
+		time_map_check( mod, i / cols, (int)( i % cols ), sec, d );
+		if( !any || mx < sec ) mx = sec;
+		any = true; descends |= d;
+		}
+	mx = key_float( float_key( mx ) );
+	return (int64_t) to_int( std::ceil( mx * sr / float( hop ) ) );
+	}
+
+} // namespace
+
+extern "C" {
+
+int pv_emu_repitch( const float * pv, int C, int64_t F, int B, float sr, const float * factor, int64_t fs, int bs,
+                    const float * mod_hz, const float * in_mod, int interp, int threads, float * out )
+	{
+	if( !strides_ok( fs, bs, B ) ) return 1;
+	const int64_t rows = fs ? F : 1;
+	std::vector<float> hz( (size_t) rows * B );
+	Table mod{ mod_hz, fs, bs };
+	if( !mod_hz )
+		{
+		const Table fac{ factor, fs, bs };
+		for( int64_t r = 0; r < rows; ++r ) bin_prefix_row( fac, r, B, sr, float( ( B - 1 ) * 2 ), hz.data() + r * B );
+		mod = Table{ hz.data(), fs ? (int64_t) B : 0, 1 };
+		}
+	RepitchArgs a{};
+	a.pv = (const float2 *) pv; a.out = (float2 *) out; a.mod = mod; a.in_mod = in_mod;
+	a.F = F; a.B = B; a.bin_width = sr / float( ( B - 1 ) * 2 ); a.interp = interp;
+	repitch_rows( a, (int64_t) C * F, threads );
+	return 0;
+	}
+
+// factor != null: PV::stretch (the map is built first); else map_seconds is the time map of PV::modify_time.
+// out == null: returns the output frame count only. force_sequential exercises the reference-order walk.
+int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, float ar, const float * factor,
+                        const float * map_seconds, int64_t fs, int bs, int interp, int chunk, int force_sequential,
+                        int * used_sequential, float * out )
+	{
+	if( !strides_ok( fs, bs, B ) ) return -1;
+	const int hop = (int)( sr / ar );
+	const int cols = bs ? B : 1;
+	std::vector<float> built;
+	Table mod{ map_seconds, fs, bs };
+	if( factor )
+		{
+		built.resize( (size_t) F * cols );
+		const Table fac{ factor, fs, bs };
+		for( int col = 0; col < cols; ++col )
+			{
+			float mx; bool d;
+			frame_prefix_column( fac, col, F, cols, sr / float( hop ), built.data(), mx, d );
+			}
+		mod = Table{ built.data(), (int64_t) cols, bs };
+		}
+	bool descends = false;
+	const int64_t out_frames = map_frames( mod, mod.frame_stride ? F : 1, cols, sr, hop, descends );
+	if( used_sequential ) *used_sequential = descends || force_sequential;
+	if( !out || out_frames <= 0 ) return out_frames;
+	StretchArgs a{};
+	a.pv = (const float2 *) pv; a.out = (float2 *) out; a.mod = mod;
+	a.F = F; a.out_frames = out_frames; a.B = B; a.sample_rate = sr; a.hop = float( hop ); a.interp = interp;
+	a.chunk = chunk; a.chunks = ( F - 1 + chunk - 1 ) / chunk;
+	if( a.chunks < 1 ) a.chunks = 1;
+	if( !descends && !force_sequential )
+		{
+		for( int c = C - 1; c >= 0; --c )
+			for( int64_t k = a.chunks - 1; k >= 0; --k )
+				for( int b = B - 1; b >= 0; --b ) stretch_chunk( a, c, k, b );
+		}
+	else
+		{
+		std::memset( out, 0, sizeof( float2 ) * (size_t) C * out_frames * B );
+		for( int c = 0; c < C; ++c )
+			for( int b = 0; b < B; ++b ) stretch_column( a, c, b );
+		}
+	return out_frames;
+	}
+
+}

@@ -1,0 +1,159 @@
+// flan_b200/csrc/pv_modify.cu -- sm_100a kernels of the PV-domain chain between analysis and resynthesis:
+// PV::repitch / PV::modify_frequency (reference PV/PVModify.cpp:196-305) and PV::stretch / PV::modify_time
+// (PVModify.cpp:307-385). Bodies in pv_modify_body.cuh. Compiled with -fmad=false: results are bit-identical to the
+// reference's float arithmetic. All of them stream MF rows once: HBM-bound integer / float work, no tensor cores.
+#include "pv_modify.h"
+
+namespace pvm {
+
+// One CTA per (channel, frame) row: stage the row in shared memory, map, scatter, store. Algorithmic bytes per row:
+// 8B read + 8B written (+ 4B of table when it is not shared between frames, + 4B for modify_frequency's in_mod).
+__global__ void __launch_bounds__( 256 ) pv_repitch_kernel( const RepitchArgs a, int64_t rows )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem[];
+	RepitchRow s( smem, a.B );
+	const int tid = threadIdx.x, nt = blockDim.x;
+	for( int64_t row = blockIdx.x; row < rows; row += gridDim.x )
+		{
+		repitch_load( a, row, tid, nt, s );
+		__syncthreads();
+		const int mine = repitch_map( a, tid, nt, s );
+		const int down = __syncthreads_or( mine & 1 );
+		const int up = __syncthreads_or( mine & 2 );
+		repitch_scatter( a, ( down ? 1 : 0 ) | ( up ? 2 : 0 ), tid, nt, s );
+		__syncthreads();
+		repitch_store( a, row, tid, nt, s );
+		__syncthreads();
+		}
+	}
+
+// Running sums along bins are sequential per row (float addition does not re-associate): one lane per row, rows
+// staged through shared memory in 32 x 32 tiles so that global loads and stores stay coalesced.
+__global__ void __launch_bounds__( 256 ) pv_bin_prefix_kernel( const Table factor, int64_t rows, int B, float sample_rate, float dft, float * out )
+	{
+	__shared__ float tile[8][32][33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t row0 = ( (int64_t) blockIdx.x * 8 + warp ) * 32;
+	if( row0 >= rows ) return;
+	float acc = 0.0f;
+	for( int b0 = 0; b0 < B; b0 += 32 )
+		{
+		for( int r = 0; r < 32; ++r )
+			if( row0 + r < rows && b0 + lane < B ) tile[warp][r][lane] = factor.at( row0 + r, b0 + lane );
+		__syncwarp();
+		if( row0 + lane < rows )
+			for( int j = 0; j < 32 && b0 + j < B; ++j )
+				{
+				const float v = tile[warp][lane][j];
+				acc = ( b0 + j == 0 ) ? v : v + acc;
+				tile[warp][lane][j] = acc * sample_rate / dft;          // PVBuffer.cpp:443-446
+				}
+		__syncwarp();
+		for( int r = 0; r < 32; ++r )
+			if( row0 + r < rows && b0 + lane < B ) out[( row0 + r ) * B + b0 + lane] = tile[warp][r][lane];
+		__syncwarp();
+		}
+	}
+
+__global__ void pv_frame_prefix_kernel( const Table factor, int64_t F, int cols, float rate, float * out, MapCheck * check )
+	{
+	const int col = blockIdx.x * blockDim.x + threadIdx.x;
+	if( col >= cols ) return;
+	float mx; bool descends;
+	frame_prefix_column( factor, col, F, cols, rate, out, mx, descends );
+	if( F > 0 ) atomicMax( &check->max_key, float_key( mx ) );
+	if( descends ) check->descends = 1;
+	}
+
+__global__ void pv_map_check_kernel( const Table mod, int64_t F, int cols, MapCheck * check )
+	{
+	const int64_t total = F * cols;
+	float mx = 0.0f; bool any = false, down = false;
+	for( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x )
+		{
+		float sec; bool d;
+		time_map_check( mod, i / cols, (int)( i % cols ), sec, d );
+		if( !any || mx < sec ) mx = sec;
+		any = true; down |= d;
+		}
+	unsigned int key = any ? float_key( mx ) : 0u;
+	for( int o = 16; o; o >>= 1 ) { const unsigned int k = __shfl_xor_sync( 0xffffffffu, key, o ); key = k > key ? k : key; }
+	down = __any_sync( 0xffffffffu, down );
+	if( ( threadIdx.x & 31 ) == 0 )
+		{
+		if( key ) atomicMax( &check->max_key, key );
+		if( down ) check->descends = 1;
+		}
+	}
+
+// thread = (channel, chunk of frame pairs, bin): reads 8 bytes per input MF once (plus one overlap frame per chunk),
+// writes every output MF once. Adjacent lanes = adjacent bins: row segments are coalesced on both sides whenever the
+// time map is shared between bins.
+__global__ void __launch_bounds__( 128 ) pv_stretch_kernel( const StretchArgs a, int bin_tiles )
+	{
+	const int64_t blk = blockIdx.x;
+	const int bin = (int)( blk % bin_tiles ) * 128 + threadIdx.x;
+	const int64_t chunk_index = blk / bin_tiles;
+	if( bin >= a.B ) return;
+	stretch_chunk( a, blockIdx.y, chunk_index, bin );
+	}
+
+__global__ void __launch_bounds__( 128 ) pv_stretch_seq_kernel( const StretchArgs a )
+	{
+	const int bin = blockIdx.x * 128 + threadIdx.x;
+	if( bin >= a.B ) return;
+	stretch_column( a, blockIdx.y, bin );
+	}
+
+cudaError_t launch_bin_prefix( const Table & factor, int64_t rows, int B, float sample_rate, float dft, float * out, cudaStream_t st )
+	{
+	const int64_t blocks = ( rows + 255 ) / 256;
+	pv_bin_prefix_kernel<<<(unsigned) blocks, 256, 0, st>>>( factor, rows, B, sample_rate, dft, out );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * out, MapCheck * check, cudaStream_t st )
+	{
+	cudaError_t e = cudaMemsetAsync( check, 0, sizeof( MapCheck ), st );
+	if( e != cudaSuccess ) return e;
+	pv_frame_prefix_kernel<<<( cols + 63 ) / 64, 64, 0, st>>>( factor, F, cols, rate, out, check );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_map_check( const Table & mod, int64_t F, int cols, MapCheck * check, int sms, cudaStream_t st )
+	{
+	cudaError_t e = cudaMemsetAsync( check, 0, sizeof( MapCheck ), st );
+	if( e != cudaSuccess ) return e;
+	int64_t blocks = ( F * cols + 255 ) / 256;
+	if( blocks > (int64_t) sms * 8 ) blocks = (int64_t) sms * 8;
+	if( blocks < 1 ) blocks = 1;
+	pv_map_check_kernel<<<(unsigned) blocks, 256, 0, st>>>( mod, F, cols, check );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, cudaStream_t st )
+	{
+	const size_t smem = RepitchRow::bytes( a.B );
+	cudaError_t e = cudaFuncSetAttribute( pv_repitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	const int64_t blocks = rows < 0x7fffffff ? rows : 0x7fffffff;
+	pv_repitch_kernel<<<(unsigned) blocks, 256, smem, st>>>( a, rows );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_stretch_parallel( const StretchArgs & a, int C, cudaStream_t st )
+	{
+	const int bin_tiles = ( a.B + 127 ) / 128;
+	const int64_t blocks = a.chunks * bin_tiles;
+	if( blocks > 0x7fffffff ) return cudaErrorInvalidValue;
+	pv_stretch_kernel<<<dim3( (unsigned) blocks, C ), 128, 0, st>>>( a, bin_tiles );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_stretch_sequential( const StretchArgs & a, int C, cudaStream_t st )
+	{
+	pv_stretch_seq_kernel<<<dim3( ( a.B + 127 ) / 128, C ), 128, 0, st>>>( a );
+	return cudaGetLastError();
+	}
+
+} // namespace pvm

@@ -1,0 +1,389 @@
+// flan_b200/csrc/pv_modify_body.cuh
+//
+// Bodies of the PV-domain kernels that sit between analysis and resynthesis (BASELINE config 4): PV::repitch /
+// PV::modify_frequency (reference PV/PVModify.cpp:196-305) and PV::stretch / PV::modify_time (PVModify.cpp:307-385).
+// Integer / float work whose results must be bit-identical to the reference: every float expression below keeps the
+// reference's operation order and this file is compiled without FMA contraction (nvcc -fmad=false, g++
+// -ffp-contract=off), with IEEE division and square root. Written as per-thread phase functions between barriers so
+// that the identical source runs on the device (pv_modify.cu) and, thread by thread, in the CPU emulator
+// (emu/pv_emu.cpp) used by the tests in a container without a GPU.
+//
+// Frame x bin tables (the reference's FunctionSample2d, PV/PV.h:31-35) are passed as strided views: element
+// (frame, bin) = p[frame * frame_stride + bin * bin_stride]. (B,1) is a full table, (0,1) one row shared by all
+// frames, (1,0) one column shared by all bins, (0,0) a single value.
+//
+// Both reference algorithms walk sequentially and scatter: repitch walks the bin pairs of a frame in order and writes
+// output bins with an order-dependent rule (PVModify.cpp:237-243); stretch walks the frame pairs of a bin in order
+// and accumulates into output frames (PVModify.cpp:353-355). When the mapped positions are monotone along the walk,
+// consecutive pairs write DISJOINT output ranges ([ceil(lo), ceil(hi)) abut), every output cell is written at most
+// once, starting from zero, and the walk order no longer matters: those rows / columns run fully parallel and
+// bit-exact. Anything else takes the sequential walk.
+#pragma once
+
+#include <cstdint>
+#include <cmath>
+
+#if defined( __CUDACC__ )
+#include <cuda_runtime.h>
+#define PVM_HD __host__ __device__ __forceinline__
+#else
+#include <vector_types.h>
+#include <vector_functions.h>
+#define PVM_HD inline
+#endif
+
+namespace pvm {
+
+struct Table
+	{
+	const float * p;
+	int64_t frame_stride;
+	int bin_stride;
+	PVM_HD float at( int64_t frame, int bin ) const { return p[frame * frame_stride + (int64_t) bin * bin_stride]; }
+	};
+
+// Utility/Interpolator.cpp:15-101. ids: 0 linear, 1 midpoint, 2 nearest, 3 floor, 4 ceil, 5 smoothstep,
+// 6 smootherstep, 7 sine, 8 sine2, 9 sqrt. 7 is cosf in the reference (evaluated here in double and rounded: the
+// correctly rounded value, which glibc's cosf returns for all but a few inputs per thousand); 8 is double sin there too.
+PVM_HD float interp_eval( int id, float x )
+	{
+	const float pi = 3.14159274101257324f;      // acosf( -1.0f ), Interpolator.cpp:8
+	const float sqrt2 = 1.41421353816986084f;   // sqrtf( 2.0f ), Interpolator.cpp:9
+	switch( id )
+		{
+		case 1: return 0.5f;
+		case 2: return roundf( x );
+		case 3: return 0.0f;
+		case 4: return 1.0f;
+		case 5: return x * x * ( 3.0f - 2.0f * x );
+		case 6: return x * x * x * ( x * ( x * 6.0f - 15.0f ) + 10.0f );
+		case 7: return ( 1.0f - (float) cos( (double)( pi * x ) ) ) / 2.0f;
+		case 8: return (float)( (double) sqrt2 * sin( (double)( pi / 4.0f * x ) ) );
+		case 9: return sqrtf( x );
+		default: return x;
+		}
+	}
+
+PVM_HD int clampi( int v, int lo, int hi ) { return v < lo ? lo : ( hi < v ? hi : v ); }
+// float -> int the way the reference's x86 build converts in range; out-of-range / NaN inputs (undefined there) saturate.
+PVM_HD int to_int( float v )
+	{
+	if( !( v > -2147483648.0f ) ) return INT32_MIN;
+	if( !( v < 2147483648.0f ) ) return INT32_MAX;
+	return (int) v;
+	}
+
+// ------------------------------------------------------------------------------------------------
+// repitch / modify_frequency: one CTA per (channel, frame) row.
+// ------------------------------------------------------------------------------------------------
+struct RepitchArgs
+	{
+	const float2 * pv;          // [C][F][B]
+	float2 * out;               // [C][F][B]
+	Table mod;                  // mapped bin positions in Hz (PVModify.cpp:217-219), shared by all channels
+	const float * in_mod;       // [C][F][B] mapped frequency of every input MF (modify_frequency), or null: the lerp of
+	                            // PV::repitch (PVModify.cpp:289-302) is evaluated from `mod`
+	int64_t F;
+	int B;
+	float bin_width;            // sample_rate / float( dft ), PVBuffer.cpp:438-441
+	int interp;
+	};
+
+// Shared-memory view of one row: five float arrays of B elements, then the output row.
+struct RepitchRow
+	{
+	float * hz; float * pos; float * m; float * fm; float2 * out;
+	PVM_HD static size_t bytes( int B ) { return sizeof( float ) * 4 * (size_t)( B + 1 ) + sizeof( float2 ) * (size_t) B + 8; }
+	PVM_HD RepitchRow( void * base, int B )
+		{
+		out = (float2 *) base;
+		hz = (float *)( out + B ); pos = hz + B + 1; m = pos + B + 1; fm = m + B + 1;
+		}
+	};
+
+// Phase 1: stage the row. fm holds the raw input frequency until phase 2.
+PVM_HD void repitch_load( const RepitchArgs & a, int64_t row, int tid, int nt, RepitchRow & s )
+	{
+	const int64_t frame = row % a.F;
+	const float2 * in = a.pv + row * a.B;
+	for( int b = tid; b < a.B; b += nt )
+		{
+		const float hz = a.mod.at( frame, b );
+		const float2 mf = in[b];
+		s.hz[b] = hz;
+		s.pos[b] = hz / a.bin_width;                                    // frequency_to_bin, PVModify.cpp:218-219
+		s.m[b] = mf.x;
+		s.fm[b] = a.in_mod ? a.in_mod[row * a.B + b] : mf.y;
+		s.out[b] = make_float2( 0.0f, 0.0f );                           // out.clear_buffer(), PVModify.cpp:205
+		}
+	}
+
+// Phase 2: PV::repitch's lerp of the integrated factor at each MF's own frequency (PVModify.cpp:293-299), plus this
+// thread's share of the monotonicity test. Returns bit 0: some pair descends (or is NaN), bit 1: some pair ascends (or NaN).
+PVM_HD int repitch_map( const RepitchArgs & a, int tid, int nt, RepitchRow & s )
+	{
+	int flags = 0;
+	const float top = (float)( a.B - 1 ) - 0.0001f;
+	for( int b = tid; b < a.B; b += nt )
+		{
+		if( !a.in_mod )
+			{
+			float fbin = s.fm[b] / a.bin_width;
+			fbin = fbin < 0.0f ? 0.0f : ( top < fbin ? top : fbin );    // std::clamp
+			const int lo = clampi( to_int( floorf( fbin ) ), 0, a.B - 2 );   // the clamp only matters for NaN input
+			const float lo_freq = s.hz[lo], hi_freq = s.hz[lo + 1];
+			const float r = fbin - (float) lo;
+			s.fm[b] = lo_freq * ( 1.0f - r ) + hi_freq * r;
+			}
+		if( b > 0 )
+			{
+			const float lo = s.pos[b - 1], hi = s.pos[b];
+			if( !( hi >= lo ) ) flags |= 1;
+			if( !( hi <= lo ) ) flags |= 2;
+			}
+		}
+	return flags;
+	}
+// fm[b] is rewritten in place while other threads read hz only, so phases 1 and 2 need one barrier between them and
+// phase 3 one after the vote.
+
+// One adjacent bin pair (PVModify.cpp:214-244).
+PVM_HD void repitch_pair( const RepitchArgs & a, int bin, RepitchRow & s )
+	{
+	const float loBin = s.pos[bin - 1], hiBin = s.pos[bin];
+	const bool forward = hiBin > loBin;
+	const int start = clampi( to_int( forward ? ceilf( loBin ) : floorf( loBin ) ), 0, a.B - 1 );
+	const int end = clampi( to_int( forward ? ceilf( hiBin ) : floorf( hiBin ) ), 0, a.B - 1 );
+	if( forward ? start >= end : start <= end ) return;
+	const float lo_m = s.m[bin - 1], lo_f = s.fm[bin - 1], hi_m = s.m[bin], hi_f = s.fm[bin];
+	const float den = hiBin - loBin;
+	const int step = forward ? 1 : -1;
+	for( int y = start; y != end; y += step )
+		{
+		const float mix = interp_eval( a.interp, ( (float) y - loBin ) / den );
+		const float w0 = ( 1.0f - mix ) * lo_m;
+		const float w1 = mix * hi_m;
+		const bool lo_wins = w0 < w1;
+		const float mm = lo_wins ? lo_m : hi_m, ff = lo_wins ? lo_f : hi_f;
+		float2 o = s.out[y];
+		if( mm > o.x )
+			{
+			o.x = o.x + mm;
+			o.y = ff;
+			s.out[y] = o;
+			}
+		}
+	}
+
+// Phase 3. flags = OR over the CTA of repitch_map's result.
+PVM_HD void repitch_scatter( const RepitchArgs & a, int flags, int tid, int nt, RepitchRow & s )
+	{
+	if( flags != 3 )
+		for( int bin = 1 + tid; bin < a.B; bin += nt ) repitch_pair( a, bin, s );      // disjoint ranges
+	else if( tid == 0 )
+		for( int bin = 1; bin < a.B; ++bin ) repitch_pair( a, bin, s );                // the reference's walk
+	}
+
+// Phase 4.
+PVM_HD void repitch_store( const RepitchArgs & a, int64_t row, int tid, int nt, RepitchRow & s )
+	{
+	float2 * out = a.out + row * a.B;
+	for( int b = tid; b < a.B; b += nt ) out[b] = s.out[b];
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Table preparation
+// ------------------------------------------------------------------------------------------------
+// PV::repitch: running sum of the factor along bins, then bin_to_frequency (PVModify.cpp:278-284). One thread per row.
+PVM_HD void bin_prefix_row( const Table & factor, int64_t row, int B, float sample_rate, float dft, float * out_row )
+	{
+	float acc = 0.0f;
+	for( int b = 0; b < B; ++b )
+		{
+		const float v = factor.at( row, b );
+		acc = b == 0 ? v : v + acc;
+		out_row[b] = acc * sample_rate / dft;                           // PVBuffer.cpp:443-446
+		}
+	}
+
+// Order-preserving unsigned key of a float, for atomicMax.
+PVM_HD uint32_t float_key( float f )
+	{
+	uint32_t u;
+#if defined( __CUDA_ARCH__ )
+	u = __float_as_uint( f );
+#else
+	union { float f; uint32_t u; } c; c.f = f; u = c.u;
+#endif
+	return ( u & 0x80000000u ) ? ~u : ( u | 0x80000000u );
+	}
+PVM_HD float key_float( uint32_t k )
+	{
+	const uint32_t u = ( k & 0x80000000u ) ? ( k & 0x7fffffffu ) : ~k;
+#if defined( __CUDA_ARCH__ )
+	return __uint_as_float( u );
+#else
+	union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+	}
+
+// PV::stretch: running sum of the factor along frames, then frame_to_time (PVModify.cpp:376-382). One thread per
+// column; returns the column maximum (in seconds) and whether it ever descends.
+PVM_HD void frame_prefix_column( const Table & factor, int col, int64_t F, int cols, float rate, float * out, float & mx, bool & descends )
+	{
+	float acc = 0.0f, prev = 0.0f;
+	mx = 0.0f; descends = false;
+	for( int64_t f = 0; f < F; ++f )
+		{
+		const float v = factor.at( f, col );
+		acc = f == 0 ? v : v + acc;
+		const float sec = acc / rate;                                   // PVBuffer.cpp:433-436
+		out[f * cols + col] = sec;
+		if( f == 0 ) mx = sec;
+		else
+			{
+			if( mx < sec ) mx = sec;                                    // std::max_element
+			if( !( sec >= prev ) ) descends = true;
+			}
+		prev = sec;
+		}
+	}
+
+// ------------------------------------------------------------------------------------------------
+// stretch / modify_time
+// ------------------------------------------------------------------------------------------------
+struct StretchArgs
+	{
+	const float2 * pv;          // [C][F][B]
+	float2 * out;               // [C][out_frames][B]
+	Table mod;                  // seconds (PVModify.cpp:331-332)
+	int64_t F, out_frames;
+	int B;
+	float sample_rate, hop;     // time_to_frame( t ) = t * sample_rate / float( hop ), PVBuffer.cpp:428-431
+	int interp;
+	int chunk;                  // frame pairs per thread in the parallel form
+	int64_t chunks;
+	};
+
+PVM_HD float time_to_frame( const StretchArgs & a, float t ) { return t * a.sample_rate / a.hop; }
+
+// One adjacent frame pair of one (channel, bin) column (PVModify.cpp:329-357). RMW = the reference's accumulate into
+// whatever earlier pairs left in the output; !RMW = the output cells are known to be untouched (zero): the same
+// expressions evaluated on zeros, and every covered cell is written, zeros included.
+template<bool RMW>
+PVM_HD void stretch_pair( const StretchArgs & a, float2 * out_col, float lFrame, float rFrame, float2 l, float2 r )
+	{
+	const bool forward = rFrame > lFrame;
+	int start = to_int( forward ? ceilf( lFrame ) : floorf( lFrame ) );
+	int end = to_int( forward ? ceilf( rFrame ) : floorf( rFrame ) );
+	const int64_t last = a.out_frames - 1;
+	// frames outside [0, out_frames) are skipped before anything is computed (PVModify.cpp:343)
+	if( forward )
+		{
+		if( start < 0 ) start = 0;
+		if( (int64_t) end > a.out_frames ) end = (int) a.out_frames;
+		if( start >= end ) return;
+		}
+	else
+		{
+		if( (int64_t) start > last ) start = (int) last;
+		if( end < -1 ) end = -1;
+		if( start <= end ) return;
+		}
+	const float den = rFrame - lFrame;
+	const int step = forward ? 1 : -1;
+	bool live = true;
+	for( int x = start; x != end; x += step )
+		{
+		float2 * o = out_col + (int64_t) x * a.B;
+		if( live )
+			{
+			const float mix = interp_eval( a.interp, ( (float) x - lFrame ) / den );
+			const float w0 = ( 1.0f - mix ) * l.x;
+			const float w1 = mix * r.x;
+			const float totalWeight = w0 + w1;
+			const float weightedFreqSum = w0 * l.y + w1 * r.y;
+			if( totalWeight == 0.0f ) live = false;                     // `return`: leaves this frame pair (PVModify.cpp:351-352)
+			else
+				{
+				const float2 old = RMW ? *o : make_float2( 0.0f, 0.0f );
+				float2 nw;
+				nw.y = ( old.y * old.x + weightedFreqSum ) / ( old.x + totalWeight );
+				nw.x = old.x + totalWeight;
+				*o = nw;
+				continue;
+				}
+			}
+		if( RMW ) return;
+		*o = make_float2( 0.0f, 0.0f );
+		}
+	}
+
+// Parallel form (every column non-descending): thread = (channel, chunk of frame pairs, bin). Covered output frames
+// are written by their pair; the first / last chunk also clear what lies below / above the column's covered range.
+PVM_HD void stretch_chunk( const StretchArgs & a, int c, int64_t chunk_index, int bin )
+	{
+	const float2 * in = a.pv + (int64_t) c * a.F * a.B + bin;
+	float2 * out_col = a.out + (int64_t) c * a.out_frames * a.B + bin;
+	const int64_t f0 = chunk_index * a.chunk;                           // pairs (f0, f0+1) ... (f1-1, f1)
+	int64_t f1 = f0 + a.chunk;
+	if( f1 > a.F - 1 ) f1 = a.F - 1;
+	float lF = time_to_frame( a, a.mod.at( f0, bin ) );
+	float2 l = in[f0 * a.B];
+	if( chunk_index == 0 )
+		{
+		int64_t head = to_int( ceilf( lF ) );
+		if( head > a.out_frames ) head = a.out_frames;
+		for( int64_t x = 0; x < head; ++x ) out_col[x * a.B] = make_float2( 0.0f, 0.0f );
+		}
+	constexpr int BATCH = 8;
+	for( int64_t f = f0; f < f1; f += BATCH )
+		{
+		float2 r[BATCH]; float rF[BATCH];
+#pragma unroll
+		for( int j = 0; j < BATCH; ++j )
+			if( f + 1 + j <= f1 )
+				{
+				r[j] = in[( f + 1 + j ) * a.B];
+				rF[j] = time_to_frame( a, a.mod.at( f + 1 + j, bin ) );
+				}
+#pragma unroll
+		for( int j = 0; j < BATCH; ++j )
+			if( f + 1 + j <= f1 )
+				{
+				stretch_pair<false>( a, out_col, lF, rF[j], l, r[j] );
+				l = r[j]; lF = rF[j];
+				}
+		}
+	if( chunk_index == a.chunks - 1 )
+		{
+		int64_t tail = to_int( ceilf( lF ) );                           // lF is now the position of frame F-1
+		if( tail < 0 ) tail = 0;
+		for( int64_t x = tail; x < a.out_frames; ++x ) out_col[x * a.B] = make_float2( 0.0f, 0.0f );
+		}
+	}
+
+// Sequential form (the reference's walk): thread = (channel, bin); the output was cleared beforehand.
+PVM_HD void stretch_column( const StretchArgs & a, int c, int bin )
+	{
+	const float2 * in = a.pv + (int64_t) c * a.F * a.B + bin;
+	float2 * out_col = a.out + (int64_t) c * a.out_frames * a.B + bin;
+	float lF = time_to_frame( a, a.mod.at( 0, bin ) );
+	float2 l = in[0];
+	for( int64_t f = 1; f < a.F; ++f )
+		{
+		const float rF = time_to_frame( a, a.mod.at( f, bin ) );
+		const float2 r = in[f * a.B];
+		stretch_pair<true>( a, out_col, lF, rF, l, r );
+		l = r; lF = rF;
+		}
+	}
+
+// Reduction over a time map: maximum (std::max_element semantics on finite data) and "some column descends".
+PVM_HD void time_map_check( const Table & mod, int64_t f, int col, float & sec, bool & descends )
+	{
+	sec = mod.at( f, col );
+	descends = f > 0 && !( sec >= mod.at( f - 1, col ) );
+	}
+
+} // namespace pvm

@@ -42,7 +42,8 @@ class Engine:
     def launch_count(self):
         return int(self.lib.flan_b200_launch_count(self.ctx.h))
 
-    KERNEL_KINDS = {"analysis": 0, "phase_seg": 1, "phase_scan": 2, "synthesis": 3, "aux": 4}
+    KERNEL_KINDS = {"analysis": 0, "phase_seg": 1, "phase_scan": 2, "synthesis": 3, "aux": 4,
+                    "repitch": 5, "stretch": 6, "modify_tables": 7}
 
     def set_timing(self, enabled):
         self.ctx.call("flan_b200_set_timing", int(enabled))
@@ -137,6 +138,67 @@ class Engine:
         self._bind_stream()
         self.ctx.call("flan_b200_mid_side", self._chk(audio), self._chk(out), audio.shape[1])
         return out
+
+    # -- PV-domain chain: PV::repitch / modify_frequency / stretch / modify_time (PV/PVModify.cpp:196-385) ----
+    def _table(self, table, F, B):
+        """Strided view of a frame x bin table: cuda float32 [F, B] (full), [B] (one row for every frame),
+        [F, 1] (one column for every bin) or a Python / numpy scalar (a constant Function)."""
+        if not torch.is_tensor(table):
+            table = torch.full((1,), float(table), dtype=torch.float32, device=self.device)
+        shape = tuple(table.shape)
+        if shape == (F, B):
+            fs, bs = B, 1
+        elif shape == (B,):
+            fs, bs = 0, 1
+        elif shape == (F, 1):
+            fs, bs = 1, 0
+        elif table.numel() == 1:
+            fs, bs = 0, 0
+        else:
+            raise ValueError("table shape %s does not fit a %d x %d grid" % (shape, F, B))
+        return table, self._chk(table), fs, bs
+
+    def repitch(self, pv, sr, factor, interp=0, out=None):
+        C, F, B, _ = pv.shape
+        t, tp, fs, bs = self._table(factor, F, B)
+        if out is None:
+            out = torch.empty_like(pv)
+        self._bind_stream()
+        self.ctx.call("flan_b200_repitch", self._chk(pv), C, F, B, sr, tp, fs, bs, interp, self._chk(out))
+        return out
+
+    def modify_frequency(self, pv, sr, mod_hz, in_mod, interp=0, out=None):
+        C, F, B, _ = pv.shape
+        t, tp, fs, bs = self._table(mod_hz, F, B)
+        assert tuple(in_mod.shape) == (C, F, B)
+        if out is None:
+            out = torch.empty_like(pv)
+        self._bind_stream()
+        self.ctx.call("flan_b200_modify_frequency", self._chk(pv), C, F, B, sr, tp, fs, bs, self._chk(in_mod), interp, self._chk(out))
+        return out
+
+    def stretch_map(self, F, B, sr, ar, factor):
+        t, tp, fs, bs = self._table(factor, F, B)
+        out = torch.empty((F, B) if bs else (F, 1), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_stretch_map", tp, fs, bs, F, B, sr, ar, self._chk(out))
+        return out
+
+    def modify_time(self, pv, sr, ar, seconds, interp=0):
+        C, F, B, _ = pv.shape
+        t, tp, fs, bs = self._table(seconds, F, B)
+        frames = ctypes.c_int64(0)
+        self._bind_stream()
+        self.ctx.call("flan_b200_modify_time_frames", tp, fs, bs, F, B, sr, ar, ctypes.byref(frames))
+        n = max(int(frames.value), 0)
+        out = torch.empty((C, n, B, 2), dtype=torch.float32, device=self.device)
+        self.ctx.call("flan_b200_modify_time", self._chk(pv), C, F, B, sr, ar, tp, fs, bs, interp, frames.value,
+                      self._chk(out) if n else None)
+        return out
+
+    def stretch(self, pv, sr, ar, factor, interp=0):
+        C, F, B, _ = pv.shape
+        return self.modify_time(pv, sr, ar, self.stretch_map(F, B, sr, ar, factor), interp)
 
     # -- host-buffer forms (the call the reference-facing C++ layer makes) -------------------------
     def convert_to_pv_host(self, audio_np, sr, W, hop, N, mid_side=False, out=None):

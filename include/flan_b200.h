@@ -60,7 +60,8 @@ int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
 /* Per-kernel device timing for bench.py's roofline line: when enabled, every kernel launch is bracketed by
  * CUDA events on the context's stream. flan_b200_kernel_time synchronises the stream, returns the summed
  * duration and launch count of one kernel kind since the last call for that kind, and resets it.
- * kinds: 0 analysis, 1 phase segment summary, 2 phase scan, 3 resynthesis, 4 mid/side + add + carry. */
+ * kinds: 0 analysis, 1 phase segment summary, 2 phase scan, 3 resynthesis, 4 mid/side + add + carry,
+ * 5 repitch / modify_frequency, 6 stretch / modify_time, 7 table preparation and checks of the PV-domain chain. */
 int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled );
 int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches );
 
@@ -133,6 +134,47 @@ int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int6
 /* ---- Audio::convert_to_mid_side / convert_to_left_right (AudioConversions.cpp:32-56) --------- */
 /* d_in, d_out: float[2][n]; the transform is its own inverse up to rounding. */
 int flan_b200_mid_side( flan_b200_ctx * ctx, const float * d_in, float * d_out, int64_t n );
+
+/* ---- PV-domain chain between analysis and resynthesis (BASELINE config 4) -------------------------------------
+ * PV::repitch / PV::modify_frequency (src/flan/PV/PVModify.cpp:196-305, decl PV/PV.h:288-330) and PV::stretch /
+ * PV::modify_time (PVModify.cpp:307-385, decl PV/PV.h:300-352) on device-resident PV data. Results are bit-identical
+ * to the reference's float arithmetic for interpolators 0-6 and 9; 7 (sine) and 8 (sine2) evaluate cos / sin in
+ * double and round, which differs from glibc's cosf in the last bit for a few inputs per thousand.
+ *
+ * The reference samples its Function<TF,float> argument over the frame x bin grid on the host (PV/PV.h:31-35);
+ * here the sampled table arrives as a strided device view: element (frame, bin) = d_table[frame * frame_stride +
+ * bin * bin_stride], strides (B,1) for a full float[F][B] table, (0,1) one row shared by every frame, (1,0) one
+ * column shared by every bin, (0,0) a single value (what a constant Function samples to).
+ * interp: 0 linear, 1 midpoint, 2 nearest, 3 floor, 4 ceil, 5 smoothstep, 6 smootherstep, 7 sine, 8 sine2, 9 sqrt
+ * (the named constructors of Utility/Interpolator.cpp:15-101). d_pv_out must not alias d_pv. */
+
+/* PV::repitch (PVModify.cpp:273-305): running sum of the factor along bins, bins -> Hz, lerp at every MF's own
+ * frequency, then the scatter of modify_frequency_base. d_pv_out: MF[C][F][B]. */
+int flan_b200_repitch( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins, float sample_rate,
+                       const float * d_factor, int64_t factor_frame_stride, int factor_bin_stride,
+                       int interp, float * d_pv_out );
+/* modify_frequency_base (PVModify.cpp:196-257) behind PV::modify_frequency (:259-271): d_mod_hz is the mod function
+ * sampled over the grid (Hz, strided view), d_in_mod float[C][F][B] the mod function evaluated by the caller at
+ * (frame time, every MF's frequency) -- a user lambda of data on the host, PVModify.cpp:263-268. */
+int flan_b200_modify_frequency( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins, float sample_rate,
+                                const float * d_mod_hz, int64_t mod_frame_stride, int mod_bin_stride,
+                                const float * d_in_mod, int interp, float * d_pv_out );
+/* PV::stretch, first half (PVModify.cpp:373-382): running sum of the factor along frames, frames -> seconds.
+ * d_map_out: dense float[F][B] when factor_bin_stride is 1, float[F] (a (1,0) view) when it is 0. */
+int flan_b200_stretch_map( flan_b200_ctx * ctx, const float * d_factor, int64_t factor_frame_stride, int factor_bin_stride,
+                           int64_t frames, int bins, float sample_rate, float analysis_rate, float * d_map_out );
+/* Output frame count of modify_time_base for a time map in seconds: ceil( time_to_frame( maximum ) )
+ * (PVModify.cpp:311-315). Synchronises the stream. A result <= 0 means an empty output. */
+int flan_b200_modify_time_frames( flan_b200_ctx * ctx, const float * d_map, int64_t map_frame_stride, int map_bin_stride,
+                                  int64_t frames, int bins, float sample_rate, float analysis_rate, int64_t * out_frames );
+/* modify_time_base (PVModify.cpp:307-362) behind PV::modify_time (:364-369) and PV::stretch (:384).
+ * d_pv_out: MF[C][out_frames][B], out_frames from flan_b200_modify_time_frames (checked). Synchronises once
+ * internally: time maps that never descend run one thread per (channel, frame chunk, bin); others take the
+ * reference's sequential walk per (channel, bin). */
+int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins,
+                           float sample_rate, float analysis_rate,
+                           const float * d_map, int64_t map_frame_stride, int map_bin_stride,
+                           int interp, int64_t out_frames, float * d_pv_out );
 
 /* ---- host-buffer forms (what flan::Audio::convert_to_PV / flan::PV::convert_to_audio call when the
  *      buffers live in std::vector): upload, transform, download, synchronise. ------------------- */

@@ -75,3 +75,67 @@ class Emu:
 
     def div_const_mismatches(self, c, first_bits, count):
         return int(self.L.pv_emu_div_const_mismatches(c, first_bits, count))
+
+
+class EmuModify:
+    """The PV-domain kernel bodies (flan_b200/csrc/pv_modify_body.cuh) run thread by thread on the host."""
+
+    def __init__(self):
+        L = Emu().L
+        i, f = ctypes.c_int, ctypes.c_float
+        L.pv_emu_repitch.argtypes = [_fp, i, _i64, i, f, _fp, _i64, i, _fp, _fp, i, i, _fp]
+        L.pv_emu_stretch.restype = _i64
+        L.pv_emu_stretch.argtypes = [_fp, i, _i64, i, f, f, _fp, _fp, _i64, i, i, i, i, ctypes.POINTER(i), _fp]
+        self.L = L
+
+    @staticmethod
+    def view(table, F, B):
+        """(array, frame_stride, bin_stride) of a table given as [F][B], [B] (shared row), [F,1] (shared column) or scalar."""
+        t = np.ascontiguousarray(table, np.float32)
+        if t.shape == (F, B):
+            return t, B, 1
+        if t.shape == (B,):
+            return t, 0, 1
+        if t.shape == (F, 1):
+            return t, 1, 0
+        assert t.size == 1
+        return t.reshape(1), 0, 0
+
+    def repitch(self, pv, sr, factor, interp=0, threads=64):
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        t, fs, bs = self.view(factor, F, B)
+        out = np.full_like(pv, np.nan)
+        assert self.L.pv_emu_repitch(_ptr(pv), C, F, B, sr, _ptr(t), fs, bs, None, None, interp, threads, _ptr(out)) == 0
+        return out
+
+    def modify_frequency(self, pv, sr, mod_hz, in_mod, interp=0, threads=64):
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        t, fs, bs = self.view(mod_hz, F, B)
+        in_mod = np.ascontiguousarray(in_mod, np.float32)
+        out = np.full_like(pv, np.nan)
+        assert self.L.pv_emu_repitch(_ptr(pv), C, F, B, sr, None, fs, bs, _ptr(t), _ptr(in_mod), interp, threads, _ptr(out)) == 0
+        return out
+
+    def _time(self, pv, sr, ar, factor, seconds, interp, chunk, force_sequential):
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        t, fs, bs = self.view(factor if factor is not None else seconds, F, B)
+        fa = _ptr(t) if factor is not None else None
+        se = _ptr(t) if factor is None else None
+        used = ctypes.c_int(0)
+        frames = int(self.L.pv_emu_stretch(_ptr(pv), C, F, B, sr, ar, fa, se, fs, bs, interp, chunk, force_sequential,
+                                           ctypes.byref(used), None))
+        if frames <= 0:
+            return np.zeros((C, 0, B, 2), np.float32), bool(used.value)
+        out = np.full((C, frames, B, 2), np.nan, np.float32)
+        assert self.L.pv_emu_stretch(_ptr(pv), C, F, B, sr, ar, fa, se, fs, bs, interp, chunk, force_sequential,
+                                     ctypes.byref(used), _ptr(out)) == frames
+        return out, bool(used.value)
+
+    def stretch(self, pv, sr, ar, factor, interp=0, chunk=32, force_sequential=0):
+        return self._time(pv, sr, ar, factor, None, interp, chunk, force_sequential)
+
+    def modify_time(self, pv, sr, ar, seconds, interp=0, chunk=32, force_sequential=0):
+        return self._time(pv, sr, ar, None, seconds, interp, chunk, force_sequential)

@@ -45,7 +45,7 @@ def main():
         fr, fs = factor_table(kind, F, B, 900 + i)
         rep = ref.repitch(pv, sr, ar, W, fr, interp)
         stz = ref.stretch(pv, sr, ar, W, fs, interp)
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), pv=pv, sr=np.float32(sr), analysis_rate=np.float32(ar), W=W,
+        np.savez_compressed(os.path.join(HERE, "modify", name + ".npz"), pv=pv, sr=np.float32(sr), analysis_rate=np.float32(ar), W=W,
                             interp=interp, repitch_factor=fr, stretch_factor=fs, repitch=rep, stretch=stz)
         print(name, pv.shape, rep.shape, stz.shape)
 

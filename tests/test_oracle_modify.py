@@ -9,7 +9,7 @@ import pytest
 
 from flan_b200.signals import make_config
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "modify_*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "modify", "modify_*.npz")))
 
 
 def bits(a):
