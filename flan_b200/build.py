@@ -95,7 +95,7 @@ def build_host(force=False):
     build_library(force)
     os.makedirs(LIB, exist_ok=True)
     root = os.path.dirname(HERE)
-    srcs = [os.path.join(HOST, "src", n) for n in ("b200_storage.cpp", "AudioBuffer.cpp", "PVBuffer.cpp", "AudioPV.cpp")]
+    srcs = [os.path.join(HOST, "src", n) for n in ("b200_storage.cpp", "AudioBuffer.cpp", "PVBuffer.cpp", "AudioPV.cpp", "PVModify.cpp")]
     hdrs = []
     for d, _, files in os.walk(os.path.join(HOST, "include")):
         hdrs += [os.path.join(d, f) for f in files]

@@ -65,6 +65,32 @@ int pv_emu_repitch( const float * pv, int C, int64_t F, int B, float sr, const f
 	RepitchArgs a{};
 	a.pv = (const float2 *) pv; a.out = (float2 *) out; a.mod = mod; a.in_mod = in_mod;
 	a.F = F; a.B = B; a.bin_width = sr / float( ( B - 1 ) * 2 ); a.interp = interp;
+	if( mod.frame_stride == 0 && mod.bin_stride == 1 )
+		{
+		// plan + gather, as pv_repitch_plan_kernel / pv_repitch_shared_kernel
+		std::vector<int> src( B ); std::vector<float> mix( B ), pos( B ); int ok = 0;
+		RepitchPlan plan{ src.data(), mix.data(), &ok };
+		const int nt = threads;
+		for( int t = nt - 1; t >= 0; --t ) repitch_plan_positions( mod.p, B, a.bin_width, t, nt, pos.data(), plan );
+		int flags = 0;
+		for( int t = nt - 1; t >= 0; --t ) flags |= repitch_plan_flags( B, t, nt, pos.data() );
+		for( int t = nt - 1; t >= 0; --t ) repitch_plan_pairs( B, interp, flags, t, nt, pos.data(), plan );
+		if( ok )
+			{
+			std::vector<float> m( B ), fm( B );
+			for( int64_t row = 0; row < (int64_t) C * F; ++row )
+				{
+				for( int b = B - 1; b >= 0; --b )
+					{
+					const float2 mf = a.pv[row * B + b];
+					m[b] = mf.x;
+					fm[b] = in_mod ? in_mod[row * B + b] : repitch_lerp( mod.p, B, a.bin_width, mf.y );
+					}
+				for( int y = B - 1; y >= 0; --y ) a.out[row * B + y] = repitch_gather( y, src.data(), mix.data(), m.data(), fm.data() );
+				}
+			return 0;
+			}
+		}
 	repitch_rows( a, (int64_t) C * F, threads );
 	return 0;
 	}
@@ -84,11 +110,9 @@ int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, flo
 		{
 		built.resize( (size_t) F * cols );
 		const Table fac{ factor, fs, bs };
-		for( int col = 0; col < cols; ++col )
-			{
-			float mx; bool d;
-			frame_prefix_column( fac, col, F, cols, sr / float( hop ), built.data(), mx, d );
-			}
+		std::vector<float> raw( (size_t) F * cols );
+		for( int col = 0; col < cols; ++col ) frame_prefix_column( fac, col, F, cols, raw.data() );
+		for( int64_t i = F * cols - 1; i >= 0; --i ) frame_prefix_convert( raw.data(), built.data(), i, sr / float( hop ) );
 		mod = Table{ built.data(), (int64_t) cols, bs };
 		}
 	bool descends = false;
@@ -100,7 +124,16 @@ int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, flo
 	a.F = F; a.out_frames = out_frames; a.B = B; a.sample_rate = sr; a.hop = float( hop ); a.interp = interp;
 	a.chunk = chunk; a.chunks = ( F - 1 + chunk - 1 ) / chunk;
 	if( a.chunks < 1 ) a.chunks = 1;
-	if( !descends && !force_sequential )
+	if( !descends && !force_sequential && bs == 0 )
+		{
+		std::vector<int> xpos( F ); std::vector<float> mix( out_frames );
+		StretchPlan plan{ xpos.data(), mix.data() };
+		for( int64_t f = F - 1; f >= 0; --f ) stretch_plan_frame( a, plan, f );
+		for( int c = C - 1; c >= 0; --c )
+			for( int64_t k = a.chunks - 1; k >= 0; --k )
+				for( int b = B - 1; b >= 0; --b ) stretch_chunk_planned( a, plan, c, k, b );
+		}
+	else if( !descends && !force_sequential )
 		{
 		for( int c = C - 1; c >= 0; --c )
 			for( int64_t k = a.chunks - 1; k >= 0; --k )

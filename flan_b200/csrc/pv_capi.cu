@@ -604,8 +604,11 @@ int check_pv_shape( flan_b200_ctx * ctx, int C, int64_t F, int B, float sr, int 
 
 bool strides_ok( int64_t fs, int bs, int B ) { return ( bs == 0 || bs == 1 ) && ( fs == 0 || fs == ( bs ? B : 1 ) ); }
 
+// mod_hz.frame_stride == 0 && bin_stride == 1 (one row of positions shared by all frames): plan + gather kernel, with
+// the general row kernel as the device-side alternative when the plan kernel finds the positions non-monotone.
+// plan_ws: 2 * B * 4 + 256 bytes of scratch for the plan, or null.
 int repitch_common( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, int B, float sr,
-                    const pvm::Table & mod_hz, const float * d_in_mod, int interp, float * d_out )
+                    const pvm::Table & mod_hz, const float * d_in_mod, int interp, float * d_out, void * plan_ws )
 	{
 	pvm::RepitchArgs a{};
 	a.pv = (const float2 *) d_pv; a.out = (float2 *) d_out;
@@ -614,9 +617,21 @@ int repitch_common( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, i
 	a.bin_width = sr / float( ( B - 1 ) * 2 );                          // PVBuffer.cpp:438-441
 	a.interp = interp;
 	if( pvm::RepitchRow::bytes( B ) > 200 * 1024 ) return fail( ctx, FLAN_B200_UNSUPPORTED, "too many bins for one shared-memory row" );
-	{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch( a, (int64_t) C * F, ctx->stream ), "repitch launch" ); }
+	const int64_t rows = (int64_t) C * F;
+	const int * skip_if = nullptr;
+	if( plan_ws && mod_hz.frame_stride == 0 && mod_hz.bin_stride == 1 && pvm::repitch_shared_supported( B ) )
+		{
+		pvm::RepitchPlan plan{};
+		plan.src = (int *) plan_ws; plan.mix = (float *)( plan.src + B ); plan.ok = (int *)( plan.mix + B );
+		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_repitch_plan( mod_hz.p, B, a.bin_width, interp, plan, ctx->stream ), "repitch plan launch" ); }
+		{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch_shared( a, plan, mod_hz.p, rows, ctx->sms, ctx->stream ), "repitch launch" ); }
+		skip_if = plan.ok;
+		}
+	{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch( a, rows, skip_if, ctx->stream ), "repitch launch" ); }
 	return FLAN_B200_OK;
 	}
+
+size_t repitch_plan_bytes( int B ) { return align_up( sizeof( float ) * 2 * (size_t) B + sizeof( int ), 256 ); }
 
 // Reads the reduction back (synchronises the stream).
 int read_map_check( flan_b200_ctx * ctx, float sr, int hop, int64_t * out_frames, bool * descends )
@@ -646,13 +661,14 @@ int flan_b200_repitch( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F
 		return fail( ctx, FLAN_B200_INVALID, "table strides must be (B,1), (0,1), (1,0) or (0,0)" );
 	const int64_t rows = factor_frame_stride ? F : 1;
 	void * ws = nullptr;
-	rc = get_workspace( ctx, sizeof( float ) * (size_t) rows * B, &ws );
+	const size_t hz_bytes = align_up( sizeof( float ) * (size_t) rows * B, 256 );
+	rc = get_workspace( ctx, hz_bytes + repitch_plan_bytes( B ), &ws );
 	if( rc ) return rc;
 	ctx->seg_key.valid = false;
 	const pvm::Table factor{ d_factor, factor_frame_stride, factor_bin_stride };
 	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_bin_prefix( factor, rows, B, sr, float( ( B - 1 ) * 2 ), (float *) ws, ctx->stream ), "repitch table launch" ); }
 	const pvm::Table mod{ (const float *) ws, factor_frame_stride ? (int64_t) B : 0, 1 };
-	return repitch_common( ctx, d_pv, C, F, B, sr, mod, nullptr, interp, d_pv_out );
+	return repitch_common( ctx, d_pv, C, F, B, sr, mod, nullptr, interp, d_pv_out, (char *) ws + hz_bytes );
 	}
 
 int flan_b200_modify_frequency( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, int B, float sr,
@@ -665,7 +681,11 @@ int flan_b200_modify_frequency( flan_b200_ctx * ctx, const float * d_pv, int C, 
 	if( !strides_ok( mod_frame_stride, mod_bin_stride, B ) )
 		return fail( ctx, FLAN_B200_INVALID, "table strides must be (B,1), (0,1), (1,0) or (0,0)" );
 	const pvm::Table mod{ d_mod_hz, mod_frame_stride, mod_bin_stride };
-	return repitch_common( ctx, d_pv, C, F, B, sr, mod, d_in_mod, interp, d_pv_out );
+	void * ws = nullptr;
+	rc = get_workspace( ctx, repitch_plan_bytes( B ), &ws );
+	if( rc ) return rc;
+	ctx->seg_key.valid = false;
+	return repitch_common( ctx, d_pv, C, F, B, sr, mod, d_in_mod, interp, d_pv_out, ws );
 	}
 
 int flan_b200_stretch_map( flan_b200_ctx * ctx, const float * d_factor, int64_t factor_frame_stride, int factor_bin_stride,
@@ -679,7 +699,11 @@ int flan_b200_stretch_map( flan_b200_ctx * ctx, const float * d_factor, int64_t 
 	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop < 1" );
 	const int cols = factor_bin_stride ? B : 1;
 	const pvm::Table factor{ d_factor, factor_frame_stride, factor_bin_stride };
-	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), d_map_out, ctx->d_check, ctx->stream ), "stretch map launch" ); }
+	void * ws = nullptr;
+	int rc = get_workspace( ctx, sizeof( float ) * (size_t) F * cols, &ws );
+	if( rc ) return rc;
+	ctx->seg_key.valid = false;
+	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), (float *) ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -728,7 +752,19 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int C, int64
 	a.chunk = 32;
 	a.chunks = ( F - 1 + a.chunk - 1 ) / a.chunk;
 	if( a.chunks < 1 ) a.chunks = 1;
-	if( !descends )
+	if( !descends && map_bin_stride == 0 && F < 0x7fffffff && out_frames < 0x7fffffff )
+		{
+		// one geometry for every bin: plan it once, then only the per-bin arithmetic remains
+		void * ws = nullptr;
+		const size_t xpos_bytes = align_up( sizeof( int ) * (size_t) F, 256 );
+		rc = get_workspace( ctx, xpos_bytes + sizeof( float ) * (size_t) out_frames, &ws );
+		if( rc ) return rc;
+		ctx->seg_key.valid = false;
+		pvm::StretchPlan plan{ (int *) ws, (float *)( (char *) ws + xpos_bytes ) };
+		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_stretch_plan( a, plan, ctx->stream ), "stretch plan launch" ); }
+		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_planned( a, plan, C, ctx->stream ), "stretch launch" ); }
+		}
+	else if( !descends )
 		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_parallel( a, C, ctx->stream ), "stretch launch" ); }
 	else
 		{

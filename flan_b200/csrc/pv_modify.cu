@@ -8,9 +8,10 @@ namespace pvm {
 
 // One CTA per (channel, frame) row: stage the row in shared memory, map, scatter, store. Algorithmic bytes per row:
 // 8B read + 8B written (+ 4B of table when it is not shared between frames, + 4B for modify_frequency's in_mod).
-__global__ void __launch_bounds__( 256 ) pv_repitch_kernel( const RepitchArgs a, int64_t rows )
+__global__ void __launch_bounds__( 256 ) pv_repitch_kernel( const RepitchArgs a, int64_t rows, const int * skip_if )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem[];
+	if( skip_if && *skip_if ) return;
 	RepitchRow s( smem, a.B );
 	const int tid = threadIdx.x, nt = blockDim.x;
 	for( int64_t row = blockIdx.x; row < rows; row += gridDim.x )
@@ -55,14 +56,17 @@ __global__ void __launch_bounds__( 256 ) pv_bin_prefix_kernel( const Table facto
 		}
 	}
 
-__global__ void pv_frame_prefix_kernel( const Table factor, int64_t F, int cols, float rate, float * out, MapCheck * check )
+__global__ void pv_frame_prefix_kernel( const Table factor, int64_t F, int cols, float * raw )
 	{
 	const int col = blockIdx.x * blockDim.x + threadIdx.x;
 	if( col >= cols ) return;
-	float mx; bool descends;
-	frame_prefix_column( factor, col, F, cols, rate, out, mx, descends );
-	if( F > 0 ) atomicMax( &check->max_key, float_key( mx ) );
-	if( descends ) check->descends = 1;
+	frame_prefix_column( factor, col, F, cols, raw );
+	}
+
+__global__ void pv_frame_convert_kernel( const float * raw, float * out, int64_t total, float rate )
+	{
+	for( int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t) gridDim.x * blockDim.x )
+		frame_prefix_convert( raw, out, i, rate );
 	}
 
 __global__ void pv_map_check_kernel( const Table mod, int64_t F, int cols, MapCheck * check )
@@ -105,6 +109,134 @@ __global__ void __launch_bounds__( 128 ) pv_stretch_seq_kernel( const StretchArg
 	stretch_column( a, blockIdx.y, bin );
 	}
 
+// ---- frame-shared repitch: plan + gather ------------------------------------------------------------------------
+__global__ void __launch_bounds__( 1024 ) pv_repitch_plan_kernel( const float * hz, int B, float bin_width, int interp, const RepitchPlan plan )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem[];
+	float * pos = (float *) smem;
+	const int tid = threadIdx.x, nt = blockDim.x;
+	repitch_plan_positions( hz, B, bin_width, tid, nt, pos, plan );
+	__syncthreads();
+	const int mine = repitch_plan_flags( B, tid, nt, pos );
+	const int down = __syncthreads_or( mine & 1 );
+	const int up = __syncthreads_or( mine & 2 );
+	repitch_plan_pairs( B, interp, ( down ? 1 : 0 ) | ( up ? 2 : 0 ), tid, nt, pos, plan );
+	}
+
+// Persistent CTAs, one row at a time: the row's (m, f) pairs are loaded one row ahead into registers, the mapped
+// frequencies go through a double-buffered shared-memory row (one barrier per row), every output bin is one gather.
+// Algorithmic bytes per row: 8B read + 8B written; the plan (12B bytes) lives in shared memory for the CTA's lifetime.
+constexpr int REPITCH_J = 5;        // bins per thread
+template<int T> __global__ void __launch_bounds__( T ) pv_repitch_shared_kernel( const RepitchArgs a, const RepitchPlan plan, const float * hz, int64_t rows )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem[];
+	if( !*plan.ok ) return;
+	const int B = a.B, tid = threadIdx.x;
+	int * src = (int *) smem;
+	float * mix = (float *)( src + B );
+	float * hzs = mix + B;
+	float * mbuf = hzs + B;          // [2][B]
+	float * fbuf = mbuf + 2 * B;     // [2][B]
+	for( int b = tid; b < B; b += T ) { src[b] = plan.src[b]; mix[b] = plan.mix[b]; hzs[b] = hz[b]; }
+	__syncthreads();
+	float2 reg[REPITCH_J];
+	int64_t row = blockIdx.x;
+	if( row < rows )
+		{
+#pragma unroll
+		for( int j = 0; j < REPITCH_J; ++j ) { const int b = tid + j * T; if( b < B ) reg[j] = __ldcs( a.pv + row * B + b ); }
+		}
+	for( int k = 0; row < rows; row += gridDim.x, k ^= 1 )
+		{
+		float * m = mbuf + k * B, * fm = fbuf + k * B;
+#pragma unroll
+		for( int j = 0; j < REPITCH_J; ++j )
+			{
+			const int b = tid + j * T;
+			if( b < B )
+				{
+				m[b] = reg[j].x;
+				fm[b] = a.in_mod ? __ldcs( a.in_mod + row * B + b ) : repitch_lerp( hzs, B, a.bin_width, reg[j].y );
+				}
+			}
+		const int64_t next = row + gridDim.x;
+		if( next < rows )
+			{
+#pragma unroll
+			for( int j = 0; j < REPITCH_J; ++j ) { const int b = tid + j * T; if( b < B ) reg[j] = __ldcs( a.pv + next * B + b ); }
+			}
+		__syncthreads();
+		float2 * out = a.out + row * B;
+#pragma unroll
+		for( int j = 0; j < REPITCH_J; ++j )
+			{
+			const int y = tid + j * T;
+			if( y < B ) __stcs( out + y, repitch_gather( y, src, mix, m, fm ) );
+			}
+		}
+	}
+
+// ---- bin-shared stretch: plan + chunk walk ----------------------------------------------------------------------
+__global__ void pv_stretch_plan_kernel( const StretchArgs a, const StretchPlan plan )
+	{
+	const int64_t f = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if( f < a.F ) stretch_plan_frame( a, plan, f );
+	}
+
+__global__ void __launch_bounds__( 128 ) pv_stretch_planned_kernel( const StretchArgs a, const StretchPlan plan, int bin_tiles )
+	{
+	const int64_t blk = blockIdx.x;
+	const int bin = (int)( blk % bin_tiles ) * 128 + threadIdx.x;
+	const int64_t chunk_index = blk / bin_tiles;
+	if( bin >= a.B ) return;
+	stretch_chunk_planned( a, plan, blockIdx.y, chunk_index, bin );
+	}
+
+bool repitch_shared_supported( int B ) { return B <= REPITCH_J * 1024; }
+
+cudaError_t launch_repitch_plan( const float * hz, int B, float bin_width, int interp, const RepitchPlan & plan, cudaStream_t st )
+	{
+	pv_repitch_plan_kernel<<<1, 1024, sizeof( float ) * B, st>>>( hz, B, bin_width, interp, plan );
+	return cudaGetLastError();
+	}
+
+template<int T> static cudaError_t launch_repitch_shared_t( const RepitchArgs & a, const RepitchPlan & plan, const float * hz, int64_t rows, int sms, cudaStream_t st )
+	{
+	const size_t smem = sizeof( float ) * 7 * (size_t) a.B;
+	cudaError_t e = cudaFuncSetAttribute( pv_repitch_shared_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, pv_repitch_shared_kernel<T>, T, smem );
+	if( e != cudaSuccess ) return e;
+	if( per_sm < 1 ) per_sm = 1;
+	int64_t blocks = (int64_t) sms * per_sm;
+	if( blocks > rows ) blocks = rows;
+	pv_repitch_shared_kernel<T><<<(unsigned) blocks, T, smem, st>>>( a, plan, hz, rows );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_repitch_shared( const RepitchArgs & a, const RepitchPlan & plan, const float * hz, int64_t rows, int sms, cudaStream_t st )
+	{
+	if( a.B <= REPITCH_J * 256 ) return launch_repitch_shared_t<256>( a, plan, hz, rows, sms, st );
+	if( a.B <= REPITCH_J * 512 ) return launch_repitch_shared_t<512>( a, plan, hz, rows, sms, st );
+	return launch_repitch_shared_t<1024>( a, plan, hz, rows, sms, st );
+	}
+
+cudaError_t launch_stretch_plan( const StretchArgs & a, const StretchPlan & plan, cudaStream_t st )
+	{
+	pv_stretch_plan_kernel<<<(unsigned)( ( a.F + 127 ) / 128 ), 128, 0, st>>>( a, plan );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, int C, cudaStream_t st )
+	{
+	const int bin_tiles = ( a.B + 127 ) / 128;
+	const int64_t blocks = a.chunks * bin_tiles;
+	if( blocks > 0x7fffffff ) return cudaErrorInvalidValue;
+	pv_stretch_planned_kernel<<<dim3( (unsigned) blocks, C ), 128, 0, st>>>( a, plan, bin_tiles );
+	return cudaGetLastError();
+	}
+
 cudaError_t launch_bin_prefix( const Table & factor, int64_t rows, int B, float sample_rate, float dft, float * out, cudaStream_t st )
 	{
 	const int64_t blocks = ( rows + 255 ) / 256;
@@ -112,11 +244,12 @@ cudaError_t launch_bin_prefix( const Table & factor, int64_t rows, int B, float 
 	return cudaGetLastError();
 	}
 
-cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * out, MapCheck * check, cudaStream_t st )
+cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * raw_scratch, float * out, int sms, cudaStream_t st )
 	{
-	cudaError_t e = cudaMemsetAsync( check, 0, sizeof( MapCheck ), st );
-	if( e != cudaSuccess ) return e;
-	pv_frame_prefix_kernel<<<( cols + 63 ) / 64, 64, 0, st>>>( factor, F, cols, rate, out, check );
+	pv_frame_prefix_kernel<<<( cols + 63 ) / 64, 64, 0, st>>>( factor, F, cols, raw_scratch );
+	int64_t blocks = ( F * cols + 255 ) / 256;
+	if( blocks > (int64_t) sms * 8 ) blocks = (int64_t) sms * 8;
+	pv_frame_convert_kernel<<<(unsigned) blocks, 256, 0, st>>>( raw_scratch, out, F * cols, rate );
 	return cudaGetLastError();
 	}
 
@@ -131,13 +264,13 @@ cudaError_t launch_map_check( const Table & mod, int64_t F, int cols, MapCheck *
 	return cudaGetLastError();
 	}
 
-cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, cudaStream_t st )
+cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, const int * skip_if, cudaStream_t st )
 	{
 	const size_t smem = RepitchRow::bytes( a.B );
 	cudaError_t e = cudaFuncSetAttribute( pv_repitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	const int64_t blocks = rows < 0x7fffffff ? rows : 0x7fffffff;
-	pv_repitch_kernel<<<(unsigned) blocks, 256, smem, st>>>( a, rows );
+	pv_repitch_kernel<<<(unsigned) blocks, 256, smem, st>>>( a, rows, skip_if );
 	return cudaGetLastError();
 	}
 

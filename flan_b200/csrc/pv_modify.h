@@ -10,9 +10,16 @@ namespace pvm {
 struct MapCheck { unsigned int max_key; int descends; };
 
 cudaError_t launch_bin_prefix( const Table & factor, int64_t rows, int B, float sample_rate, float dft, float * out, cudaStream_t st );
-cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * out, MapCheck * check, cudaStream_t st );
+cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * raw_scratch, float * out, int sms, cudaStream_t st );
 cudaError_t launch_map_check( const Table & mod, int64_t F, int cols, MapCheck * check, int sms, cudaStream_t st );
-cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, cudaStream_t st );
+// skip_if (may be null): device flag; the general row kernel returns at once when it is non-zero (the plan is valid and
+// the gather kernel does the rows), the gather kernel when it is zero.
+cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, const int * skip_if, cudaStream_t st );
+bool repitch_shared_supported( int B );
+cudaError_t launch_repitch_plan( const float * hz, int B, float bin_width, int interp, const RepitchPlan & plan, cudaStream_t st );
+cudaError_t launch_repitch_shared( const RepitchArgs & a, const RepitchPlan & plan, const float * hz, int64_t rows, int sms, cudaStream_t st );
+cudaError_t launch_stretch_plan( const StretchArgs & a, const StretchPlan & plan, cudaStream_t st );
+cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, int C, cudaStream_t st );
 cudaError_t launch_stretch_parallel( const StretchArgs & a, int C, cudaStream_t st );
 cudaError_t launch_stretch_sequential( const StretchArgs & a, int C, cudaStream_t st );
 

@@ -192,6 +192,82 @@ PVM_HD void repitch_store( const RepitchArgs & a, int64_t row, int tid, int nt, 
 	}
 
 // ------------------------------------------------------------------------------------------------
+// repitch, frame-shared table (a constant or frequency-only factor): the mapped positions, hence every pair's output
+// range and every output bin's mix value, are the same for all rows. A one-CTA plan kernel evaluates them once; when
+// the positions are monotone each output bin has at most ONE source pair and the row kernel becomes a gather:
+//     out[y] = select( (1-mix[y]) * m[p-1] < mix[y] * m[p] ) ...   with p = src[y]
+// which is exactly what the reference's walk leaves in a zero-initialised row (PVModify.cpp:232-243 with outMF = 0).
+// ------------------------------------------------------------------------------------------------
+struct RepitchPlan
+	{
+	int * src;                  // [B] upper bin of the pair that covers output bin y; 0 = none
+	float * mix;                // [B] interp( ( y - loBin ) / ( hiBin - loBin ) ) of that pair
+	int * ok;                   // 1: plan valid (monotone positions); 0: rows must take the general kernel
+	};
+
+// Plan phases (one CTA; `pos` is a B-float scratch in shared memory).
+PVM_HD int repitch_plan_positions( const float * hz, int B, float bin_width, int tid, int nt, float * pos, const RepitchPlan & plan )
+	{
+	for( int b = tid; b < B; b += nt ) { pos[b] = hz[b] / bin_width; plan.src[b] = 0; plan.mix[b] = 0.0f; }
+	return 0;
+	}
+PVM_HD int repitch_plan_flags( int B, int tid, int nt, const float * pos )
+	{
+	int flags = 0;
+	for( int b = 1 + tid; b < B; b += nt )
+		{
+		const float lo = pos[b - 1], hi = pos[b];
+		if( !( hi >= lo ) ) flags |= 1;
+		if( !( hi <= lo ) ) flags |= 2;
+		}
+	return flags;
+	}
+PVM_HD void repitch_plan_pairs( int B, int interp, int flags, int tid, int nt, const float * pos, const RepitchPlan & plan )
+	{
+	if( tid == 0 ) *plan.ok = flags != 3;
+	if( flags == 3 ) return;
+	for( int bin = 1 + tid; bin < B; bin += nt )
+		{
+		const float loBin = pos[bin - 1], hiBin = pos[bin];
+		const bool forward = hiBin > loBin;
+		const int start = clampi( to_int( forward ? ceilf( loBin ) : floorf( loBin ) ), 0, B - 1 );
+		const int end = clampi( to_int( forward ? ceilf( hiBin ) : floorf( hiBin ) ), 0, B - 1 );
+		if( forward ? start >= end : start <= end ) continue;
+		const float den = hiBin - loBin;
+		const int step = forward ? 1 : -1;
+		for( int y = start; y != end; y += step )
+			{
+			plan.src[y] = bin;
+			plan.mix[y] = interp_eval( interp, ( (float) y - loBin ) / den );
+			}
+		}
+	}
+
+// Row phases of the gather kernel. m / fm: shared-memory rows of B floats (double-buffered by the caller).
+PVM_HD float repitch_lerp( const float * hz, int B, float bin_width, float f )
+	{
+	const float top = (float)( B - 1 ) - 0.0001f;
+	float fbin = f / bin_width;
+	fbin = fbin < 0.0f ? 0.0f : ( top < fbin ? top : fbin );
+	const int lo = clampi( to_int( floorf( fbin ) ), 0, B - 2 );
+	const float r = fbin - (float) lo;
+	return hz[lo] * ( 1.0f - r ) + hz[lo + 1] * r;
+	}
+PVM_HD float2 repitch_gather( int y, const int * src, const float * mix, const float * m, const float * fm )
+	{
+	const int p = src[y];
+	if( p == 0 ) return make_float2( 0.0f, 0.0f );
+	const float mx = mix[y];
+	const float lo_m = m[p - 1], hi_m = m[p];
+	const float w0 = ( 1.0f - mx ) * lo_m;
+	const float w1 = mx * hi_m;
+	const bool lo_wins = w0 < w1;
+	const float mm = lo_wins ? lo_m : hi_m;
+	if( !( mm > 0.0f ) ) return make_float2( 0.0f, 0.0f );
+	return make_float2( 0.0f + mm, lo_wins ? fm[p - 1] : fm[p] );
+	}
+
+// ------------------------------------------------------------------------------------------------
 // Table preparation
 // ------------------------------------------------------------------------------------------------
 // PV::repitch: running sum of the factor along bins, then bin_to_frequency (PVModify.cpp:278-284). One thread per row.
@@ -227,26 +303,28 @@ PVM_HD float key_float( uint32_t k )
 #endif
 	}
 
-// PV::stretch: running sum of the factor along frames, then frame_to_time (PVModify.cpp:376-382). One thread per
-// column; returns the column maximum (in seconds) and whether it ever descends.
-PVM_HD void frame_prefix_column( const Table & factor, int col, int64_t F, int cols, float rate, float * out, float & mx, bool & descends )
+// PV::stretch: running sum of the factor along frames (PVModify.cpp:376-378) -- the one inherently sequential step
+// (float addition does not re-associate): one thread per column, nothing but the add and a store in its loop.
+PVM_HD void frame_prefix_column( const Table & factor, int col, int64_t F, int cols, float * out )
 	{
-	float acc = 0.0f, prev = 0.0f;
-	mx = 0.0f; descends = false;
-	for( int64_t f = 0; f < F; ++f )
+	float acc = 0.0f;
+	constexpr int U = 16;       // loads of a batch are issued together, ahead of the dependent chain of adds
+	for( int64_t f = 0; f < F; f += U )
 		{
-		const float v = factor.at( f, col );
-		acc = f == 0 ? v : v + acc;
-		const float sec = acc / rate;                                   // PVBuffer.cpp:433-436
-		out[f * cols + col] = sec;
-		if( f == 0 ) mx = sec;
-		else
-			{
-			if( mx < sec ) mx = sec;                                    // std::max_element
-			if( !( sec >= prev ) ) descends = true;
-			}
-		prev = sec;
+		float v[U];
+#pragma unroll
+		for( int j = 0; j < U; ++j ) if( f + j < F ) v[j] = factor.at( f + j, col );
+#pragma unroll
+		for( int j = 0; j < U; ++j )
+			if( f + j < F ) { acc = ( f + j == 0 ) ? v[j] : v[j] + acc; v[j] = acc; }
+#pragma unroll
+		for( int j = 0; j < U; ++j ) if( f + j < F ) out[( f + j ) * cols + col] = v[j];
 		}
+	}
+// ... then frame_to_time (PVModify.cpp:381-382, PVBuffer.cpp:433-436) element-wise, raw sums -> seconds.
+PVM_HD void frame_prefix_convert( const float * raw, float * out, int64_t i, float rate )
+	{
+	out[i] = raw[i] / rate;
 	}
 
 // ------------------------------------------------------------------------------------------------
@@ -361,6 +439,84 @@ PVM_HD void stretch_chunk( const StretchArgs & a, int c, int64_t chunk_index, in
 		if( tail < 0 ) tail = 0;
 		for( int64_t x = tail; x < a.out_frames; ++x ) out_col[x * a.B] = make_float2( 0.0f, 0.0f );
 		}
+	}
+
+// Bin-shared time map (a constant or time-only factor), never descending: the pair geometry is the same for every
+// bin, so it is evaluated once by a plan kernel -- xpos[f] = first output frame at or after frame f's mapped position,
+// clamped to [0, out_frames]; pair (f-1, f) covers [xpos[f-1], xpos[f]) -- together with mix[x] of every covered
+// output frame. The chunk kernel then only does the per-bin arithmetic of PVModify.cpp:346-355.
+struct StretchPlan
+	{
+	int * xpos;                 // [F]
+	float * mix;                // [out_frames]
+	};
+
+PVM_HD void stretch_plan_frame( const StretchArgs & a, const StretchPlan & plan, int64_t f )
+	{
+	const float pos = time_to_frame( a, a.mod.at( f, 0 ) );
+	int64_t x = to_int( ceilf( pos ) );
+	x = x < 0 ? 0 : ( x > a.out_frames ? a.out_frames : x );
+	plan.xpos[f] = (int) x;
+	if( f == 0 ) return;
+	const float lFrame = time_to_frame( a, a.mod.at( f - 1, 0 ) );
+	if( !( pos > lFrame ) ) return;
+	int64_t xs = to_int( ceilf( lFrame ) );
+	xs = xs < 0 ? 0 : xs;
+	const float den = pos - lFrame;
+	for( ; xs < x; ++xs ) plan.mix[xs] = interp_eval( a.interp, ( (float) xs - lFrame ) / den );
+	}
+
+PVM_HD void stretch_chunk_planned( const StretchArgs & a, const StretchPlan & plan, int c, int64_t chunk_index, int bin )
+	{
+	const float2 * in = a.pv + (int64_t) c * a.F * a.B + bin;
+	float2 * out_col = a.out + (int64_t) c * a.out_frames * a.B + bin;
+	const int64_t f0 = chunk_index * a.chunk;
+	int64_t f1 = f0 + a.chunk;
+	if( f1 > a.F - 1 ) f1 = a.F - 1;
+	float2 l = in[f0 * a.B];
+	int x = plan.xpos[f0];
+	if( chunk_index == 0 )
+		for( int64_t z = 0; z < x; ++z ) out_col[z * a.B] = make_float2( 0.0f, 0.0f );
+	constexpr int BATCH = 8;
+	for( int64_t f = f0; f < f1; f += BATCH )
+		{
+		float2 r[BATCH]; int xe[BATCH];
+#pragma unroll
+		for( int j = 0; j < BATCH; ++j )
+			if( f + 1 + j <= f1 )
+				{
+				r[j] = in[( f + 1 + j ) * a.B];
+				xe[j] = plan.xpos[f + 1 + j];
+				}
+#pragma unroll
+		for( int j = 0; j < BATCH; ++j )
+			if( f + 1 + j <= f1 )
+				{
+				bool live = true;
+				for( ; x < xe[j]; ++x )
+					{
+					float2 nw = make_float2( 0.0f, 0.0f );
+					if( live )
+						{
+						const float mix = plan.mix[x];
+						const float w0 = ( 1.0f - mix ) * l.x;
+						const float w1 = mix * r[j].x;
+						const float totalWeight = w0 + w1;
+						const float weightedFreqSum = w0 * l.y + w1 * r[j].y;
+						if( totalWeight == 0.0f ) live = false;
+						else
+							{
+							nw.y = ( 0.0f * 0.0f + weightedFreqSum ) / ( 0.0f + totalWeight );
+							nw.x = 0.0f + totalWeight;
+							}
+						}
+					out_col[(int64_t) x * a.B] = nw;
+					}
+				l = r[j];
+				}
+		}
+	if( chunk_index == a.chunks - 1 )
+		for( int64_t z = x; z < a.out_frames; ++z ) out_col[z * a.B] = make_float2( 0.0f, 0.0f );
 	}
 
 // Sequential form (the reference's walk): thread = (channel, bin); the output was cleared beforehand.

@@ -58,4 +58,54 @@ int api_cancelled_is_null( void )
 	return pv.is_null() ? 1 : 0;
 	}
 
+
+// BASELINE config 4's chain the way user code writes it (the reference's tests/flanTest.cpp:39-44):
+//     audio.convert_to_PV( W, hop, N ).repitch( ... ).stretch( ... ).convert_to_audio()
+// kind 0: constants (repitch 1.5, stretch 2), 1: lambdas of time / frequency. pv_out (may be null) receives the PV after
+// both PV-domain steps, audio_out the resynthesis. Returns output samples per channel, or -1 on a null result.
+int api_chain( const float * audio, int C, int n, float sr, int W, int hop, int N, int kind, int interp,
+               float * pv_out, int * pv_frames, float * audio_out )
+	{
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	PV pv = a.convert_to_PV( W, hop, N );
+	if( pv.is_null() ) return -1;
+	auto make_interp = [interp]
+		{
+		switch( interp )
+			{
+			case 5: return Interpolator::smoothstep();
+			case 2: return Interpolator::nearest();
+			default: return Interpolator::linear();
+			}
+		};
+	PV shaped = kind == 0
+		? pv.repitch( 1.5f, make_interp() ).stretch( 2.0f, make_interp() )
+		: pv.repitch( []( TF tf ) { return 0.75f + 0.5f * tf.t; }, make_interp() )
+		    .stretch( []( TF tf ) { return 1.0f + tf.f / 24000.0f; }, make_interp() );
+	if( shaped.is_null() ) return -1;
+	*pv_frames = shaped.get_num_frames();
+	if( pv_out ) std::memcpy( pv_out, shaped.get_buffer().data(), sizeof( MF ) * shaped.get_buffer().size() );
+	Audio out = shaped.convert_to_audio();
+	if( out.is_null() ) return -1;
+	if( audio_out ) std::memcpy( audio_out, out.get_buffer().data(), sizeof( float ) * out.get_buffer().size() );
+	return out.get_num_frames();
+	}
+
+// modify_time / modify_frequency with lambdas; a user-callable Interpolator has no device form -> null PV.
+int api_modify_maps( const float * audio, int C, int n, float sr, int W, int hop, int N, float * pv_time_out, int * time_frames,
+                     float * pv_freq_out )
+	{
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	PV pv = a.convert_to_PV( W, hop, N );
+	if( pv.is_null() ) return -1;
+	PV t = pv.modify_time( []( TF tf ) { return tf.t * 1.25f + 0.01f; } );
+	PV f = pv.modify_frequency( []( TF tf ) { return tf.f * 0.8f + 30.0f; }, Interpolator::smoothstep() );
+	if( t.is_null() || f.is_null() ) return -1;
+	*time_frames = t.get_num_frames();
+	std::memcpy( pv_time_out, t.get_buffer().data(), sizeof( MF ) * t.get_buffer().size() );
+	std::memcpy( pv_freq_out, f.get_buffer().data(), sizeof( MF ) * f.get_buffer().size() );
+	PV custom = pv.repitch( 1.5f, Interpolator( []( float x ) { return x * x; } ) );
+	return custom.is_null() ? 1 : 0;
+	}
+
 }
