@@ -110,9 +110,19 @@ int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, flo
 		{
 		built.resize( (size_t) F * cols );
 		const Table fac{ factor, fs, bs };
-		std::vector<float> raw( (size_t) F * cols );
-		for( int col = 0; col < cols; ++col ) frame_prefix_column( fac, col, F, cols, raw.data() );
-		for( int64_t i = F * cols - 1; i >= 0; --i ) frame_prefix_convert( raw.data(), built.data(), i, sr / float( hop ) );
+		if( fs == 0 && bs == 0 )
+			{
+			std::vector<PrefixSeg> segs( PREFIX_MAX_SEGS );
+			const int ns = constant_prefix_segments( *factor, F, segs.data() );
+			if( ns > PREFIX_MAX_SEGS ) return -2;
+			for( int64_t k = F - 1; k >= 0; --k ) built[k] = constant_prefix_value( segs.data(), ns, *factor, k ) / ( sr / float( hop ) );
+			}
+		else
+			{
+			std::vector<float> raw( (size_t) F * cols );
+			for( int col = 0; col < cols; ++col ) frame_prefix_column( fac, col, F, cols, raw.data() );
+			for( int64_t i = F * cols - 1; i >= 0; --i ) frame_prefix_convert( raw.data(), built.data(), i, sr / float( hop ) );
+			}
 		mod = Table{ built.data(), (int64_t) cols, bs };
 		}
 	bool descends = false;
@@ -146,6 +156,29 @@ int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, flo
 			for( int b = 0; b < B; ++b ) stretch_column( a, c, b );
 		}
 	return out_frames;
+	}
+
+}
+
+extern "C" {
+
+// Closed-form running sum of a constant (constant_prefix_segments / constant_prefix_value) against the plain loop:
+// returns the number of mismatching elements; *segments receives the segment count.
+int64_t pv_emu_constant_prefix_mismatches( float c, int64_t F, int * segments )
+	{
+	std::vector<PrefixSeg> segs( PREFIX_MAX_SEGS );
+	const int ns = constant_prefix_segments( c, F, segs.data() );
+	if( segments ) *segments = ns;
+	if( ns > PREFIX_MAX_SEGS ) return -1;
+	int64_t bad = 0;
+	float acc = 0.0f;
+	for( int64_t k = 0; k < F; ++k )
+		{
+		acc = k == 0 ? c : c + acc;
+		const float got = constant_prefix_value( segs.data(), ns, c, k );
+		if( std::memcmp( &got, &acc, 4 ) != 0 && !( got != got && acc != acc ) ) ++bad;
+		}
+	return bad;
 	}
 
 }

@@ -700,10 +700,16 @@ int flan_b200_stretch_map( flan_b200_ctx * ctx, const float * d_factor, int64_t 
 	const int cols = factor_bin_stride ? B : 1;
 	const pvm::Table factor{ d_factor, factor_frame_stride, factor_bin_stride };
 	void * ws = nullptr;
-	int rc = get_workspace( ctx, sizeof( float ) * (size_t) F * cols, &ws );
+	const bool constant = factor_frame_stride == 0 && factor_bin_stride == 0;
+	int rc = get_workspace( ctx, constant ? pvm::constant_prefix_scratch_bytes() : sizeof( float ) * (size_t) F * cols, &ws );
 	if( rc ) return rc;
 	ctx->seg_key.valid = false;
-	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), (float *) ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" ); }
+	LaunchTimer lt( ctx, 7 );
+	if( constant )      // closed form per binade instead of F dependent additions
+		CK( pvm::launch_constant_prefix( d_factor, F, sr / float( hop ), ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" );
+	else
+		CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), (float *) ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" );
+	ctx->launches += 1;
 	return FLAN_B200_OK;
 	}
 

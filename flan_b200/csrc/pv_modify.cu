@@ -109,6 +109,23 @@ __global__ void __launch_bounds__( 128 ) pv_stretch_seq_kernel( const StretchArg
 	stretch_column( a, blockIdx.y, bin );
 	}
 
+// ---- constant factor: closed-form running sum (see constant_prefix_segments) ---------------------------------------
+__global__ void pv_constant_prefix_kernel( const float * factor, int64_t F, PrefixSeg * segs, int * count )
+	{
+	*count = constant_prefix_segments( *factor, F, segs );
+	}
+
+__global__ void pv_constant_fill_kernel( const float * factor, int64_t F, const PrefixSeg * segs, const int * count, float rate, float * out )
+	{
+	__shared__ PrefixSeg s_segs[PREFIX_MAX_SEGS];
+	const int ns = *count < PREFIX_MAX_SEGS ? *count : PREFIX_MAX_SEGS;
+	for( int i = threadIdx.x; i < ns; i += blockDim.x ) s_segs[i] = segs[i];
+	__syncthreads();
+	const float c = *factor;
+	for( int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; k < F; k += (int64_t) gridDim.x * blockDim.x )
+		out[k] = constant_prefix_value( s_segs, ns, c, k ) / rate;      // frame_to_time, PVBuffer.cpp:433-436
+	}
+
 // ---- frame-shared repitch: plan + gather ------------------------------------------------------------------------
 __global__ void __launch_bounds__( 1024 ) pv_repitch_plan_kernel( const float * hz, int B, float bin_width, int interp, const RepitchPlan plan )
 	{
@@ -250,6 +267,17 @@ cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, floa
 	int64_t blocks = ( F * cols + 255 ) / 256;
 	if( blocks > (int64_t) sms * 8 ) blocks = (int64_t) sms * 8;
 	pv_frame_convert_kernel<<<(unsigned) blocks, 256, 0, st>>>( raw_scratch, out, F * cols, rate );
+	return cudaGetLastError();
+	}
+
+cudaError_t launch_constant_prefix( const float * factor, int64_t F, float rate, void * scratch, float * out, int sms, cudaStream_t st )
+	{
+	PrefixSeg * segs = (PrefixSeg *) scratch;
+	int * count = (int *)( segs + PREFIX_MAX_SEGS );
+	pv_constant_prefix_kernel<<<1, 1, 0, st>>>( factor, F, segs, count );
+	int64_t blocks = ( F + 255 ) / 256;
+	if( blocks > (int64_t) sms * 4 ) blocks = (int64_t) sms * 4;
+	pv_constant_fill_kernel<<<(unsigned) blocks, 256, 0, st>>>( factor, F, segs, count, rate, out );
 	return cudaGetLastError();
 	}
 

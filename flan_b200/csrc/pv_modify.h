@@ -11,6 +11,9 @@ struct MapCheck { unsigned int max_key; int descends; };
 
 cudaError_t launch_bin_prefix( const Table & factor, int64_t rows, int B, float sample_rate, float dft, float * out, cudaStream_t st );
 cudaError_t launch_frame_prefix( const Table & factor, int64_t F, int cols, float rate, float * raw_scratch, float * out, int sms, cudaStream_t st );
+// Constant factor (strides (0,0)): closed-form running sum. scratch: constant_prefix_scratch_bytes() of device memory.
+inline size_t constant_prefix_scratch_bytes() { return sizeof( PrefixSeg ) * PREFIX_MAX_SEGS + 256; }
+cudaError_t launch_constant_prefix( const float * factor, int64_t F, float rate, void * scratch, float * out, int sms, cudaStream_t st );
 cudaError_t launch_map_check( const Table & mod, int64_t F, int cols, MapCheck * check, int sms, cudaStream_t st );
 // skip_if (may be null): device flag; the general row kernel returns at once when it is non-zero (the plan is valid and
 // the gather kernel does the rows), the gather kernel when it is zero.

@@ -307,20 +307,106 @@ PVM_HD float key_float( uint32_t k )
 // (float addition does not re-associate): one thread per column, nothing but the add and a store in its loop.
 PVM_HD void frame_prefix_column( const Table & factor, int col, int64_t F, int cols, float * out )
 	{
+	const float * src = factor.p + (int64_t) col * factor.bin_stride;
+	float * dst = out + col;
 	float acc = 0.0f;
-	constexpr int U = 16;       // loads of a batch are issued together, ahead of the dependent chain of adds
-	for( int64_t f = 0; f < F; f += U )
+	constexpr int U = 16;       // the loads of a batch are issued together, ahead of the dependent chain of adds
+	int64_t f = 0;
+	for( ; f + U <= F; f += U )
 		{
 		float v[U];
 #pragma unroll
-		for( int j = 0; j < U; ++j ) if( f + j < F ) v[j] = factor.at( f + j, col );
+		for( int j = 0; j < U; ++j ) v[j] = src[j * factor.frame_stride];
 #pragma unroll
-		for( int j = 0; j < U; ++j )
-			if( f + j < F ) { acc = ( f + j == 0 ) ? v[j] : v[j] + acc; v[j] = acc; }
+		for( int j = 0; j < U; ++j ) { acc = ( f + j == 0 ) ? v[j] : v[j] + acc; v[j] = acc; }
 #pragma unroll
-		for( int j = 0; j < U; ++j ) if( f + j < F ) out[( f + j ) * cols + col] = v[j];
+		for( int j = 0; j < U; ++j ) dst[(int64_t) j * cols] = v[j];
+		src += U * factor.frame_stride; dst += (int64_t) U * cols;
+		}
+	for( ; f < F; ++f, src += factor.frame_stride, dst += cols )
+		{
+		acc = f == 0 ? *src : *src + acc;
+		*dst = acc;
 		}
 	}
+
+// Constant factor: acc[k] = fl( acc[k-1] + c ) has a closed form per binade. Inside [2^e, 2^(e+1)) every value is a
+// multiple of u = ulp, so fl( x + c ) = x + u * round( c / u ) with the SAME increment for every x -- except that an
+// exact tie ( c / u = n + 1/2 ) rounds to even and the first step in the binade may differ by one ulp, after which the
+// parity, hence the increment, is fixed. So: take real float steps until two consecutive increments inside one binade
+// agree, then jump to the end of the binade in one go. A few steps per binade instead of F dependent additions; the
+// values are then filled in parallel from the segment list, bit-identical to the sequential sum.
+struct PrefixSeg { int64_t k0; int64_t n; double a0; double d; };      // acc[k0 + i] = float( a0 + i * d ), 0 <= i < n
+constexpr int PREFIX_MAX_SEGS = 1024;
+
+PVM_HD uint32_t float_bits( float f )
+	{
+#if defined( __CUDA_ARCH__ )
+	return __float_as_uint( f );
+#else
+	union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+	}
+PVM_HD int exponent_field( float x ) { return (int)( ( float_bits( x ) >> 23 ) & 0xffu ); }
+
+// Single thread. Segments describe |acc|; the fill applies the sign of c. Returns the segment count.
+PVM_HD int constant_prefix_segments( float c, int64_t F, PrefixSeg * segs )
+	{
+	const float a = fabsf( c );
+	int ns = 0;
+	auto emit = [&]( int64_t k0, int64_t n, double a0, double d ) { if( ns < PREFIX_MAX_SEGS ) segs[ns] = PrefixSeg{ k0, n, a0, d }; ++ns; };
+	if( F < 1 ) return 0;
+	emit( 0, 1, a, 0.0 );
+	int64_t k = 0;                  // last index produced
+	float x0 = a;                   // its value
+	while( k < F - 1 )
+		{
+		if( !( x0 < INFINITY ) || ns >= PREFIX_MAX_SEGS - 2 )      // inf / NaN are absorbing; segment budget: finish sequentially in spirit
+			{
+			if( !( x0 < INFINITY ) ) { emit( k + 1, F - 1 - k, x0 + a, 0.0 ); return ns; }
+			}
+		const float x1 = x0 + a, x2 = x1 + a;
+		const int e = exponent_field( x0 );
+		const double d01 = (double) x1 - (double) x0, d12 = (double) x2 - (double) x1;
+		if( e != 0xff && exponent_field( x1 ) == e && exponent_field( x2 ) == e && d01 == d12 )
+			{
+			int64_t cnt;                                           // values x1, x1 + d, ... produced by this run
+			if( d12 == 0.0 ) cnt = F - 1 - k;
+			else
+				{
+				const double u = ldexp( 1.0, ( e ? e : 1 ) - 150 );    // ulp of the binade (denormals share 2^-149)
+				const double top = ldexp( 1.0, ( e ? e : 1 ) - 126 );
+				const int64_t steps = (int64_t) floor( ( top - u - (double) x1 ) / d12 );     // valid steps from x1
+				cnt = steps + 1;
+				if( cnt > F - 1 - k ) cnt = F - 1 - k;
+				}
+			emit( k + 1, cnt, (double) x1, d12 );
+			k += cnt;
+			x0 = (float)( (double) x1 + (double)( cnt - 1 ) * d12 );
+			}
+		else
+			{
+			emit( k + 1, 1, (double) x1, 0.0 );
+			k += 1;
+			x0 = x1;
+			}
+		}
+	return ns;
+	}
+
+// Value at index k from the segment list (binary search), with the sign of c.
+PVM_HD float constant_prefix_value( const PrefixSeg * segs, int ns, float c, int64_t k )
+	{
+	int lo = 0, hi = ns - 1;
+	while( lo < hi )
+		{
+		const int mid = ( lo + hi + 1 ) >> 1;
+		if( segs[mid].k0 <= k ) lo = mid; else hi = mid - 1;
+		}
+	const float v = (float)( segs[lo].a0 + (double)( k - segs[lo].k0 ) * segs[lo].d );
+	return c < 0.0f ? -v : v;
+	}
+
 // ... then frame_to_time (PVModify.cpp:381-382, PVBuffer.cpp:433-436) element-wise, raw sums -> seconds.
 PVM_HD void frame_prefix_convert( const float * raw, float * out, int64_t i, float rate )
 	{

@@ -137,3 +137,24 @@ def test_sine_interpolators_within_an_ulp(oracle, emu, pv_case):
         assert got.shape == want.shape
         assert np.allclose(got, want, rtol=3e-6, atol=1e-9)
         assert np.mean(bits(got) == bits(want)) > 0.95
+
+
+def test_constant_running_sum_closed_form_is_exact():
+    # constant_prefix_segments / constant_prefix_value against the plain sequential float32 loop (PVModify.cpp:376-378
+    # with a constant factor), including exact-tie increments, denormals, overflow to inf and negative constants.
+    import ctypes
+    from emu_lib import Emu
+    L = Emu().L
+    L.pv_emu_constant_prefix_mismatches.restype = ctypes.c_int64
+    L.pv_emu_constant_prefix_mismatches.argtypes = [ctypes.c_float, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    rng = np.random.default_rng(0)
+    vals = [2.0, 1.5, 1.0, 0.1, 1 / 3, 1e-3, 1e-10, 1e10, 0.0, -1.5, -0.1, 1e-40, 3e-39, float("inf"), 1.0000001, 16777216.0, 1e30, 3e38]
+    vals += [1 + 2 ** -23, 3 * 2 ** -24, 5 * 2 ** -25, 1.5 * 2 ** -20, (2 ** 24 - 1) * 2.0 ** -24, 0.5 + 2 ** -24]
+    vals += list(rng.uniform(0, 4, 20).astype(np.float32)) + list(np.exp(rng.uniform(-30, 30, 20)).astype(np.float32))
+    worst = 0
+    for c in vals:
+        for F in (1, 2, 3, 100, 300007):
+            ns = ctypes.c_int(0)
+            assert L.pv_emu_constant_prefix_mismatches(c, F, ctypes.byref(ns)) == 0, (c, F)
+            worst = max(worst, ns.value)
+    assert worst < 512
