@@ -43,9 +43,9 @@ def build_library(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     # (source, extra flags): the PV-domain kernels must reproduce the reference's float arithmetic bit for bit, so
     # their translation unit is compiled without FMA contraction.
-    units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_modify.cu", ["-fmad=false"])]
+    units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_modify.cu", ["-fmad=false"]), ("pv_io.cu", ["-fmad=false"])]
     srcs = _sources(*[u for u, _ in units])
-    deps = srcs + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_launch.h", "pv_modify.h", "pv_modify_body.cuh") + \
+    deps = srcs + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_launch.h", "pv_modify.h", "pv_modify_body.cuh", "pv_io.h") + \
         [os.path.join(os.path.dirname(HERE), "include", "flan_b200.h")]
     if not force and not _newer(lib_path(), deps):
         return lib_path()

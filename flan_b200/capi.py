@@ -46,6 +46,17 @@ SYMBOLS = [
     ("flan_b200_stretch_map", _int, [_vp, _vp, _i64, _int, _i64, _int, _f, _f, _vp]),
     ("flan_b200_modify_time_frames", _int, [_vp, _vp, _i64, _int, _i64, _int, _f, _f, ctypes.POINTER(_i64)]),
     ("flan_b200_modify_time", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _vp, _i64, _int, _int, _i64, _vp]),
+    ("flan_b200_flan_encode", _int, [_vp, _vp, _i64, _f, _f, _vp]),
+    ("flan_b200_flan_decode", _int, [_vp, _vp, _i64, _f, _f, _vp]),
+    ("flan_b200_save_flan", _int, [_vp, ctypes.c_char_p, _vp, _int, _i64, _int, _f, _f, _int]),
+    ("flan_b200_flan_info", _int, [_vp, ctypes.c_char_p, ctypes.POINTER(_int), ctypes.POINTER(_i64), ctypes.POINTER(_int),
+                                   ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_int)]),
+    ("flan_b200_load_flan", _int, [_vp, ctypes.c_char_p, _vp, _i64]),
+    ("flan_b200_pcm24_encode", _int, [_vp, _vp, _int, _i64, _vp]),
+    ("flan_b200_pcm24_decode", _int, [_vp, _vp, _int, _i64, _vp]),
+    ("flan_b200_save_wav", _int, [_vp, ctypes.c_char_p, _vp, _int, _i64, _f]),
+    ("flan_b200_wav_info", _int, [_vp, ctypes.c_char_p, ctypes.POINTER(_int), ctypes.POINTER(_i64), ctypes.POINTER(_f)]),
+    ("flan_b200_load_wav", _int, [_vp, ctypes.c_char_p, _vp, _i64]),
     ("flan_b200_convert_to_pv_host", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _int, _vp, _vp]),
     ("flan_b200_convert_to_audio_host", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _int, _vp, _vp, ctypes.POINTER(_int)]),
 ]

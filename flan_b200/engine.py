@@ -43,7 +43,7 @@ class Engine:
         return int(self.lib.flan_b200_launch_count(self.ctx.h))
 
     KERNEL_KINDS = {"analysis": 0, "phase_seg": 1, "phase_scan": 2, "synthesis": 3, "aux": 4,
-                    "repitch": 5, "stretch": 6, "modify_tables": 7}
+                    "repitch": 5, "stretch": 6, "modify_tables": 7, "io_codec": 8}
 
     def set_timing(self, enabled):
         self.ctx.call("flan_b200_set_timing", int(enabled))
@@ -199,6 +199,64 @@ class Engine:
     def stretch(self, pv, sr, ar, factor, interp=0):
         C, F, B, _ = pv.shape
         return self.modify_time(pv, sr, ar, self.stretch_map(F, B, sr, ar, factor), interp)
+
+    # -- file formats either side of the path (PVBuffer::save / load, AudioBuffer::save / load) -----------------
+    def flan_encode(self, pv, sr):
+        C, F, B, _ = pv.shape
+        out = torch.empty((C * F * B * 6,), dtype=torch.uint8, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_flan_encode", self._chk(pv), C * F * B, float((B - 1) * 2), sr, self._chk(out, torch.uint8))
+        return out
+
+    def flan_decode(self, data, shape, sr):
+        C, F, B = shape
+        out = torch.empty((C, F, B, 2), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_flan_decode", self._chk(data, torch.uint8), C * F * B, float((B - 1) * 2), sr, self._chk(out))
+        return out
+
+    def save_flan(self, path, pv, sr, ar, W):
+        C, F, B, _ = pv.shape
+        self._bind_stream()
+        self.ctx.call("flan_b200_save_flan", path.encode(), self._chk(pv), C, F, B, sr, ar, W)
+
+    def load_flan(self, path):
+        """Returns (pv, sample_rate, rate_field, window_size); rate_field is what the reference's load stores as the
+        analysis rate (the hop that save wrote, PVBuffer.cpp:134 vs :245)."""
+        C, F, B, W = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+        sr, rf = ctypes.c_float(), ctypes.c_float()
+        self.ctx.call("flan_b200_flan_info", path.encode(), ctypes.byref(C), ctypes.byref(F), ctypes.byref(B),
+                      ctypes.byref(sr), ctypes.byref(rf), ctypes.byref(W))
+        pv = torch.empty((C.value, F.value, B.value, 2), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_load_flan", path.encode(), self._chk(pv), pv.numel() // 2)
+        return pv, sr.value, rf.value, W.value
+
+    def pcm24_encode(self, audio):
+        C, n = audio.shape
+        out = torch.empty((C * n * 3,), dtype=torch.uint8, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_pcm24_encode", self._chk(audio), C, n, self._chk(out, torch.uint8))
+        return out
+
+    def pcm24_decode(self, data, C, n):
+        out = torch.empty((C, n), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_pcm24_decode", self._chk(data, torch.uint8), C, n, self._chk(out))
+        return out
+
+    def save_wav(self, path, audio, sr):
+        C, n = audio.shape
+        self._bind_stream()
+        self.ctx.call("flan_b200_save_wav", path.encode(), self._chk(audio), C, n, sr)
+
+    def load_wav(self, path):
+        C, n, sr = ctypes.c_int(), ctypes.c_int64(), ctypes.c_float()
+        self.ctx.call("flan_b200_wav_info", path.encode(), ctypes.byref(C), ctypes.byref(n), ctypes.byref(sr))
+        audio = torch.empty((C.value, n.value), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_load_wav", path.encode(), self._chk(audio), audio.numel())
+        return audio, sr.value
 
     # -- host-buffer forms (the call the reference-facing C++ layer makes) -------------------------
     def convert_to_pv_host(self, audio_np, sr, W, hop, N, mid_side=False, out=None):

@@ -1,10 +1,12 @@
 // flan::AudioBuffer of the B200 build: the reference's public surface (src/flan/Audio/AudioBuffer.h:20-228) for
 // everything on the phase-vocoder path, over device-resident storage (flan/b200_storage.h). Layout contract:
 // planar, channel-major, pos = channel * num_frames + frame (AudioBuffer.cpp:479-482) -- computed in 64 bits here.
-// File I/O (libsndfile load/save, AudioBuffer.cpp:80-192) is outside the scope of this build.
+// File I/O: 24-bit PCM WAV, the reference's default save format (AudioBuffer.cpp:136), with the sample conversion and the
+// (de)interleave on the GPU; libsndfile's other formats and its metadata strings are outside the scope of this build.
 #pragma once
 
 #include <iosfwd>
+#include <string>
 #include <vector>
 
 #include "flan/defines.h"
@@ -59,6 +61,12 @@ public:
 	size_t get_buffer_pos( Channel, Frame ) const;
 
 	// B200 build: device-side view for the conversion entry points (not part of the reference's surface)
+	/** Load a 24-bit PCM WAV file (reference AudioBuffer::load, AudioBuffer.cpp:80-128). false + message on failure. */
+	bool load( const std::string & filename );
+	/** Save as 24-bit PCM WAV, samples clamped to [-1,1] (reference AudioBuffer::save with its default format,
+	 *  AudioBuffer.cpp:130-170). Any other \param format prints a message and returns false. */
+	bool save( const std::string & filename, int format = -1 ) const;
+
 	const b200::Mirror<Sample> & storage() const { return buffer; }
 	static AudioBuffer from_device_result( const Format & format, b200::Mirror<Sample> && data );
 

@@ -1,11 +1,12 @@
 // flan::PVBuffer of the B200 build: the reference's public surface (src/flan/PV/PVBuffer.h:27-288) for everything on
 // the phase-vocoder path, over device-resident storage. Layout contract: channel -> frame -> bin,
 // pos = c * F * B + f * B + b (PVBuffer.cpp:526-529) -- computed in 64 bits here (the reference's int32 product
-// overflows beyond 2^31 elements, which BASELINE configs 3 and 4 exceed). The .flan RIFF load/save
-// (PVBuffer.cpp:99-140,216-273) is outside the scope of this build.
+// overflows beyond 2^31 elements, which BASELINE configs 3 and 4 exceed). The .flan RIFF load / save
+// (PVBuffer.cpp:99-140,216-273) quantise / dequantise on the GPU and write the reference's bytes.
 #pragma once
 
 #include <iosfwd>
+#include <string>
 #include <vector>
 
 #include "flan/defines.h"
@@ -75,6 +76,12 @@ public:
 	std::vector<MF>::const_iterator channel_begin( Channel channel ) const;
 	std::vector<MF>::const_iterator channel_end( Channel channel ) const;
 	size_t get_buffer_pos( Channel, Frame, Bin ) const;
+
+	/** Load a .flan RIFF-PV file (reference PVBuffer::load, PVBuffer.cpp:216-273; format PVBuffer.h:84-115). As in the
+	 *  reference the analysis rate comes back as the stored HOP (PVBuffer.cpp:134 vs :245). */
+	bool load( const std::string & filename );
+	/** Save as .flan: 24-bit magnitude / dft size and frequency / sample rate (reference PVBuffer::save, :99-140). */
+	bool save( const std::string & filename ) const;
 
 	// B200 build: device-side view for the conversion entry points (not part of the reference's surface)
 	const b200::Mirror<MF> & storage() const { return buffer; }

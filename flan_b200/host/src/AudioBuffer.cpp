@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <iostream>
 #include <ostream>
+
+#include "flan_b200.h"
 
 namespace flan {
 
@@ -103,6 +106,49 @@ std::ostream & operator<<( std::ostream & os, const AudioBuffer & a )
 	   << "\nLength:\t\t" << a.get_length() << " seconds"
 	   << "\n========================================================================\n\n";
 	return os;
+	}
+
+
+// ---- WAV files (reference AudioBuffer.cpp:80-192 through libsndfile): 24-bit PCM through the GPU codec -------------
+bool AudioBuffer::save( const std::string & filename, int file_format ) const
+	{
+	if( file_format != -1 )
+		{
+		std::cout << "Sound file formatting invalid while attempting to save to " << filename << ",\n"
+		          << "(the B200 build writes the reference's default, 24-bit PCM WAV, only)" << std::endl;
+		return false;
+		}
+	flan_b200_ctx * ctx = b200::context();
+	if( !ctx ) return false;
+	const Sample * d = buffer.empty() ? nullptr : buffer.device();
+	if( !buffer.empty() && !d ) return false;
+	const int rc = flan_b200_save_wav( ctx, filename.c_str(), d, get_num_channels(), get_num_frames(), get_sample_rate() );
+	if( rc != FLAN_B200_OK ) std::cout << flan_b200_last_error( ctx ) << std::endl;
+	return rc == FLAN_B200_OK;
+	}
+
+bool AudioBuffer::load( const std::string & filename )
+	{
+	flan_b200_ctx * ctx = b200::context();
+	if( !ctx ) return false;
+	int C = 0; int64_t n = 0; float sr = 0;
+	if( flan_b200_wav_info( ctx, filename.c_str(), &C, &n, &sr ) != FLAN_B200_OK )
+		{
+		std::cout << filename << " could not be opened: " << flan_b200_last_error( ctx ) << std::endl;     // AudioBuffer.cpp:88-92
+		return false;
+		}
+	Format f;
+	f.num_channels = C; f.num_frames = Frame( n ); f.sample_rate = sr;   // AudioBuffer.cpp:95-97
+	Sample * d = nullptr;
+	b200::Mirror<Sample> data = b200::Mirror<Sample>::device_result( size_t( C ) * size_t( n ), &d );
+	if( !d ) return false;
+	if( flan_b200_load_wav( ctx, filename.c_str(), d, int64_t( C ) * n ) != FLAN_B200_OK )
+		{
+		std::cout << flan_b200_last_error( ctx ) << std::endl;
+		return false;
+		}
+	*this = from_device_result( f, std::move( data ) );
+	return true;
 	}
 
 }

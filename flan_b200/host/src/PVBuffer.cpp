@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <iostream>
 #include <ostream>
+
+#include "flan_b200.h"
 
 namespace flan {
 
@@ -118,6 +121,45 @@ std::ostream & operator<<( std::ostream & os, const PVBuffer & p )
 	   << "\nDFT size:\t" << p.get_dft_size()
 	   << "\n======================================================================\n\n";
 	return os;
+	}
+
+
+// ---- .flan files (reference PVBuffer.cpp:99-140, 216-273): header on the host, samples through the GPU codec --------
+bool PVBuffer::save( const std::string & filename ) const
+	{
+	flan_b200_ctx * ctx = b200::context();
+	if( !ctx ) return false;
+	const MF * d = buffer.empty() ? nullptr : buffer.device();
+	if( !buffer.empty() && !d ) return false;
+	const int rc = flan_b200_save_flan( ctx, filename.c_str(), reinterpret_cast<const float *>( d ), get_num_channels(),
+		get_num_frames(), get_num_bins(), get_sample_rate(), get_analysis_rate(), get_window_size() );
+	if( rc != FLAN_B200_OK ) std::cout << flan_b200_last_error( ctx ) << std::endl;
+	return rc == FLAN_B200_OK;
+	}
+
+bool PVBuffer::load( const std::string & filename )
+	{
+	flan_b200_ctx * ctx = b200::context();
+	if( !ctx ) return false;
+	int C = 0, B = 0, W = 0; int64_t F = 0; float sr = 0, rate = 0;
+	if( flan_b200_flan_info( ctx, filename.c_str(), &C, &F, &B, &sr, &rate, &W ) != FLAN_B200_OK )
+		{
+		std::cout << flan_b200_last_error( ctx ) << std::endl;
+		return false;
+		}
+	Format f;
+	f.num_channels = C; f.num_frames = Frame( F ); f.num_bins = B;
+	f.sample_rate = sr; f.analysis_rate = rate; f.window_size = W;       // PVBuffer.cpp:241-246
+	MF * d = nullptr;
+	b200::Mirror<MF> data = b200::Mirror<MF>::device_result( size_t( C ) * size_t( F ) * size_t( B ), &d );
+	if( !d ) return false;
+	if( flan_b200_load_flan( ctx, filename.c_str(), reinterpret_cast<float *>( d ), int64_t( C ) * F * B ) != FLAN_B200_OK )
+		{
+		std::cout << flan_b200_last_error( ctx ) << std::endl;
+		return false;
+		}
+	*this = from_device_result( f, std::move( data ) );
+	return true;
 	}
 
 }

@@ -61,7 +61,7 @@ int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
  * CUDA events on the context's stream. flan_b200_kernel_time synchronises the stream, returns the summed
  * duration and launch count of one kernel kind since the last call for that kind, and resets it.
  * kinds: 0 analysis, 1 phase segment summary, 2 phase scan, 3 resynthesis, 4 mid/side + add + carry,
- * 5 repitch / modify_frequency, 6 stretch / modify_time, 7 table preparation and checks of the PV-domain chain. */
+ * 5 repitch / modify_frequency, 6 stretch / modify_time, 7 table preparation and checks of the PV-domain chain, 8 file-format sample codecs. */
 int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled );
 int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches );
 
@@ -175,6 +175,32 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int channels
                            float sample_rate, float analysis_rate,
                            const float * d_map, int64_t map_frame_stride, int map_bin_stride,
                            int interp, int64_t out_frames, float * d_pv_out );
+
+/* ---- file formats either side of the path ---------------------------------------------------------
+ * .flan RIFF-PV (PVBuffer::save / load, src/flan/PV/PVBuffer.cpp:99-140, 216-273; format described at
+ * PV/PVBuffer.h:84-115): 24-bit signed samples, magnitude / dft size and frequency / sample rate, clamped to [-1,1],
+ * times 2^23, truncated. Bit-identical to the reference's bytes. */
+/* Sample codec on device buffers: count MF elements <-> 6 * count bytes (16-byte aligned). */
+int flan_b200_flan_encode( flan_b200_ctx * ctx, const float * d_pv, int64_t count, float dft_size, float sample_rate, uint8_t * d_bytes );
+int flan_b200_flan_decode( flan_b200_ctx * ctx, const uint8_t * d_bytes, int64_t count, float dft_size, float sample_rate, float * d_pv );
+/* Whole files: header + samples streamed between the file and the device in chunks (synchronous). */
+int flan_b200_save_flan( flan_b200_ctx * ctx, const char * path, const float * d_pv, int channels, int64_t frames, int bins,
+                         float sample_rate, float analysis_rate, int window_size );
+/* Header fields as PVBuffer::load reads them. *rate_field is the value load() stores as the analysis rate
+ * (PVBuffer.cpp:245) -- which is the HOP that save() wrote there (:134): a reference quirk kept as is. */
+int flan_b200_flan_info( flan_b200_ctx * ctx, const char * path, int * channels, int64_t * frames, int * bins,
+                         float * sample_rate, float * rate_field, int * window_size );
+int flan_b200_load_flan( flan_b200_ctx * ctx, const char * path, float * d_pv, int64_t capacity_mf );
+
+/* WAV PCM-24, the format AudioBuffer::save defaults to (src/flan/Audio/AudioBuffer.cpp:136; load :80-128). The reference
+ * goes through libsndfile (external, not vendored, version unpinned): its published 24-bit conversions are restated --
+ * write: clamp to [-1,1] (AudioBuffer.cpp:158-161), lrintf( x * 0x7FFFFF ); read: value / 2^23 -- with the
+ * planar <-> interleaved reshuffle of AudioBuffer.cpp:122-125,152-155 fused in. Metadata strings are not carried. */
+int flan_b200_pcm24_encode( flan_b200_ctx * ctx, const float * d_audio, int channels, int64_t n, uint8_t * d_bytes );
+int flan_b200_pcm24_decode( flan_b200_ctx * ctx, const uint8_t * d_bytes, int channels, int64_t n, float * d_audio );
+int flan_b200_save_wav( flan_b200_ctx * ctx, const char * path, const float * d_audio, int channels, int64_t n, float sample_rate );
+int flan_b200_wav_info( flan_b200_ctx * ctx, const char * path, int * channels, int64_t * n, float * sample_rate );
+int flan_b200_load_wav( flan_b200_ctx * ctx, const char * path, float * d_audio, int64_t capacity_samples );
 
 /* ---- host-buffer forms (what flan::Audio::convert_to_PV / flan::PV::convert_to_audio call when the
  *      buffers live in std::vector): upload, transform, download, synchronise. ------------------- */

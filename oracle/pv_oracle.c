@@ -438,3 +438,66 @@ int64_t pvo_stretch( const float * pv, int C, int64_t F, int B, float sample_rat
 	free( fs );
 	return out_frames;
 	}
+
+/* ---------- file formats either side of the path ---------- */
+
+/* PVBuffer::save's sample codec, PV/PVBuffer.cpp:99-127: 24-bit signed little-endian, magnitude scaled by the dft
+ * size, frequency by the sample rate, (m, f) interleaved. count = number of MF elements; bytes: 6 * count. */
+void pvo_flan_encode( const float * pv, int64_t count, float dft_size, float sample_rate, uint8_t * bytes )
+	{
+	const double limit = 8388608.0;                                        /* pow( 2, 8 * 3 - 1 ), :102 */
+	for( int64_t i = 0; i < 2 * count; ++i )
+		{
+		const float div = ( i & 1 ) ? sample_rate : dft_size;              /* :103-104 */
+		float v = pv[i] / div;
+		v = v < -1.0f ? -1.0f : ( 1.0f < v ? 1.0f : v );                   /* std::clamp, :112-113 */
+		const double scaled = (double) v * limit;
+		const int32_t q = ( scaled != scaled ) ? (int32_t) 0x80000000u : (int32_t) scaled;   /* x86 cvttsd2si of NaN */
+		bytes[3 * i + 0] = (uint8_t)( ( q >> 0 ) & 0xFF );                 /* :117-123 */
+		bytes[3 * i + 1] = (uint8_t)( ( q >> 8 ) & 0xFF );
+		bytes[3 * i + 2] = (uint8_t)( ( q >> 16 ) & 0xFF );
+		}
+	}
+
+/* PVBuffer::load's sample codec, PV/PVBuffer.cpp:253-268. */
+void pvo_flan_decode( const uint8_t * bytes, int64_t count, float dft_size, float sample_rate, float * pv )
+	{
+	const double limit = 8388608.0;                                        /* :253 */
+	for( int64_t i = 0; i < 2 * count; ++i )
+		{
+		int32_t q = (int32_t)( bytes[3 * i] | ( bytes[3 * i + 1] << 8 ) | ( bytes[3 * i + 2] << 16 ) );   /* :259-260 */
+		if( q & 0x800000 ) q |= (int32_t) 0xFF000000u;                     /* :261 */
+		pv[i] = (float)( (double) q / limit ) * ( ( i & 1 ) ? sample_rate : dft_size );      /* :262 */
+		}
+	}
+
+/* AudioBuffer::save (Audio/AudioBuffer.cpp:136-161) hands interleaved, clamped floats to libsndfile with
+ * SF_FORMAT_WAV | SF_FORMAT_PCM_24. libsndfile is an external dependency, neither vendored nor installed here
+ * (version unpinned; cmake/FindSndFile.cmake accepts any): PARITY UNPINNED for this codec. Its published float -> 24-bit
+ * conversion (src/pcm.c, f2let_array with normalisation on, the default) is restated: lrintf( x * 0x7FFFFF ), three
+ * little-endian bytes, frames interleaved. audio: planar float[C][n]; bytes: 3 * C * n. */
+void pvo_pcm24_encode( const float * audio, int C, int64_t n, uint8_t * bytes )
+	{
+	for( int c = 0; c < C; ++c )
+		for( int64_t i = 0; i < n; ++i )
+			{
+			float s = audio[(int64_t) c * n + i];
+			s = s < -1.0f ? -1.0f : ( 1.0f < s ? 1.0f : s );               /* AudioBuffer.cpp:158-161 */
+			const int32_t q = (int32_t) lrintf( s * 8388607.0f );          /* pcm.c f2let_array */
+			uint8_t * o = bytes + 3 * ( i * C + c );                       /* AudioBuffer.cpp:153-155 */
+			o[0] = (uint8_t)( q & 0xFF ); o[1] = (uint8_t)( ( q >> 8 ) & 0xFF ); o[2] = (uint8_t)( ( q >> 16 ) & 0xFF );
+			}
+	}
+
+/* AudioBuffer::load (Audio/AudioBuffer.cpp:112-125): sf_readf_float of 24-bit PCM = value / 2^23 (pcm.c let2f_array:
+ * ( sample << 8 ) * ( 1 / 0x80000000 ) ), then de-interleave. */
+void pvo_pcm24_decode( const uint8_t * bytes, int C, int64_t n, float * audio )
+	{
+	for( int c = 0; c < C; ++c )
+		for( int64_t i = 0; i < n; ++i )
+			{
+			const uint8_t * b = bytes + 3 * ( i * C + c );
+			const int32_t v = (int32_t)( ( (uint32_t) b[0] << 8 ) | ( (uint32_t) b[1] << 16 ) | ( (uint32_t) b[2] << 24 ) );
+			audio[(int64_t) c * n + i] = (float) v * ( 1.0f / 2147483648.0f );
+			}
+	}

@@ -58,6 +58,15 @@ int64_t pvo_stretch( const float * pv, int C, int64_t F, int B, float sample_rat
 int64_t pvo_modify_time( const float * pv, int C, int64_t F, int B, float sample_rate, float analysis_rate,
                          const float * mod_seconds, int interp, float * out );
 
+/* ---- file formats either side of the path ----
+ * .flan RIFF-PV sample codec, PV/PVBuffer.cpp:99-127 (save) and :253-268 (load); count = MF elements, bytes = 6 * count. */
+void pvo_flan_encode( const float * pv, int64_t count, float dft_size, float sample_rate, uint8_t * bytes );
+void pvo_flan_decode( const uint8_t * bytes, int64_t count, float dft_size, float sample_rate, float * pv );
+/* WAV PCM-24 as Audio/AudioBuffer.cpp:136-170 writes it through libsndfile (clamp, interleave, lrintf( x * 0x7FFFFF ))
+ * and :112-125 reads it (value / 2^23, de-interleave). libsndfile's conversion restated: parity unpinned. */
+void pvo_pcm24_encode( const float * audio, int C, int64_t n, uint8_t * bytes );
+void pvo_pcm24_decode( const uint8_t * bytes, int C, int64_t n, float * audio );
+
 #ifdef __cplusplus
 }
 #endif

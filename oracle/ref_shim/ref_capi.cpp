@@ -75,4 +75,28 @@ int flan_ref_bench( const float * audio, int C, int n, float sample_rate,
 	return pv.get_num_frames();
 	}
 
+
+// The reference's own .flan writer / reader (PV/PVBuffer.cpp:99-140, 216-273). save: 0 on success.
+int flan_ref_save_flan( const char * path, const float * pv, int C, int F, int B, float sample_rate, float analysis_rate, int window_size )
+	{
+	PVBuffer::Format fmt;
+	fmt.num_channels = C; fmt.num_frames = F; fmt.num_bins = B;
+	fmt.sample_rate = sample_rate; fmt.analysis_rate = analysis_rate; fmt.window_size = window_size;
+	PV p( fmt );
+	std::memcpy( p.get_buffer().data(), pv, sizeof( MF ) * (size_t) C * F * B );
+	return p.save( path ) ? 0 : 1;
+	}
+
+// shape_out: C, F, B, window; rates_out: sample_rate, analysis_rate (as the reference's load fills them). pv_out may be
+// null (shape query). Returns 0 on success.
+int flan_ref_load_flan( const char * path, int * shape_out, float * rates_out, float * pv_out )
+	{
+	PV p;
+	if( !p.load( path ) ) return 1;
+	shape_out[0] = p.get_num_channels(); shape_out[1] = p.get_num_frames(); shape_out[2] = p.get_num_bins(); shape_out[3] = p.get_window_size();
+	rates_out[0] = p.get_sample_rate(); rates_out[1] = p.get_analysis_rate();
+	if( pv_out ) std::memcpy( pv_out, p.get_buffer().data(), sizeof( MF ) * p.get_buffer().size() );
+	return 0;
+	}
+
 }

@@ -108,4 +108,33 @@ int api_modify_maps( const float * audio, int C, int n, float sr, int W, int hop
 	return custom.is_null() ? 1 : 0;
 	}
 
+
+// Files either side of the path, as user code does it (the reference's tests/flanTest.cpp:34-44 loads a WAV, converts and
+// saves): audio -> save WAV -> load WAV -> convert_to_PV -> save .flan -> load .flan -> fix the rate -> convert_to_audio.
+// Returns output samples per channel or a negative code.
+int api_file_round_trip( const float * audio, int C, int n, float sr, int W, int hop, int N, const char * wav_path,
+                         const char * flan_path, float * loaded_audio, float * loaded_pv, float * loaded_rate, float * audio_out )
+	{
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	if( !a.save( wav_path ) ) return -1;
+	Audio b;
+	if( !b.load( wav_path ) || b.get_num_channels() != C || b.get_num_frames() != n ) return -2;
+	std::memcpy( loaded_audio, b.get_buffer().data(), sizeof( float ) * b.get_buffer().size() );
+	PV pv = b.convert_to_PV( W, hop, N );
+	if( pv.is_null() || !pv.save( flan_path ) ) return -3;
+	PV q;
+	if( !q.load( flan_path ) || q.get_num_frames() != pv.get_num_frames() || q.get_num_bins() != pv.get_num_bins() ) return -4;
+	*loaded_rate = q.get_analysis_rate();
+	std::memcpy( loaded_pv, q.get_buffer().data(), sizeof( MF ) * q.get_buffer().size() );
+	// the loaded analysis rate is the hop (reference quirk): rebuild the buffer with the true rate before resynthesis
+	PVBuffer::Format f = q.get_format();
+	f.analysis_rate = pv.get_analysis_rate();
+	PV fixed( ( PVBuffer( f ) ) );
+	std::memcpy( fixed.get_buffer().data(), q.get_buffer().data(), sizeof( MF ) * q.get_buffer().size() );
+	Audio out = fixed.convert_to_audio();
+	if( out.is_null() ) return -5;
+	std::memcpy( audio_out, out.get_buffer().data(), sizeof( float ) * out.get_buffer().size() );
+	return out.get_num_frames();
+	}
+
 }

@@ -47,7 +47,40 @@ class Oracle:
             fn.restype = ctypes.c_int64
             fn.argtypes = [_fp, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp,
                            ctypes.c_int, _fp]
+        _bp = ctypes.POINTER(ctypes.c_uint8)
+        L.pvo_flan_encode.argtypes = [_fp, ctypes.c_int64, ctypes.c_float, ctypes.c_float, _bp]
+        L.pvo_flan_decode.argtypes = [_bp, ctypes.c_int64, ctypes.c_float, ctypes.c_float, _fp]
+        L.pvo_pcm24_encode.argtypes = [_fp, ctypes.c_int, ctypes.c_int64, _bp]
+        L.pvo_pcm24_decode.argtypes = [_bp, ctypes.c_int, ctypes.c_int64, _fp]
         self.L = L
+
+    # file formats either side of the path (PVBuffer.cpp:99-140,216-273; AudioBuffer.cpp:80-192)
+    def flan_encode(self, pv, sr):
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        out = np.empty(C * F * B * 6, np.uint8)
+        self.L.pvo_flan_encode(_ptr(pv), C * F * B, float((B - 1) * 2), sr, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return out
+
+    def flan_decode(self, data, shape, sr):
+        C, F, B = shape
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.empty((C, F, B, 2), np.float32)
+        self.L.pvo_flan_decode(data.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), C * F * B, float((B - 1) * 2), sr, _ptr(out))
+        return out
+
+    def pcm24_encode(self, audio):
+        audio = np.ascontiguousarray(audio, np.float32)
+        C, n = audio.shape
+        out = np.empty(C * n * 3, np.uint8)
+        self.L.pvo_pcm24_encode(_ptr(audio), C, n, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+        return out
+
+    def pcm24_decode(self, data, C, n):
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.empty((C, n), np.float32)
+        self.L.pvo_pcm24_decode(data.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), C, n, _ptr(out))
+        return out
 
     def num_frames(self, n, hop):
         return int(self.L.pvo_num_frames(n, hop))
@@ -170,6 +203,23 @@ class RefLib:
         if rc < 0:
             return None
         return out
+
+    def save_flan(self, path, pv, sr, ar, W):
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        self.L.flan_ref_save_flan.argtypes = [ctypes.c_char_p, _fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                              ctypes.c_float, ctypes.c_int]
+        assert self.L.flan_ref_save_flan(path.encode(), _ptr(pv), C, F, B, sr, ar, W) == 0
+
+    def load_flan(self, path):
+        """The reference's own PVBuffer::load: returns (pv, sample_rate, analysis_rate_as_loaded, window_size)."""
+        self.L.flan_ref_load_flan.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), _fp, _fp]
+        shape = (ctypes.c_int * 4)()
+        rates = (ctypes.c_float * 2)()
+        assert self.L.flan_ref_load_flan(path.encode(), shape, rates, None) == 0
+        pv = np.empty((shape[0], shape[1], shape[2], 2), np.float32)
+        assert self.L.flan_ref_load_flan(path.encode(), shape, rates, _ptr(pv)) == 0
+        return pv, rates[0], rates[1], shape[3]
 
     def bench(self, audio, sr, W, hop, N, mode):
         audio = np.ascontiguousarray(audio, np.float32)
