@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=SECONDS_PER_GPU, help="signal length per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain", action="store_true",
+                    help="instead of the headline line: BASELINE config 4's chain (analysis -> repitch -> stretch -> resynthesis) "
+                         "on one channel per GPU, with the reference's own PVModify.cpp timed beside it")
     return ap.parse_args()
 
 
@@ -414,6 +417,79 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------
+# secondary line: BASELINE config 4's PV-domain chain (python bench.py --chain)
+# ------------------------------------------------------------------------------------------------------
+def run_chain(args):
+    import torch
+    from flan_b200.engine import Engine
+    from flan_b200.signals import noise_chirp
+    sr, w, hop, n_dft = 48000.0, 2048, 128, 2048
+    steps = args.steps if args.steps is not None else 10
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    eng = Engine(0)
+    n = int(sr * 1800)                                   # one of config 4's eight channels: 30 min at 48 kHz
+    x = torch.from_numpy(np.stack([noise_chirp(n, sr, 40)])).cuda()
+    F, B = eng.num_frames(n, hop), n_dft // 2 + 1
+    ar = eng.analysis_rate(sr, hop)
+    pv = torch.empty((1, F, B, 2), device="cuda")
+    rp = torch.empty_like(pv)
+
+    def step():
+        eng.convert_to_pv(x, sr, w, hop, n_dft, out=pv)
+        eng.repitch(pv, sr, 1.5, 0, out=rp)
+        st = eng.stretch(rp, sr, ar, 2.0, 0)
+        return st.shape[1], eng.convert_to_audio(st, sr, ar, w)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    eng.set_timing(True)
+    for k in eng.KERNEL_KINDS:
+        eng.kernel_time(k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        e0.record()
+        for _ in range(steps):
+            F2, _y = step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kt = {k: eng.kernel_time(k)[0] / steps for k in eng.KERNEL_KINDS}
+    peak, peak_src = measured_peak()
+    row = 8.0 * B
+    stage_bytes = {"analysis": 4.0 * n + row * F, "repitch": 2 * row * F, "stretch": row * F + row * F2,
+                   "synthesis": row * F2 + 4.0 * F2 * hop}
+    line = {"metric": "PV frames/sec (analysis + repitch + stretch + resynth, config 4 chain)", "value": F / (ms * 1e-3),
+            "unit": "input frames/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg4, one channel per GPU: 48 kHz 30 min noise+chirp, window 2048 hop 128, convert_to_PV -> "
+                                   "repitch(1.5) -> stretch(2.0) -> convert_to_audio, PV data resident in HBM throughout",
+                       "frames_in": F, "frames_out": F2, "bins": B},
+            "kernels": {k: {"ms_per_step": v, "achieved_gbs": stage_bytes[k] / (v * 1e-3) / 1e9 if k in stage_bytes and v else None,
+                            "frac": stage_bytes[k] / (v * 1e-3) / 1e9 / peak if k in stage_bytes and v else None} for k, v in kt.items()},
+            "peak_source": peak_src, "clocks": clocks.summary()}
+    if not args.no_cpu_baseline:
+        try:        # the reference's own PVModify.cpp (oracle/_ref/libflan_ref_modify.so) on a bounded sample of the same PV data
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle_lib import RefModifyLib
+            ref = RefModifyLib()
+            frames = 4000
+            sample = np.ascontiguousarray(pv[:, 1000:1000 + frames].cpu().numpy())
+            t0 = time.perf_counter()
+            r = ref.repitch(sample, sr, ar, w, np.full((frames, B), 1.5, np.float32), 0)
+            ref.stretch(r, sr, ar, w, np.full((frames, B), 2.0, np.float32), 0)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": frames / dt, "unit": "input frames/s (PV::repitch + PV::stretch only)", "cores": 1, "kind": "reference",
+                                    "sample": "%d frames of the same PV data through the reference's PV/PVModify.cpp compiled verbatim, "
+                                              "one thread (no TBB here: its par_unseq loops run serially); the GPU's repitch + stretch "
+                                              "stages take %.3f ms for %d frames" % (frames, kt["repitch"] + kt["stretch"], F),
+                                    "gpu_same_stages_frames_per_s": F / ((kt["repitch"] + kt["stretch"]) * 1e-3)}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "sample": "unavailable: %s" % e}
+    emit(line)
+
+
 def main():
     # Only the JSON line may reach stdout: libraries (NCCL prints its version there) are diverted to stderr.
     global _REAL_STDOUT
@@ -422,6 +498,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.chain:
+        run_chain(args)
     else:
         run_ours(args)
 

@@ -107,6 +107,10 @@ def build_host(force=False):
     drv = os.path.join(root, "tests", "cpp", "flan_api_driver.cpp")
     if force or _newer(api_test_path(), [drv, host_path()] + hdrs):
         subprocess.run(common + ["-o", api_test_path(), drv] + link + ["-lflan_b200_host", "-lflan_b200"], check=True)
+    ex = os.path.join(root, "examples", "pv_chain.cpp")
+    exe = os.path.join(LIB, "pv_chain")
+    if os.path.exists(ex) and (force or _newer(exe, [ex, host_path()] + hdrs)):
+        subprocess.run(["g++", "-O2", "-std=c++20", "-Wall"] + inc + ["-o", exe, ex] + link + ["-lflan_b200_host", "-lflan_b200"], check=True)
     return host_path()
 
 

@@ -160,3 +160,29 @@ def test_cpp_api_modify_time_and_frequency(api, oracle):
     for fi in (0, F // 2, F - 1):
         assert np.isin(got_f[0, fi, nz[0, fi], 0], pv[0, fi, :, 0]).all()
         assert np.isin(got_f[0, fi, nz[0, fi], 1], mapped[0, fi]).all()
+
+
+@pytest.mark.gpu
+def test_example_program_runs_the_chain_from_file_to_file(tmp_path):
+    # examples/pv_chain.cpp: WAV in -> convert_to_PV -> repitch -> stretch -> convert_to_audio -> WAV out, all through the
+    # reference-shaped C++ API (the reference's own tests/flanTest.cpp:32-47 does the same with Flan + FFTW + libsndfile)
+    import os
+    import subprocess
+    import wave
+    from flan_b200 import build
+    build.build_host()
+    exe = os.path.join(os.path.dirname(build.host_path()), "pv_chain")
+    mid, out = str(tmp_path / "mid.wav"), str(tmp_path / "out.wav")
+    r = subprocess.run([exe, "--synthetic", "3", mid, "1.0", "1.0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe, mid, out, "1.5", "2.0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    with wave.open(mid, "rb") as w:
+        n_mid = w.getnframes()
+    with wave.open(out, "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (2, 3, 48000)
+        n_out = w.getnframes()
+        raw = np.frombuffer(w.readframes(n_out), np.uint8).reshape(-1, 3).astype(np.int32)
+    assert abs(n_out - 2 * n_mid) <= 2 * 2048                     # stretched by two
+    v = ((raw[:, 0] | (raw[:, 1] << 8) | (raw[:, 2] << 16)) << 8) >> 8
+    assert np.sqrt(np.mean((v / 8388608.0) ** 2)) > 0.01          # and audible
