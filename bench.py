@@ -360,7 +360,7 @@ def run_ours(args):
         if an_n:
             kern.append(("pv_analysis_kernel<4096>", an_bytes, an_ms / an_n))
         if sy_n:
-            kern.append(("pv_synthesis_kernel<4096>", sy_bytes, sy_ms / sy_n))
+            kern.append(("pv_synthesis_mirror_kernel<4096>", sy_bytes, sy_ms / sy_n))
         dom = max(kern, key=lambda k: k[2]) if kern else None
         roofline = None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernel on the same workload (ncu)

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <barrier>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -22,7 +23,11 @@ struct HostEnv
 	{
 	int tid;
 	std::barrier<> * bar;
+	unsigned long long bulk_waits;
+	std::barrier<> * warpbar;       // barrier of this thread's warp
 	void sync() { bar->arrive_and_wait(); }
+	void syncwarp() { warpbar->arrive_and_wait(); }
+	bool any( bool p ) { return p || tid < 32; }    // used with predicates that only thread 0 raises
 	float ldg( const float * p ) { return *p; }
 	float2 ldg2( const float2 * p ) { return *p; }
 	float4 ldg4( const float4 * p ) { return *p; }
@@ -34,19 +39,35 @@ struct HostEnv
 	void cp_async8( float2 * dst, const float2 * src ) { *dst = *src; }
 	void cp_async_commit() {}
 	void cp_async_wait_all() {}
+	// bulk copy: performed at issue, completion published through a counter (the mbarrier phase); each thread counts
+	// the phases it has waited for
+	typedef unsigned long long BulkBarrier;
+	void bulk_init( BulkBarrier * bar ) { std::atomic_ref<BulkBarrier>( *bar ).store( 0 ); }
+	void bulk_load( void * dst, const void * src, unsigned bytes, BulkBarrier * bar )
+		{
+		std::memcpy( dst, src, bytes );
+		std::atomic_ref<BulkBarrier>( *bar ).fetch_add( 1, std::memory_order_release );
+		}
+	void bulk_wait( BulkBarrier * bar, unsigned )
+		{
+		while( std::atomic_ref<BulkBarrier>( *bar ).load( std::memory_order_acquire ) <= bulk_waits ) std::this_thread::yield();
+		++bulk_waits;
+		}
 	};
 
 template<int N, int PT, class Body> void run_cta( Body && body )
 	{
 	constexpr int T = N / ( 2 * PT );
 	std::vector<float> ring( N );
-	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size ), rowbuf( N / 2 + 2 );
+	std::vector<float2> x0( XBuf<N / 2>::size ), x1( XBuf<N / 2>::size ), rowbuf( N / 2 + 16 );
 	std::barrier<> bar( T );
+	std::vector<std::unique_ptr<std::barrier<>>> warpbars;
+	for( int w = 0; w < ( T + 31 ) / 32; ++w ) warpbars.emplace_back( new std::barrier<>( T - 32 * w < 32 ? T - 32 * w : 32 ) );
 	std::vector<std::thread> th;
 	for( int t = 0; t < T; ++t )
 		th.emplace_back( [&, t]
 			{
-			HostEnv env{ t, &bar };
+			HostEnv env{ t, &bar, 0, warpbars[t / 32].get() };
 			body( env, ring.data(), x0.data(), x1.data(), rowbuf.data() );
 			} );
 	for( auto & x : th ) x.join();
@@ -55,13 +76,31 @@ template<int N, int PT, class Body> void run_cta( Body && body )
 template<int N, int PT> void analysis_n( const AnalysisArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT>( a, b, env, x0, x1 ); } );
+		{
+		if( a.one_buffer && PT == 16 )
+			run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true>( a, b, env, x0, x0 ); } );
+		else
+			run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, false>( a, b, env, x0, x1 ); } );
+		}
+	}
+
+template<int N> void analysis_mirror_n( const AnalysisArgs & a, int64_t blocks )
+	{
+	for( int64_t b = 0; b < blocks; ++b )
+		run_cta<N, 16>( [&]( HostEnv & env, float * ring, float2 * x0, float2 * x1, float2 * scratch ) { analysis_cta_mirror<N>( a, b, env, x0, a.one_buffer ? x0 : x1, (float2 *) ring, scratch ); } );
 	}
 
 template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
 		run_cta<N, 8>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta<N>( a, b, env, ola, x0, x1, rowbuf ); } );
+	}
+
+template<int N> void synthesis_mirror_n( const SynthArgs & a, int64_t blocks )
+	{
+	HostEnv::BulkBarrier bar_word = 0;
+	for( int64_t b = 0; b < blocks; ++b )
+		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta_mirror<N>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); } );
 	}
 
 } // namespace
@@ -73,6 +112,8 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
                      float sr, int W, int hop, int N, int64_t frame_begin, int64_t frame_end, int seg_len, int sms,
                      float * pv_rows, int64_t pv_channel_stride, int points_per_thread )
 	{
+	const bool one_buffer = points_per_thread >= 100;      // +100: the exchange buffers alias
+	points_per_thread %= 100;
 	const bool pt16 = points_per_thread == 16 && N >= 512;
 	HostTables tb;
 	if( !build_tables( N, W, hop, sr, sr / hop, tb ) ) return 1;
@@ -87,8 +128,21 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 ) && ( (uintptr_t) audio % 8 == 0 );
 	a.win = tb.win_analysis.data(); a.binc = tb.binc.data(); a.binc4 = tb.binc4.data(); a.post_rot = tb.post_rot.data();
 	a.pass_tw = pt16 ? tb.pass_tw16.data() : tb.pass_tw.data();
+	a.one_buffer = one_buffer;
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;
+	if( points_per_thread == 17 )       // PV_PT_MIRROR
+		{
+		if( !( W == N && hop == N / 16 ) ) return 3;
+		a.pass_tw = tb.pass_tw16.data();
+		switch( N )
+			{
+			case 1024: analysis_mirror_n<1024>( a, blocks ); return 0;
+			case 2048: analysis_mirror_n<2048>( a, blocks ); return 0;
+			case 4096: analysis_mirror_n<4096>( a, blocks ); return 0;
+			default: return 2;
+			}
+		}
 	switch( N )
 		{
 		case 256: analysis_n<256, 8>( a, blocks ); break;
@@ -106,7 +160,7 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, int64_t frame_begin, int64_t frame_end,
                       int64_t frames_total, int B, float sr, float ar, int W, int seg_len, int sms,
                       const PhaseSeg * carry_in, PhaseSeg * carry_out,
-                      float * out, int64_t out_stride, int64_t out_offset, int64_t out_len, int * nan_flag )
+                      float * out, int64_t out_stride, int64_t out_offset, int64_t out_len, int * nan_flag, int variant )
 	{
 	const int N = ( B - 1 ) * 2;
 	const int hop = (int)( sr / ar );
@@ -153,8 +207,22 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 	a.acc_start = acc.data(); a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop; a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
 	a.win = tb.win_synthesis.data(); a.post_tw = tb.post_tw.data(); a.pass_tw = tb.pass_tw.data();
+	a.pass_tw_rev = tb.pass_tw_rev.data();
+	a.out_aligned2 = ( out_stride % 2 == 0 ) && ( out_offset % 2 == 0 ) && ( (uintptr_t) out % 8 == 0 );
+	a.pv_aligned16 = ( (uintptr_t) pv_rows % 16 == 0 ); a.channels = C;
 	a.k = tb.k; a.P = tb.P; a.rcpP = tb.rcpP;
 	const int64_t blocks = (int64_t) C * segs;
+	if( variant == 17 )     // PV_PT_MIRROR; the caller checks the shape conditions (W == N, hop a multiple of N/16)
+		{
+		if( !( W == N && hop == N / 16 ) ) return 3;
+		switch( N )
+			{
+			case 1024: synthesis_mirror_n<1024>( a, blocks ); return 0;
+			case 2048: synthesis_mirror_n<2048>( a, blocks ); return 0;
+			case 4096: synthesis_mirror_n<4096>( a, blocks ); return 0;
+			default: return 2;
+			}
+		}
 	switch( N )
 		{
 		case 256: synthesis_n<256>( a, blocks ); break;

@@ -25,7 +25,7 @@ namespace pvk {
 // FFT pass chain over the ping-pong exchange buffers x0/x1 (XBuf<M>::size float2 each).
 // Pass 0 (radix 8, no twiddles) is issued by the caller; this runs passes 1..last.
 // ------------------------------------------------------------------------------------------------
-template<int M, int PT, int p, bool STORE_LAST, class Env>
+template<int M, int PT, int p, bool STORE_LAST, bool ONE, class Env>
 PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env )
 	{
 	using P = FftPlan<M, PT>;
@@ -33,9 +33,12 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 		{
 		constexpr int NSp = P::ns( p - 1 );     // layout our input was written in
 		constexpr int R = P::radix( p ), NS = P::ns( p );
-		float2 * in  = ( ( p - 1 ) % 2 == 0 ) ? x0 : x1;
-		float2 * out = ( p % 2 == 0 ) ? x0 : x1;
+		// ONE: a single exchange buffer (half the shared memory, so more L1 for the tables, and one base register less)
+		// at the price of a barrier between a pass's reads and its writes
+		float2 * in  = ( ONE || ( p - 1 ) % 2 == 0 ) ? x0 : x1;
+		float2 * out = ( ONE || p % 2 == 0 ) ? x0 : x1;
 		fft_load<M, PT, NSp>( t, v, in );
+		if constexpr( ONE ) env.sync();      // everyone has read before anyone writes
 		fft_butterflies<M, PT, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
 		if constexpr( p < P::num_passes - 1 )
 			{
@@ -50,14 +53,14 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 			for( int s = PT / 2; s < PT; ++s ) out[t + s * ( M / PT )] = v[s];
 			env.sync();
 			}
-		fft_pass_chain<M, PT, p + 1, STORE_LAST>( t, v, x0, x1, tw, env );
+		fft_pass_chain<M, PT, p + 1, STORE_LAST, ONE>( t, v, x0, x1, tw, env );
 		}
 	}
 
 // Buffer that receives the natural-order output of the last pass when STORE_LAST is set (its Ns >= 16: no padding).
-template<int M, int PT> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
+template<int M, int PT, bool ONE = false> PV_HD float2 * fft_result_buffer( float2 * x0, float2 * x1 )
 	{
-	return ( ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
+	return ( ONE || ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) ? x0 : x1;
 	}
 
 // ------------------------------------------------------------------------------------------------
@@ -82,10 +85,11 @@ struct AnalysisArgs
 	const float4 * binc4;       // [N/4+1] the same constants per unpack pair: (binf[k], binf[M-k], expected[k], -expected[M-k])
 	const float2 * post_rot;    // [N/4+1] -i e^{-2 pi i k/N}
 	const float2 * pass_tw;     // concatenated per-pass twiddles
+	int one_buffer;             // the two exchange buffers alias (half the shared memory, two more barriers per frame)
 	PvConsts k;
 	};
 
-template<int N, int PT, class Env>
+template<int N, int PT, bool ONE, class Env>
 PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1 )
 	{
 	constexpr int M = N / 2, T = M / PT, H = PT / 2;      // H pairs of bins (k, M-k) per thread
@@ -172,9 +176,9 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			}
 
 #ifndef PV_ABL_NOFFT
-		fft_pass_chain<M, PT, 1, true>( t, v, x0, x1, a.pass_tw, env );
+		fft_pass_chain<M, PT, 1, true, ONE>( t, v, x0, x1, a.pass_tw, env );
 #endif
-		const float2 * z = fft_result_buffer<M, PT>( x0, x1 );     // upper half of Z/2 in natural order
+		const float2 * z = fft_result_buffer<M, PT, ONE>( x0, x1 );     // upper half of Z/2 in natural order
 
 		// real-FFT unpack + phase vocoder (AudioPV.cpp:69-73). The warm-up frame runs the same code with its stores
 		// predicated off: only the phases it leaves in prev[] matter.
@@ -221,7 +225,208 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			if( emit ) env.st_stream2( row_mid, mh );
 			}
 		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
-		if( ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) env.sync();
+		if( ONE || ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) env.sync();
+		}
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Analysis, mirrored last pass (16 points per thread, dft 1024 / 2048 / 4096: passes 16, 16, R with R = 2 / 4 / 8)
+//
+// The last Stockham pass consists of NS = M/R butterflies; butterfly j produces Z[j + r*NS], r = 0..R-1, and the
+// real-FFT unpack pairs Z[k] with Z[M-k] = Z[(NS-j) + (R-1-r)*NS], i.e. butterfly j with butterfly NS-j. Here one
+// thread computes BOTH butterflies of such a pair (p, NS-p), p = t + q*T, so the unpack and the phase vocoder run
+// entirely on the thread's own registers: no third exchange through shared memory, no barrier after the last pass.
+// The one irregular pair is p = 0: butterflies 0 and NS/2 are each their own mirror (thread 0, q = 0); that thread
+// publishes its 2R values and 2R+1 lanes of its warp finish the bins that are multiples of NS/2 one each.
+// Samples: a thread's window positions are the same absolute samples in every frame (window == dft, hop == dft/16),
+// so it keeps them in a private ring in shared memory and fetches one new pair per frame, one frame ahead.
+// Same butterflies and per-bin operation order as analysis_cta; bins above M/2 of the upper slots are computed as
+// X[k] directly instead of through the conjugate of their mirror, so results agree to rounding (parity-tested alike).
+// ------------------------------------------------------------------------------------------------
+template<int R, int S> PV_HD void dft_r( float2 * a )
+	{
+	if( R == 16 ) dft16<S>( a );
+	if( R == 8 ) dft8<S>( a );
+	if( R == 4 ) dft4<S>( a );
+	if( R == 2 ) dft2<S>( a );
+	}
+
+template<int N> struct MirrorPlan
+	{
+	static constexpr int PT = 16, M = N / 2, T = M / PT;
+	using P = FftPlan<M, PT>;
+	static_assert( P::num_passes == 3 && P::last_r >= 2, "mirrored passes need radices 16, 16, R" );
+	static constexpr int R = P::last_r;          // radix of the mirrored pass
+	static constexpr int NS = M / R;             // its butterfly count (= 256)
+	static constexpr int Q = PT / R / 2;         // mirrored butterfly pairs per thread
+	static constexpr int KHI = -( M - NS ) / 2;  // bin offset of the upper slots of the irregular pair
+	};
+
+template<int N, class Env>
+PV_HD void analysis_cta_mirror( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1, float2 * ring, float2 * scratch )
+	{
+	using MP = MirrorPlan<N>;
+	using P = typename MP::P;
+	constexpr int PT = 16, M = MP::M, T = MP::T, R = MP::R, NS = MP::NS, Q = MP::Q;
+	constexpr int hop = 2 * T, half = N / 2;           // window == N, hop == N/16 (checked by the launcher)
+	const int t = env.tid;
+	const int c = (int)( block / a.segs_per_channel );
+	const int seg = (int)( block % a.segs_per_channel );
+	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
+	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
+	if( fa >= fb ) return;
+
+	const float * xch = a.audio + (int64_t) c * a.audio_stride;
+
+	float w[2 * PT];
+#pragma unroll
+	for( int s = 0; s < PT; ++s )
+		{
+		w[2 * s]     = 0.5f * env.ldg( a.win + 2 * ( t + s * T ) );
+		w[2 * s + 1] = 0.5f * env.ldg( a.win + 2 * ( t + s * T ) + 1 );
+		}
+	float2 prev[Q][R];
+	float prev_irr = 0.0f;
+#pragma unroll
+	for( int q = 0; q < Q; ++q )
+#pragma unroll
+		for( int r = 0; r < R; ++r ) { prev[q][r].x = 0.0f; prev[q][r].y = 0.0f; }
+
+	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
+	const bool irregular = ( t == 0 );                 // owner of the butterflies 0 and NS/2
+	const bool warp0 = ( t < 32 );
+
+	// The window of frame f is sample pairs t + T*(f + s - 8), s = 0..15, of this thread: the same absolute samples
+	// reappear one slot lower in the next frame, so each thread keeps ITS 16 pairs in a private ring (entry
+	// (f + s + 8) & 15 at ring[t + T*entry], i.e. the natural circular buffer of N samples) and fetches ONE new pair
+	// per frame, a frame ahead. Samples outside [0, n_total) read as zero (AudioPV.cpp:54-62).
+	auto load_pair = [&]( int64_t f, int s )
+		{
+		const int64_t pos = (int64_t) hop * f - half + 2 * ( t + s * T );
+		const float * src = xch + ( pos - a.audio_offset );
+		float2 r; r.x = 0.0f; r.y = 0.0f;
+		if( f < fb )        // frames past the segment are never transformed, and their samples may lie outside the local buffer
+			{
+			if( a.aligned2 && pos >= 0 && pos + 1 < a.n_total ) r = env.ldg2( reinterpret_cast<const float2 *>( src ) );
+			else
+				{
+				if( pos >= 0 && pos < a.n_total ) r.x = env.ldg( src );
+				if( pos + 1 >= 0 && pos + 1 < a.n_total ) r.y = env.ldg( src + 1 );
+				}
+			}
+		return r;
+		};
+#pragma unroll 1
+	for( int s = 0; s < PT; ++s ) ring[t + T * (int)( ( first + s + 8 ) & 15 )] = load_pair( first, s );
+	float2 nxt = load_pair( first + 1, PT - 1 );        // beyond the last frame this reads zeros or real samples; never used
+
+	// Output row of frame f; per-thread bases advanced by one row per frame.
+	const int64_t row0 = (int64_t) c * a.pv_channel_stride + ( first - a.frame_begin ) * (int64_t)( M + 1 );
+	float2 * row_lo = a.pv + ( row0 + t );             // bins k = p + r*NS ascend from here
+	float2 * row_hi = a.pv + ( row0 + M - t );         // mirrors M-k descend from here
+	float2 * row_irr = a.pv + ( row0 + ( NS / 2 ) * ( t & 31 ) );   // lanes 0..2R of warp 0: bin (NS/2)*lane
+	const float2 * tw_last = a.pass_tw + P::tw_offset( 2 );
+	auto ldtw = [&]( const float2 * q ) { return env.ldg2( q ); };
+
+	for( int64_t f = first; f < fb; ++f, row_lo += M + 1, row_hi += M + 1, row_irr += M + 1 )
+		{
+		float2 v[PT];
+			{
+			const unsigned xb = ( (unsigned) t + (unsigned) T * (unsigned)( ( f + 8 ) & 15 ) ) * 8u;
+#pragma unroll
+			for( int s = 0; s < PT; ++s )
+				{
+				const float2 r = *reinterpret_cast<const float2 *>( reinterpret_cast<const char *>( ring ) + ( ( xb + (unsigned)( s * T * 8 ) ) & (unsigned)( 16 * T * 8 - 1 ) ) );
+				float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
+				v[s] = mul2( r, ww );
+				}
+			// entry of slot 0 is free now: it is slot 15 of the next frame
+			*reinterpret_cast<float2 *>( reinterpret_cast<char *>( ring ) + xb ) = nxt;
+			nxt = load_pair( f + 2, PT - 1 );
+			}
+		fft_butterflies<M, PT, PT, 1>( t, v, (const float2 *) nullptr, ldtw );
+		fft_store<M, PT, PT, 1>( t, v, x0 );
+		env.sync();
+
+		fft_load<M, PT, 1>( t, v, x0 );
+		if( x0 == x1 ) env.sync();      // one exchange buffer: everyone has read before anyone writes
+		fft_butterflies<M, PT, PT, PT>( t, v, a.pass_tw + P::tw_offset( 1 ), ldtw );
+		fft_store<M, PT, PT, PT>( t, v, x1 );
+		env.sync();
+
+		const bool emit = ( f >= fa );
+#pragma unroll
+		for( int q = 0; q < Q; ++q )
+			{
+			const int p = t + q * T;
+			const bool irr = ( q == 0 ) && irregular;
+			const int jA = p, jB = irr ? NS / 2 : NS - p;
+			float2 * za = v + 2 * R * q, * zb = za + R;
+#pragma unroll
+			for( int r = 0; r < R; ++r ) { za[r] = x1[jA + r * NS]; zb[r] = x1[jB + r * NS]; }
+			if( q == Q - 1 && x0 == x1 ) env.sync();    // one exchange buffer: the next frame's first pass writes it again
+			// Twiddles of butterfly jB = NS - p': w^(r (NS - p')) = W_R^r conj(w^(r p')), p' = NS - jB (= p, or NS/2 for the
+			// irregular thread). The factor W_R^r rotates the DFT by one bin (DFT_R{ u_r W_R^r }[k] = U[k+1]), so the
+			// butterfly multiplies by the CONJUGATE of butterfly jA's twiddles -- no second table read except in the
+			// warp of the irregular thread -- and its outputs are taken one register further on.
+			const bool own_tw = ( q == 0 ) && warp0;                // warp-uniform
+#pragma unroll
+			for( int r = 1; r < R; ++r )
+				{
+				const float2 wa = ldtw( tw_last + ( r - 1 ) * NS + jA );
+				float2 wb = wa;
+				if( own_tw ) wb = ldtw( tw_last + ( r - 1 ) * NS + ( NS - jB ) );
+				za[r] = cmul2( za[r], wa );
+				zb[r] = cmulc2( zb[r], wb );
+				}
+			dft_r<R, 1>( za );
+			dft_r<R, 1>( zb );
+			// za[r] = Z[jA + r NS], zb[(r + 1) % R] = Z[jB + r NS]; slot r pairs Z[k], k = p + r NS, with Z[M-k] = Z[jB + (R-1-r) NS]
+#pragma unroll
+			for( int r = 0; r < R; ++r )
+				{
+				const int k = p + r * NS;
+				const float2 zk = za[r], zm = zb[( R - r ) % R];
+				const float2 A = add2( zk, pn2( zm ) );
+				const float2 D = add2( zk, np2( zm ) );
+				const float2 Pq = cmul2( D, env.ldg2( a.post_rot + k ) );
+				const float2 xk = add2( A, Pq ), xmc = sub2( A, Pq );
+				const float4 cc = env.ldg4( a.binc4 + k );
+				float2 binf, expd; binf.x = cc.x; binf.y = cc.y; expd.x = cc.z; expd.y = cc.w;
+				float2 mk, mm;
+				phase_vocoder_pair( xk, xmc, prev[q][r], binf, expd, a.k, mk, mm );
+				// the irregular thread's pairing is meaningless (its two butterflies are each their own mirror): see below
+				if( emit && !irr )
+					{
+					env.st_stream2( row_lo + ( q * T + r * NS ), mk );
+					env.st_stream2( row_hi - ( q * T + r * NS ), mm );
+					}
+				}
+			// Bins that are multiples of NS/2 (2R+1 of them, 0 .. M): the irregular thread publishes its two butterflies,
+			// scratch[j] = Z[(NS/2) j], and lanes 0..2R of its warp each finish one bin with the scalar form of the same
+			// arithmetic: X[k] = (Z[k] + conj Z[M-k]) + (-i w_k)(Z[k] - conj Z[M-k]).
+			if( q == 0 && warp0 )
+				{
+				if( irregular )
+					{
+#pragma unroll
+					for( int r = 0; r < R; ++r ) { scratch[2 * r] = za[r]; scratch[2 * r + 1] = zb[( r + 1 ) % R]; }
+					}
+				env.syncwarp();
+				if( t <= 2 * R )
+					{
+					const int k = ( NS / 2 ) * t;
+					const float2 zk = scratch[t & ( 2 * R - 1 )], zm = scratch[( 2 * R - t ) & ( 2 * R - 1 )];
+					const float2 A = add2( zk, pn2( zm ) );
+					const float2 D = add2( zk, np2( zm ) );
+					const float2 Pq = cmul2( D, env.ldg2( a.post_rot + k ) );
+					const float2 xk = add2( A, Pq );
+					const float2 ch = env.ldg2( a.binc + k );
+					const float2 mh = phase_vocoder_bin( xk.x, xk.y, prev_irr, ch.x, ch.y, a.k );
+					if( emit ) env.st_stream2( row_irr, mh );
+					}
+				}
+			}
 		}
 	}
 
@@ -298,6 +503,10 @@ struct SynthArgs
 	const float * win;          // [W] Hann * window_scale, host-evaluated (AudioPV.cpp:99-102)
 	const float2 * post_tw;
 	const float2 * pass_tw;
+	const float2 * pass_tw_rev; // twiddles of the small-radix-first plan (synthesis_cta_mirror)
+	int out_aligned2;           // every even absolute sample of every channel sits on an 8-byte boundary of `out`
+	int pv_aligned16;           // `pv` is 16-byte aligned (bulk row copies)
+	int channels;
 	PvConsts k;
 	double P, rcpP;             // double(pi2) and its reciprocal
 	};
@@ -448,7 +657,7 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 		fft_store<M, 8, 8, 1>( t, v, x0 );
 		env.sync();
 #ifndef PV_ABL_NOFFT
-		fft_pass_chain<M, 8, 1, false>( t, v, x0, x1, a.pass_tw, env );
+		fft_pass_chain<M, 8, 1, false, false>( t, v, x0, x1, a.pass_tw, env );
 #endif
 
 		// v[s] = swapped z[n], n = t + s*T: y[2n] = v.y, y[2n+1] = v.x. Windowed overlap-add (AudioPV.cpp:133-134).
@@ -511,6 +720,256 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 	// remainder of the last window
 	const int64_t last_start = (int64_t) hop * ( fb - 1 ) - half;
 	flush( last_start + fin, last_start + W );
+	}
+
+// ------------------------------------------------------------------------------------------------
+// Resynthesis, mirrored first pass (16 points per thread; dft 1024 / 2048 / 4096, window == dft, hop a multiple of
+// dft/16). The transpose of analysis_cta_mirror: the inverse FFT runs as passes R, 16, 16 (R = 2 / 4 / 8), and one
+// thread computes the two first-pass butterflies p and NS-p, whose inputs Z'[p + r NS] and Z'[(NS-p) + r NS] are
+// exactly the packed values of the bin pairs (k, M-k), k = p + r NS. So a thread reads ITS OWN bins of the row,
+// accumulates their phases in registers, packs and transforms them without any exchange, and
+//   * the (m,f) row is a thread-private prefetch FIFO in shared memory: every thread stages (8-byte cp.async) and
+//     reads only its own 2R+1 bins, so no barrier guards it;
+//   * with hop == j * dft/16 the overlap-add positions of a thread are the same absolute samples in every frame
+//     (pair index mod T == t), so the ring is thread-private as well: no barrier, and the `hop` samples a frame
+//     finalises are the thread's slots s < j, which go from registers straight to global memory.
+// Two barriers per frame remain: the two FFT exchanges. Contributions are added in increasing frame order
+// (AudioPV.cpp:133-134), every product and sum rounded separately, exactly like synthesis_cta.
+// ------------------------------------------------------------------------------------------------
+template<int M, int R> struct RevPlan
+	{
+	// Stockham passes R, 16, 16 of a complex M-point FFT, 16 points per thread
+	static constexpr int NS1 = R, NS2 = 16 * R;
+	static_assert( NS2 * 16 == M, "M = R * 256" );
+	static constexpr int tw1 = 0;                  // pass 1 (radix 16, Ns = R):   [15][R]
+	static constexpr int tw2 = 15 * NS1;           // pass 2 (radix 16, Ns = 16R): [15][16R]
+	static constexpr int tw_total = tw2 + 15 * NS2;
+	};
+
+// Exchange layout after the radix-16 pass with Ns = R (lanes write 16R*(jj/R) + jj%R + R*r): blocks of 16R elements
+// are shifted by R each, which makes the 16 accesses of a half-warp hit 16 distinct 8-byte bank pairs; the reads
+// t + s*T of the next pass (T = 16R) stay contiguous.
+template<int R> PV_HD int xpad_rev( int i ) { return i + R * ( i / ( 16 * R ) ); }
+
+template<int N, class Env>
+PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, float2 * ring, float2 * x0, float2 * x1, float2 * rowbuf,
+                                 typename Env::BulkBarrier * bar )
+	{
+	using MP = MirrorPlan<N>;
+	constexpr int PT = 16, M = MP::M, T = MP::T, R = MP::R, NS = MP::NS, Q = MP::Q, B = M + 1;
+	using RP = RevPlan<M, R>;
+	static_assert( T == 16 * R, "threads per frame" );
+	const int t = env.tid;
+	const int c = (int)( block / a.segs_per_channel );
+	const int seg = (int)( block % a.segs_per_channel );
+	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
+	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
+	if( fa >= fb ) return;
+
+	constexpr int hop = 2 * T;                   // == a.hop == N/16; window == N
+	constexpr int half = N / 2;
+	const bool irregular = ( t == 0 );
+	const int khi = irregular ? MP::KHI : 0;
+
+	float w[2 * PT];
+#pragma unroll
+	for( int s = 0; s < PT; ++s )
+		{
+		w[2 * s]     = env.ldg( a.win + 2 * ( t + s * T ) );
+		w[2 * s + 1] = env.ldg( a.win + 2 * ( t + s * T ) + 1 );
+		}
+	// bin of slot (q, r): k = kbase + r*NS with kbase = p (+ khi for the irregular upper slots); its mirror is M - k
+	double acc[Q][R][2], acc_mid = 0.0;
+	const double * acc0 = a.acc_start + ( (int64_t) c * a.segs_per_channel + seg ) * B;
+#pragma unroll
+	for( int q = 0; q < Q; ++q )
+#pragma unroll
+		for( int r = 0; r < R; ++r )
+			{
+			const int k = t + q * T + ( ( q == 0 && r >= R / 2 ) ? khi : 0 ) + r * NS;
+			acc[q][r][0] = acc0[k];
+			acc[q][r][1] = acc0[M - k];
+			}
+	if( irregular ) acc_mid = acc0[M / 2];
+
+	// thread-private overlap-add ring: 16 pairs at ring[t + T*j]; absolute pair index t + T*A lives in slot A & 15
+#pragma unroll
+	for( int j = 0; j < PT; ++j ) { float2 z; z.x = 0.0f; z.y = 0.0f; ring[t + T * j] = z; }
+
+	// Row staging. A row is 8 B * (M+1) long and only 8-byte aligned, so the bulk (TMA) copy fetches the enclosing
+	// 16-byte aligned span -- at most one (m,f) pair of a neighbouring row on either side -- and the row starts `shift`
+	// elements into the buffer. One thread issues it, completion arrives on an mbarrier. Where the span would leave
+	// the PV buffer (its very last row) or the buffer is not 16-byte aligned, every thread copies its own bins with
+	// 8-byte cp.async instead.
+	const float2 * pv_ch = a.pv + (int64_t) c * a.pv_channel_stride;
+	const int64_t pv_end = (int64_t)( a.channels - 1 ) * a.pv_channel_stride + ( a.frame_end - a.frame_begin ) * (int64_t) B;   // elements in the buffer
+	auto row_elem = [&]( int64_t f ) { return (int64_t) c * a.pv_channel_stride + ( f - a.frame_begin ) * (int64_t) B; };
+	auto row_is_bulk = [&]( int64_t f )
+		{
+		const int64_t e = row_elem( f );
+		return a.pv_aligned16 && ( ( ( e + B + 1 ) & ~(int64_t) 1 ) <= pv_end );
+		};
+	auto stage_row_own = [&]( int64_t f )
+		{
+		const float2 * src = pv_ch + ( f - a.frame_begin ) * (int64_t) B;
+#pragma unroll 1
+		for( int i = 0; i < 2 * R * Q; ++i )
+			{
+			const int q = i / ( 2 * R ), r = ( i / 2 ) % R;
+			int k = t + q * T + ( ( q == 0 && r >= R / 2 ) ? khi : 0 ) + r * NS;
+			if( i & 1 ) k = M - k;
+			env.cp_async8( rowbuf + k, src + k );
+			}
+		if( irregular ) env.cp_async8( rowbuf + M / 2, src + M / 2 );
+		env.cp_async_commit();
+		};
+	auto stage_row_bulk = [&]( int64_t f )       // one thread
+		{
+		const int64_t e = row_elem( f ), e0 = e & ~(int64_t) 1, e1 = ( e + B + 1 ) & ~(int64_t) 1;
+		env.bulk_load( rowbuf, a.pv + e0, (unsigned)( ( e1 - e0 ) * sizeof( float2 ) ), bar );
+		};
+	if( t == 0 ) env.bulk_init( bar );
+	env.sync();
+	unsigned bulk_phase = 0;
+	bool cur_bulk = row_is_bulk( fa );
+	if( cur_bulk ) { if( t == 0 ) stage_row_bulk( fa ); }
+	else stage_row_own( fa );
+
+	float * och = a.out + (int64_t) c * a.out_stride;
+	const int64_t interior_lo = (int64_t) hop * fa + half - hop;
+	const int64_t interior_hi = (int64_t) hop * fb - half;
+	// one finished sample: stored when every contributing frame lies in this segment, else combined with the
+	// neighbouring segment's partial sum by red.add (exactly two partial sums meet; a + b is commutative)
+	auto emit = [&]( int64_t pos, float val )
+		{
+		if( pos >= a.out_lo && pos < a.out_hi )
+			{
+			float * dst = och + ( pos - a.out_offset );
+			if( pos >= interior_lo && pos < interior_hi ) env.st_stream( dst, val );
+			else env.red_add( dst, val );
+			}
+		};
+	auto ldtw = [&]( const float2 * q ) { return env.ldg2( q ); };
+
+	for( int64_t f = fa; f < fb; ++f )
+		{
+		const int64_t start = (int64_t) hop * f - half;                          // AudioPV.cpp:125
+		const float2 * row = rowbuf;
+		if( cur_bulk ) { env.bulk_wait( bar, bulk_phase & 1 ); ++bulk_phase; row = rowbuf + ( row_elem( f ) & 1 ); }
+		else env.cp_async_wait_all();                                            // this thread's bins of row f have landed
+		float2 v[PT];
+#pragma unroll
+		for( int q = 0; q < Q; ++q )
+			{
+			const int p = t + q * T;
+			const bool irr = ( q == 0 ) && irregular;
+			float2 zk[R], zm[R];
+#pragma unroll
+			for( int r = 0; r < R; ++r )
+				{
+				const int k = p + ( ( q == 0 && r >= R / 2 ) ? khi : 0 ) + r * NS;
+				float2 xk, xm;
+				inverse_pv_pair( row[k], row[M - k], acc[q][r][0], acc[q][r][1], a.k, a.P, a.rcpP, xk, xm );
+				// a c2r transform ignores the imaginary parts of bins 0 and N/2 (slot 0 of the irregular pair)
+				if( r == 0 && irr ) { xk.y = 0.0f; xm.y = 0.0f; }
+				const float2 tw = env.ldg2( a.post_tw + k );
+				const float2 A = add2( xk, pn2( xm ) );
+				const float2 Bv = add2( xk, np2( xm ) );
+				const float2 Qv = cmulc2( Bv, tw );
+				zk[r] = add2( swap2( A ), pn2( Qv ) );            // Z'[k], (im, re) swapped: the forward passes then invert
+				zm[r] = add2( np2( swap2( A ) ), Qv );            // Z'[M-k]
+				}
+			float2 * za = v + 2 * R * q, * zb = za + R;
+#pragma unroll
+			for( int r = 0; r < R; ++r ) { za[r] = zk[r]; zb[R - 1 - r] = zm[r]; }
+			if( irr )
+				{
+				// butterflies 0 and NS/2 take their inputs in another arrangement, plus bin M/2
+				float sn, cs;
+				const float2 mh = row[M / 2];
+				phase_accumulate( acc_mid, phase_increment( mh.y, a.k ), a.P, a.rcpP );      // phase_vocoder.cpp:57-59
+				sincos_pv( (float) acc_mid, &sn, &cs );
+				float2 zs; zs.y = 2.0f * mul_rn( mh.x, cs ); zs.x = -2.0f * mul_rn( mh.x, sn );   // Z'[M/2] = 2 conj X[M/2], swapped
+#pragma unroll
+				for( int r = 0; r < R; ++r )
+					{
+					if( r < R / 2 ) { za[r] = zk[r]; if( r > 0 ) za[R - r] = zm[r]; }
+					else            { zb[r - R / 2] = zk[r]; zb[3 * R / 2 - 1 - r] = zm[r]; }
+					}
+				za[R / 2] = zs;
+				}
+			}
+		// pass 0: radix R, no twiddles, butterflies p and NS-p; outputs R*jj + r in the padded layout
+#pragma unroll
+		for( int q = 0; q < Q; ++q )
+			{
+			const int p = t + q * T;
+			const int jA = p, jB = ( q == 0 && irregular ) ? NS / 2 : NS - p;
+			float2 * za = v + 2 * R * q, * zb = za + R;
+			dft_r<R, 1>( za );
+			dft_r<R, 1>( zb );
+			float2 * oa = x0 + xpad<1>( R * jA ), * ob = x0 + xpad<1>( R * jB );
+#pragma unroll
+			for( int r = 0; r < R; ++r ) { oa[r] = za[r]; ob[r] = zb[r]; }
+			}
+		env.sync();
+		// every thread has consumed row f: fetch row f+1 behind the transform
+		const bool next_bulk = ( f + 1 < fb ) && row_is_bulk( f + 1 );
+		if( f + 1 < fb )
+			{
+			if( next_bulk ) { if( t == 0 ) stage_row_bulk( f + 1 ); }
+			else stage_row_own( f + 1 );
+			}
+		cur_bulk = next_bulk;
+		// pass 1: radix 16, Ns = R
+		fft_load<M, PT, 1>( t, v, x0 );
+		fft_butterflies<M, PT, PT, RP::NS1>( t, v, a.pass_tw_rev + RP::tw1, ldtw );
+			{
+			const int base = xpad_rev<R>( ( t / R ) * R * PT + ( t & ( R - 1 ) ) );
+#pragma unroll
+			for( int r = 0; r < PT; ++r ) x1[base + r * R] = v[r];
+			}
+		env.sync();
+		// pass 2: radix 16, Ns = 16R = T: outputs t + r*T, i.e. v[s] = swapped z[t + s*T]: y[2n] = v.y, y[2n+1] = v.x
+			{
+			const float2 * base = x1 + t;
+#pragma unroll
+			for( int s = 0; s < PT; ++s ) v[s] = base[s * ( T + R )];
+			}
+		fft_butterflies<M, PT, PT, RP::NS2>( t, v, a.pass_tw_rev + RP::tw2, ldtw );
+
+		// windowed overlap-add (AudioPV.cpp:133-134) on the thread's own ring; slot s of this frame is absolute pair
+		// t + T*(f + s - 8) (half/2 == 8T), i.e. ring entry (f + s + 8) & 15
+		// (byte offsets: (t + T*((f + 8 + s) & 15)) * 8 == ((t + T*(f + 8)) * 8 + s*T*8) & (16*T*8 - 1), one add and one mask per slot)
+		const unsigned xb = ( (unsigned) t + (unsigned) T * (unsigned)( ( f + 8 ) & 15 ) ) * 8u;
+		auto slot = [&]( int s ) { return reinterpret_cast<float2 *>( reinterpret_cast<char *>( ring ) + ( ( xb + (unsigned)( s * T * 8 ) ) & (unsigned)( 16 * T * 8 - 1 ) ) ); };
+		float2 sum[PT];
+#pragma unroll
+		for( int s = 0; s < PT; ++s )
+			{
+			float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
+			const float2 prod = mul2( swap2( v[s] ), ww );
+			// slot 15 receives its first contribution (its ring entry is simply overwritten)
+			sum[s] = ( s == PT - 1 ) ? prod : add2( *slot( s ), prod );
+			}
+#pragma unroll
+		for( int s = 1; s < PT; ++s ) *slot( s ) = sum[s];
+		// slot 0: no later frame reaches these two samples
+		const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
+		const int64_t pos = start + 2 * t;
+		if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[0] );
+		else { emit( pos, sum[0].x ); emit( pos + 1, sum[0].y ); }
+		}
+	// remainder of the last window
+	const int64_t last_start = (int64_t) hop * ( fb - 1 ) - half;
+	const int j0 = (int)( ( ( fb - 1 ) + 8 ) & 15 );
+#pragma unroll 1
+	for( int s = 1; s < PT; ++s )
+		{
+		const float2 val = ring[t + T * ( ( j0 + s ) & 15 )];
+		const int64_t pos = last_start + 2 * ( t + s * T );
+		emit( pos, val.x ); emit( pos + 1, val.y );
+		}
 	}
 
 } // namespace pvk

@@ -41,6 +41,7 @@ struct DevicePlan
 	float4 * binc4 = nullptr;
 	float2 * pass_tw = nullptr;
 	float2 * pass_tw16 = nullptr;
+	float2 * pass_tw_rev = nullptr;
 	};
 
 thread_local std::string g_create_error;
@@ -68,6 +69,9 @@ struct flan_b200_ctx
 	// (resident threads per SM the kernel is compiled for; 0 = 512 with 16 points per thread, else 768).
 	int tps_analysis = 0, tps_synthesis = 768;
 	int pt_analysis = 0;
+	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
+	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
+	int tps_synthesis_mirror = 384;
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
 	};
@@ -123,6 +127,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	CK( upload_vec( plan->host.binc4, &plan->binc4, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw, &plan->pass_tw, ctx->stream ), "plan upload" );
 	CK( upload_vec( plan->host.pass_tw16, &plan->pass_tw16, ctx->stream ), "plan upload" );
+	CK( upload_vec( plan->host.pass_tw_rev, &plan->pass_tw_rev, ctx->stream ), "plan upload" );
 	*out = plan.get();
 	ctx->plans[key] = std::move( plan );
 	return FLAN_B200_OK;
@@ -242,9 +247,12 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	a.seg_len = seg_len; a.segs_per_channel = segs;
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 );
-	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw;
+	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw; a.pass_tw_rev = plan->pass_tw_rev;
+	a.out_aligned2 = ( out_stride % 2 == 0 ) && ( out_offset % 2 == 0 ) && ( (uintptr_t) d_out % 8 == 0 );
+	a.pv_aligned16 = ( (uintptr_t) d_pv_rows % 16 == 0 ); a.channels = C;
 	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 3 ); CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, ctx->tps_synthesis ), "synthesis launch" ); }
+	{ LaunchTimer lt( ctx, 3 ); const bool mirror = ctx->synth_variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a );
+	  CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, mirror ? ctx->tps_synthesis_mirror : ctx->tps_synthesis, ctx->synth_variant ), "synthesis launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -285,8 +293,10 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	auto * ctx = new flan_b200_ctx;
 	ctx->device = device;
 	if( const char * e = std::getenv( "FLAN_B200_TPS_ANALYSIS" ) ) ctx->tps_analysis = std::atoi( e );
-	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) ctx->tps_synthesis = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) { ctx->tps_synthesis = std::atoi( e ); ctx->tps_synthesis_mirror = ctx->tps_synthesis; }
 	if( const char * e = std::getenv( "FLAN_B200_PT_ANALYSIS" ) ) ctx->pt_analysis = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_ONEBUF" ) ) ctx->one_buffer = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_SYNTH_VARIANT" ) ) ctx->synth_variant = std::atoi( e );
 	ctx->sms = prop.multiProcessorCount;
 	e = cudaMalloc( (void **) &ctx->d_flag, sizeof( int ) );
 	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flag, 0, sizeof( int ) );
@@ -440,11 +450,15 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 )
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
-	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : 8 );
-	if( pt != 16 || N < 512 ) pt = 8;
-	const int tps_a = ctx->tps_analysis ? ctx->tps_analysis : ( pt == 16 ? 512 : 768 );
+	// measured on B200 (tools/exp_r1*.sh): 16 points per thread with one exchange buffer from dft 4096 up; the mirrored
+	// last pass for dft 1024 with the standard window / hop; 8 points per thread otherwise
+	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : ( N == 1024 ? PV_PT_MIRROR : 8 ) );
+	if( pt == PV_PT_MIRROR && !( mirror_supported( N ) && W == N && hop == N / 16 ) ) pt = ( N >= 4096 ) ? 16 : 8;
+	if( pt != PV_PT_MIRROR && ( pt != 16 || N < 512 ) ) pt = 8;
+	const int tps_a = ctx->tps_analysis ? ctx->tps_analysis : ( pt >= 16 ? 512 : 768 );
 	a.win = plan->win_analysis; a.binc = plan->binc; a.binc4 = plan->binc4; a.post_rot = plan->post_rot;
-	a.pass_tw = ( pt == 16 ) ? plan->pass_tw16 : plan->pass_tw;
+	a.pass_tw = ( pt >= 16 ) ? plan->pass_tw16 : plan->pass_tw;
+	a.one_buffer = ctx->one_buffer >= 0 ? ctx->one_buffer : ( ( N >= 4096 || pt == PV_PT_MIRROR ) ? 1 : 0 );
 	a.k = plan->host.k;
 	ctx->seg_key.valid = false;
 	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, tps_a, pt ), "analysis launch" ); }

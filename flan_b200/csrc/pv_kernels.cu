@@ -20,6 +20,8 @@ namespace pvk {
 struct DeviceEnv
 	{
 	int tid;
+	__device__ __forceinline__ void syncwarp() { __syncwarp(); }
+	__device__ __forceinline__ bool any( bool p ) { return __any_sync( 0xffffffffu, p ); }
 	__device__ __forceinline__ void sync()
 		{
 #ifndef PV_ABL_NOSYNC
@@ -41,21 +43,68 @@ struct DeviceEnv
 		}
 	__device__ __forceinline__ void cp_async_commit() { asm volatile( "cp.async.commit_group;\n" ::: "memory" ); }
 	__device__ __forceinline__ void cp_async_wait_all() { asm volatile( "cp.async.wait_group 0;\n" ::: "memory" ); }
+	// Bulk (TMA) global->shared copy tracked by an mbarrier: one thread arms the barrier with the byte count and issues
+	// the copy; every thread waits on the phase parity. Addresses and size are multiples of 16 bytes.
+	typedef unsigned long long BulkBarrier;
+	__device__ __forceinline__ void bulk_init( BulkBarrier * bar )
+		{
+		const unsigned b = (unsigned) __cvta_generic_to_shared( bar );
+		asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"( b ) : "memory" );
+		asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
+		}
+	__device__ __forceinline__ void bulk_load( void * dst, const void * src, unsigned bytes, BulkBarrier * bar )
+		{
+		const unsigned b = (unsigned) __cvta_generic_to_shared( bar );
+		const unsigned d = (unsigned) __cvta_generic_to_shared( dst );
+		asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"( b ), "r"( bytes ) : "memory" );
+		asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+		              :: "r"( d ), "l"( src ), "r"( bytes ), "r"( b ) : "memory" );
+		}
+	__device__ __forceinline__ void bulk_wait( BulkBarrier * bar, unsigned parity )
+		{
+		const unsigned b = (unsigned) __cvta_generic_to_shared( bar );
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"WAIT_%=:\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+			"@p bra DONE_%=;\n"
+			"bra WAIT_%=;\n"
+			"DONE_%=:\n"
+			"}\n" :: "r"( b ), "r"( parity ) : "memory" );
+		}
+#ifdef PV_PREFETCH_L1
+	__device__ __forceinline__ void prefetch( const void * p ) { asm volatile( "prefetch.global.L1 [%0];" :: "l"( p ) ); }
+#else
 	__device__ __forceinline__ void prefetch( const void * p ) { asm volatile( "prefetch.global.L2 [%0];" :: "l"( p ) ); }
+#endif
 	};
 
 // TPS = resident threads per SM the register allocation is sized for (512 -> 128, 768 -> 85, 1024 -> 64 registers).
 constexpr int min_blocks( int threads, int TPS ) { return TPS / threads > 32 ? 32 : ( TPS / threads > 0 ? TPS / threads : 1 ); }
 
 // PT = complex points per thread: 8 (radix-8 passes, N/16 threads per frame) or 16 (radix-16 passes, N/32 threads).
-template<int N, int PT, int TPS>
+template<int N, int PT, int TPS, bool ONE>
 __global__ void __launch_bounds__( N / ( 2 * PT ), min_blocks( N / ( 2 * PT ), TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
-	float2 * x1 = x0 + XBuf<N / 2>::size;
+	float2 * x1 = ONE ? x0 : x0 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	analysis_cta<N, PT>( a, (int64_t) blockIdx.x, env, x0, x1 );
+	analysis_cta<N, PT, ONE>( a, (int64_t) blockIdx.x, env, x0, x1 );
+	}
+
+// Mirrored last pass (pv_body.cuh: analysis_cta_mirror): 16 points per thread, unpack + phase vocoder on the thread's own registers.
+template<int N, int TPS>
+__global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_analysis_mirror_kernel( const AnalysisArgs a )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
+	float2 * x1 = a.one_buffer ? x0 : x0 + XBuf<N / 2>::size;
+	float2 * ring = x1 + XBuf<N / 2>::size;            // N/2 pairs: the window's samples, thread-private entries
+	float2 * scratch = ring + N / 2;                   // 16 pairs
+	DeviceEnv env; env.tid = threadIdx.x;
+	analysis_cta_mirror<N>( a, (int64_t) blockIdx.x, env, x0, x1, ring, scratch );
 	}
 
 template<int N, int TPS>
@@ -68,6 +117,20 @@ __global__ void __launch_bounds__( N / 16, min_blocks( N / 16, TPS ) ) pv_synthe
 	float2 * rowbuf = x1 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
 	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1, rowbuf );
+	}
+
+// Mirrored first pass (pv_body.cuh: synthesis_cta_mirror): 16 points per thread, thread-private row FIFO and overlap-add ring.
+template<int N, int TPS>
+__global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_synthesis_mirror_kernel( const SynthArgs a )
+	{
+	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+	float2 * ring = reinterpret_cast<float2 *>( smem_raw );                 // N/2 pairs
+	float2 * x0 = ring + N / 2;
+	float2 * x1 = x0 + XBuf<N / 2>::size;
+	float2 * rowbuf = x1 + XBuf<N / 2>::size;                               // N/2 + 2 pairs
+	__shared__ __align__( 8 ) DeviceEnv::BulkBarrier bar;
+	DeviceEnv env; env.tid = threadIdx.x;
+	synthesis_cta_mirror<N>( a, (int64_t) blockIdx.x, env, ring, x0, x1, rowbuf, &bar );
 	}
 
 // One thread per (channel, segment, bin): summary of the segment's phase increments.
@@ -169,22 +232,62 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 // Development aid: FLAN_B200_SMEM_PAD=<bytes> inflates the dynamic shared memory request so that fewer CTAs fit per
 // SM (occupancy experiments). Unset in production.
+// Development aid: FLAN_B200_CARVEOUT=<percent> sets the preferred shared-memory carveout of the transform kernels.
+static int carveout()
+	{
+	static const int v = [] { const char * e = std::getenv( "FLAN_B200_CARVEOUT" ); return e ? std::atoi( e ) : -1; }();
+	return v;
+	}
+template<class K> static void apply_carveout( K kernel )
+	{
+	if( carveout() >= 0 ) cudaFuncSetAttribute( kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout() );
+	}
 static size_t smem_pad()
 	{
 	static const size_t pad = [] { const char * e = std::getenv( "FLAN_B200_SMEM_PAD" ); return e ? (size_t) std::atol( e ) : (size_t) 0; }();
 	return pad;
 	}
 
+template<int N, int PT, int TPS, bool ONE> static cudaError_t launch_analysis_nto( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	const size_t smem = ( ONE ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + smem_pad();
+	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	apply_carveout( pv_analysis_kernel<N, PT, TPS, ONE> );
+	pv_analysis_kernel<N, PT, TPS, ONE><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
+	return cudaGetLastError();
+	}
+// the one-buffer form is built for 16 points per thread only (the variant the large transforms use)
 template<int N, int PT, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = 2 * sizeof( float2 ) * XBuf<N / 2>::size + smem_pad();
-	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if constexpr( PT == 16 ) { if( a.one_buffer ) return launch_analysis_nto<N, PT, TPS, true>( a, blocks, st ); }
+	return launch_analysis_nto<N, PT, TPS, false>( a, blocks, st );
+	}
+bool analysis_mirror_applies( int N, const AnalysisArgs & a )
+	{
+	return mirror_supported( N ) && a.W == N && a.hop == N / 16;
+	}
+template<int N, int TPS> static cudaError_t launch_analysis_mirror_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	const size_t smem = ( a.one_buffer ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 16 ) + smem_pad();
+	cudaError_t e = cudaFuncSetAttribute( pv_analysis_mirror_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	pv_analysis_kernel<N, PT, TPS><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
+	apply_carveout( pv_analysis_mirror_kernel<N, TPS> );
+	pv_analysis_mirror_kernel<N, TPS><<<(unsigned) blocks, N / 32, smem, st>>>( a );
 	return cudaGetLastError();
 	}
 template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps, int pt )
 	{
+	if constexpr( N == 1024 || N == 2048 || N == 4096 )
+		{
+		if( pt == PV_PT_MIRROR && analysis_mirror_applies( N, a ) )
+			{
+			if( tps >= 768 ) return launch_analysis_mirror_nt<N, 768>( a, blocks, st );
+			if( tps >= 640 ) return launch_analysis_mirror_nt<N, 640>( a, blocks, st );
+			if( tps >= 512 ) return launch_analysis_mirror_nt<N, 512>( a, blocks, st );
+			return launch_analysis_mirror_nt<N, 384>( a, blocks, st );
+			}
+		}
 	if constexpr( N >= 512 )
 		{
 		if( pt == 16 )
@@ -206,8 +309,29 @@ template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs
 	pv_synthesis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
-template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps )
+template<int N, int TPS> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
+	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	if( e != cudaSuccess ) return e;
+	apply_carveout( pv_synthesis_mirror_kernel<N, TPS> );
+	pv_synthesis_mirror_kernel<N, TPS><<<(unsigned) blocks, N / 32, smem, st>>>( a );
+	return cudaGetLastError();
+	}
+bool synthesis_mirror_applies( int N, const SynthArgs & a )
+	{
+	return mirror_supported( N ) && a.W == N && a.hop == N / 16;
+	}
+template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps, int variant )
+	{
+	if constexpr( N == 1024 || N == 2048 || N == 4096 )
+		{
+		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
+			{
+			if( tps >= 512 ) return launch_synthesis_mirror_nt<N, 512>( a, blocks, st );
+			return launch_synthesis_mirror_nt<N, 384>( a, blocks, st );
+			}
+		}
 	if( tps >= 1024 ) return launch_synthesis_nt<N, 1024>( a, blocks, st );
 	if( tps >= 768 ) return launch_synthesis_nt<N, 768>( a, blocks, st );
 	return launch_synthesis_nt<N, 512>( a, blocks, st );
@@ -232,16 +356,16 @@ cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cuda
 		}
 	}
 
-cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps )
+cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps, int variant )
 	{
 	switch( N )
 		{
-		case 256:  return launch_synthesis_n<256>( a, blocks, st, tps );
-		case 512:  return launch_synthesis_n<512>( a, blocks, st, tps );
-		case 1024: return launch_synthesis_n<1024>( a, blocks, st, tps );
-		case 2048: return launch_synthesis_n<2048>( a, blocks, st, tps );
-		case 4096: return launch_synthesis_n<4096>( a, blocks, st, tps );
-		case 8192: return launch_synthesis_n<8192>( a, blocks, st, tps );
+		case 256:  return launch_synthesis_n<256>( a, blocks, st, tps, variant );
+		case 512:  return launch_synthesis_n<512>( a, blocks, st, tps, variant );
+		case 1024: return launch_synthesis_n<1024>( a, blocks, st, tps, variant );
+		case 2048: return launch_synthesis_n<2048>( a, blocks, st, tps, variant );
+		case 4096: return launch_synthesis_n<4096>( a, blocks, st, tps, variant );
+		case 8192: return launch_synthesis_n<8192>( a, blocks, st, tps, variant );
 		default:   return cudaErrorInvalidValue;
 		}
 	}

@@ -30,9 +30,18 @@ struct PhaseScanArgs
 	double P, rcpP;
 	};
 
+// points_per_thread values of launch_analysis: 8, 16, or PV_PT_MIRROR (16 points per thread with the mirrored last
+// pass; dft 1024 / 2048 / 4096 only)
+#define PV_PT_MIRROR 17
+inline bool mirror_supported( int N ) { return N == 1024 || N == 2048 || N == 4096; }
+
 bool dft_size_supported( int N );
 cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm, int points_per_thread );
-cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm );
+// variant: 8 = 8 points per thread (every size and shape); PV_PT_MIRROR = synthesis_cta_mirror where it applies
+// (synthesis_mirror_applies), the 8-point kernel otherwise
+cudaError_t launch_synthesis( int N, const SynthArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm, int variant );
+bool synthesis_mirror_applies( int N, const SynthArgs & a );
+bool analysis_mirror_applies( int N, const AnalysisArgs & a );
 cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st );
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st );
 cudaError_t launch_phase_carry( const PhaseSeg * all, int rank, int64_t per_rank, PhaseSeg * carry, double P, double rcpP, cudaStream_t st );

@@ -22,11 +22,12 @@ struct HostTables
 	std::vector<float> expected;        // bin_frequency / analysis_rate * pi2, per bin      phase_vocoder.cpp:47
 	std::vector<float> binf;            // bin_to_frequency(b) = b * float(sr) / float(dft)   PVBuffer.cpp:443-446
 	std::vector<float2> binc;           // (binf, expected) interleaved, as the analysis kernel reads them
-	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/4
+	std::vector<float2> post_tw;        // e^{-2 pi i k / N}, k = 0..N/2 (the 8-point-per-thread kernels use k <= N/4 only)
 	std::vector<float2> post_rot;       // -i e^{-2 pi i k / N} = (sin, -cos)(-2 pi k / N): the analysis unpack's multiplier
-	std::vector<float4> binc4;          // per unpack pair k = 0..N/4: (binf[k], binf[M-k], expected[k], -expected[M-k])
+	std::vector<float4> binc4;          // per unpack pair k = 0..N/2: (binf[k], binf[M-k], expected[k], -expected[M-k])
 	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated (8 points per thread plan)
 	std::vector<float2> pass_tw16;      // same for the 16-points-per-thread plan (dft >= 512)
+	std::vector<float2> pass_tw_rev;    // passes R, 16, 16 of synthesis_cta_mirror (dft 1024 / 2048 / 4096; empty otherwise)
 	PvConsts k{};
 	double P = 0.0, rcpP = 0.0;
 	};
@@ -55,6 +56,19 @@ template<int M, int PT> inline void append_pass_twiddles( std::vector<float2> & 
 				out.push_back( w );
 				}
 		}
+	}
+
+// Twiddles of one Stockham pass (radix R, Ns): w^(r*jm), w = e^{-2 pi i / (Ns*R)}, laid out [r-1][jm].
+inline void append_one_pass_twiddles( std::vector<float2> & out, int R, int NS )
+	{
+	const long double two_pi = 6.283185307179586476925286766559005768L;
+	for( int r = 1; r < R; ++r )
+		for( int jm = 0; jm < NS; ++jm )
+			{
+			const long double a = -two_pi * (long double) r * (long double) jm / (long double)( NS * R );
+			float2 w; w.x = (float) cosl( a ); w.y = (float) sinl( a );
+			out.push_back( w );
+			}
 	}
 
 inline bool build_tables( int N, int W, int hop, float sample_rate, float analysis_rate, HostTables & t )
@@ -99,17 +113,17 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 	for( int b = 0; b < B; ++b ) { t.binc[b].x = t.binf[b]; t.binc[b].y = t.expected[b]; }
 
 	const long double two_pi = 6.283185307179586476925286766559005768L;
-	t.post_tw.resize( M / 2 + 1 );
-	for( int k = 0; k <= M / 2; ++k )
+	t.post_tw.resize( M + 1 );
+	for( int k = 0; k <= M; ++k )
 		{
 		const long double a = -two_pi * (long double) k / (long double) N;
 		t.post_tw[k].x = (float) cosl( a );
 		t.post_tw[k].y = (float) sinl( a );
 		}
 
-	t.post_rot.resize( M / 2 + 1 );
-	t.binc4.resize( M / 2 + 1 );
-	for( int k = 0; k <= M / 2; ++k )
+	t.post_rot.resize( M + 1 );
+	t.binc4.resize( M + 1 );
+	for( int k = 0; k <= M; ++k )
 		{
 		t.post_rot[k].x = t.post_tw[k].y;
 		t.post_rot[k].y = -t.post_tw[k].x;
@@ -128,6 +142,13 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		case 2048: append_pass_twiddles<2048, 8>( t.pass_tw );  append_pass_twiddles<2048, 16>( t.pass_tw16 ); break;
 		case 4096: append_pass_twiddles<4096, 8>( t.pass_tw );  append_pass_twiddles<4096, 16>( t.pass_tw16 ); break;
 		default: return false;
+		}
+	t.pass_tw_rev.clear();
+	if( M == 512 || M == 1024 || M == 2048 )
+		{
+		const int R = M / 256;                              // passes R (no twiddles), 16 (Ns = R), 16 (Ns = 16 R)
+		append_one_pass_twiddles( t.pass_tw_rev, 16, R );
+		append_one_pass_twiddles( t.pass_tw_rev, 16, 16 * R );
 		}
 	return true;
 	}

@@ -25,7 +25,7 @@ class Emu:
                                       ctypes.c_int, _i64, _i64, ctypes.c_int, ctypes.c_int, _fp, _i64, ctypes.c_int]
         L.pv_emu_synthesis.argtypes = [_fp, _i64, ctypes.c_int, _i64, _i64, _i64, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                                       ctypes.c_void_p, _fp, _i64, _i64, _i64, ctypes.POINTER(ctypes.c_int)]
+                                       ctypes.c_void_p, _fp, _i64, _i64, _i64, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.pv_emu_tables.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp, _fp, _fp]
         L.pv_emu_div_const_mismatches.restype = _i64
         L.pv_emu_div_const_mismatches.argtypes = [ctypes.c_float, ctypes.c_uint32, _i64]
@@ -49,7 +49,7 @@ class Emu:
         return pv
 
     def synthesis(self, pv, sr, ar, W, frame_begin=0, frames_total=None, seg_len=0, sms=4, carry_in=None,
-                  want_carry=False, out_offset=None, out_len=None, synth=True):
+                  want_carry=False, out_offset=None, out_len=None, synth=True, variant=8):
         pv = np.ascontiguousarray(pv, np.float32)
         C, rows, B, _ = pv.shape
         hop = int(np.float32(sr) / np.float32(ar))
@@ -64,7 +64,7 @@ class Emu:
         rc = self.L.pv_emu_synthesis(_ptr(pv), rows * B, C, frame_begin, frame_end, frames_total, B, sr, ar, W, seg_len, sms,
                                      None if carry_in is None else carry_in.ctypes.data,
                                      None if carry_out is None else carry_out.ctypes.data,
-                                     _ptr(out) if synth else None, out_len, out_offset, out_len, ctypes.byref(flag))
+                                     _ptr(out) if synth else None, out_len, out_offset, out_len, ctypes.byref(flag), variant)
         assert rc == 0, rc
         return out, carry_out, flag.value
 

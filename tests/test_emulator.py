@@ -36,6 +36,20 @@ def test_emulated_analysis_matches_oracle(emu, oracle, W, h, N, seg, kind):
     assert_analysis_parity(pv, oracle.convert_to_pv(x, sr, W, h, N), sr, h, N)
 
 
+@pytest.mark.parametrize("W,h,N,seg,pt", [(4096, 256, 4096, 5, 16), (4096, 256, 4096, 0, 116), (8192, 512, 8192, 3, 116),
+                                          (2048, 128, 2048, 7, 116), (1000, 100, 1024, 0, 116), (4096, 256, 4096, 6, 117)])
+def test_emulated_analysis_variants_are_bit_identical(emu, W, h, N, seg, pt):
+    # 16 points per thread and the one-buffer exchange (+100) only re-time the same arithmetic
+    sr = 48000.0
+    x = np.stack([noise_chirp(9000, sr, 5), sine_sweep(9000, sr)])
+    a = emu.analysis(x, sr, W, h, N, seg_len=seg, points_per_thread=pt)
+    b = emu.analysis(x, sr, W, h, N, seg_len=seg, points_per_thread=pt % 100)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if pt % 100 == 16:
+        c = emu.analysis(x, sr, W, h, N, seg_len=seg, points_per_thread=8)
+        assert_analysis_parity(a, c, sr, h, N)
+
+
 @pytest.mark.parametrize("W,h,N,seg", SHAPES)
 def test_emulated_synthesis_matches_oracle(emu, oracle, W, h, N, seg):
     sr = 48000.0
@@ -47,6 +61,57 @@ def test_emulated_synthesis_matches_oracle(emu, oracle, W, h, N, seg):
     out, _, flag = emu.synthesis(pv, sr, ar, W, seg_len=seg_len)
     assert flag == 0
     assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+
+
+# Mirrored kernels (16 points per thread; window == dft, hop == dft/16): the butterfly pair (p, NS-p) in one thread,
+# thread-private row FIFO / overlap-add ring / sample ring, bulk row copies with their unaligned-row and last-row cases.
+MIRROR_SHAPES = [(4096, 0, 9000), (4096, 17, 9001), (2048, 20, 6000), (2048, 0, 5000), (1024, 16, 6000), (1024, 0, 3001)]
+
+
+@pytest.mark.parametrize("N,seg,n", MIRROR_SHAPES)
+def test_emulated_mirror_synthesis_matches_oracle(emu, oracle, N, seg, n):
+    sr, W, h = 48000.0, N, N // 16
+    x = np.stack([noise_chirp(n, sr, 6), sine_sweep(n, sr), noise_chirp(n, sr, 7)])   # odd row counts: both row alignments
+    pv = oracle.convert_to_pv(x, sr, W, h, N)
+    ar = oracle.analysis_rate(sr, h)
+    out, _, flag = emu.synthesis(pv, sr, ar, W, seg_len=seg, variant=17)
+    assert flag == 0
+    assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+    # the 8-point kernel adds the same products in the same order: identical up to the FFT's rounding
+    old, _, _ = emu.synthesis(pv, sr, ar, W, seg_len=seg, variant=8)
+    assert np.abs(out - old).max() < 1e-6
+
+
+@pytest.mark.parametrize("N,seg,n", MIRROR_SHAPES)
+def test_emulated_mirror_analysis_matches_oracle(emu, oracle, N, seg, n):
+    sr, W, h = 48000.0, N, N // 16
+    x = np.stack([noise_chirp(n, sr, 5), sine_sweep(n, sr)])
+    pv = emu.analysis(x, sr, W, h, N, seg_len=seg, points_per_thread=17)
+    assert not np.isnan(pv).any()
+    assert_analysis_parity(pv, oracle.convert_to_pv(x, sr, W, h, N), sr, h, N)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_mirror_frame_range_shards(emu, oracle, world):
+    sr, W, h, N = 48000.0, 1024, 64, 1024
+    n = 9000
+    x = np.stack([noise_chirp(n, sr, 21), sine_sweep(n, sr)])
+    ref_pv = oracle.convert_to_pv(x, sr, W, h, N)
+    ar = oracle.analysis_rate(sr, h)
+    ref_audio = oracle.convert_to_audio(ref_pv, sr, ar, W)
+    full = emu.analysis(x, sr, W, h, N, points_per_thread=17)
+    carry = None
+    total = np.zeros_like(ref_audio)
+    for r in range(world):
+        s = frame_shard(n, h, W, world, r)
+        local = np.ascontiguousarray(x[:, s.audio_lo:s.audio_hi])
+        pv = emu.analysis(local, sr, W, h, N, s.f0, s.f1, audio_offset=s.audio_lo, n_total=n, points_per_thread=17)
+        assert np.array_equal(pv.view(np.uint32), full[:, s.f0:s.f1].view(np.uint32))
+        out, carry, _ = emu.synthesis(ref_pv[:, s.f0:s.f1], sr, ar, W, frame_begin=s.f0, frames_total=s.frames_total,
+                                      carry_in=carry, want_carry=True, out_offset=s.span_lo,
+                                      out_len=s.span_hi - s.span_lo, variant=17)
+        total[:, s.span_lo:s.span_hi] += out
+    assert_synthesis_parity(total, ref_audio)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
