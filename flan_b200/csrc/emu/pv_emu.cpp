@@ -93,7 +93,7 @@ template<int N> void analysis_mirror_n( const AnalysisArgs & a, int64_t blocks )
 template<int N> void synthesis_n( const SynthArgs & a, int64_t blocks )
 	{
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N, 8>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta<N>( a, b, env, ola, x0, x1, rowbuf ); } );
+		run_cta<N, 8>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { if( N == 8192 ) synthesis_cta<N, true>( a, b, env, ola, x0, x0, rowbuf ); else synthesis_cta<N, false>( a, b, env, ola, x0, x1, rowbuf ); } );
 	}
 
 template<int N> void synthesis_mirror_n( const SynthArgs & a, int64_t blocks )

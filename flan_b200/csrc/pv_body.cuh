@@ -25,8 +25,21 @@ namespace pvk {
 // FFT pass chain over the ping-pong exchange buffers x0/x1 (XBuf<M>::size float2 each).
 // Pass 0 (radix 8, no twiddles) is issued by the caller; this runs passes 1..last.
 // ------------------------------------------------------------------------------------------------
-template<int M, int PT, int p, bool STORE_LAST, bool ONE, class Env>
-PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env )
+// Twiddles of pass p into w[] (at most PT-1 values); no-op past the last pass.
+template<int M, int PT, int p, class Env>
+PV_HD void fft_chain_twiddles( int t, float2 * w, const float2 * tw, Env & env )
+	{
+	using P = FftPlan<M, PT>;
+	if constexpr( p < P::num_passes )
+		fft_load_twiddles<M, PT, P::radix( p ), P::ns( p )>( t, w, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
+	}
+
+// PRE: `w` holds the twiddles of pass p on entry: the caller requests them (fft_chain_twiddles) BEFORE the barrier that
+// publishes pass p-1's outputs, and each pass requests the next one's before its own barrier, so the table reads never
+// wait behind a barrier. Measured: a gain where registers are free at the barrier (resynthesis), a loss in the
+// analysis kernels, whose 128 registers are full (cfg2 1.66 -> 1.70 ms); those read the table inside the pass (!PRE).
+template<int M, int PT, int p, bool STORE_LAST, bool ONE, bool PRE, class Env>
+PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const float2 * tw, Env & env, float2 * w )
 	{
 	using P = FftPlan<M, PT>;
 	if constexpr( p < P::num_passes )
@@ -38,11 +51,14 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 		float2 * in  = ( ONE || ( p - 1 ) % 2 == 0 ) ? x0 : x1;
 		float2 * out = ( ONE || p % 2 == 0 ) ? x0 : x1;
 		fft_load<M, PT, NSp>( t, v, in );
-		if constexpr( ONE ) env.sync();      // everyone has read before anyone writes
-		fft_butterflies<M, PT, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
+		// everyone has read before anyone writes (a last pass that stores nothing needs no such barrier)
+		if constexpr( ONE && ( p < P::num_passes - 1 || STORE_LAST ) ) env.sync();
+		if constexpr( PRE ) fft_butterflies_w<M, PT, R, NS>( v, w );
+		else fft_butterflies<M, PT, R, NS>( t, v, tw + P::tw_offset( p ), [&]( const float2 * q ) { return env.ldg2( q ); } );
 		if constexpr( p < P::num_passes - 1 )
 			{
 			fft_store<M, PT, R, NS>( t, v, out );
+			if constexpr( PRE ) fft_chain_twiddles<M, PT, p + 1>( t, w, tw, env );
 			env.sync();
 			}
 		else if constexpr( STORE_LAST )
@@ -53,7 +69,7 @@ PV_HD void fft_pass_chain( int t, float2 * v, float2 * x0, float2 * x1, const fl
 			for( int s = PT / 2; s < PT; ++s ) out[t + s * ( M / PT )] = v[s];
 			env.sync();
 			}
-		fft_pass_chain<M, PT, p + 1, STORE_LAST, ONE>( t, v, x0, x1, tw, env );
+		fft_pass_chain<M, PT, p + 1, STORE_LAST, ONE, PRE>( t, v, x0, x1, tw, env, w );
 		}
 	}
 
@@ -176,7 +192,7 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			}
 
 #ifndef PV_ABL_NOFFT
-		fft_pass_chain<M, PT, 1, true, ONE>( t, v, x0, x1, a.pass_tw, env );
+		fft_pass_chain<M, PT, 1, true, ONE, false>( t, v, x0, x1, a.pass_tw, env, (float2 *) nullptr );
 #endif
 		const float2 * z = fft_result_buffer<M, PT, ONE>( x0, x1 );     // upper half of Z/2 in natural order
 
@@ -346,12 +362,18 @@ PV_HD void analysis_cta_mirror( const AnalysisArgs & a, int64_t block, Env & env
 			}
 		fft_butterflies<M, PT, PT, 1>( t, v, (const float2 *) nullptr, ldtw );
 		fft_store<M, PT, PT, 1>( t, v, x0 );
+		float2 tw[PT - 1];          // the next pass's twiddles, requested before the barrier (v is dead here)
+		fft_load_twiddles<M, PT, PT, PT>( t, tw, a.pass_tw + P::tw_offset( 1 ), ldtw );
 		env.sync();
 
 		fft_load<M, PT, 1>( t, v, x0 );
 		if( x0 == x1 ) env.sync();      // one exchange buffer: everyone has read before anyone writes
-		fft_butterflies<M, PT, PT, PT>( t, v, a.pass_tw + P::tw_offset( 1 ), ldtw );
+		fft_butterflies_w<M, PT, PT, PT>( v, tw );
 		fft_store<M, PT, PT, PT>( t, v, x1 );
+#pragma unroll
+		for( int q = 0; q < Q; ++q )
+#pragma unroll
+			for( int r = 1; r < R; ++r ) tw[q * ( R - 1 ) + r - 1] = ldtw( tw_last + ( r - 1 ) * NS + t + q * T );
 		env.sync();
 
 		const bool emit = ( f >= fa );
@@ -373,7 +395,7 @@ PV_HD void analysis_cta_mirror( const AnalysisArgs & a, int64_t block, Env & env
 #pragma unroll
 			for( int r = 1; r < R; ++r )
 				{
-				const float2 wa = ldtw( tw_last + ( r - 1 ) * NS + jA );
+				const float2 wa = tw[q * ( R - 1 ) + r - 1];
 				float2 wb = wa;
 				if( own_tw ) wb = ldtw( tw_last + ( r - 1 ) * NS + ( NS - jB ) );
 				za[r] = cmul2( za[r], wa );
@@ -511,7 +533,9 @@ struct SynthArgs
 	double P, rcpP;             // double(pi2) and its reciprocal
 	};
 
-template<int N, class Env>
+// ONE: the two exchange buffers alias (x1 == x0): three more barriers per frame, 37 KB less shared memory at dft 8192,
+// which lets two CTAs share an SM there.
+template<int N, bool ONE, class Env>
 PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf )
 	{
 	constexpr int M = N / 2, T = M / 8, B = M + 1;
@@ -653,11 +677,14 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 
 #pragma unroll
 		for( int s = 4; s < 8; ++s ) v[s] = x1[t + s * T];          // upper half of Z' from the mirror threads
+		if constexpr( ONE ) env.sync();
 		fft_butterflies<M, 8, 8, 1>( t, v, (const float2 *) nullptr, [&]( const float2 * q ) { return env.ldg2( q ); } );
 		fft_store<M, 8, 8, 1>( t, v, x0 );
+		float2 tw[7];
+		fft_chain_twiddles<M, 8, 1>( t, tw, a.pass_tw, env );
 		env.sync();
 #ifndef PV_ABL_NOFFT
-		fft_pass_chain<M, 8, 1, false, false>( t, v, x0, x1, a.pass_tw, env );
+		fft_pass_chain<M, 8, 1, false, ONE, true>( t, v, x0, x1, a.pass_tw, env, tw );
 #endif
 
 		// v[s] = swapped z[n], n = t + s*T: y[2n] = v.y, y[2n+1] = v.x. Windowed overlap-add (AudioPV.cpp:133-134).
@@ -912,6 +939,8 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 #pragma unroll
 			for( int r = 0; r < R; ++r ) { oa[r] = za[r]; ob[r] = zb[r]; }
 			}
+		float2 tw[PT - 1];          // the next pass's twiddles, requested before the barrier (v is dead here)
+		fft_load_twiddles<M, PT, PT, RP::NS1>( t, tw, a.pass_tw_rev + RP::tw1, ldtw );
 		env.sync();
 		// every thread has consumed row f: fetch row f+1 behind the transform
 		const bool next_bulk = ( f + 1 < fb ) && row_is_bulk( f + 1 );
@@ -923,12 +952,13 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 		cur_bulk = next_bulk;
 		// pass 1: radix 16, Ns = R
 		fft_load<M, PT, 1>( t, v, x0 );
-		fft_butterflies<M, PT, PT, RP::NS1>( t, v, a.pass_tw_rev + RP::tw1, ldtw );
+		fft_butterflies_w<M, PT, PT, RP::NS1>( v, tw );
 			{
 			const int base = xpad_rev<R>( ( t / R ) * R * PT + ( t & ( R - 1 ) ) );
 #pragma unroll
 			for( int r = 0; r < PT; ++r ) x1[base + r * R] = v[r];
 			}
+		fft_load_twiddles<M, PT, PT, RP::NS2>( t, tw, a.pass_tw_rev + RP::tw2, ldtw );
 		env.sync();
 		// pass 2: radix 16, Ns = 16R = T: outputs t + r*T, i.e. v[s] = swapped z[t + s*T]: y[2n] = v.y, y[2n+1] = v.x
 			{
@@ -936,7 +966,7 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 #pragma unroll
 			for( int s = 0; s < PT; ++s ) v[s] = base[s * ( T + R )];
 			}
-		fft_butterflies<M, PT, PT, RP::NS2>( t, v, a.pass_tw_rev + RP::tw2, ldtw );
+		fft_butterflies_w<M, PT, PT, RP::NS2>( v, tw );
 
 		// windowed overlap-add (AudioPV.cpp:133-134) on the thread's own ring; slot s of this frame is absolute pair
 		// t + T*(f + s - 8) (half/2 == 8T), i.e. ring entry (f + s + 8) & 15

@@ -72,6 +72,7 @@ struct flan_b200_ctx
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
+	bool tps_synthesis_set = false;     // dft 8192 defaults to the 1024-thread (two CTAs per SM, one exchange buffer) variant
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
 	};
@@ -252,7 +253,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	a.pv_aligned16 = ( (uintptr_t) d_pv_rows % 16 == 0 ); a.channels = C;
 	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
 	{ LaunchTimer lt( ctx, 3 ); const bool mirror = ctx->synth_variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a );
-	  CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, mirror ? ctx->tps_synthesis_mirror : ctx->tps_synthesis, ctx->synth_variant ), "synthesis launch" ); }
+	  CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, mirror ? ctx->tps_synthesis_mirror : ( ( N == 8192 && !ctx->tps_synthesis_set ) ? 1024 : ctx->tps_synthesis ), ctx->synth_variant ), "synthesis launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -293,7 +294,7 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	auto * ctx = new flan_b200_ctx;
 	ctx->device = device;
 	if( const char * e = std::getenv( "FLAN_B200_TPS_ANALYSIS" ) ) ctx->tps_analysis = std::atoi( e );
-	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) { ctx->tps_synthesis = std::atoi( e ); ctx->tps_synthesis_mirror = ctx->tps_synthesis; }
+	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) { ctx->tps_synthesis = std::atoi( e ); ctx->tps_synthesis_mirror = ctx->tps_synthesis; ctx->tps_synthesis_set = true; }
 	if( const char * e = std::getenv( "FLAN_B200_PT_ANALYSIS" ) ) ctx->pt_analysis = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_ONEBUF" ) ) ctx->one_buffer = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_SYNTH_VARIANT" ) ) ctx->synth_variant = std::atoi( e );

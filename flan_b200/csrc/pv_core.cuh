@@ -281,6 +281,36 @@ PV_HD void fft_butterflies( int t, float2 * v, const float2 * tw, TwLoad && ldtw
 		}
 	}
 
+// The same pass with its twiddles fetched ahead of time (fft_load_twiddles before the barrier that publishes the pass's
+// inputs, while the thread's value registers are dead), so the table reads' latency is not exposed behind the barrier.
+template<int M, int PT, int R, int NS, class TwLoad>
+PV_HD void fft_load_twiddles( int t, float2 * w, const float2 * tw, TwLoad && ldtw )
+	{
+	constexpr int T = M / PT, U = PT / R;
+#pragma unroll
+	for( int u = 0; u < U; ++u )
+		{
+		const int jm = ( t + u * T ) & ( NS - 1 );
+#pragma unroll
+		for( int r = 1; r < R; ++r ) w[u * ( R - 1 ) + r - 1] = ldtw( tw + ( r - 1 ) * NS + jm );
+		}
+	}
+template<int M, int PT, int R, int NS>
+PV_HD void fft_butterflies_w( float2 * v, const float2 * w )
+	{
+	constexpr int U = PT / R;
+#pragma unroll
+	for( int u = 0; u < U; ++u )
+		{
+#pragma unroll
+		for( int r = 1; r < R; ++r ) v[u + r * U] = cmul2( v[u + r * U], w[u * ( R - 1 ) + r - 1] );
+		if( R == 16 ) dft16<U>( v + u );
+		if( R == 8 ) dft8<U>( v + u );
+		if( R == 4 ) dft4<U>( v + u );
+		if( R == 2 ) dft2<U>( v + u );
+		}
+	}
+
 // Scatter the pass's outputs: element r of butterfly u goes to pad(expand(jj_u)) + r*NS (the pad of a butterfly's
 // base does not depend on r for any of the layouts).
 template<int M, int PT, int R, int NS>

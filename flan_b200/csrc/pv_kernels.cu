@@ -107,16 +107,16 @@ __global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_analys
 	analysis_cta_mirror<N>( a, (int64_t) blockIdx.x, env, x0, x1, ring, scratch );
 	}
 
-template<int N, int TPS>
+template<int N, int TPS, bool ONE>
 __global__ void __launch_bounds__( N / 16, min_blocks( N / 16, TPS ) ) pv_synthesis_kernel( const SynthArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float * ola = reinterpret_cast<float *>( smem_raw );
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw + sizeof( float ) * N );
-	float2 * x1 = x0 + XBuf<N / 2>::size;
+	float2 * x1 = ONE ? x0 : x0 + XBuf<N / 2>::size;
 	float2 * rowbuf = x1 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	synthesis_cta<N>( a, (int64_t) blockIdx.x, env, ola, x0, x1, rowbuf );
+	synthesis_cta<N, ONE>( a, (int64_t) blockIdx.x, env, ola, x0, x1, rowbuf );
 	}
 
 // Mirrored first pass (pv_body.cuh: synthesis_cta_mirror): 16 points per thread, thread-private row FIFO and overlap-add ring.
@@ -294,19 +294,20 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 			{
 			if( tps >= 768 ) return launch_analysis_nt<N, 16, 768>( a, blocks, st );
 			if( tps >= 640 ) return launch_analysis_nt<N, 16, 640>( a, blocks, st );
-			return launch_analysis_nt<N, 16, 512>( a, blocks, st );
+			if( tps >= 512 ) return launch_analysis_nt<N, 16, 512>( a, blocks, st );
+			return launch_analysis_nt<N, 16, 384>( a, blocks, st );
 			}
 		}
 	if( tps >= 1024 ) return launch_analysis_nt<N, 8, 1024>( a, blocks, st );
 	if( tps >= 768 ) return launch_analysis_nt<N, 8, 768>( a, blocks, st );
 	return launch_analysis_nt<N, 8, 512>( a, blocks, st );
 	}
-template<int N, int TPS> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
-	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	const size_t smem = sizeof( float ) * N + ( ONE ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	pv_synthesis_kernel<N, TPS><<<(unsigned) blocks, N / 16, smem, st>>>( a );
+	pv_synthesis_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
 template<int N, int TPS> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
@@ -332,9 +333,11 @@ template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int6
 			return launch_synthesis_mirror_nt<N, 384>( a, blocks, st );
 			}
 		}
-	if( tps >= 1024 ) return launch_synthesis_nt<N, 1024>( a, blocks, st );
-	if( tps >= 768 ) return launch_synthesis_nt<N, 768>( a, blocks, st );
-	return launch_synthesis_nt<N, 512>( a, blocks, st );
+	// dft 8192: one exchange buffer and 64 registers per thread let two 512-thread CTAs share an SM (FLAN_B200_TPS_SYNTHESIS=1024)
+	if constexpr( N == 8192 ) { if( tps >= 1024 ) return launch_synthesis_nt<N, 1024, true>( a, blocks, st ); }
+	if( tps >= 1024 ) return launch_synthesis_nt<N, 1024, false>( a, blocks, st );
+	if( tps >= 768 ) return launch_synthesis_nt<N, 768, false>( a, blocks, st );
+	return launch_synthesis_nt<N, 512, false>( a, blocks, st );
 	}
 
 bool dft_size_supported( int N )
