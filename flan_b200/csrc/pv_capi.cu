@@ -69,6 +69,7 @@ struct flan_b200_ctx
 	// (resident threads per SM the kernel is compiled for; 0 = 512 with 16 points per thread, else 768).
 	int tps_analysis = 0, tps_synthesis = 768;
 	int pt_analysis = 0;
+	int max_seg_len = 64;   // frames per CTA at most (FLAN_B200_SEG_LEN)
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
@@ -193,7 +194,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	if( frames == 0 ) return FLAN_B200_OK;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
 	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
@@ -297,6 +298,7 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) { ctx->tps_synthesis = std::atoi( e ); ctx->tps_synthesis_mirror = ctx->tps_synthesis; ctx->tps_synthesis_set = true; }
 	if( const char * e = std::getenv( "FLAN_B200_PT_ANALYSIS" ) ) ctx->pt_analysis = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_ONEBUF" ) ) ctx->one_buffer = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_SEG_LEN" ) ) { const int v = std::atoi( e ); if( v >= 4 ) ctx->max_seg_len = v; }
 	if( const char * e = std::getenv( "FLAN_B200_SYNTH_VARIANT" ) ) ctx->synth_variant = std::atoi( e );
 	ctx->sms = prop.multiProcessorCount;
 	e = cudaMalloc( (void **) &ctx->d_flag, sizeof( int ) );
@@ -441,7 +443,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	if( need_hi > need_lo && ( audio_offset > need_lo || audio_offset + audio_len < need_hi ) )
 		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	AnalysisArgs a{};
 	a.audio = d_audio_local; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;

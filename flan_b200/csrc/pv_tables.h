@@ -156,12 +156,12 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 // Frames per CTA. Long enough that the warm-up FFT (analysis) and the shared overlap regions
 // (resynthesis: a sample may be shared by at most two segments, which needs seg_len*hop >= W-hop) are
 // amortised; short enough that the grid covers the SMs several times over.
-inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop )
+inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len = 64 )
 	{
 	const int64_t min_len = ( W + hop - 1 ) / hop;           // >= W/hop
 	int64_t target_ctas = (int64_t) sms * 8;
 	int64_t len = ( frames * channels + target_ctas - 1 ) / target_ctas;
-	if( len > 64 ) len = 64;
+	if( len > max_len ) len = max_len;
 	if( len < min_len ) len = min_len;
 	if( len < 4 ) len = 4;
 	if( len > frames ) len = frames > 0 ? frames : 1;
