@@ -69,7 +69,7 @@ struct flan_b200_ctx
 	// (resident threads per SM the kernel is compiled for; 0 = 512 with 16 points per thread, else 768).
 	int tps_analysis = 0, tps_synthesis = 768;
 	int pt_analysis = 0;
-	int max_seg_len = 64;   // frames per CTA at most (FLAN_B200_SEG_LEN)
+	int max_seg_len = 0;    // frames per CTA at most; 0 = by size: 128 from dft 4096 up (3.96 -> 3.91 ms on cfg2, mostly the shorter scan), else 64 (FLAN_B200_SEG_LEN)
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
@@ -194,7 +194,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	if( frames == 0 ) return FLAN_B200_OK;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 4096 ? 128 : 64 ) );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
 	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
@@ -443,7 +443,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	if( need_hi > need_lo && ( audio_offset > need_lo || audio_offset + audio_len < need_hi ) )
 		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 4096 ? 128 : 64 ) );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	AnalysisArgs a{};
 	a.audio = d_audio_local; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;
