@@ -69,7 +69,7 @@ struct flan_b200_ctx
 	// (resident threads per SM the kernel is compiled for; 0 = 512 with 16 points per thread, else 768).
 	int tps_analysis = 0, tps_synthesis = 768;
 	int pt_analysis = 0;
-	int max_seg_len = 0;    // frames per CTA at most; 0 = by size: 128 from dft 4096 up (3.96 -> 3.91 ms on cfg2, mostly the shorter scan), else 64 (FLAN_B200_SEG_LEN)
+	int max_seg_len = 0;    // frames per CTA at most; 0 = by size: 128 from dft 2048 up (cfg2 3.96 -> 3.91 ms, cfg4 chain 15.1 -> 14.8 ms: mostly the shorter scan), else 64 (FLAN_B200_SEG_LEN)
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
@@ -194,7 +194,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	if( frames == 0 ) return FLAN_B200_OK;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 4096 ? 128 : 64 ) );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 2048 ? 128 : 64 ) );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
 	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
@@ -443,7 +443,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	if( need_hi > need_lo && ( audio_offset > need_lo || audio_offset + audio_len < need_hi ) )
 		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 4096 ? 128 : 64 ) );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 2048 ? 128 : 64 ) );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	AnalysisArgs a{};
 	a.audio = d_audio_local; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;
@@ -455,13 +455,17 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
 	// measured on B200 (tools/exp_r1*.sh): 16 points per thread with one exchange buffer from dft 4096 up; the mirrored
 	// last pass for dft 1024 with the standard window / hop; 8 points per thread otherwise
-	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : ( N == 1024 ? PV_PT_MIRROR : 8 ) );
+	// (dft 2048: 16 points per thread once the grid covers the SMs a few times over -- 2.52 -> 2.31 ms on a cfg4 channel --
+	// 8 for short signals, where twice the threads per frame matter more)
+	// (decided on the WHOLE signal's frame count, so that every frame-range shard of a signal runs the same arithmetic)
+	const bool large = (int64_t) C * ( n_total / hop + 1 ) >= (int64_t) ctx->sms * 128;
+	int pt = ctx->pt_analysis ? ctx->pt_analysis : ( N >= 4096 ? 16 : ( N == 2048 ? ( large ? 16 : 8 ) : ( N == 1024 ? PV_PT_MIRROR : 8 ) ) );
 	if( pt == PV_PT_MIRROR && !( mirror_supported( N ) && W == N && hop == N / 16 ) ) pt = ( N >= 4096 ) ? 16 : 8;
 	if( pt != PV_PT_MIRROR && ( pt != 16 || N < 512 ) ) pt = 8;
 	const int tps_a = ctx->tps_analysis ? ctx->tps_analysis : ( pt >= 16 ? 512 : 768 );
 	a.win = plan->win_analysis; a.binc = plan->binc; a.binc4 = plan->binc4; a.post_rot = plan->post_rot;
 	a.pass_tw = ( pt >= 16 ) ? plan->pass_tw16 : plan->pass_tw;
-	a.one_buffer = ctx->one_buffer >= 0 ? ctx->one_buffer : ( ( N >= 4096 || pt == PV_PT_MIRROR ) ? 1 : 0 );
+	a.one_buffer = ctx->one_buffer >= 0 ? ctx->one_buffer : ( ( pt == 16 || pt == PV_PT_MIRROR ) ? 1 : 0 );
 	a.k = plan->host.k;
 	ctx->seg_key.valid = false;
 	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, tps_a, pt ), "analysis launch" ); }

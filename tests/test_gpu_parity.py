@@ -152,9 +152,10 @@ def test_negative_frequency_phase_representative(eng, oracle):
 # ---- frame-range shards on one GPU (the multi-GPU path, ranks emulated serially) --------------------------
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_frame_range_shards_reproduce_unsharded(eng, world):
+@pytest.mark.parametrize("name", ["cfg3", "cfg2", "cfg5"])      # 8-point one-buffer kernel; mirrored kernels (dft 4096, 1024)
+def test_frame_range_shards_reproduce_unsharded(eng, world, name):
     import torch
-    x, sr, W, h, N = make_config("cfg3", 2.0)
+    x, sr, W, h, N = make_config(name, 2.0)
     n = x.shape[1]
     xd = dev(x)
     full_pv = eng.convert_to_pv(xd, sr, W, h, N)
@@ -176,6 +177,35 @@ def test_frame_range_shards_reproduce_unsharded(eng, world):
         total[:, s.span_lo:s.span_hi] += out
     err = (total - full_audio).abs().max().item()
     assert err <= 2e-6, err
+
+
+# ---- kernel variants agree: the mirrored 16-point kernels and their fall-backs against the 8-point kernels ---------
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg5"])
+def test_kernel_variants_agree(eng, name, monkeypatch):
+    import torch
+    from flan_b200.engine import Engine
+    x, sr, W, h, N = make_config(name, 2.0)
+    x = np.concatenate([x, x[:1] * 0.5], axis=0)            # an odd number of rows before the last channel: both row alignments
+    xd = dev(x)
+    pv = eng.convert_to_pv(xd, sr, W, h, N)
+    ar = eng.analysis_rate(sr, h)
+    y = eng.convert_to_audio(pv, sr, ar, W)
+    # PV buffer that is only 8-byte aligned: bulk row copies are not possible, every thread stages its own bins
+    flat = torch.empty(pv.numel() + 2, device="cuda")
+    v = flat[2:].view_as(pv)
+    v.copy_(pv)
+    assert v.data_ptr() % 16 == 8
+    assert torch.equal(eng.convert_to_audio(v, sr, ar, W), y)
+    # the 8-point kernels (launch policy overridden through the environment, read when a context is created)
+    monkeypatch.setenv("FLAN_B200_SYNTH_VARIANT", "8")
+    monkeypatch.setenv("FLAN_B200_PT_ANALYSIS", "8")
+    eng8 = Engine(0)
+    y8 = eng8.convert_to_audio(pv, sr, ar, W)
+    assert (y8 - y).abs().max().item() <= 1e-6
+    pv8 = eng8.convert_to_pv(xd, sr, W, h, N)
+    rep = assert_analysis_parity(pv.cpu().numpy(), pv8.cpu().numpy(), sr, h, N)
+    assert rep["max_rel_m"] <= 1e-4
 
 
 # ---- BASELINE.json full sizes: size-independent properties ------------------------------------------------
