@@ -100,7 +100,7 @@ template<int N> void synthesis_mirror_n( const SynthArgs & a, int64_t blocks )
 	{
 	HostEnv::BulkBarrier bar_word = 0;
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { synthesis_cta_mirror<N>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); } );
+		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { if( a.one_buffer ) synthesis_cta_mirror<N, true>( a, b, env, (float2 *) ola, x0, x0, rowbuf, &bar_word ); else synthesis_cta_mirror<N, false>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); } );
 	}
 
 } // namespace
@@ -212,6 +212,7 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 	a.pv_aligned16 = ( (uintptr_t) pv_rows % 16 == 0 ); a.channels = C;
 	a.k = tb.k; a.P = tb.P; a.rcpP = tb.rcpP;
 	const int64_t blocks = (int64_t) C * segs;
+	a.one_buffer = ( variant >= 100 ); variant %= 100;      // +100: one exchange buffer
 	if( variant == 17 )     // PV_PT_MIRROR; the caller checks the shape conditions (W == N, hop a multiple of N/16)
 		{
 		if( !( W == N && hop == N / 16 ) ) return 3;

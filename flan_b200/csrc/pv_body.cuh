@@ -528,6 +528,7 @@ struct SynthArgs
 	const float2 * pass_tw_rev; // twiddles of the small-radix-first plan (synthesis_cta_mirror)
 	int out_aligned2;           // every even absolute sample of every channel sits on an 8-byte boundary of `out`
 	int pv_aligned16;           // `pv` is 16-byte aligned (bulk row copies)
+	int one_buffer;             // mirrored kernel: the two exchange buffers alias
 	int channels;
 	PvConsts k;
 	double P, rcpP;             // double(pi2) and its reciprocal
@@ -778,7 +779,9 @@ template<int M, int R> struct RevPlan
 // t + s*T of the next pass (T = 16R) stay contiguous.
 template<int R> PV_HD int xpad_rev( int i ) { return i + R * ( i / ( 16 * R ) ); }
 
-template<int N, class Env>
+// ONE: the two exchange buffers alias (x1 == x0): two more barriers per frame, 18 KB less shared memory per CTA, which
+// moves the SM's carve-out from 228 KB to 164 KB and so gives the twiddle tables (32 KB) an L1 they fit in.
+template<int N, bool ONE, class Env>
 PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, float2 * ring, float2 * x0, float2 * x1, float2 * rowbuf,
                                  typename Env::BulkBarrier * bar )
 	{
@@ -927,6 +930,7 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 				}
 			}
 		// pass 0: radix R, no twiddles, butterflies p and NS-p; outputs R*jj + r in the padded layout
+		if constexpr( ONE ) env.sync();     // the previous frame's last pass has read the buffer (long ago: the barrier is cheap)
 #pragma unroll
 		for( int q = 0; q < Q; ++q )
 			{
@@ -952,6 +956,7 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 		cur_bulk = next_bulk;
 		// pass 1: radix 16, Ns = R
 		fft_load<M, PT, 1>( t, v, x0 );
+		if constexpr( ONE ) env.sync();     // everyone has read before anyone writes
 		fft_butterflies_w<M, PT, PT, RP::NS1>( v, tw );
 			{
 			const int base = xpad_rev<R>( ( t / R ) * R * PT + ( t & ( R - 1 ) ) );

@@ -73,6 +73,7 @@ struct flan_b200_ctx
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
+	int synth_one_buffer = 0;           // mirrored resynthesis with one exchange buffer (FLAN_B200_SYNTH_ONEBUF)
 	bool tps_synthesis_set = false;     // dft 8192 defaults to the 1024-thread (two CTAs per SM, one exchange buffer) variant
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
@@ -231,12 +232,17 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	sc.carry_in = d_carry_in; sc.carry_out = d_carry_out;
 	sc.acc_start = summary_only ? nullptr : d_acc;
 	sc.P = plan->host.P; sc.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); ctx->launches += summary_only ? 1 : 2; }
+	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); ctx->launches += ( segs <= 256 ) ? 0 : ( summary_only ? 1 : 2 ); }     // launch_phase_scan: one launch for short signals, else 2 or 3
 	if( summary_only ) return FLAN_B200_OK;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
-	for( int c = 0; c < C; ++c )
-		CK( cudaMemsetAsync( d_out + (int64_t) c * out_stride, 0, sizeof( float ) * (size_t) out_len, ctx->stream ), "output clear" );
+	// The kernels store every sample that only one segment reaches and red.add the rest onto zeros: clear just those
+	// (a few per cent of the output) when the frames' windows leave no gaps, everything otherwise.
+	if( hop <= W && C < 65535 )
+		{ CK( launch_zero_shared( d_out, out_stride, out_offset, out_len, C, frame_begin, frame_end, seg_len, segs, W, hop, ctx->stream ), "output clear" ); ctx->launches++; }
+	else
+		for( int c = 0; c < C; ++c )
+			CK( cudaMemsetAsync( d_out + (int64_t) c * out_stride, 0, sizeof( float ) * (size_t) out_len, ctx->stream ), "output clear" );
 
 	SynthArgs a{};
 	a.pv = (const float2 *) d_pv_rows; a.pv_channel_stride = pv_channel_stride;
@@ -252,6 +258,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw; a.pass_tw_rev = plan->pass_tw_rev;
 	a.out_aligned2 = ( out_stride % 2 == 0 ) && ( out_offset % 2 == 0 ) && ( (uintptr_t) d_out % 8 == 0 );
 	a.pv_aligned16 = ( (uintptr_t) d_pv_rows % 16 == 0 ); a.channels = C;
+	a.one_buffer = ctx->synth_one_buffer;
 	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
 	{ LaunchTimer lt( ctx, 3 ); const bool mirror = ctx->synth_variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a );
 	  CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, mirror ? ctx->tps_synthesis_mirror : ( ( N == 8192 && !ctx->tps_synthesis_set ) ? 1024 : ctx->tps_synthesis ), ctx->synth_variant ), "synthesis launch" ); }
@@ -298,6 +305,7 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	if( const char * e = std::getenv( "FLAN_B200_TPS_SYNTHESIS" ) ) { ctx->tps_synthesis = std::atoi( e ); ctx->tps_synthesis_mirror = ctx->tps_synthesis; ctx->tps_synthesis_set = true; }
 	if( const char * e = std::getenv( "FLAN_B200_PT_ANALYSIS" ) ) ctx->pt_analysis = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_ONEBUF" ) ) ctx->one_buffer = std::atoi( e );
+	if( const char * e = std::getenv( "FLAN_B200_SYNTH_ONEBUF" ) ) ctx->synth_one_buffer = std::atoi( e );
 	if( const char * e = std::getenv( "FLAN_B200_SEG_LEN" ) ) { const int v = std::atoi( e ); if( v >= 4 ) ctx->max_seg_len = v; }
 	if( const char * e = std::getenv( "FLAN_B200_SYNTH_VARIANT" ) ) ctx->synth_variant = std::atoi( e );
 	ctx->sms = prop.multiProcessorCount;

@@ -120,17 +120,17 @@ __global__ void __launch_bounds__( N / 16, min_blocks( N / 16, TPS ) ) pv_synthe
 	}
 
 // Mirrored first pass (pv_body.cuh: synthesis_cta_mirror): 16 points per thread, thread-private row FIFO and overlap-add ring.
-template<int N, int TPS>
+template<int N, int TPS, bool ONE>
 __global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_synthesis_mirror_kernel( const SynthArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * ring = reinterpret_cast<float2 *>( smem_raw );                 // N/2 pairs
 	float2 * x0 = ring + N / 2;
-	float2 * x1 = x0 + XBuf<N / 2>::size;
+	float2 * x1 = ONE ? x0 : x0 + XBuf<N / 2>::size;
 	float2 * rowbuf = x1 + XBuf<N / 2>::size;                               // N/2 + 2 pairs
 	__shared__ __align__( 8 ) DeviceEnv::BulkBarrier bar;
 	DeviceEnv env; env.tid = threadIdx.x;
-	synthesis_cta_mirror<N>( a, (int64_t) blockIdx.x, env, ring, x0, x1, rowbuf, &bar );
+	synthesis_cta_mirror<N, ONE>( a, (int64_t) blockIdx.x, env, ring, x0, x1, rowbuf, &bar );
 	}
 
 // One thread per (channel, segment, bin): summary of the segment's phase increments.
@@ -168,6 +168,19 @@ __global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanAr
 	if( b >= a.B ) return;
 	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
 	PhaseSeg * grp = a.group + (int64_t) c * a.groups * a.B + b;
+	if( mode == 3 )     // short signals: one serial walk over all segments, a single launch
+		{
+		if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
+		const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
+		double * dst = a.acc_start ? a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b : nullptr;
+		for( int s = 0; s < a.segs_per_channel; ++s )
+			{
+			if( dst ) dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
+			phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+			}
+		if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = st;
+		return;
+		}
 	if( mode == 1 )
 		{
 		if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
@@ -218,6 +231,41 @@ __global__ void __launch_bounds__( 256 ) pv_mid_side_kernel( const float * in, f
 		out[i]     = __fdiv_rn( __fadd_rn( l, r ), sqrt2 );
 		out[n + i] = __fdiv_rn( __fsub_rn( l, r ), sqrt2 );
 		}
+	}
+
+// Clears the output samples the resynthesis kernels reach with red.add (those shared by two segments, and the head and
+// tail of the local span) instead of the whole output: every other sample is written exactly once by a plain store.
+// Region j of a channel lies between the interior of segment j-1 and the interior of segment j (pv_body.cuh:
+// interior_lo = hop*fa + W/2 - hop, interior_hi = hop*fb - W/2; an empty interior counts as the point interior_lo).
+// Requires hop <= window (no gaps between the frames' windows).
+__global__ void __launch_bounds__( 256 ) pv_zero_shared_kernel( float * out, int64_t out_stride, int64_t out_offset, int64_t out_len,
+                                                                 int64_t frame_begin, int64_t frame_end, int seg_len, int segs, int W, int hop )
+	{
+	const int j = blockIdx.x;            // 0 .. segs
+	const int c = blockIdx.y;
+	const int half = W / 2;
+	auto seg_lo = [&]( int s ) { return (int64_t) hop * ( frame_begin + (int64_t) s * seg_len ) + half - hop; };
+	auto seg_hi = [&]( int s )
+		{
+		const int64_t fa = frame_begin + (int64_t) s * seg_len;
+		const int64_t fb = ( fa + seg_len < frame_end ) ? fa + seg_len : frame_end;
+		const int64_t hi = (int64_t) hop * fb - half, lo = seg_lo( s );
+		return hi > lo ? hi : lo;
+		};
+	int64_t lo = ( j == 0 ) ? out_offset : seg_hi( j - 1 );
+	int64_t hi = ( j == segs ) ? out_offset + out_len : seg_lo( j );
+	if( lo < out_offset ) lo = out_offset;
+	if( hi > out_offset + out_len ) hi = out_offset + out_len;
+	float * dst = out + (int64_t) c * out_stride - out_offset;
+	for( int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x ) dst[i] = 0.0f;
+	}
+
+cudaError_t launch_zero_shared( float * out, int64_t out_stride, int64_t out_offset, int64_t out_len, int C,
+                                int64_t frame_begin, int64_t frame_end, int seg_len, int segs, int W, int hop, cudaStream_t st )
+	{
+	const dim3 grid( (unsigned)( segs + 1 ), (unsigned) C );
+	pv_zero_shared_kernel<<<grid, 256, 0, st>>>( out, out_stride, out_offset, out_len, frame_begin, frame_end, seg_len, segs, W, hop );
+	return cudaGetLastError();
 	}
 
 // out[i] += add[i] (overlap-add halo received from a neighbouring frame-range shard)
@@ -310,13 +358,13 @@ template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_nt( const
 	pv_synthesis_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
-template<int N, int TPS> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
-	const size_t smem = sizeof( float ) * N + 2 * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
-	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	const size_t smem = sizeof( float ) * N + ( ONE ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	apply_carveout( pv_synthesis_mirror_kernel<N, TPS> );
-	pv_synthesis_mirror_kernel<N, TPS><<<(unsigned) blocks, N / 32, smem, st>>>( a );
+	apply_carveout( pv_synthesis_mirror_kernel<N, TPS, ONE> );
+	pv_synthesis_mirror_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 32, smem, st>>>( a );
 	return cudaGetLastError();
 	}
 bool synthesis_mirror_applies( int N, const SynthArgs & a )
@@ -329,8 +377,9 @@ template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int6
 		{
 		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
 			{
-			if( tps >= 512 ) return launch_synthesis_mirror_nt<N, 512>( a, blocks, st );
-			return launch_synthesis_mirror_nt<N, 384>( a, blocks, st );
+			if( tps >= 512 ) return launch_synthesis_mirror_nt<N, 512, false>( a, blocks, st );
+			if( a.one_buffer ) return launch_synthesis_mirror_nt<N, 384, true>( a, blocks, st );
+			return launch_synthesis_mirror_nt<N, 384, false>( a, blocks, st );
 			}
 		}
 	// dft 8192: one exchange buffer and 64 registers per thread let two 512-thread CTAs share an SM (FLAN_B200_TPS_SYNTHESIS=1024)
@@ -383,6 +432,11 @@ cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st )
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 	{
 	const dim3 wide( ( a.B + 127 ) / 128, a.groups, C ), narrow( ( a.B + 127 ) / 128, 1, C );
+	if( a.segs_per_channel <= 256 )     // latency-bound sizes: one launch instead of three
+		{
+		pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 3 );
+		return cudaGetLastError();
+		}
 	pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
 	pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
 	if( a.acc_start ) pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 2 );

@@ -46,6 +46,8 @@ cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st );
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st );
 cudaError_t launch_phase_carry( const PhaseSeg * all, int rank, int64_t per_rank, PhaseSeg * carry, double P, double rcpP, cudaStream_t st );
 cudaError_t launch_mid_side( const float * in, float * out, int64_t n, int sms, cudaStream_t st );
+cudaError_t launch_zero_shared( float * out, int64_t out_stride, int64_t out_offset, int64_t out_len, int C,
+                                int64_t frame_begin, int64_t frame_end, int seg_len, int segs, int W, int hop, cudaStream_t st );
 cudaError_t launch_add( float * out, const float * add, int64_t n, int sms, cudaStream_t st );
 
 } // namespace pvk

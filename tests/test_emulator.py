@@ -77,6 +77,8 @@ def test_emulated_mirror_synthesis_matches_oracle(emu, oracle, N, seg, n):
     out, _, flag = emu.synthesis(pv, sr, ar, W, seg_len=seg, variant=17)
     assert flag == 0
     assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+    one, _, _ = emu.synthesis(pv, sr, ar, W, seg_len=seg, variant=117)      # one exchange buffer: same arithmetic
+    assert np.array_equal(one.view(np.uint32), out.view(np.uint32))
     # the 8-point kernel adds the same products in the same order: identical up to the FFT's rounding
     old, _, _ = emu.synthesis(pv, sr, ar, W, seg_len=seg, variant=8)
     assert np.abs(out - old).max() < 1e-6
