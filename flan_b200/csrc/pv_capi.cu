@@ -461,7 +461,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	a.W = W; a.hop = hop;
 	a.aligned2 = ( hop % 2 == 0 ) && ( ( W / 2 ) % 2 == 0 ) && ( audio_stride % 2 == 0 ) && ( audio_offset % 2 == 0 )
 	          && ( (uintptr_t) d_audio_local % 8 == 0 );
-	// measured on B200 (tools/exp_r1*.sh): 16 points per thread with one exchange buffer from dft 4096 up; the mirrored
+	// measured on B200 (tools/experiments/exp_r1*.sh): 16 points per thread with one exchange buffer from dft 4096 up; the mirrored
 	// last pass for dft 1024 with the standard window / hop; 8 points per thread otherwise
 	// (dft 2048: 16 points per thread once the grid covers the SMs a few times over -- 2.52 -> 2.31 ms on a cfg4 channel --
 	// 8 for short signals, where twice the threads per frame matter more)
