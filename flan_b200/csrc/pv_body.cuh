@@ -5,16 +5,20 @@
 // identical source runs on the device (pv_kernels.cu) and in the CPU thread emulator (emu/pv_emu.cpp).
 //
 // Work decomposition (both directions): a CTA owns one contiguous SEGMENT of frames of one channel and
-// walks it in frame order. A frame of N-point real FFT is computed by T = N/16 threads, 8 complex
-// points each (the real transform is a packed N/2-point complex FFT). Walking in order lets
+// walks it in frame order. A frame of N-point real FFT is computed by T = N/16 (8 complex points per thread)
+// or N/32 threads (16 points; the real transform is a packed N/2-point complex FFT). Walking in order lets
 //   * analysis keep the previous frame's phase of "its" bins in registers (the serial dependency of
 //     AudioPV.cpp:47/phase_vocoder.cpp:44-45), at the cost of one warm-up FFT per segment; consecutive
 //     windows overlap by W-hop samples, which stay in L1, so each input sample leaves HBM once;
 //   * resynthesis keep the fp64 phase accumulators (phase_vocoder.cpp:58-59) in registers and the
-//     overlap-add in a shared-memory ring that is flushed hop by hop, so every output sample is
-//     written once, contributions added in increasing frame order like AudioPV.cpp:133-134.
+//     overlap-add in a shared-memory ring, so every output sample is written once, contributions added in
+//     increasing frame order like AudioPV.cpp:133-134.
 // Window coefficients and bin constants for a thread's fixed positions stay in registers across the walk;
 // every shared-memory access is "per-thread base + immediate" (see xpad in pv_core.cuh).
+//
+// Bodies: analysis_cta (8 / 16 points per thread, any window and hop), analysis_cta_mirror and
+// synthesis_cta_mirror (16 points, the butterfly pair (p, NS-p) in one thread: window == dft, hop == dft/16),
+// synthesis_cta (8 points, any window and hop). DESIGN.md section 4 says which one serves which call and why.
 #pragma once
 
 #include "pv_core.cuh"
@@ -23,7 +27,7 @@ namespace pvk {
 
 // ------------------------------------------------------------------------------------------------
 // FFT pass chain over the ping-pong exchange buffers x0/x1 (XBuf<M>::size float2 each).
-// Pass 0 (radix 8, no twiddles) is issued by the caller; this runs passes 1..last.
+// Pass 0 (radix 8 or 16, no twiddles) is issued by the caller; this runs passes 1..last.
 // ------------------------------------------------------------------------------------------------
 // Twiddles of pass p into w[] (at most PT-1 values); no-op past the last pass.
 template<int M, int PT, int p, class Env>
