@@ -23,7 +23,7 @@ def emu():
 
 SHAPES = [(256, 16, 256, 20), (512, 32, 512, 17), (1024, 64, 1024, 16), (2048, 128, 2048, 7), (4096, 256, 4096, 5),
           (8192, 512, 8192, 3), (256, 64, 1024, 0), (1000, 100, 1024, 0), (2048, 128, 4096, 0), (512, 512, 512, 0),
-          (300, 7, 512, 0)]
+          (300, 7, 512, 0), (256, 400, 256, 0)]
 
 
 @pytest.mark.parametrize("W,h,N,seg", SHAPES)

@@ -53,7 +53,8 @@ def test_convert_to_audio_matches_oracle(eng, oracle, name, sec):
 
 
 @pytest.mark.parametrize("W,h,N", [(256, 16, 256), (512, 32, 512), (256, 64, 1024), (1000, 100, 1024), (2048, 128, 4096),
-                                   (512, 512, 512), (300, 7, 512), (2048, 2048, 2048), (8192, 64, 8192)])
+                                   (512, 512, 512), (300, 7, 512), (2048, 2048, 2048), (8192, 64, 8192),
+                                   (256, 400, 256)])        # hop > window: gaps between frames stay zero (full output clear)
 def test_odd_shapes_match_oracle(eng, oracle, W, h, N):
     sr = 32000.0
     n = 9001
