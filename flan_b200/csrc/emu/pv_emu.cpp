@@ -221,6 +221,7 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 			case 1024: synthesis_mirror_n<1024>( a, blocks ); return 0;
 			case 2048: synthesis_mirror_n<2048>( a, blocks ); return 0;
 			case 4096: synthesis_mirror_n<4096>( a, blocks ); return 0;
+			case 8192: synthesis_mirror_n<8192>( a, blocks ); return 0;
 			default: return 2;
 			}
 		}

@@ -274,10 +274,9 @@ template<int R, int S> PV_HD void dft_r( float2 * a )
 template<int N> struct MirrorPlan
 	{
 	static constexpr int PT = 16, M = N / 2, T = M / PT;
-	using P = FftPlan<M, PT>;
-	static_assert( P::num_passes == 3 && P::last_r >= 2, "mirrored passes need radices 16, 16, R" );
-	static constexpr int R = P::last_r;          // radix of the mirrored pass
-	static constexpr int NS = M / R;             // its butterfly count (= 256)
+	using P = FftPlan<M, PT>;                    // the analysis kernel's passes 16, 16, R (dft 1024 / 2048 / 4096)
+	static constexpr int R = ( M >= 2048 ) ? 8 : M / 256;    // radix of the mirrored pass: 2, 4, 8 (dft 8192: 8, resynthesis only)
+	static constexpr int NS = M / R;             // its butterfly count (256; 512 at dft 8192)
 	static constexpr int Q = PT / R / 2;         // mirrored butterfly pairs per thread
 	static constexpr int KHI = -( M - NS ) / 2;  // bin offset of the upper slots of the irregular pair
 	};
@@ -287,6 +286,7 @@ PV_HD void analysis_cta_mirror( const AnalysisArgs & a, int64_t block, Env & env
 	{
 	using MP = MirrorPlan<N>;
 	using P = typename MP::P;
+	static_assert( P::num_passes == 3 && P::last_r == MP::R, "mirrored analysis needs radices 16, 16, R" );
 	constexpr int PT = 16, M = MP::M, T = MP::T, R = MP::R, NS = MP::NS, Q = MP::Q;
 	constexpr int hop = 2 * T, half = N / 2;           // window == N, hop == N/16 (checked by the launcher)
 	const int t = env.tid;
@@ -770,17 +770,19 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 // ------------------------------------------------------------------------------------------------
 template<int M, int R> struct RevPlan
 	{
-	// Stockham passes R, 16, 16 of a complex M-point FFT, 16 points per thread
-	static constexpr int NS1 = R, NS2 = 16 * R;
-	static_assert( NS2 * 16 == M, "M = R * 256" );
-	static constexpr int tw1 = 0;                  // pass 1 (radix 16, Ns = R):   [15][R]
-	static constexpr int tw2 = 15 * NS1;           // pass 2 (radix 16, Ns = 16R): [15][16R]
-	static constexpr int tw_total = tw2 + 15 * NS2;
+	// Stockham passes R, 16, 16 (and a last radix-2 pass at 4096 points) of a complex M-point FFT, 16 points per thread
+	static constexpr int NS1 = R, NS2 = 16 * R, NS3 = 256 * R;
+	static constexpr int R3 = M / NS3;             // 1 (no fourth pass) or 2
+	static_assert( R3 == 1 || R3 == 2, "M = 256 R or 512 R" );
+	static constexpr int tw1 = 0;                  // pass 1 (radix 16, Ns = R):    [15][R]
+	static constexpr int tw2 = 15 * NS1;           // pass 2 (radix 16, Ns = 16R):  [15][16R]
+	static constexpr int tw3 = tw2 + 15 * NS2;     // pass 3 (radix 2, Ns = 256R):  [1][256R]
+	static constexpr int tw_total = tw3 + ( R3 - 1 ) * NS3;
 	};
 
 // Exchange layout after the radix-16 pass with Ns = R (lanes write 16R*(jj/R) + jj%R + R*r): blocks of 16R elements
 // are shifted by R each, which makes the 16 accesses of a half-warp hit 16 distinct 8-byte bank pairs; the reads
-// t + s*T of the next pass (T = 16R) stay contiguous.
+// t + s*T of the next pass (T a multiple of 16R) stay contiguous per half-warp.
 template<int R> PV_HD int xpad_rev( int i ) { return i + R * ( i / ( 16 * R ) ); }
 
 // ONE: the two exchange buffers alias (x1 == x0): two more barriers per frame, 18 KB less shared memory per CTA, which
@@ -792,7 +794,7 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 	using MP = MirrorPlan<N>;
 	constexpr int PT = 16, M = MP::M, T = MP::T, R = MP::R, NS = MP::NS, Q = MP::Q, B = M + 1;
 	using RP = RevPlan<M, R>;
-	static_assert( T == 16 * R, "threads per frame" );
+	static_assert( T % ( 16 * R ) == 0, "threads per frame" );
 	const int t = env.tid;
 	const int c = (int)( block / a.segs_per_channel );
 	const int seg = (int)( block % a.segs_per_channel );
@@ -934,7 +936,9 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 				}
 			}
 		// pass 0: radix R, no twiddles, butterflies p and NS-p; outputs R*jj + r in the padded layout
-		if constexpr( ONE ) env.sync();     // the previous frame's last pass has read the buffer (long ago: the barrier is cheap)
+		// the previous frame's last pass has read this buffer (long ago: the barrier is cheap); with the fourth pass of
+		// dft 8192 that holds for x0 even when the two buffers are distinct
+		if constexpr( ONE || RP::R3 > 1 ) env.sync();
 #pragma unroll
 		for( int q = 0; q < Q; ++q )
 			{
@@ -969,13 +973,30 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			}
 		fft_load_twiddles<M, PT, PT, RP::NS2>( t, tw, a.pass_tw_rev + RP::tw2, ldtw );
 		env.sync();
-		// pass 2: radix 16, Ns = 16R = T: outputs t + r*T, i.e. v[s] = swapped z[t + s*T]: y[2n] = v.y, y[2n+1] = v.x
+		// pass 2: radix 16, Ns = 16R. Without a fourth pass (T == 16R) its outputs are t + r*T, i.e. v[s] = swapped z[t + s*T]:
+		// y[2n] = v.y, y[2n+1] = v.x
 			{
-			const float2 * base = x1 + t;
+			const float2 * base = x1 + xpad_rev<R>( t );
 #pragma unroll
-			for( int s = 0; s < PT; ++s ) v[s] = base[s * ( T + R )];
+			for( int s = 0; s < PT; ++s ) v[s] = base[s * ( T + R * ( T / ( 16 * R ) ) )];
 			}
+		if constexpr( ONE && RP::R3 > 1 ) env.sync();       // everyone has read before anyone writes
 		fft_butterflies_w<M, PT, PT, RP::NS2>( v, tw );
+		if constexpr( RP::R3 > 1 )
+			{
+			// pass 3 (dft 8192): radix 2, Ns = 256R, eight butterflies per thread; outputs in natural order
+			float2 * xo = ONE ? x1 : x0;
+				{
+				const int base = ( t / RP::NS2 ) * RP::NS2 * PT + ( t & ( RP::NS2 - 1 ) );
+#pragma unroll
+				for( int r = 0; r < PT; ++r ) xo[base + r * RP::NS2] = v[r];
+				}
+			fft_load_twiddles<M, PT, RP::R3, RP::NS3>( t, tw, a.pass_tw_rev + RP::tw3, ldtw );
+			env.sync();
+#pragma unroll
+			for( int s = 0; s < PT; ++s ) v[s] = xo[t + s * T];
+			fft_butterflies_w<M, PT, RP::R3, RP::NS3>( v, tw );
+			}
 
 		// windowed overlap-add (AudioPV.cpp:133-134) on the thread's own ring; slot s of this frame is absolute pair
 		// t + T*(f + s - 8) (half/2 == 8T), i.e. ring entry (f + s + 8) & 15

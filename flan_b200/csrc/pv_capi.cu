@@ -73,7 +73,7 @@ struct flan_b200_ctx
 	int one_buffer = -1;    // analysis exchange buffers alias: -1 = by size (FLAN_B200_ONEBUF)
 	int synth_variant = PV_PT_MIRROR;  // PV_PT_MIRROR = mirrored first pass where it applies; 8 = always the 8-point kernel (FLAN_B200_SYNTH_VARIANT)
 	int tps_synthesis_mirror = 384;
-	int synth_one_buffer = 0;           // mirrored resynthesis with one exchange buffer (FLAN_B200_SYNTH_ONEBUF)
+	int synth_one_buffer = -1;          // mirrored resynthesis with one exchange buffer: -1 = by size (FLAN_B200_SYNTH_ONEBUF)
 	bool tps_synthesis_set = false;     // dft 8192 defaults to the 1024-thread (two CTAs per SM, one exchange buffer) variant
 	struct Timed { int kind; cudaEvent_t start, stop; };
 	std::vector<Timed> timed;
@@ -258,7 +258,7 @@ int synth_range( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channe
 	a.win = plan->win_synthesis; a.post_tw = plan->post_tw; a.pass_tw = plan->pass_tw; a.pass_tw_rev = plan->pass_tw_rev;
 	a.out_aligned2 = ( out_stride % 2 == 0 ) && ( out_offset % 2 == 0 ) && ( (uintptr_t) d_out % 8 == 0 );
 	a.pv_aligned16 = ( (uintptr_t) d_pv_rows % 16 == 0 ); a.channels = C;
-	a.one_buffer = ctx->synth_one_buffer;
+	a.one_buffer = ctx->synth_one_buffer >= 0 ? ctx->synth_one_buffer : ( N == 8192 ? 1 : 0 );    // dft 8192: two 256-thread CTAs per SM
 	a.k = plan->host.k; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
 	{ LaunchTimer lt( ctx, 3 ); const bool mirror = ctx->synth_variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a );
 	  CK( launch_synthesis( N, a, (int64_t) C * segs, ctx->stream, mirror ? ctx->tps_synthesis_mirror : ( ( N == 8192 && !ctx->tps_synthesis_set ) ? 1024 : ctx->tps_synthesis ), ctx->synth_variant ), "synthesis launch" ); }

@@ -369,10 +369,19 @@ template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_mirror_nt
 	}
 bool synthesis_mirror_applies( int N, const SynthArgs & a )
 	{
-	return mirror_supported( N ) && a.W == N && a.hop == N / 16;
+	return synth_mirror_supported( N ) && a.W == N && a.hop == N / 16;
 	}
 template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps, int variant )
 	{
+	if constexpr( N == 8192 )
+		{
+		// 256 threads: two CTAs per SM need 128 registers and one exchange buffer (102 KB of shared memory each)
+		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
+			{
+			if( a.one_buffer ) return launch_synthesis_mirror_nt<N, 512, true>( a, blocks, st );
+			return launch_synthesis_mirror_nt<N, 256, false>( a, blocks, st );
+			}
+		}
 	if constexpr( N == 1024 || N == 2048 || N == 4096 )
 		{
 		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )

@@ -33,7 +33,8 @@ struct PhaseScanArgs
 // points_per_thread values of launch_analysis: 8, 16, or PV_PT_MIRROR (16 points per thread with the mirrored last
 // pass; dft 1024 / 2048 / 4096 only)
 #define PV_PT_MIRROR 17
-inline bool mirror_supported( int N ) { return N == 1024 || N == 2048 || N == 4096; }
+inline bool mirror_supported( int N ) { return N == 1024 || N == 2048 || N == 4096; }                 // analysis
+inline bool synth_mirror_supported( int N ) { return mirror_supported( N ) || N == 8192; }            // resynthesis
 
 bool dft_size_supported( int N );
 cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm, int points_per_thread );

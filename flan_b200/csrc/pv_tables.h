@@ -27,7 +27,7 @@ struct HostTables
 	std::vector<float4> binc4;          // per unpack pair k = 0..N/2: (binf[k], binf[M-k], expected[k], -expected[M-k])
 	std::vector<float2> pass_tw;        // per-pass Stockham twiddles, concatenated (8 points per thread plan)
 	std::vector<float2> pass_tw16;      // same for the 16-points-per-thread plan (dft >= 512)
-	std::vector<float2> pass_tw_rev;    // passes R, 16, 16 of synthesis_cta_mirror (dft 1024 / 2048 / 4096; empty otherwise)
+	std::vector<float2> pass_tw_rev;    // passes R, 16, 16 [, 2] of synthesis_cta_mirror (dft 1024 ... 8192; empty otherwise)
 	PvConsts k{};
 	double P = 0.0, rcpP = 0.0;
 	};
@@ -144,11 +144,12 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		default: return false;
 		}
 	t.pass_tw_rev.clear();
-	if( M == 512 || M == 1024 || M == 2048 )
+	if( M == 512 || M == 1024 || M == 2048 || M == 4096 )
 		{
-		const int R = M / 256;                              // passes R (no twiddles), 16 (Ns = R), 16 (Ns = 16 R)
+		const int R = M >= 2048 ? 8 : M / 256;              // passes R (no twiddles), 16 (Ns = R), 16 (Ns = 16 R) [, 2 (Ns = 256 R)]
 		append_one_pass_twiddles( t.pass_tw_rev, 16, R );
 		append_one_pass_twiddles( t.pass_tw_rev, 16, 16 * R );
+		if( M == 512 * R ) append_one_pass_twiddles( t.pass_tw_rev, 2, 256 * R );
 		}
 	return true;
 	}

@@ -66,9 +66,10 @@ def test_emulated_synthesis_matches_oracle(emu, oracle, W, h, N, seg):
 # Mirrored kernels (16 points per thread; window == dft, hop == dft/16): the butterfly pair (p, NS-p) in one thread,
 # thread-private row FIFO / overlap-add ring / sample ring, bulk row copies with their unaligned-row and last-row cases.
 MIRROR_SHAPES = [(4096, 0, 9000), (4096, 17, 9001), (2048, 20, 6000), (2048, 0, 5000), (1024, 16, 6000), (1024, 0, 3001)]
+MIRROR_SYNTH_SHAPES = MIRROR_SHAPES + [(8192, 0, 20000), (8192, 19, 17001)]      # dft 8192: resynthesis only (a fourth, radix-2 pass)
 
 
-@pytest.mark.parametrize("N,seg,n", MIRROR_SHAPES)
+@pytest.mark.parametrize("N,seg,n", MIRROR_SYNTH_SHAPES)
 def test_emulated_mirror_synthesis_matches_oracle(emu, oracle, N, seg, n):
     sr, W, h = 48000.0, N, N // 16
     x = np.stack([noise_chirp(n, sr, 6), sine_sweep(n, sr), noise_chirp(n, sr, 7)])   # odd row counts: both row alignments
