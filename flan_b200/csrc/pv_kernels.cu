@@ -386,7 +386,7 @@ template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int6
 		{
 		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
 			{
-			if( tps >= 512 ) return launch_synthesis_mirror_nt<N, 512, false>( a, blocks, st );
+			if( tps >= 512 ) return a.one_buffer ? launch_synthesis_mirror_nt<N, 512, true>( a, blocks, st ) : launch_synthesis_mirror_nt<N, 512, false>( a, blocks, st );
 			if( a.one_buffer ) return launch_synthesis_mirror_nt<N, 384, true>( a, blocks, st );
 			return launch_synthesis_mirror_nt<N, 384, false>( a, blocks, st );
 			}
