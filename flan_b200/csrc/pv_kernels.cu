@@ -168,19 +168,6 @@ __global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanAr
 	if( b >= a.B ) return;
 	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
 	PhaseSeg * grp = a.group + (int64_t) c * a.groups * a.B + b;
-	if( mode == 3 )     // short signals: one serial walk over all segments, a single launch
-		{
-		if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
-		const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
-		double * dst = a.acc_start ? a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b : nullptr;
-		for( int s = 0; s < a.segs_per_channel; ++s )
-			{
-			if( dst ) dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
-			phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
-			}
-		if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = st;
-		return;
-		}
 	if( mode == 1 )
 		{
 		if( a.carry_in ) st = a.carry_in[(int64_t) c * a.B + b];
@@ -203,6 +190,49 @@ __global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanAr
 		return;
 		}
 	st = grp[(int64_t) g * a.B];
+	double * dst = a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b;
+	for( int s = s0; s < s1; ++s )
+		{
+		dst[(int64_t) s * a.B] = phase_state_value( st, a.P );
+		phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+		}
+	}
+
+// The same scan for signals of a few hundred segments per channel, where the three launches above are all latency:
+// one launch, a CTA per (channel, 32 bins), 16 thread rows that each reduce a contiguous run of segments, one serial
+// scan over the 16 run totals in shared memory, then every row re-walks its run from its prefix. Serial depth
+// 2 * ceil(segs / 16) + 16 instead of segs.
+__global__ void __launch_bounds__( 512 ) pv_phase_scan_small_kernel( const PhaseScanArgs a )
+	{
+	constexpr int G = 16;
+	__shared__ PhaseSeg tot[G][32];
+	const int lane = threadIdx.x, g = threadIdx.y;
+	const int b = blockIdx.x * 32 + lane;
+	const int c = blockIdx.y;
+	const bool live = b < a.B;
+	const int per = ( a.segs_per_channel + G - 1 ) / G;
+	const int s0 = g * per;
+	const int s1 = ( s0 + per < a.segs_per_channel ) ? s0 + per : a.segs_per_channel;
+	const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
+	PhaseSeg st; st.sum.q = 0.0; st.sum.r = 0.0; st.mx.q = 0.0; st.mx.r = 0.0;
+	if( live ) for( int s = s0; s < s1; ++s ) phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+	tot[g][lane] = st;
+	__syncthreads();
+	if( g == 0 && live )
+		{
+		PhaseSeg run; run.sum.q = 0.0; run.sum.r = 0.0; run.mx.q = 0.0; run.mx.r = 0.0;
+		if( a.carry_in ) run = a.carry_in[(int64_t) c * a.B + b];
+		for( int i = 0; i < G; ++i )
+			{
+			const PhaseSeg tmp = tot[i][lane];
+			tot[i][lane] = run;
+			phase_state_combine( run, tmp, a.P, a.rcpP );
+			}
+		if( a.carry_out ) a.carry_out[(int64_t) c * a.B + b] = run;
+		}
+	__syncthreads();
+	if( !live || !a.acc_start ) return;
+	st = tot[g][lane];
 	double * dst = a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b;
 	for( int s = s0; s < s1; ++s )
 		{
@@ -441,9 +471,9 @@ cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st )
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 	{
 	const dim3 wide( ( a.B + 127 ) / 128, a.groups, C ), narrow( ( a.B + 127 ) / 128, 1, C );
-	if( a.segs_per_channel <= 256 )     // latency-bound sizes: one launch instead of three
+	if( a.segs_per_channel <= 256 && C <= 65535 )     // latency-bound sizes: one launch instead of three
 		{
-		pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 3 );
+		pv_phase_scan_small_kernel<<<dim3( ( a.B + 31 ) / 32, C ), dim3( 32, 16 ), 0, st>>>( a );
 		return cudaGetLastError();
 		}
 	pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
