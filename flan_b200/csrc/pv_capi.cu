@@ -451,7 +451,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	if( need_hi > need_lo && ( audio_offset > need_lo || audio_offset + audio_len < need_hi ) )
 		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 2048 ? 128 : 64 ) );
+	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, ctx->max_seg_len ? ctx->max_seg_len : ( N >= 2048 ? 128 : 64 ), true );
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	AnalysisArgs a{};
 	a.audio = d_audio_local; a.audio_stride = audio_stride; a.audio_offset = audio_offset; a.n_total = n_total;

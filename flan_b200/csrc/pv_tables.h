@@ -157,9 +157,12 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 // Frames per CTA. Long enough that the warm-up FFT (analysis) and the shared overlap regions
 // (resynthesis: a sample may be shared by at most two segments, which needs seg_len*hop >= W-hop) are
 // amortised; short enough that the grid covers the SMs several times over.
-inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len = 64 )
+// `analysis_only`: the overlap constraint does not apply; short signals then get segments down to 8 frames (one
+// warm-up FFT per 8) so that the grid still covers the SMs.
+inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len = 64, bool analysis_only = false )
 	{
-	const int64_t min_len = ( W + hop - 1 ) / hop;           // >= W/hop
+	int64_t min_len = ( W + hop - 1 ) / hop;                 // >= W/hop
+	if( analysis_only && min_len > 8 ) min_len = 8;
 	int64_t target_ctas = (int64_t) sms * 8;
 	int64_t len = ( frames * channels + target_ctas - 1 ) / target_ctas;
 	if( len > max_len ) len = max_len;
