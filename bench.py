@@ -11,9 +11,14 @@ Audio::convert_to_PV followed by PV::convert_to_audio, inputs resident in HBM. W
 as long and frame-range sharded (weak scaling): each rank transforms its contiguous frame range; resynthesis
 exchanges the per-bin phase state (all_gather) and the window-hop overlap-add halo (send/recv) over NCCL.
 
-One JSON line on stdout (rank 0). `value` = frames of all ranks / max-over-ranks device time (CUDA events).
-`e2e` = the same step driven from pinned HOST buffers: H2D of the audio, both transforms, D2H of the result.
-`roofline` = algorithmic bytes of the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json.
+One JSON line on stdout (rank 0). `value` = frames of all ranks / max-over-ranks device time (CUDA events); the K timed
+steps are repeated for `rounds` rounds (each bracketed by its own events) until about a second of device time has been
+measured, and `ms_per_step` is the mean over all of them.
+`e2e` = the same step through the reference-facing C++ API (tools/cpp/e2e_bench.cpp: flan::Audio holding a host
+std::vector -> convert_to_PV -> convert_to_audio -> get_buffer()), host vectors in and out every step, beside the
+copy-only ceiling of the same bytes over PCIe.
+`roofline` = algorithmic bytes of the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json; `roofline_legs`
+the same for each leg and for the whole round trip.
 `cpu_baseline` = the reference's own sources (oracle/_ref, vendored pffft as the FFTW stand-in), one thread as
 written, on a bounded sample of the same signal.
 """
@@ -49,6 +54,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=SECONDS_PER_GPU, help="signal length per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="device time to cover with rounds of K steps")
     ap.add_argument("--chain", action="store_true",
                     help="instead of the headline line: BASELINE config 4's chain (analysis -> repitch -> stretch -> resynthesis) "
                          "on one channel per GPU, with the reference's own PVModify.cpp timed beside it")
@@ -216,6 +222,75 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------
 # our arm
+
+def copy_only_ceiling(torch, dev, nbytes_up, nbytes_down, steps):
+    """Seconds per step of moving one step's input up and one step's output down over PCIe and nothing else: pinned
+    buffers, two streams, both directions at once (what a perfectly overlapped pipeline would be left with)."""
+    up_h = torch.empty(nbytes_up, dtype=torch.uint8).pin_memory()
+    dn_h = torch.empty(nbytes_down, dtype=torch.uint8).pin_memory()
+    up_d = torch.empty(nbytes_up, dtype=torch.uint8, device=dev)
+    dn_d = torch.empty(nbytes_down, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def go(k):
+        for _ in range(k):
+            with torch.cuda.stream(s1):
+                up_d.copy_(up_h, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dn_h.copy_(dn_d, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+
+    go(2)
+    t0 = time.perf_counter()
+    go(steps)
+    return (time.perf_counter() - t0) / steps
+
+
+def e2e_cpp(args, local_rank, world, rank, steps, dist, dev):
+    import ctypes
+    import torch
+    from flan_b200 import build
+    from flan_b200.signals import noise_chirp
+    os.environ["FLAN_B200_DEVICE"] = str(local_rank)      # the C++ layer's process-wide context
+    build.build_host()
+    L = ctypes.CDLL(build.e2e_bench_path())
+    L.e2e_round_trips.restype = ctypes.c_double
+    L.e2e_round_trips.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    n = int(SR * args.seconds)
+    audio = np.stack([noise_chirp(n, SR, 1234 + c + 100 * rank) for c in range(CH)])
+    F = n // HOP + 1
+    chk = ctypes.c_double(0)
+
+    def run(threads, k, warm):
+        if dist is not None:
+            dist.barrier()
+        dt = L.e2e_round_trips(audio.ctypes.data, CH, n, SR, W, HOP, N_DFT, threads, warm, k, ctypes.byref(chk))
+        if dt < 0:
+            raise RuntimeError("the C++ API returned a null object in the e2e leg")
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * threads * k * CH * F / float(t.item())
+
+    k = max(steps, 10)
+    two = run(2, k, 5)          # 5 untimed passes: by then the host vectors are recycled and page-locked
+    one = run(1, k, 5)
+    ceil_s = copy_only_ceiling(torch, dev, 4 * CH * n, 4 * CH * F * HOP, k)
+    tc = torch.tensor([ceil_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    ceiling = world * CH * F / float(tc.item())
+    return {"value": two, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n), "d2h_bytes_per_step": int(4 * CH * F * HOP),
+            "host_threads": 2, "single_thread_value": one, "steps_per_thread": k,
+            "copy_only_ceiling": ceiling, "frac_of_copy_ceiling": two / ceiling,
+            "how": "tools/cpp/e2e_bench.cpp, user code against the reference-facing C++ API: flan::Audio (host std::vector, touched through "
+                   "get_buffer() every step) -> convert_to_PV -> convert_to_audio -> get_buffer() on the result; 2 host threads on independent "
+                   "signals (single_thread_value: one thread); copy_only_ceiling = the same bytes up and down over PCIe from pinned memory, "
+                   "both directions at once, nothing else"
+                   + ("; every rank converts its own signal on its own GPU" if world > 1 else "")}
+
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -247,7 +322,6 @@ def run_ours(args):
     pv = torch.empty((CH, sh.frames, B, 2), dtype=torch.float32, device=dev)
     out_len = sh.span_hi - sh.span_lo
     y = torch.empty((CH, out_len), dtype=torch.float32, device=dev)
-    host_out = torch.empty((CH, out_len), dtype=torch.float32).pin_memory()
 
     def allgather(state):
         if world == 1:
@@ -278,26 +352,44 @@ def run_ours(args):
     barrier()
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream -----------------------
+    # K steps per round; rounds are repeated until ~1 s of device time is covered so that the clock sampler sees the
+    # kernels under load (20 x 3.9 ms gave it one sample).
     eng.set_timing(True)
     for k in eng.KERNEL_KINDS:
         eng.kernel_time(k)
     launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe0, probe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    probe0.record()
+    step(x)
+    probe1.record()
+    barrier()
+    est = torch.tensor([probe0.elapsed_time(probe1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    rounds = int(max(1, min(200, np.ceil(args.min_seconds * 1e3 / max(float(est.item()) * steps, 1e-3)))))
+    for k in eng.KERNEL_KINDS:
+        eng.kernel_time(k)
+    launches0 = eng.launch_count()
+    round_ms = []
     with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            step(x)
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
+        for _ in range(rounds):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                step(x)
+            e1.record()
+            barrier()
+            round_ms.append(e0.elapsed_time(e1))
+    launches = (eng.launch_count() - launches0) // rounds
     ktimes = {k: eng.kernel_time(k) for k in eng.KERNEL_KINDS}
     eng.set_timing(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor(round_ms, dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)         # per round: the slowest rank
+    ms_max = float(t.mean().item())                      # mean round, K steps each
+    ms = ms_max
     frames_rank = CH * sh.frames
     frames_all = torch.tensor([frames_rank], dtype=torch.float64, device=dev)
     if world > 1:
@@ -305,49 +397,15 @@ def run_ours(args):
     frames_all = float(frames_all.item())
     value = frames_all * steps / (ms_max * 1e-3)
 
-    # ---- end to end: pinned host audio in, pinned host audio out, every step --------------------------------
-    # Every step uploads its input from pinned host memory and downloads its result to pinned host memory. As a
-    # user converting a batch of files would, the copies run on their own streams with double-buffered device
-    # buffers, so step i+1's upload and step i-1's download overlap step i's kernels (PCIe is full duplex).
-    s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    s_comp = torch.cuda.current_stream(dev)
-    x_bufs = [torch.empty_like(x) for _ in range(2)]
-    y_bufs = [torch.empty((CH, out_len), dtype=torch.float32, device=dev) for _ in range(2)]
-    host_outs = [torch.empty((CH, out_len), dtype=torch.float32).pin_memory() for _ in range(2)]
-    ev_h2d = [torch.cuda.Event() for _ in range(2)]
-    ev_comp = [torch.cuda.Event() for _ in range(2)]
-    ev_d2h = [torch.cuda.Event() for _ in range(2)]
-    keep = [None, None]
-
-    def e2e_step(i):
-        b = i % 2
-        with torch.cuda.stream(s_h2d):
-            s_h2d.wait_event(ev_comp[b])          # the kernels that read x_bufs[b] two steps ago are done
-            x_bufs[b].copy_(host_audio, non_blocking=True)
-            ev_h2d[b].record(s_h2d)
-        s_comp.wait_event(ev_h2d[b])
-        s_comp.wait_event(ev_d2h[b])              # y_bufs[b] has been downloaded
-        o = step(x_bufs[b], y_bufs[b])
-        ev_comp[b].record(s_comp)
-        keep[b] = o
-        with torch.cuda.stream(s_d2h):
-            s_d2h.wait_event(ev_comp[b])
-            host_outs[b].copy_(o, non_blocking=True)
-            ev_d2h[b].record(s_d2h)
-
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(steps):
-        e2e_step(i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = frames_all * steps / float(te.item())
-
+    # ---- end to end: through the reference-facing C++ API, host std::vector in, host std::vector out, every step ----
+    # tools/cpp/e2e_bench.cpp is user code against flan::Audio / flan::PV: each step the Audio's host vector is the newest
+    # copy (the upload happens inside convert_to_PV), and get_buffer() on the result brings the samples back. Two host
+    # threads convert independent signals at the same time, as a program working through a batch of files would, so
+    # one thread's download overlaps the other's upload (PCIe is full duplex); the single-thread figure is reported too.
+    # With N > 1 every rank converts its own signal of the per-GPU shape on its own GPU (no exchange on this leg).
+    del pv, y, x
+    torch.cuda.empty_cache()
+    e2e = e2e_cpp(args, local_rank, world, rank, steps, dist if world > 1 else None, dev)
     if rank == 0:
         peak, peak_src = measured_peak()
         an_ms, an_n = ktimes["analysis"]
@@ -383,6 +441,15 @@ def run_ours(args):
         # the whole round trip against its compulsory traffic 2 * (4h + 8B) bytes per frame
         rt_bytes = (an_bytes + sy_bytes) * steps
         step_gbs = rt_bytes / (ms * 1e-3) / 1e9
+
+        def leg(byts, m):
+            return {"ms": m, "algorithmic_bytes": byts, "achieved_gbs": byts / (m * 1e-3) / 1e9, "frac": byts / (m * 1e-3) / 1e9 / peak} if m else None
+        legs_roofline = {
+            "analysis (pv_analysis_kernel)": leg(an_bytes, an_ms / an_n if an_n else 0),
+            "resynthesis kernel (pv_synthesis_mirror_kernel)": leg(sy_bytes, sy_ms / sy_n if sy_n else 0),
+            "resynthesis leg (phase summary + scan + kernel)": leg(sy_bytes, (sy_ms + seg_ms + scan_ms) / sy_n if sy_n else 0),
+            "round trip (one step)": leg(an_bytes + sy_bytes, ms / steps),
+            "peak_gbs": peak, "peak_source": peak_src}
         line = {
             "metric": "PV frames/sec (analysis+resynth)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
@@ -395,10 +462,8 @@ def run_ours(args):
                      "audio_samples_per_s": value * HOP,
                      "round_trip_hbm_gbs": step_gbs, "round_trip_frac_of_peak": step_gbs / peak},
             "roofline": roofline, "kernels": per_kernel,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n_local),
-                    "d2h_bytes_per_step": int(4 * CH * out_len),
-                    "how": "pinned host -> device upload, convert_to_PV, convert_to_audio, device -> pinned host download every "
-                           "step; copies on their own streams, double-buffered, overlapping the neighbouring steps' kernels"},
+            "e2e": e2e, "rounds": rounds, "timed_seconds": sum(round_ms) * 1e-3,
+            "roofline_legs": legs_roofline,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -39,30 +39,42 @@ def emu_path():
     return os.path.join(LIB, "libpv_emu.so")
 
 
-def build_library(force=False, verbose=False):
+def debug_lib_path():
+    """Development build with the FLAN_B200_* experiment knobs and every kernel variant (tools/experiments)."""
+    return os.path.join(LIB, "libflan_b200_debug.so")
+
+
+def build_library(force=False, verbose=False, debug=False):
     os.makedirs(LIB, exist_ok=True)
     # (source, extra flags): the PV-domain kernels must reproduce the reference's float arithmetic bit for bit, so
     # their translation unit is compiled without FMA contraction.
-    units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_modify.cu", ["-fmad=false"]), ("pv_io.cu", ["-fmad=false"])]
+    units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_capi_modify.cu", []), ("pv_capi_io.cu", []),
+             ("pv_modify.cu", ["-fmad=false"]), ("pv_io.cu", ["-fmad=false"])]
+    units = [u for u in units if os.path.exists(os.path.join(CSRC, u[0]))]
+    for extra_unit in ("pv_generic.cu", "pv_capi_multi.cu"):
+        if os.path.exists(os.path.join(CSRC, extra_unit)):
+            units.append((extra_unit, []))
     srcs = _sources(*[u for u, _ in units])
-    deps = srcs + _sources("pv_core.cuh", "pv_body.cuh", "pv_tables.h", "pv_launch.h", "pv_modify.h", "pv_modify_body.cuh", "pv_io.h") + \
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
         [os.path.join(os.path.dirname(HERE), "include", "flan_b200.h")]
-    if not force and not _newer(lib_path(), deps):
-        return lib_path()
-    objdir = os.path.join(LIB, "obj")
+    target = debug_lib_path() if debug else lib_path()
+    if not force and not _newer(target, deps):
+        return target
+    objdir = os.path.join(LIB, "obj_debug" if debug else "obj")
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for (name, extra), src in zip(units, srcs):
         obj = os.path.join(objdir, name + ".o")
         objs.append(obj)
-        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-DFLAN_B200_DEBUG"] if debug else []) + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-c", "-o", obj, src]
         procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
-    subprocess.run(["nvcc", "-shared", "-o", lib_path()] + objs, check=True)
-    return lib_path()
+    subprocess.run(["nvcc", "-shared", "-o", target] + objs, check=True)
+    return target
 
 
 def build_emulator(force=False):
@@ -90,6 +102,10 @@ def api_test_path():
     return os.path.join(LIB, "libflan_api_test.so")
 
 
+def e2e_bench_path():
+    return os.path.join(LIB, "libflan_e2e_bench.so")
+
+
 def build_host(force=False):
     """The C++ side of the boundary (flan::Audio / flan::PV over the C ABI) and the API test driver."""
     build_library(force)
@@ -107,6 +123,9 @@ def build_host(force=False):
     drv = os.path.join(root, "tests", "cpp", "flan_api_driver.cpp")
     if force or _newer(api_test_path(), [drv, host_path()] + hdrs):
         subprocess.run(common + ["-o", api_test_path(), drv] + link + ["-lflan_b200_host", "-lflan_b200"], check=True)
+    e2e = os.path.join(root, "tools", "cpp", "e2e_bench.cpp")
+    if os.path.exists(e2e) and (force or _newer(e2e_bench_path(), [e2e, host_path()] + hdrs)):
+        subprocess.run(common + ["-o", e2e_bench_path(), e2e] + link + ["-lflan_b200_host", "-lflan_b200", "-lpthread"], check=True)
     ex = os.path.join(root, "examples", "pv_chain.cpp")
     exe = os.path.join(LIB, "pv_chain")
     if os.path.exists(ex) and (force or _newer(exe, [ex, host_path()] + hdrs)):
@@ -121,6 +140,9 @@ def build_all(force=False):
 
 
 if __name__ == "__main__":
+    if "--debug" in sys.argv:
+        print(build_library(force="--force" in sys.argv, debug=True))
+        sys.exit(0)
     build_all(force="--force" in sys.argv)
     print(lib_path())
     print(emu_path())

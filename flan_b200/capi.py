@@ -22,6 +22,13 @@ SYMBOLS = [
     ("flan_b200_last_error", ctypes.c_char_p, [_vp]),
     ("flan_b200_set_stream", _int, [_vp, _vp]),
     ("flan_b200_synchronize", _int, [_vp]),
+    ("flan_b200_wait", _int, [_vp, _vp]),
+    ("flan_b200_wait_copies", _int, [_vp, _vp]),
+    ("flan_b200_trim", _int, [_vp]),
+    ("flan_b200_host_register", _int, [_vp, _vp, ctypes.c_size_t]),
+    ("flan_b200_host_unregister", _int, [_vp, _vp]),
+    ("flan_b200_convert_to_pv_h2d", _int, [_vp, _vp, _vp, _int, _i64, _f, _int, _int, _int, _vp, _vp]),
+    ("flan_b200_convert_to_audio_d2h", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
     ("flan_b200_sm_count", _int, [_vp]),
     ("flan_b200_launch_count", _i64, [_vp]),
     ("flan_b200_set_timing", _int, [_vp, _int]),
@@ -61,7 +68,7 @@ SYMBOLS = [
     ("flan_b200_convert_to_audio_host", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _int, _vp, _vp, ctypes.POINTER(_int)]),
 ]
 
-_lib = None
+_libs = {}
 
 
 class FlanB200Error(RuntimeError):
@@ -70,12 +77,12 @@ class FlanB200Error(RuntimeError):
         self.code = code
 
 
-def load():
-    """Load libflan_b200.so (built in-tree by flan_b200.build). Raises if it cannot be loaded."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = os.environ.get("FLAN_B200_LIB") or build.lib_path()      # override: experiment builds only
+def load(path=None):
+    """Load libflan_b200.so (built in-tree by flan_b200.build). Raises if it cannot be loaded.
+    path: another build of the same library (the FLAN_B200_DEBUG development build of tools/experiments)."""
+    path = path or os.environ.get("FLAN_B200_LIB") or build.lib_path()
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise FileNotFoundError(
             "%s is missing: run `python -m flan_b200.build` (nvcc). flan_b200 has no CPU fallback." % path)
@@ -84,15 +91,15 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
 class Context:
     """Owns a flan_b200_ctx bound to one CUDA device."""
 
-    def __init__(self, device=0):
-        self.lib = load()
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load(lib_path)
         h = _vp()
         rc = self.lib.flan_b200_create(device, ctypes.byref(h))
         if rc != OK:

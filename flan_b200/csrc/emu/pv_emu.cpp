@@ -7,6 +7,7 @@
 // math library, so results agree with the device to rounding, not bit for bit.
 #include "../pv_body.cuh"
 #include "../pv_tables.h"
+#include "../pv_generic.h"
 
 #include <atomic>
 #include <barrier>
@@ -103,6 +104,31 @@ template<int N> void synthesis_mirror_n( const SynthArgs & a, int64_t blocks )
 		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { if( a.one_buffer ) synthesis_cta_mirror<N, true>( a, b, env, (float2 *) ola, x0, x0, rowbuf, &bar_word ); else synthesis_cta_mirror<N, false>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); } );
 	}
 
+// The run-time-sized transform (pv_generic_body.cuh): `blocks` persistent CTAs of T threads share the segments, each
+// with its slab of scratch, exactly like the device launch (pv_generic.cu) -- here one CTA after the other.
+template<class Body> void run_generic_ctas( const GenericFft & g, int64_t state_bytes, int64_t blocks, int T, Body && body )
+	{
+	const int64_t stride = generic_align16( state_bytes + generic_fft_bytes( g ) );
+	std::vector<unsigned char> scratch( (size_t)( stride * blocks ) );
+	for( int64_t b = 0; b < blocks; ++b )
+		{
+		std::barrier<> bar( T );
+		std::vector<std::thread> th;
+		for( int t = 0; t < T; ++t )
+			th.emplace_back( [&, t]
+				{
+				HostEnv env{ t, &bar, 0, nullptr };
+				body( env, b, scratch.data(), stride );
+				} );
+		for( auto & x : th ) x.join();
+		}
+	}
+
+GenericFft generic_fft_of( const GenericHost & h )
+	{
+	return GenericFft{ h.N, h.even, h.L, h.B, h.M, h.bluestein, h.tw.data(), h.chirp.data(), h.chirp_fft.data() };
+	}
+
 } // namespace
 
 extern "C" {
@@ -131,6 +157,20 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.one_buffer = one_buffer;
 	a.k = tb.k;
 	const int64_t blocks = (int64_t) C * segs;
+	if( !dft_size_is_templated( N ) )
+		{
+		GenericHost gh;
+		if( !build_generic( N, gh ) ) return 4;
+		GenericAnalysisArgs ga{};
+		ga.a = a; ga.g = generic_fft_of( gh ); ga.fft_in_smem = 0; ga.total_segments = blocks;
+		const int64_t ctas = blocks < 3 ? blocks : 3;          // fewer CTAs than segments: the round-robin walk is exercised
+		run_generic_ctas( ga.g, generic_analysis_state_bytes( ga.g ), ctas, 24, [&]( HostEnv & env, int64_t b, unsigned char * scratch, int64_t stride )
+			{
+			GenericAnalysisArgs mine = ga; mine.scratch = scratch; mine.scratch_stride = stride;
+			generic_analysis_cta( mine, b, ctas, 24, env, (float2 *) nullptr );
+			} );
+		return 0;
+		}
 	if( points_per_thread == 17 )       // PV_PT_MIRROR
 		{
 		if( !( W == N && hop == N / 16 ) ) return 3;
@@ -213,6 +253,20 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 	a.k = tb.k; a.P = tb.P; a.rcpP = tb.rcpP;
 	const int64_t blocks = (int64_t) C * segs;
 	a.one_buffer = ( variant >= 100 ); variant %= 100;      // +100: one exchange buffer
+	if( !dft_size_is_templated( N ) )
+		{
+		GenericHost gh;
+		if( !build_generic( N, gh ) ) return 4;
+		GenericSynthArgs ga{};
+		ga.a = a; ga.g = generic_fft_of( gh ); ga.fft_in_smem = 0;
+		const int64_t ctas = blocks < 3 ? blocks : 3;
+		run_generic_ctas( ga.g, generic_synthesis_state_bytes( ga.g, W ), ctas, 24, [&]( HostEnv & env, int64_t b, unsigned char * scratch, int64_t stride )
+			{
+			GenericSynthArgs mine = ga; mine.scratch = scratch; mine.scratch_stride = stride;
+			generic_synthesis_cta( mine, b, ctas, 24, env, (float2 *) nullptr );
+			} );
+		return 0;
+		}
 	if( variant == 17 )     // PV_PT_MIRROR; the caller checks the shape conditions (W == N, hop a multiple of N/16)
 		{
 		if( !( W == N && hop == N / 16 ) ) return 3;

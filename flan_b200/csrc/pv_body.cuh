@@ -524,6 +524,8 @@ struct SynthArgs
 	const double * acc_start;   // [C][segs_per_channel][B] accumulator value entering each segment
 	int seg_len;
 	int segs_per_channel;
+	int seg_first, seg_count;   // this launch covers segments [seg_first, seg_first + seg_count) of every channel (0: all of them):
+	                            // the pipelined host forms launch a signal in a few slices so that downloads can follow them
 	int W, hop;
 	int aligned2;
 	const float * win;          // [W] Hann * window_scale, host-evaluated (AudioPV.cpp:99-102)
@@ -545,8 +547,9 @@ PV_HD void synthesis_cta( const SynthArgs & a, int64_t block, Env & env, float *
 	{
 	constexpr int M = N / 2, T = M / 8, B = M + 1;
 	const int t = env.tid;
-	const int c = (int)( block / a.segs_per_channel );
-	const int seg = (int)( block % a.segs_per_channel );
+	const int per_launch = a.seg_count > 0 ? a.seg_count : a.segs_per_channel;
+	const int c = (int)( block / per_launch );
+	const int seg = a.seg_first + (int)( block % per_launch );
 	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
 	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
 	if( fa >= fb ) return;
@@ -796,8 +799,9 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 	using RP = RevPlan<M, R>;
 	static_assert( T % ( 16 * R ) == 0, "threads per frame" );
 	const int t = env.tid;
-	const int c = (int)( block / a.segs_per_channel );
-	const int seg = (int)( block % a.segs_per_channel );
+	const int per_launch = a.seg_count > 0 ? a.seg_count : a.segs_per_channel;
+	const int c = (int)( block / per_launch );
+	const int seg = a.seg_first + (int)( block % per_launch );
 	const int64_t fa = a.frame_begin + (int64_t) seg * a.seg_len;
 	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
 	if( fa >= fb ) return;

@@ -311,9 +311,9 @@ __global__ void __launch_bounds__( 256 ) pv_add_kernel( float * out, const float
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-// Development aid: FLAN_B200_SMEM_PAD=<bytes> inflates the dynamic shared memory request so that fewer CTAs fit per
-// SM (occupancy experiments). Unset in production.
-// Development aid: FLAN_B200_CARVEOUT=<percent> sets the preferred shared-memory carveout of the transform kernels.
+// Development aids (FLAN_B200_DEBUG builds only): FLAN_B200_SMEM_PAD=<bytes> inflates the dynamic shared memory request
+// so that fewer CTAs fit per SM; FLAN_B200_CARVEOUT=<percent> sets the preferred shared-memory carveout of the transforms.
+#ifdef FLAN_B200_DEBUG
 static int carveout()
 	{
 	static const int v = [] { const char * e = std::getenv( "FLAN_B200_CARVEOUT" ); return e ? std::atoi( e ) : -1; }();
@@ -328,6 +328,20 @@ static size_t smem_pad()
 	static const size_t pad = [] { const char * e = std::getenv( "FLAN_B200_SMEM_PAD" ); return e ? (size_t) std::atol( e ) : (size_t) 0; }();
 	return pad;
 	}
+#else
+template<class K> static void apply_carveout( K ) {}
+static constexpr size_t smem_pad() { return 0; }
+#endif
+
+// blocks < 0 asks the launchers for the kernel's resident CTAs per SM instead of a launch (the pipelined host forms cut a
+// signal into slices of whole waves); the answer is left here.
+static thread_local int g_occupancy = 0;
+template<class K> static cudaError_t report_occupancy( K kernel, int threads, size_t smem )
+	{
+	g_occupancy = 0;
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor( &g_occupancy, kernel, threads, smem );
+	}
+int last_occupancy() { return g_occupancy; }
 
 template<int N, int PT, int TPS, bool ONE> static cudaError_t launch_analysis_nto( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
@@ -335,14 +349,19 @@ template<int N, int PT, int TPS, bool ONE> static cudaError_t launch_analysis_nt
 	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	apply_carveout( pv_analysis_kernel<N, PT, TPS, ONE> );
+	if( blocks < 0 ) return report_occupancy( pv_analysis_kernel<N, PT, TPS, ONE>, N / ( 2 * PT ), smem );
 	pv_analysis_kernel<N, PT, TPS, ONE><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
 	return cudaGetLastError();
 	}
 // the one-buffer form is built for 16 points per thread only (the variant the large transforms use)
 template<int N, int PT, int TPS> static cudaError_t launch_analysis_nt( const AnalysisArgs & a, int64_t blocks, cudaStream_t st )
 	{
+#ifdef FLAN_B200_DEBUG
 	if constexpr( PT == 16 ) { if( a.one_buffer ) return launch_analysis_nto<N, PT, TPS, true>( a, blocks, st ); }
 	return launch_analysis_nto<N, PT, TPS, false>( a, blocks, st );
+#else
+	return launch_analysis_nto<N, PT, TPS, PT == 16>( a, blocks, st );      // the policy: one buffer exactly when 16 points per thread
+#endif
 	}
 bool analysis_mirror_applies( int N, const AnalysisArgs & a )
 	{
@@ -354,40 +373,51 @@ template<int N, int TPS> static cudaError_t launch_analysis_mirror_nt( const Ana
 	cudaError_t e = cudaFuncSetAttribute( pv_analysis_mirror_kernel<N, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	apply_carveout( pv_analysis_mirror_kernel<N, TPS> );
+	if( blocks < 0 ) return report_occupancy( pv_analysis_mirror_kernel<N, TPS>, N / 32, smem );
 	pv_analysis_mirror_kernel<N, TPS><<<(unsigned) blocks, N / 32, smem, st>>>( a );
 	return cudaGetLastError();
 	}
+// Release builds instantiate only what the launch policy (pv_capi.cu: analysis_range) selects -- 8 points per thread at
+// 85 registers, 16 points per thread / mirrored at 128 registers; FLAN_B200_DEBUG builds carry every register variant
+// for the experiments under tools/experiments.
 template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int tps, int pt )
 	{
 	if constexpr( N == 1024 || N == 2048 || N == 4096 )
 		{
 		if( pt == PV_PT_MIRROR && analysis_mirror_applies( N, a ) )
 			{
+#ifdef FLAN_B200_DEBUG
 			if( tps >= 768 ) return launch_analysis_mirror_nt<N, 768>( a, blocks, st );
 			if( tps >= 640 ) return launch_analysis_mirror_nt<N, 640>( a, blocks, st );
-			if( tps >= 512 ) return launch_analysis_mirror_nt<N, 512>( a, blocks, st );
-			return launch_analysis_mirror_nt<N, 384>( a, blocks, st );
+			if( tps < 512 ) return launch_analysis_mirror_nt<N, 384>( a, blocks, st );
+#endif
+			return launch_analysis_mirror_nt<N, 512>( a, blocks, st );
 			}
 		}
 	if constexpr( N >= 512 )
 		{
 		if( pt == 16 )
 			{
+#ifdef FLAN_B200_DEBUG
 			if( tps >= 768 ) return launch_analysis_nt<N, 16, 768>( a, blocks, st );
 			if( tps >= 640 ) return launch_analysis_nt<N, 16, 640>( a, blocks, st );
-			if( tps >= 512 ) return launch_analysis_nt<N, 16, 512>( a, blocks, st );
-			return launch_analysis_nt<N, 16, 384>( a, blocks, st );
+			if( tps < 512 ) return launch_analysis_nt<N, 16, 384>( a, blocks, st );
+#endif
+			return launch_analysis_nt<N, 16, 512>( a, blocks, st );
 			}
 		}
+#ifdef FLAN_B200_DEBUG
 	if( tps >= 1024 ) return launch_analysis_nt<N, 8, 1024>( a, blocks, st );
-	if( tps >= 768 ) return launch_analysis_nt<N, 8, 768>( a, blocks, st );
-	return launch_analysis_nt<N, 8, 512>( a, blocks, st );
+	if( tps < 768 ) return launch_analysis_nt<N, 8, 512>( a, blocks, st );
+#endif
+	return launch_analysis_nt<N, 8, 768>( a, blocks, st );
 	}
 template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = sizeof( float ) * N + ( ONE ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
 	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_kernel<N, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
+	if( blocks < 0 ) return report_occupancy( pv_synthesis_kernel<N, TPS, ONE>, N / 16, smem );
 	pv_synthesis_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
@@ -397,6 +427,7 @@ template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_mirror_nt
 	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	apply_carveout( pv_synthesis_mirror_kernel<N, TPS, ONE> );
+	if( blocks < 0 ) return report_occupancy( pv_synthesis_mirror_kernel<N, TPS, ONE>, N / 32, smem );
 	pv_synthesis_mirror_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 32, smem, st>>>( a );
 	return cudaGetLastError();
 	}
@@ -411,24 +442,30 @@ template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int6
 		// 256 threads: two CTAs per SM need 128 registers and one exchange buffer (102 KB of shared memory each)
 		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
 			{
-			if( a.one_buffer ) return launch_synthesis_mirror_nt<N, 512, true>( a, blocks, st );
-			return launch_synthesis_mirror_nt<N, 256, false>( a, blocks, st );
+#ifdef FLAN_B200_DEBUG
+			if( !a.one_buffer ) return launch_synthesis_mirror_nt<N, 256, false>( a, blocks, st );
+#endif
+			return launch_synthesis_mirror_nt<N, 512, true>( a, blocks, st );
 			}
 		}
 	if constexpr( N == 1024 || N == 2048 || N == 4096 )
 		{
 		if( variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a ) )
 			{
+#ifdef FLAN_B200_DEBUG
 			if( tps >= 512 ) return a.one_buffer ? launch_synthesis_mirror_nt<N, 512, true>( a, blocks, st ) : launch_synthesis_mirror_nt<N, 512, false>( a, blocks, st );
 			if( a.one_buffer ) return launch_synthesis_mirror_nt<N, 384, true>( a, blocks, st );
+#endif
 			return launch_synthesis_mirror_nt<N, 384, false>( a, blocks, st );
 			}
 		}
-	// dft 8192: one exchange buffer and 64 registers per thread let two 512-thread CTAs share an SM (FLAN_B200_TPS_SYNTHESIS=1024)
+	// dft 8192: one exchange buffer and 64 registers per thread let two 512-thread CTAs share an SM
 	if constexpr( N == 8192 ) { if( tps >= 1024 ) return launch_synthesis_nt<N, 1024, true>( a, blocks, st ); }
+#ifdef FLAN_B200_DEBUG
 	if( tps >= 1024 ) return launch_synthesis_nt<N, 1024, false>( a, blocks, st );
-	if( tps >= 768 ) return launch_synthesis_nt<N, 768, false>( a, blocks, st );
-	return launch_synthesis_nt<N, 512, false>( a, blocks, st );
+	if( tps < 768 ) return launch_synthesis_nt<N, 512, false>( a, blocks, st );
+#endif
+	return launch_synthesis_nt<N, 768, false>( a, blocks, st );
 	}
 
 bool dft_size_supported( int N )

@@ -37,6 +37,8 @@ inline bool mirror_supported( int N ) { return N == 1024 || N == 2048 || N == 40
 inline bool synth_mirror_supported( int N ) { return mirror_supported( N ) || N == 8192; }            // resynthesis
 
 bool dft_size_supported( int N );
+// launch_analysis / launch_synthesis with blocks < 0 launch nothing and leave the kernel's resident CTAs per SM here
+int last_occupancy();
 cudaError_t launch_analysis( int N, const AnalysisArgs & a, int64_t blocks, cudaStream_t st, int threads_per_sm, int points_per_thread );
 // variant: 8 = 8 points per thread (every size and shape); PV_PT_MIRROR = synthesis_cta_mirror where it applies
 // (synthesis_mirror_applies), the 8-point kernel otherwise

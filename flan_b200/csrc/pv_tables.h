@@ -83,7 +83,7 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 	const float pi = std::acos( -1.0f );            // defines.h:44
 	t.k.pi2 = pi * 2.0f;                            // defines.h:45
 	t.k.rcp_pi2 = 1.0f / t.k.pi2;
-	t.k.bin_scale = 1.0f / (float) N;               // exact: N is a power of two
+	t.k.bin_scale = 1.0f / (float) N;               // exact when N is a power of two (bin_frequency_of; the tables below divide)
 	t.k.use_wrapping = analysis_rate < sample_rate; // phase_vocoder.cpp:37
 	t.k.wrap_pi2 = t.k.use_wrapping ? t.k.pi2 : 0.0f;
 	t.P = (double) t.k.pi2;
@@ -105,7 +105,8 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 	t.binf.resize( B );
 	for( int b = 0; b < B; ++b )
 		{
-		const float binf = (float) b * sample_rate / (float) N;     // PVBuffer.cpp:443-446
+		// PVBuffer.cpp:443-446 divides by get_dft_size() = (num_bins - 1) * 2 (PVBuffer.cpp:356-359), which is N - 1 for an odd dft size
+		const float binf = (float) b * sample_rate / (float)( ( B - 1 ) * 2 );
 		t.binf[b] = binf;
 		t.expected[b] = binf / analysis_rate * t.k.pi2;             // phase_vocoder.cpp:47
 		}
@@ -141,7 +142,7 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 		case 1024: append_pass_twiddles<1024, 8>( t.pass_tw );  append_pass_twiddles<1024, 16>( t.pass_tw16 ); break;
 		case 2048: append_pass_twiddles<2048, 8>( t.pass_tw );  append_pass_twiddles<2048, 16>( t.pass_tw16 ); break;
 		case 4096: append_pass_twiddles<4096, 8>( t.pass_tw );  append_pass_twiddles<4096, 16>( t.pass_tw16 ); break;
-		default: return false;
+		default: break;     // every other size: the run-time-sized transform (pv_generic.h) brings its own tables
 		}
 	t.pass_tw_rev.clear();
 	if( M == 512 || M == 1024 || M == 2048 || M == 4096 )

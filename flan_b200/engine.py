@@ -13,12 +13,12 @@ from . import capi
 
 
 class Engine:
-    def __init__(self, device=0):
+    def __init__(self, device=0, lib_path=None):
         if not torch.cuda.is_available():
             raise RuntimeError("flan_b200 needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        self.ctx = capi.Context(device)
+        self.ctx = capi.Context(device, lib_path)
         self.lib = self.ctx.lib
 
     # -- helpers ---------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include "flan/Audio/Audio.h"
 #include "flan/PV/PV.h"
 
+#include <functional>
 #include <iostream>
 
 #include "flan_b200.h"
@@ -29,7 +30,10 @@ Audio Audio::create_from_format( const AudioBuffer::Format & f ) { return AudioB
 
 namespace {
 
-// std::atomic<bool> canceller -> the plain int flag the C ABI polls between launches
+// std::atomic<bool> canceller -> the plain int flag the C ABI polls on entry and between the slices of its pipelined
+// forms. The calls only ENQUEUE GPU work (microseconds), so the protocol of flan_CANCEL_POINT (defines.h:52-62) is kept
+// by checking the canceller before the call and again before the result object is handed out; work already enqueued is
+// not recalled, its result is dropped.
 struct CancelFlag
 	{
 	volatile int value;
@@ -60,15 +64,31 @@ PV Audio::convert_to_PV( Frame window_size, Frame hop, Frame dft_size, flan_CANC
 	f.window_size = window_size;
 	if( f.num_channels < 1 ) return PV( PVBuffer( f ) );
 
-	const Sample * d_audio = storage().device();
-	if( !d_audio ) return PV();
 	MF * d_pv = nullptr;
 	b200::Mirror<MF> data = b200::Mirror<MF>::device_result( size_t( f.num_channels ) * size_t( f.num_frames ) * size_t( f.num_bins ), &d_pv );
 	if( !d_pv ) return PV();
 
 	CancelFlag cancel( canceller );
-	const int rc = report( ctx, "Audio::convert_to_PV", flan_b200_convert_to_pv( ctx, d_audio, f.num_channels, get_num_frames(),
-		get_sample_rate(), window_size, hop, dft_size, reinterpret_cast<float *>( d_pv ), &cancel.value ) );
+	const Frame n = get_num_frames();
+	const Channel C = f.num_channels;
+	const FrameRate sr = get_sample_rate();
+	// When the newest copy of the samples is the host vector, the upload is pipelined with the transform: the engine
+	// copies the samples in a few slices and analyses each slice's frames as soon as they have arrived.
+	int up_rc = FLAN_B200_OK;
+	const std::function<int( const Sample *, Sample * )> pipelined = [&]( const Sample * h, Sample * d )
+		{
+		up_rc = flan_b200_convert_to_pv_h2d( ctx, h, d, C, n, sr, window_size, hop, dft_size, reinterpret_cast<float *>( d_pv ), &cancel.value );
+		return up_rc;
+		};
+	bool transformed = false;
+	const Sample * d_audio = storage().device_with( &pipelined, &transformed );
+	if( !d_audio )
+		{
+		if( up_rc != FLAN_B200_OK ) report( ctx, "Audio::convert_to_PV", up_rc );
+		return PV();
+		}
+	const int rc = transformed ? FLAN_B200_OK : report( ctx, "Audio::convert_to_PV", flan_b200_convert_to_pv( ctx, d_audio, C, n,
+		sr, window_size, hop, dft_size, reinterpret_cast<float *>( d_pv ), &cancel.value ) );
 	if( rc != FLAN_B200_OK || canceller ) return PV();
 	return PV( PVBuffer::from_device_result( f, std::move( data ) ) );
 	}
@@ -116,17 +136,33 @@ Audio PV::convert_to_audio( flan_CANCEL_ARG_CPP ) const
 	if( storage().empty() ) return Audio( AudioBuffer( af ) );
 
 	const MF * d_pv = storage().device();
-	Sample * d_audio = nullptr;
-	b200::Mirror<Sample> data = b200::Mirror<Sample>::device_result( size_t( af.num_channels ) * size_t( af.num_frames ), &d_audio );
+	Sample * d_audio = nullptr, * h_audio = nullptr;
+	b200::Mirror<Sample> data = b200::Mirror<Sample>::device_result( size_t( af.num_channels ) * size_t( af.num_frames ), &d_audio, &h_audio );
 	if( !d_pv || !d_audio ) return Audio::create_null();
 
 	CancelFlag cancel( canceller );
-	int nan_or_inf = 0;
-	const int rc = report( ctx, "PV::convert_to_audio", flan_b200_convert_to_audio( ctx, reinterpret_cast<const float *>( d_pv ),
-		get_num_channels(), get_num_frames(), get_num_bins(), get_sample_rate(), get_analysis_rate(), get_window_size(),
-		d_audio, &cancel.value, &nan_or_inf ) );
-	if( nan_or_inf )                                                     // AudioPV.cpp:88-89: warn and carry on
-		std::cout << "flan::convert_to_audio recieved a nan or infinite value. This often happens when dividing by zero in an earlier algorithm.";
+	// No stream-wide synchronise here: the is_nan_or_inf() pre-scan of AudioPV.cpp:88 runs on the device with the phase
+	// summaries, and its warning is printed by the first host access of the result (b200_storage.cpp: sync_to_host).
+	// When a recycled page-locked vector is at hand, the engine also copies the samples to the host slice by slice behind
+	// the transform, so a later get_buffer() only waits for the tail of that copy.
+	int rc;
+	if( h_audio )
+		{
+		const volatile int * flag = nullptr;
+		rc = report( ctx, "PV::convert_to_audio", flan_b200_convert_to_audio_d2h( ctx, reinterpret_cast<const float *>( d_pv ),
+			get_num_channels(), get_num_frames(), get_num_bins(), get_sample_rate(), get_analysis_rate(), get_window_size(),
+			d_audio, h_audio, &cancel.value, &flag ) );
+		data.set_nan_flag( flag );
+		}
+	else
+		{
+		int nan_or_inf = 0;
+		rc = report( ctx, "PV::convert_to_audio", flan_b200_convert_to_audio( ctx, reinterpret_cast<const float *>( d_pv ),
+			get_num_channels(), get_num_frames(), get_num_bins(), get_sample_rate(), get_analysis_rate(), get_window_size(),
+			d_audio, &cancel.value, &nan_or_inf ) );
+		if( nan_or_inf )                                                     // AudioPV.cpp:88-89: warn and carry on
+			std::cout << "flan::convert_to_audio recieved a nan or infinite value. This often happens when dividing by zero in an earlier algorithm.";
+		}
 	if( rc != FLAN_B200_OK || canceller ) return Audio::create_null();
 	return Audio( AudioBuffer::from_device_result( af, std::move( data ) ) );
 	}

@@ -122,7 +122,8 @@ PV PV::repitch( const Function<TF, float> & factor, const Interpolator & interp 
 	if( !d_pv || !d_out ) return PV();
 	if( report( ctx, "PV::repitch", flan_b200_repitch( ctx, as_floats( d_pv ), get_num_channels(), get_num_frames(), get_num_bins(),
 			get_sample_rate(), t.d, t.frame_stride, t.bin_stride, id, reinterpret_cast<float *>( d_out ) ) ) ) return PV();
-	if( flan_b200_synchronize( ctx ) != FLAN_B200_OK ) return PV();      // the factor table dies with this scope
+	// the factor table dies with this scope: its device block goes back to the engine's cache, which orders the next user
+	// after the kernels enqueued here -- no synchronise
 	return PV( PVBuffer::from_device_result( get_format(), std::move( data ) ) );
 	}
 
@@ -151,7 +152,6 @@ PV PV::modify_frequency( const Function<TF, Frequency> & mod, const Interpolator
 	if( !d_in_mod || !d_pv || !d_out ) return PV();
 	if( report( ctx, "PV::modify_frequency", flan_b200_modify_frequency( ctx, as_floats( d_pv ), get_num_channels(), F, B, get_sample_rate(),
 			t.d, t.frame_stride, t.bin_stride, d_in_mod, id, reinterpret_cast<float *>( d_out ) ) ) ) return PV();
-	if( flan_b200_synchronize( ctx ) != FLAN_B200_OK ) return PV();
 	return PV( PVBuffer::from_device_result( get_format(), std::move( data ) ) );
 	}
 

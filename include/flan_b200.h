@@ -17,8 +17,12 @@
  *     MF{float m; float f;} [C][F][B], B = dft/2+1 (PVBuffer.cpp:526-529). All offsets are 64-bit.
  *   - "d_" pointers are device memory on the context's GPU; "h_" pointers are host memory.
  *   - Device-pointer calls are asynchronous on the context's stream (flan_b200_set_stream) unless noted.
- *   - Every call returns FLAN_B200_OK or an error code; flan_b200_last_error() gives the text. The C++
- *     layer maps any failure to the reference's "print and return a null object" (AudioPV.cpp:82,143).
+ *   - Every call returns FLAN_B200_OK or an error code; flan_b200_last_error() gives the text of the calling THREAD's
+ *     last failure. The C++ layer maps any failure to the reference's "print and return a null object" (AudioPV.cpp:82,143).
+ *   - Thread safety: like the reference's const conversions (re-entrant; FFTW's planner mutex, FFTHelper.cpp:9,19, is
+ *     its only lock), every entry point may be called from any host thread on the same context. A call holds the
+ *     context's call lock while it enqueues, so calls on one context are ordered, never interleaved; waiting
+ *     (flan_b200_synchronize, flan_b200_wait) happens outside the lock.
  *   - There is no CPU fallback: without a CUDA device flan_b200_create() fails.
  *   - dft sizes: powers of two from 256 to 8192, window <= dft, hop >= 1. Other sizes return
  *     FLAN_B200_UNSUPPORTED (the reference only guarantees powers of two, Audio.h:151-153).
@@ -52,7 +56,13 @@ int  flan_b200_create( int device, flan_b200_ctx ** out );
 void flan_b200_destroy( flan_b200_ctx * ctx );
 const char * flan_b200_last_error( const flan_b200_ctx * ctx );   /* ctx may be NULL: error of the last failed create */
 int  flan_b200_set_stream( flan_b200_ctx * ctx, void * cuda_stream );   /* cudaStream_t; NULL = legacy default stream */
-int  flan_b200_synchronize( flan_b200_ctx * ctx );
+int  flan_b200_synchronize( flan_b200_ctx * ctx );                    /* the stream and both copy streams */
+/* Waits until everything enqueued so far that touches the block holding d_ptr (kernels on the stream, copies on the copy
+ * streams) has completed -- what a host accessor calls before it hands out the buffer's host copy. */
+int  flan_b200_wait( flan_b200_ctx * ctx, const void * d_ptr );
+/* The same for the copies only (uploads into / downloads out of the block): the host side of those copies is safe to
+ * reuse afterwards; kernels that read or write the block may still be running. */
+int  flan_b200_wait_copies( flan_b200_ctx * ctx, const void * d_ptr );
 int  flan_b200_sm_count( const flan_b200_ctx * ctx );
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
@@ -65,11 +75,23 @@ int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
 int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled );
 int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches );
 
-/* ---- device buffers (storage behind flan::AudioBuffer / flan::PVBuffer) ---------------------- */
+/* ---- device buffers (storage behind flan::AudioBuffer / flan::PVBuffer) ----------------------
+ * Blocks are cached: flan_b200_free keeps the allocation for the next flan_b200_malloc of a similar size (no cudaMalloc /
+ * cudaFree on the steady-state path); flan_b200_trim returns the cache to the driver. Each block remembers its last use
+ * on the stream and on the copy streams, so copies and kernels on the same block are ordered against each other and
+ * against nothing else. */
 int flan_b200_malloc( flan_b200_ctx * ctx, size_t bytes, void ** d_out );
 int flan_b200_free( flan_b200_ctx * ctx, void * d_ptr );
-int flan_b200_upload( flan_b200_ctx * ctx, void * d_dst, const void * h_src, size_t bytes );     /* async on the stream */
-int flan_b200_download( flan_b200_ctx * ctx, void * h_dst, const void * d_src, size_t bytes );   /* async on the stream */
+int flan_b200_trim( flan_b200_ctx * ctx );
+/* Copies on the context's copy streams, ordered after / before the stream's work on the same block. Page-locked host
+ * memory: asynchronous. Pageable host memory: staged through a pinned ring by a few copy threads -- an upload returns
+ * once the last slice is staged, a download once the bytes have arrived. flan_b200_wait( d ) awaits either. */
+int flan_b200_upload( flan_b200_ctx * ctx, void * d_dst, const void * h_src, size_t bytes );
+int flan_b200_download( flan_b200_ctx * ctx, void * h_dst, const void * d_src, size_t bytes );
+/* Page-lock a host range (a std::vector's storage) so that copies to and from it run asynchronously at PCIe speed.
+ * Costs tens of milliseconds per 100 MB: worth it for buffers that are moved repeatedly. */
+int flan_b200_host_register( flan_b200_ctx * ctx, void * h_ptr, size_t bytes );
+int flan_b200_host_unregister( flan_b200_ctx * ctx, void * h_ptr );
 
 /* ---- shapes (reference arithmetic) ---------------------------------------------------------- */
 /* F = n / hop + 1 with an integer quotient (AudioPV.cpp:17). */
@@ -202,8 +224,24 @@ int flan_b200_save_wav( flan_b200_ctx * ctx, const char * path, const float * d_
 int flan_b200_wav_info( flan_b200_ctx * ctx, const char * path, int * channels, int64_t * n, float * sample_rate );
 int flan_b200_load_wav( flan_b200_ctx * ctx, const char * path, float * d_audio, int64_t capacity_samples );
 
-/* ---- host-buffer forms (what flan::Audio::convert_to_PV / flan::PV::convert_to_audio call when the
- *      buffers live in std::vector): upload, transform, download, synchronise. ------------------- */
+/* ---- pipelined host-buffer forms: what flan::Audio::convert_to_PV / flan::PV::convert_to_audio call when the newest
+ *      copy of the data is the object's host std::vector. --------------------------------------------------------
+ * Analysis: h_audio (float[C][n]) is uploaded into d_audio (the object's device block) in a few slices on the copy
+ * stream; the frames of each slice are transformed as soon as its samples have arrived. d_pv: MF[C][F][dft/2+1]. */
+int flan_b200_convert_to_pv_h2d( flan_b200_ctx * ctx, const float * h_audio, float * d_audio, int channels, int64_t n,
+                                 float sample_rate, int window_size, int hop, int dft_size,
+                                 float * d_pv, const volatile int * cancel );
+/* Resynthesis with the result prefetched to the host: the frames are transformed in a few slices, and the samples each
+ * slice completes are copied into h_audio_out (float[C][F*hop]) on the download stream while the next slice computes.
+ * Asynchronous when h_audio_out is page-locked; flan_b200_wait( ctx, d_audio_out ) awaits the download. *nan_flag (may
+ * be NULL) receives a pointer to a pinned int that holds the is_nan_or_inf() result of AudioPV.cpp:88 once that wait
+ * has returned (valid until 255 further calls). */
+int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins,
+                                    float sample_rate, float analysis_rate, int window_size,
+                                    float * d_audio_out, float * h_audio_out,
+                                    const volatile int * cancel, const volatile int ** nan_flag );
+
+/* ---- plain host-buffer forms: upload, transform, download, wait (device blocks from the cache). ------------- */
 int flan_b200_convert_to_pv_host( flan_b200_ctx * ctx, const float * h_audio, int channels, int64_t n,
                                   float sample_rate, int window_size, int hop, int dft_size, int mid_side,
                                   float * h_pv, const volatile int * cancel );

@@ -17,22 +17,35 @@
 #include <stdlib.h>
 #include <string.h>
 
-/* ---------- double-precision FFT stand-in for FFTW (power-of-two sizes) ---------- */
+/* ---------- double-precision FFT stand-in for FFTW: radix-2 for powers of two, the O(n^2) definition in long double
+ * for every other size -- operation for operation oracle/ref_shim/fftw_standin.cpp's F64Plan, so that this file and
+ * the verbatim reference build agree bit for bit at any dft size (FFTW itself plans any size, FFTHelper.cpp:16-26) ---------- */
 
 typedef struct { double re, im; } cpx_t;
 
 typedef struct
 	{
 	int n;
+	int pow2;
 	cpx_t * tw;     /* exp(-2 pi i k / n), k < n/2 */
 	int * rev;
 	cpx_t * work;
+	cpx_t * out;    /* O(n^2) path only */
 	} fft_t;
 
 static int fft_init( fft_t * f, int n )
 	{
-	if( n < 2 || ( n & ( n - 1 ) ) != 0 ) return -1;
+	if( n < 2 ) return -1;
 	f->n = n;
+	f->pow2 = ( n & ( n - 1 ) ) == 0;
+	f->out = NULL;
+	f->work = NULL; f->tw = NULL; f->rev = NULL;
+	if( !f->pow2 )
+		{
+		f->work = (cpx_t *) malloc( sizeof( cpx_t ) * n );
+		f->out = (cpx_t *) malloc( sizeof( cpx_t ) * n );
+		return 0;
+		}
 	f->tw = (cpx_t *) malloc( sizeof( cpx_t ) * ( n / 2 ) );
 	f->rev = (int *) malloc( sizeof( int ) * n );
 	f->work = (cpx_t *) malloc( sizeof( cpx_t ) * n );
@@ -54,12 +67,31 @@ static int fft_init( fft_t * f, int n )
 	return 0;
 	}
 
-static void fft_free( fft_t * f ) { free( f->tw ); free( f->rev ); free( f->work ); }
+static void fft_free( fft_t * f ) { free( f->tw ); free( f->rev ); free( f->work ); free( f->out ); }
 
 static void fft_run( fft_t * f, int sign )
 	{
 	const int n = f->n;
 	cpx_t * w = f->work;
+	if( !f->pow2 )
+		{
+		const long double two_pi = 6.283185307179586476925286766559005768L;
+		for( int k = 0; k < n; ++k )
+			{
+			long double acc_re = 0, acc_im = 0;
+			for( int j = 0; j < n; ++j )
+				{
+				const long double a = sign * two_pi * (long double)( ( (long long) k * j ) % n ) / n;
+				const long double c = cosl( a ), s = sinl( a );
+				const long double xr = w[j].re, xi = w[j].im;
+				acc_re += xr * c - xi * s;
+				acc_im += xr * s + xi * c;
+				}
+			f->out[k].re = (double) acc_re; f->out[k].im = (double) acc_im;
+			}
+		memcpy( w, f->out, sizeof( cpx_t ) * n );
+		return;
+		}
 	for( int i = 0; i < n; ++i )
 		if( i < f->rev[i] ) { cpx_t t = w[i]; w[i] = w[f->rev[i]]; w[f->rev[i]] = t; }
 	for( int len = 2; len <= n; len <<= 1 )
@@ -169,7 +201,7 @@ int pvo_convert_to_pv( const float * audio, int C, int64_t n, float sample_rate,
 	double * phase_buffer = (double *) malloc( sizeof( double ) * num_bins );   /* :37 */
 	float * bin_frequency = (float *) malloc( sizeof( float ) * num_bins );
 	for( int b = 0; b < num_bins; ++b )
-		bin_frequency[b] = (float) b * sample_rate / (float) dft_size;    /* PVBuffer.cpp:443-446 */
+		bin_frequency[b] = (float) b * sample_rate / (float)( ( num_bins - 1 ) * 2 );    /* PVBuffer.cpp:443-446 with get_dft_size() = (num_bins - 1) * 2, :356-359 */
 
 	const int64_t rows = frame_end - frame_begin;
 	for( int c = 0; c < C; ++c )                                          /* :41 */

@@ -138,3 +138,59 @@ int api_file_round_trip( const float * audio, int C, int n, float sr, int W, int
 	}
 
 }
+
+// ---- concurrency and steady-state reuse (round 2) ----------------------------------------------------------------
+#include <thread>
+#include <vector>
+
+extern "C" {
+
+// The reference's conversions are const and re-entrant (FFTHelper.cpp:9 is its only lock): `threads` host threads run
+// convert_to_PV -> convert_to_audio at the same time, each on its own Audio (thread t reads audio + t * C * n and writes
+// audio_out + t * C * out_n), `reps` times each. Returns output samples per channel, or -1 if any call returned null.
+int api_concurrent_round_trips( const float * audio, int threads, int reps, int C, int n, float sr, int W, int hop, int N, float * audio_out )
+	{
+	const int F = n / hop + 1;
+	const size_t out_n = size_t( F ) * hop;
+	std::vector<int> ok( threads, 1 );
+	std::vector<std::thread> pool;
+	for( int t = 0; t < threads; ++t )
+		pool.emplace_back( [&, t]
+			{
+			const float * src = audio + size_t( t ) * C * n;
+			for( int r = 0; r < reps; ++r )
+				{
+				Audio a = Audio::create_from_buffer( std::vector<float>( src, src + size_t( C ) * n ), C, sr );
+				PV pv = a.convert_to_PV( W, hop, N );
+				if( pv.is_null() ) { ok[t] = 0; return; }
+				Audio out = pv.convert_to_audio();
+				if( out.is_null() || size_t( out.get_num_frames() ) != out_n ) { ok[t] = 0; return; }
+				std::memcpy( audio_out + size_t( t ) * C * out_n, out.get_buffer().data(), sizeof( float ) * C * out_n );
+				}
+			} );
+	for( auto & th : pool ) th.join();
+	for( int v : ok ) if( !v ) return -1;
+	return int( out_n );
+	}
+
+// One long-lived Audio whose samples are edited on the host before every pass (get_buffer() drops the device copy), the
+// way a program that synthesises or filters on the CPU between conversions behaves. From the third pass on the host
+// vectors are recycled and page-locked and the download is prefetched. out[r] receives pass r's result.
+int api_repeated_round_trips( const float * audio, int reps, int C, int n, float sr, int W, int hop, int N, float gain_step, float * audio_out )
+	{
+	const int F = n / hop + 1;
+	const size_t out_n = size_t( F ) * hop;
+	Audio a = Audio::create_from_buffer( std::vector<float>( audio, audio + size_t( C ) * n ), C, sr );
+	for( int r = 0; r < reps; ++r )
+		{
+		std::vector<float> & h = a.get_buffer();
+		const float g = 1.0f + gain_step * r;
+		for( size_t i = 0; i < h.size(); ++i ) h[i] = audio[i] * g;
+		Audio out = a.convert_to_PV( W, hop, N ).convert_to_audio();
+		if( out.is_null() ) return -1;
+		std::memcpy( audio_out + size_t( r ) * C * out_n, out.get_buffer().data(), sizeof( float ) * C * out_n );
+		}
+	return int( out_n );
+	}
+
+}

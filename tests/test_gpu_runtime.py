@@ -1,0 +1,188 @@
+"""The engine's runtime behind the C ABI: concurrent callers, the block cache, the pipelined host-buffer forms.
+
+The reference's conversions are const and re-entrant (its only lock is FFTW's planner mutex, FFTHelper.cpp:9,19), and
+they take and return host vectors; these tests hold the B200 build to the same contract."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+from flan_b200.signals import noise_chirp, sine_sweep
+from parity import assert_analysis_parity, assert_synthesis_parity
+
+pytestmark = pytest.mark.gpu
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from flan_b200.engine import Engine
+    return Engine(0)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from flan_b200 import build
+    build.build_host()
+    L = ctypes.CDLL(build.api_test_path())
+    L.api_concurrent_round_trips.argtypes = [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, _fp]
+    L.api_repeated_round_trips.argtypes = [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_float, _fp]
+    L.api_round_trip.argtypes = [_fp, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, _fp]
+    return L
+
+
+def test_four_threads_through_the_cpp_api_match_the_oracle(api, oracle):
+    """4 host threads x {convert_to_PV, convert_to_audio} on different objects at the same time."""
+    sr, W, h, N = 48000.0, 1024, 64, 1024
+    C, n, T = 2, 60000, 4
+    x = np.stack([np.stack([noise_chirp(n, sr, 10 * t + c) for c in range(C)]) for t in range(T)])
+    F = n // h + 1
+    out = np.zeros((T, C, F * h), np.float32)
+    assert api.api_concurrent_round_trips(_ptr(x), T, 6, C, n, sr, W, h, N, _ptr(out)) == F * h
+    ar = oracle.analysis_rate(sr, h)
+    single = np.zeros((C, F * h), np.float32)
+    for t in range(T):
+        # the same call alone gives the same bits: nothing of another thread's call leaked into this one
+        assert api.api_round_trip(_ptr(x[t]), C, n, sr, W, h, N, 0, 0, _ptr(single)) == F * h
+        assert np.array_equal(out[t], single)
+    # ... and one of them against the oracle, stage-wise on the oracle's own PV is covered elsewhere; here end to end
+    ref = oracle.convert_to_audio(oracle.convert_to_pv(x[0], sr, W, h, N), sr, ar, W)
+    assert np.abs(out[0] - ref).max() < 5e-3        # independent analysis -> synthesis chains (2.7e-3 .. 4.7e-3)
+
+
+def test_concurrent_c_abi_calls_on_one_context(eng, oracle):
+    """Two Python threads drive the same context through the C ABI (ctypes releases the GIL): different shapes, so the
+    workspace sizes differ; every result equals its single-threaded value bit for bit."""
+    import torch
+    cases = [(48000.0, 1024, 64, 1024, 90000, 3), (44100.0, 2048, 128, 2048, 150000, 4), (48000.0, 512, 32, 512, 40000, 5)]
+    inputs = [torch.from_numpy(np.stack([noise_chirp(n, sr, s), noise_chirp(n, sr, s + 1)])).cuda() for sr, W, h, N, n, s in cases]
+    expect = []
+    for (sr, W, h, N, n, s), x in zip(cases, inputs):
+        pv = eng.convert_to_pv(x, sr, W, h, N)
+        expect.append((pv.clone(), eng.convert_to_audio(pv, sr, eng.analysis_rate(sr, h), W).clone()))
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(i):
+        try:
+            sr, W, h, N, n, s = cases[i]
+            for _ in range(20):        # every thread enqueues on the same (default) stream; the context orders whole calls
+                pv = eng.convert_to_pv(inputs[i], sr, W, h, N)
+                y = eng.convert_to_audio(pv, sr, eng.analysis_rate(sr, h), W)
+                torch.cuda.synchronize()
+                if not (torch.equal(pv, expect[i][0]) and torch.equal(y, expect[i][1])):
+                    errors.append("case %d differs" % i)
+                    return
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
+def test_block_cache_reuses_allocations(eng):
+    ctx, lib = eng.ctx, eng.lib
+    a, b = ctypes.c_void_p(), ctypes.c_void_p()
+    ctx.call("flan_b200_malloc", 10 << 20, ctypes.byref(a))
+    ctx.call("flan_b200_free", a)
+    ctx.call("flan_b200_malloc", (10 << 20) - 4096, ctypes.byref(b))        # a similar size: the cached block comes back
+    assert a.value == b.value
+    ctx.call("flan_b200_free", b)
+    ctx.call("flan_b200_trim")
+    ctx.call("flan_b200_malloc", 1 << 20, ctypes.byref(a))
+    ctx.call("flan_b200_free", a)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_host_forms_are_bit_identical_to_the_device_forms(eng, pinned):
+    """flan_b200_convert_to_pv_h2d / _convert_to_audio_d2h slice the work to overlap the copies; slicing must not change
+    a bit (pageable source staged through the ring by the copy threads, and page-locked source as one DMA per slice)."""
+    import torch
+    sr, W, h, N = 48000.0, 1024, 64, 1024
+    C, n = 2, 3_000_000                                  # 24 MB of audio: several slices
+    x = np.stack([noise_chirp(n, sr, 7), sine_sweep(n, sr)])
+    xh = torch.from_numpy(x)
+    if pinned:
+        xh = xh.pin_memory()
+    F, B = eng.num_frames(n, h), N // 2 + 1
+    ar = eng.analysis_rate(sr, h)
+    pv_ref = eng.convert_to_pv(xh.cuda(), sr, W, h, N)
+    y_ref = eng.convert_to_audio(pv_ref, sr, ar, W)
+    torch.cuda.synchronize()
+
+    d_audio, d_pv, d_out = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    ctx = eng.ctx
+    ctx.call("flan_b200_malloc", 4 * C * n, ctypes.byref(d_audio))
+    ctx.call("flan_b200_malloc", 8 * C * F * B, ctypes.byref(d_pv))
+    ctx.call("flan_b200_malloc", 4 * C * F * h, ctypes.byref(d_out))
+    eng._bind_stream()
+    ctx.call("flan_b200_convert_to_pv_h2d", ctypes.c_void_p(xh.data_ptr()), d_audio, C, n, sr, W, h, N, d_pv, None)
+    yh = torch.empty((C, F * h), dtype=torch.float32)
+    if pinned:
+        yh = yh.pin_memory()
+    flag = ctypes.c_void_p()
+    ctx.call("flan_b200_convert_to_audio_d2h", d_pv, C, F, B, sr, ar, W, d_out, ctypes.c_void_p(yh.data_ptr()), None, ctypes.byref(flag))
+    ctx.call("flan_b200_wait", d_out)
+    assert ctypes.cast(flag, ctypes.POINTER(ctypes.c_int))[0] == 0
+    pv_host = np.empty((C, F, B, 2), np.float32)
+    ctx.call("flan_b200_download", ctypes.c_void_p(pv_host.ctypes.data), d_pv, pv_host.nbytes)
+    ctx.call("flan_b200_wait", d_pv)
+    assert np.array_equal(pv_host, pv_ref.cpu().numpy())
+    assert np.array_equal(yh.numpy(), y_ref.cpu().numpy())
+    for p in (d_audio, d_pv, d_out):
+        ctx.call("flan_b200_free", p)
+
+
+def test_host_buffer_calls_match_device_calls(eng, oracle):
+    """flan_b200_convert_to_pv_host / _convert_to_audio_host (numpy in, numpy out), incl. the NaN/Inf pre-scan flag."""
+    import torch
+    sr, W, h, N = 44100.0, 2048, 128, 2048
+    n = 200000
+    x = np.stack([noise_chirp(n, sr, 3), noise_chirp(n, sr, 4)])
+    pv = eng.convert_to_pv_host(x, sr, W, h, N)
+    pv_dev = eng.convert_to_pv(torch.from_numpy(x).cuda(), sr, W, h, N).cpu().numpy()
+    assert np.array_equal(pv, pv_dev)
+    ar = eng.analysis_rate(sr, h)
+    y, bad = eng.convert_to_audio_host(pv, sr, ar, W)
+    assert not bad
+    assert np.array_equal(y, eng.convert_to_audio(torch.from_numpy(pv).cuda(), sr, ar, W).cpu().numpy())
+    assert_synthesis_parity(y, oracle.convert_to_audio(pv, sr, ar, W))
+    pv_bad = pv.copy()
+    pv_bad[1, 5, 7, 1] = np.inf
+    _, bad = eng.convert_to_audio_host(pv_bad, sr, ar, W)
+    assert bad
+    # mid/side and left/right variants
+    pv_ms = eng.convert_to_pv_host(x, sr, W, h, N, mid_side=True)
+    assert_analysis_parity(pv_ms, oracle.convert_to_pv(oracle.mid_side(x), sr, W, h, N), sr, h, N)
+    y_lr, _ = eng.convert_to_audio_host(pv, sr, ar, W, left_right=True)
+    assert np.array_equal(y_lr, oracle.mid_side(y))
+
+
+def test_repeated_round_trips_recycle_and_prefetch(api, oracle):
+    """A long-lived Audio edited on the host before every pass: from the third pass on its vector is page-locked, the
+    result vectors are recycled and the download is prefetched behind the transform. Every pass must still be right."""
+    sr, W, h, N = 48000.0, 2048, 128, 2048
+    C, n, reps = 2, 400000, 6
+    x = np.stack([noise_chirp(n, sr, 21), noise_chirp(n, sr, 22)])
+    F = n // h + 1
+    out = np.zeros((reps, C, F * h), np.float32)
+    step = np.float32(0.125)
+    assert api.api_repeated_round_trips(_ptr(x), reps, C, n, sr, W, h, N, step, _ptr(out)) == F * h
+    ar = oracle.analysis_rate(sr, h)
+    single = np.zeros((C, F * h), np.float32)
+    for r in range(reps):
+        xr = (x * np.float32(1.0 + 0.125 * r)).astype(np.float32)
+        assert api.api_round_trip(_ptr(xr), C, n, sr, W, h, N, 0, 0, _ptr(single)) == F * h
+        assert np.array_equal(out[r], single), "pass %d" % r

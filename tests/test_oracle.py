@@ -40,6 +40,21 @@ def test_oracle_bit_identical_zero_padded_and_odd_sizes(oracle, reflib):
                               bits(reflib.convert_to_audio(pv_r, 32000, ar, W))), (W, h, N)
 
 
+def test_oracle_bit_identical_at_any_dft_size(oracle, reflib):
+    """FFTW plans any size (FFTHelper.cpp:16-26): the restatement follows the reference build's stand-in (radix-2 for
+    powers of two, the O(n^2) definition in long double otherwise) at small, non-power-of-two and odd sizes. For an odd
+    dft size the reference derives bin frequencies -- and, in convert_to_audio, the inverse transform's size -- from
+    get_dft_size() = (num_bins - 1) * 2 (PVBuffer.cpp:356-359,443-446), i.e. from dft_size - 1."""
+    x = np.stack([noise_chirp(2100, 32000, 11)])
+    for W, h, N in [(64, 8, 64), (100, 10, 128), (300, 30, 300), (96, 12, 192), (250, 25, 375), (201, 20, 201), (120, 15, 255)]:
+        pv_o = oracle.convert_to_pv(x, 32000, W, h, N)
+        pv_r, ar = reflib.convert_to_pv(x, 32000, W, h, N)
+        assert np.array_equal(bits(pv_o), bits(pv_r)), (W, h, N)
+        if W <= (N // 2) * 2:       # the inverse runs at (num_bins - 1) * 2 points: the window must still fit
+            assert np.array_equal(bits(oracle.convert_to_audio(pv_r, 32000, ar, W)),
+                                  bits(reflib.convert_to_audio(pv_r, 32000, ar, W))), (W, h, N)
+
+
 def test_oracle_hann_matches_reference_build(oracle, reflib):
     for W in (64, 1000, 2048, 8192):
         assert np.array_equal(bits(oracle.hann(W)), bits(reflib.hann(W)))

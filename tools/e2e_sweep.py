@@ -1,0 +1,26 @@
+"""e2e through the C++ API (tools/cpp/e2e_bench.cpp) for 1..4 host threads on the cfg2 shape; prints ms per round trip."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flan_b200 import build  # noqa: E402
+from flan_b200.signals import noise_chirp  # noqa: E402
+
+SR, W, HOP, N, CH = 48000.0, 4096, 256, 4096, 2
+seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
+L = ctypes.CDLL(build.e2e_bench_path())
+L.e2e_round_trips.restype = ctypes.c_double
+L.e2e_round_trips.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+n = int(SR * seconds)
+audio = np.stack([noise_chirp(n, SR, 1234 + c) for c in range(CH)])
+F = n // HOP + 1
+chk = ctypes.c_double(0)
+for threads in (1, 2, 3, 4):
+    for rep in range(2):
+        dt = L.e2e_round_trips(audio.ctypes.data, CH, n, SR, W, HOP, N, threads, 5 if rep == 0 else 1, 20, ctypes.byref(chk))
+        print("threads %d: %.3f ms per round trip, %.1f M frames/s" % (threads, dt / (20 * threads) * 1e3, threads * 20 * CH * F / dt / 1e6), flush=True)
