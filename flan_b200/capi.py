@@ -14,6 +14,24 @@ _f = ctypes.c_float
 
 OK, INVALID, UNSUPPORTED, CUDA, CANCELLED, NOMEM = range(6)
 
+MAX_DEVICES = 16
+
+
+class ShardedAudio(ctypes.Structure):
+    _fields_ = [("channels", _int), ("n", _i64), ("shards", _int),
+                ("lo", _i64 * MAX_DEVICES), ("hi", _i64 * MAX_DEVICES),
+                ("own_lo", _i64 * MAX_DEVICES), ("own_hi", _i64 * MAX_DEVICES),
+                ("d", _vp * MAX_DEVICES)]
+
+
+class ShardedPV(ctypes.Structure):
+    _fields_ = [("channels", _int), ("frames", _i64), ("bins", _int),
+                ("sample_rate", _f), ("analysis_rate", _f), ("window_size", _int), ("shards", _int),
+                ("frame_begin", _i64 * (MAX_DEVICES + 1)), ("d", _vp * MAX_DEVICES)]
+
+
+_pa, _pp = ctypes.POINTER(ShardedAudio), ctypes.POINTER(ShardedPV)
+
 # every symbol include/flan_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("flan_b200_device_count", _int, []),
@@ -64,6 +82,22 @@ SYMBOLS = [
     ("flan_b200_save_wav", _int, [_vp, ctypes.c_char_p, _vp, _int, _i64, _f]),
     ("flan_b200_wav_info", _int, [_vp, ctypes.c_char_p, ctypes.POINTER(_int), ctypes.POINTER(_i64), ctypes.POINTER(_f)]),
     ("flan_b200_load_wav", _int, [_vp, ctypes.c_char_p, _vp, _i64]),
+    ("flan_b200_multi_create", _int, [ctypes.POINTER(_int), _int, ctypes.POINTER(_vp)]),
+    ("flan_b200_multi_destroy", None, [_vp]),
+    ("flan_b200_multi_last_error", ctypes.c_char_p, [_vp]),
+    ("flan_b200_multi_device_count", _int, [_vp]),
+    ("flan_b200_multi_ctx", _vp, [_vp, _int]),
+    ("flan_b200_multi_synchronize", _int, [_vp]),
+    ("flan_b200_multi_plan", _int, [_vp, _int, _i64, _int, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_i64)]),
+    ("flan_b200_multi_scatter_audio", _int, [_vp, _vp, _int, _i64, _int, _int, _int, _pa]),
+    ("flan_b200_multi_convert_to_pv", _int, [_vp, _pa, _f, _int, _int, _int, _pp]),
+    ("flan_b200_multi_convert_to_audio", _int, [_vp, _pp, _pa]),
+    ("flan_b200_multi_gather_audio", _int, [_vp, _pa, _vp]),
+    ("flan_b200_multi_gather_pv", _int, [_vp, _pp, _vp, _int, _vp]),
+    ("flan_b200_multi_free_audio", _int, [_vp, _pa]),
+    ("flan_b200_multi_free_pv", _int, [_vp, _pp]),
+    ("flan_b200_multi_convert_to_pv_host", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _pp]),
+    ("flan_b200_multi_convert_to_audio_host", _int, [_vp, _pp, _vp, ctypes.POINTER(_int)]),
     ("flan_b200_convert_to_pv_host", _int, [_vp, _vp, _int, _i64, _f, _int, _int, _int, _int, _vp, _vp]),
     ("flan_b200_convert_to_audio_host", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _int, _int, _vp, _vp, ctypes.POINTER(_int)]),
 ]

@@ -458,7 +458,10 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	if( frames == 0 ) return FLAN_B200_OK;
 	if( cancelled( s.cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ) );
+	// s.seg_len: the multi-device forms pass the segment length of the WHOLE signal and cut their shards at multiples of
+	// it, so that a shard walks exactly the segments the uncut signal would and gives the same bits
+	int seg_len = s.seg_len ? s.seg_len : choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ) );
+	if( seg_len > frames ) seg_len = (int) frames;
 	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
 	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
@@ -484,10 +487,10 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 
 	flan_b200_ctx::SegKey key;
 	key.pv = s.d_pv_rows; key.stride = s.pv_channel_stride; key.fb = s.frame_begin; key.fe = s.frame_end;
-	key.C = C; key.B = B; key.W = W; key.sr = fbits( s.sr ); key.ar = fbits( s.ar ); key.valid = true;
+	key.C = C; key.B = B; key.W = W; key.seg_len = seg_len; key.sr = fbits( s.sr ); key.ar = fbits( s.ar ); key.valid = true;
 	const flan_b200_ctx::SegKey & old = ctx->seg_key;
 	const bool have_summaries = s.reuse_summary && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
-	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.sr == key.sr && old.ar == key.ar;
+	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.seg_len == key.seg_len && old.sr == key.sr && old.ar == key.ar;
 	ctx->seg_key = key;
 
 	PhaseSegArgs sa{};
@@ -542,7 +545,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	const bool mirror = variant == PV_PT_MIRROR && synthesis_mirror_applies( N, a );
 	// One launch, or -- for the pipelined host forms -- slices of whole waves of CTAs so that a download can follow each.
 	int segs_per_slice = segs;
-	if( s.on_chunk )
+	if( s.on_chunk && s.head_segments <= 0 )
 		{
 		int64_t wave = ctx->sms;
 		if( plan->generic ) wave = geo.blocks;
@@ -554,9 +557,10 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 		segs_per_slice = (int) std::max<int64_t>( 1, ctas_per_slice( (int64_t) C * segs, wave, s.copy_bytes ) / C );
 		}
 	int k = 0;
-	for( int s0 = 0; s0 < segs; s0 += segs_per_slice, ++k )
+	for( int s0 = 0; s0 < segs; ++k )
 		{
-		const int s1 = std::min( segs, s0 + segs_per_slice );
+		int s1 = std::min( segs, s0 + segs_per_slice );
+		if( s.head_segments > 0 ) s1 = ( s0 == 0 ) ? std::min( segs, s.head_segments ) : segs;
 		a.seg_first = s0; a.seg_count = s1 - s0;
 		{ LaunchTimer lt( ctx, 3 );
 		  if( plan->generic ) { ga.a = a; CK( launch_generic_synthesis( ga, geo, ctx->stream ), "synthesis launch" ); }
@@ -570,6 +574,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 			rc = s.on_chunk( k, done );
 			if( rc ) return rc;
 			}
+		s0 = s1;
 		}
 	return FLAN_B200_OK;
 	}

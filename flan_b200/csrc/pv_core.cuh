@@ -588,12 +588,18 @@ PV_HD void inverse_pv_pair( float2 mfk, float2 mfm, double & acck, double & accm
 	xm = mul2( em, splat2( mfm.x ) );
 	}
 
-// Split form of a plain double sum (|s| far below 2^53 * P).
+// Split form of a plain double sum (|s| far below 2^53 * P). The remainder is rounded to a multiple of 2^-44 rad (6e-14):
+// P = double(pi2_float) is a multiple of 2^-21, so from here on every sum, difference and reduction of split values is
+// EXACT in double, the canonical form (q integral, r in [0,P)) of a value is unique, and combining segment summaries
+// gives the same bits in any association -- a signal cut into frame-range shards (several GPUs, or slices of one launch)
+// resynthesises bit for bit like the uncut signal.
 PV_HD void phase_sum_from_double( double s, double P, double rcpP, double & q, double & r )
 	{
 	double n = floor( s * rcpP );
 	double rem = fma( -n, P, s );
 	if( rem < 0.0 ) { rem += P; n -= 1.0; }
+	if( rem >= P ) { rem -= P; n += 1.0; }
+	rem = rint( rem * 17592186044416.0 ) * 5.6843418860808015e-14;      // 2^44, 2^-44
 	if( rem >= P ) { rem -= P; n += 1.0; }
 	q = n; r = rem;
 	}

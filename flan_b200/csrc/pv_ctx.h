@@ -116,7 +116,7 @@ struct flan_b200_ctx
 	int64_t launches = 0;
 	bool timing = false;
 	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
-	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0; uint32_t sr = 0, ar = 0; bool valid = false; } seg_key;
+	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0, seg_len = 0; uint32_t sr = 0, ar = 0; bool valid = false; } seg_key;
 	int max_seg_len = 0;                    // frames per CTA at most; 0 = by size (FLAN_B200_DEBUG builds: FLAN_B200_SEG_LEN)
 #ifdef FLAN_B200_DEBUG
 	// experiment knobs of development builds only (tools/experiments); release builds carry the measured policy
@@ -207,6 +207,7 @@ struct SynthCall
 	const pvk::PhaseSeg * d_carry_in = nullptr; pvk::PhaseSeg * d_carry_out = nullptr;
 	float * d_out = nullptr; int64_t out_stride = 0, out_offset = 0, out_len = 0;
 	bool summary_only = false; bool reuse_summary = false;
+	int seg_len = 0;                        // frames per CTA; 0: chosen from the local frame count
 	const volatile int * cancel = nullptr;
 	int * d_nan_flag = nullptr;             // device int the pre-scan raises; null: a scratch slot
 	// pipelining: with on_chunk set the frames are launched in slices of whole waves of CTAs (at least 4 MiB of
@@ -214,6 +215,10 @@ struct SynthCall
 	// sample up to which the local span is final (every contribution enqueued)
 	size_t copy_bytes = 0;
 	std::function<int( int, int64_t )> on_chunk;
+	// head_segments > 0 (multi-device forms): the first slice is exactly the first head_segments segments -- the frames
+	// whose windows reach into the previous shard -- and the rest follows as one launch, so the halo can travel while
+	// the interior computes
+	int head_segments = 0;
 	};
 int synth_range( flan_b200_ctx * ctx, const SynthCall & s );
 // Slices of whole waves: CTAs per slice for `ctas` CTAs of a kernel with `wave` resident CTAs on the device.

@@ -25,12 +25,25 @@
 #include <vector>
 
 struct flan_b200_ctx;
+struct flan_b200_multi;
 
 namespace flan::b200 {
 
 // Process-wide engine context (device from $FLAN_B200_DEVICE, default 0). Returns nullptr and prints the reason
 // when no CUDA device / library is usable: there is no CPU fallback.
 flan_b200_ctx * context();
+
+// Every visible GPU behind one handle (include/flan_b200.h: flan_b200_multi_*), or nullptr when the process uses a
+// single device: $FLAN_B200_DEVICE names one, or only one is visible. $FLAN_B200_DEVICES="0,1,..." picks a subset.
+// When it exists, context() is its device 0. Long signals are then cut into frame-range shards, one per GPU, by
+// Audio::convert_to_PV, and PV::convert_to_audio resynthesises them with the phase-state and halo exchange between
+// the devices; the result is the single-device result bit for bit.
+flan_b200_multi * multi();
+
+// A PV that lives as frame-range shards on several devices (defined in b200_storage.cpp; owns the device blocks).
+struct ShardedStore;
+std::shared_ptr<ShardedStore> new_sharded_store();
+void * sharded_descriptor( ShardedStore & );      // flan_b200_sharded_pv * (include/flan_b200.h)
 
 // Recycled host vectors (see the header comment). `pinned` reports whether the vector's storage is page-locked.
 template<typename T> std::vector<T> pool_take( size_t count, bool zeroed, bool * pinned, bool only_if_pooled = false );
@@ -70,6 +83,14 @@ public:
 	static Mirror device_result( size_t count, T ** d_out, T ** h_prefetch = nullptr );
 	// Where the producing call reports the is_nan_or_inf() pre-scan (printed, like AudioPV.cpp:88-89, by the first host access)
 	void set_nan_flag( const volatile int * flag ) { nan_flag_ = flag; }
+	// A host vector that came from pool_take (its page-locked state travels with it).
+	static Mirror adopt_host( std::vector<T> && v, bool pinned );
+	// Storage sharded over several devices: host accessors gather it, device() gathers it onto device 0.
+	static Mirror from_shards( size_t count, std::shared_ptr<ShardedStore> shards );
+	const std::shared_ptr<ShardedStore> & shards() const { return shards_; }
+	// The host vector holds the newest copy (a multi-device scatter reads it directly).
+	bool host_is_current() const { return host_valid_.load( std::memory_order_acquire ); }
+	const T * host_data_if_current() const { return host_is_current() ? host_.data() : nullptr; }
 
 	Mirror deep_copy() const;
 
@@ -85,6 +106,7 @@ private:
 	mutable std::atomic<bool> host_valid_{ true };
 	mutable std::atomic<bool> device_valid_{ false };
 	mutable std::shared_ptr<DeviceMem> dev_;
+	mutable std::shared_ptr<ShardedStore> shards_;
 	mutable std::mutex lazy_;              // serialises the lazy upload / download
 	mutable bool host_pinned_ = false;     // host_'s storage is page-locked (pooled vector or registered here)
 	mutable const T * pinned_ptr_ = nullptr;   // the range that was registered (a user may have reallocated the vector since)

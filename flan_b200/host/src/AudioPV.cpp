@@ -30,6 +30,9 @@ Audio Audio::create_from_format( const AudioBuffer::Format & f ) { return AudioB
 
 namespace {
 
+// Below this much PV data one GPU finishes before several could be fed (a 10 s stereo signal at dft 2048 is 56 MB).
+constexpr size_t MULTI_MIN_PV_BYTES = size_t( 256 ) << 20;
+
 // std::atomic<bool> canceller -> the plain int flag the C ABI polls on entry and between the slices of its pipelined
 // forms. The calls only ENQUEUE GPU work (microseconds), so the protocol of flan_CANCEL_POINT (defines.h:52-62) is kept
 // by checking the canceller before the call and again before the result object is handed out; work already enqueued is
@@ -63,6 +66,28 @@ PV Audio::convert_to_PV( Frame window_size, Frame hop, Frame dft_size, flan_CANC
 	f.analysis_rate = flan_b200_analysis_rate( get_sample_rate(), hop );
 	f.window_size = window_size;
 	if( f.num_channels < 1 ) return PV( PVBuffer( f ) );
+
+	// Several GPUs and a long signal whose newest copy is the host vector: frame-range shards, one per device, each
+	// uploaded with its halo and analysed where it lands (no exchange); the PV stays sharded on the devices.
+	if( flan_b200_multi * m = b200::multi() )
+		if( const Sample * h = storage().host_data_if_current() )
+			{
+			const size_t pv_bytes = sizeof( MF ) * size_t( f.num_channels ) * size_t( f.num_frames ) * size_t( f.num_bins );
+			int shards = 1; int64_t begin[FLAN_B200_MAX_DEVICES + 1];
+			if( pv_bytes >= MULTI_MIN_PV_BYTES
+			 && flan_b200_multi_plan( m, f.num_channels, get_num_frames(), window_size, hop, dft_size, &shards, begin ) == FLAN_B200_OK && shards > 1 )
+				{
+				auto store = b200::new_sharded_store();
+				auto * desc = static_cast<flan_b200_sharded_pv *>( b200::sharded_descriptor( *store ) );
+				if( flan_b200_multi_convert_to_pv_host( m, h, f.num_channels, get_num_frames(), get_sample_rate(), window_size, hop, dft_size, desc ) != FLAN_B200_OK )
+					{
+					std::cout << "flan::Audio::convert_to_PV failed on the GPU engine: " << flan_b200_multi_last_error( m ) << std::endl;
+					return PV();
+					}
+				if( canceller ) return PV();
+				return PV( PVBuffer::from_device_result( f, b200::Mirror<MF>::from_shards( pv_bytes / sizeof( MF ), std::move( store ) ) ) );
+				}
+			}
 
 	MF * d_pv = nullptr;
 	b200::Mirror<MF> data = b200::Mirror<MF>::device_result( size_t( f.num_channels ) * size_t( f.num_frames ) * size_t( f.num_bins ), &d_pv );
@@ -134,6 +159,27 @@ Audio PV::convert_to_audio( flan_CANCEL_ARG_CPP ) const
 	af.num_frames = get_num_frames() * get_hop_size();
 	af.sample_rate = get_sample_rate();
 	if( storage().empty() ) return Audio( AudioBuffer( af ) );
+
+	// A PV sharded over several GPUs: every device resynthesises its frames (phase state and overlap-add halo exchanged
+	// device to device) and copies the samples it owns straight into the result's host vector.
+	if( const auto & store = storage().shards() )
+		if( flan_b200_multi * m = b200::multi() )
+			{
+			bool pinned = false;
+			std::vector<Sample> host = b200::pool_take<Sample>( size_t( af.num_channels ) * size_t( af.num_frames ), false, &pinned );
+			int nan_or_inf = 0;
+			const int rc = flan_b200_multi_convert_to_audio_host( m, static_cast<const flan_b200_sharded_pv *>( b200::sharded_descriptor( *store ) ),
+				host.data(), &nan_or_inf );
+			if( rc != FLAN_B200_OK )
+				{
+				std::cout << "flan::PV::convert_to_audio failed on the GPU engine: " << flan_b200_multi_last_error( m ) << std::endl;
+				return Audio::create_null();
+				}
+			if( nan_or_inf )                                                 // AudioPV.cpp:88-89: warn and carry on
+				std::cout << "flan::convert_to_audio recieved a nan or infinite value. This often happens when dividing by zero in an earlier algorithm.";
+			if( canceller ) return Audio::create_null();
+			return Audio( AudioBuffer::from_device_result( af, b200::Mirror<Sample>::adopt_host( std::move( host ), pinned ) ) );
+			}
 
 	const MF * d_pv = storage().device();
 	Sample * d_audio = nullptr, * h_audio = nullptr;

@@ -13,22 +13,68 @@
 
 namespace flan::b200 {
 
-flan_b200_ctx * context()
+namespace {
+
+// The process-wide engine: one device, or every visible one behind a multi handle whose device 0 is the primary context.
+struct Engine { flan_b200_ctx * ctx = nullptr; flan_b200_multi * multi = nullptr; };
+
+Engine & engine()
 	{
 	static std::once_flag once;
-	static flan_b200_ctx * ctx = nullptr;
+	static Engine e;
 	std::call_once( once, []
 		{
-		int device = 0;
-		if( const char * e = std::getenv( "FLAN_B200_DEVICE" ) ) device = std::atoi( e );
-		if( flan_b200_create( device, &ctx ) != FLAN_B200_OK )
+		const char * one = std::getenv( "FLAN_B200_DEVICE" );
+		const char * many = std::getenv( "FLAN_B200_DEVICES" );
+		if( !one && ( many || flan_b200_device_count() > 1 ) )
+			{
+			std::vector<int> ids;
+			if( many )
+				for( const char * p = many; *p; )
+					{
+					char * end = nullptr;
+					const long v = std::strtol( p, &end, 10 );
+					if( end == p ) break;
+					ids.push_back( int( v ) );
+					p = ( *end == ',' ) ? end + 1 : end;
+					}
+			if( flan_b200_multi_create( ids.empty() ? nullptr : ids.data(), int( ids.size() ), &e.multi ) == FLAN_B200_OK )
+				{
+				e.ctx = flan_b200_multi_ctx( e.multi, 0 );
+				if( flan_b200_multi_device_count( e.multi ) < 2 ) { /* one device after all: keep the handle for its context only */ }
+				return;
+				}
+			std::cout << "flan_b200: cannot create the multi-GPU engine (" << flan_b200_multi_last_error( nullptr ) << "), using one device" << std::endl;
+			e.multi = nullptr;
+			}
+		const int device = one ? std::atoi( one ) : 0;
+		if( flan_b200_create( device, &e.ctx ) != FLAN_B200_OK )
 			{
 			std::cout << "flan_b200: cannot create the GPU engine: " << flan_b200_last_error( nullptr ) << std::endl;
-			ctx = nullptr;
+			e.ctx = nullptr;
 			}
 		} );
-	return ctx;
+	return e;
 	}
+
+}
+
+flan_b200_ctx * context() { return engine().ctx; }
+
+flan_b200_multi * multi()
+	{
+	Engine & e = engine();
+	return ( e.multi && flan_b200_multi_device_count( e.multi ) > 1 ) ? e.multi : nullptr;
+	}
+
+struct ShardedStore
+	{
+	flan_b200_sharded_pv desc{};
+	~ShardedStore() { if( flan_b200_multi * m = engine().multi ) flan_b200_multi_free_pv( m, &desc ); }
+	};
+
+std::shared_ptr<ShardedStore> new_sharded_store() { return std::make_shared<ShardedStore>(); }
+void * sharded_descriptor( ShardedStore & s ) { return &s.desc; }
 
 namespace {
 
@@ -140,7 +186,7 @@ Mirror<T>::Mirror( size_t count ) : count_( count )
 template<typename T>
 void Mirror<T>::take( Mirror & o )
 	{
-	host_ = std::move( o.host_ ); count_ = o.count_; dev_ = std::move( o.dev_ );
+	host_ = std::move( o.host_ ); count_ = o.count_; dev_ = std::move( o.dev_ ); shards_ = std::move( o.shards_ );
 	host_valid_ = o.host_valid_.load(); device_valid_ = o.device_valid_.load();
 	host_pinned_ = o.host_pinned_; pinned_ptr_ = o.pinned_ptr_;
 	download_in_flight_ = o.download_in_flight_; upload_in_flight_ = o.upload_in_flight_;
@@ -163,6 +209,7 @@ void Mirror<T>::release()
 	host_ = std::vector<T>();
 	host_pinned_ = false; pinned_ptr_ = nullptr;
 	dev_.reset();
+	shards_.reset();
 	count_ = 0; host_valid_ = true; device_valid_ = false; uploads_ = 0; nan_flag_ = nullptr;
 	}
 
@@ -178,6 +225,7 @@ std::vector<T> & Mirror<T>::host_mut()
 		upload_in_flight_ = false;
 		}
 	device_valid_ = false;
+	shards_.reset();
 	return host_;
 	}
 
@@ -212,6 +260,19 @@ const T * Mirror<T>::device_with( const std::function<int( const T * h, T * d )>
 		auto mem = std::make_shared<DeviceMem>();
 		if( flan_b200_malloc( ctx, sizeof( T ) * count_, &mem->ptr ) != FLAN_B200_OK ) { complain( ctx ); return nullptr; }
 		dev_ = mem;
+		}
+	if( shards_ )
+		{
+		// a single-device consumer (a PV-domain method): the shards are gathered onto device 0, device to device
+		flan_b200_multi * m = multi();
+		if( !m || flan_b200_multi_gather_pv( m, &shards_->desc, nullptr, 0, static_cast<float *>( dev_->ptr ) ) != FLAN_B200_OK )
+			{
+			std::cout << "flan_b200: " << flan_b200_multi_last_error( m ) << std::endl;
+			return nullptr;
+			}
+		shards_.reset();           // freed on their devices' streams, after the copies above
+		device_valid_ = true;
+		return static_cast<const T *>( dev_->ptr );
 		}
 	if( count_ )
 		{
@@ -265,11 +326,46 @@ Mirror<T> Mirror<T>::device_result( size_t count, T ** d_out, T ** h_prefetch )
 	}
 
 template<typename T>
+Mirror<T> Mirror<T>::adopt_host( std::vector<T> && v, bool pinned )
+	{
+	Mirror<T> m;
+	m.count_ = v.size();
+	m.host_ = std::move( v );
+	m.host_pinned_ = pinned; m.pinned_ptr_ = pinned ? m.host_.data() : nullptr;
+	return m;
+	}
+
+template<typename T>
+Mirror<T> Mirror<T>::from_shards( size_t count, std::shared_ptr<ShardedStore> shards )
+	{
+	Mirror<T> m;
+	m.count_ = count;
+	m.shards_ = std::move( shards );
+	m.host_valid_ = false;
+	m.device_valid_ = false;
+	return m;
+	}
+
+template<typename T>
 void Mirror<T>::sync_to_host() const
 	{
 	std::lock_guard<std::mutex> lock( lazy_ );
 	if( host_valid_ ) return;
 	flan_b200_ctx * ctx = context();
+	if( shards_ && !device_valid_ )
+		{
+		// frame-range shards on several devices: every device copies its rows into the host vector
+		if( host_.size() != count_ )
+			{
+			host_ = pool_take<T>( count_, false, &host_pinned_ );
+			pinned_ptr_ = host_pinned_ ? host_.data() : nullptr;
+			}
+		flan_b200_multi * m = multi();
+		if( !m || flan_b200_multi_gather_pv( m, &shards_->desc, reinterpret_cast<float *>( host_.data() ), 0, nullptr ) != FLAN_B200_OK )
+			std::cout << "flan_b200: " << flan_b200_multi_last_error( m ) << std::endl;
+		host_valid_.store( true, std::memory_order_release );
+		return;
+		}
 	if( download_in_flight_ )
 		{
 		if( ctx && dev_ && flan_b200_wait_copies( ctx, dev_->ptr ) != FLAN_B200_OK ) complain( ctx );

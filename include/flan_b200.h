@@ -24,8 +24,11 @@
  *     context's call lock while it enqueues, so calls on one context are ordered, never interleaved; waiting
  *     (flan_b200_synchronize, flan_b200_wait) happens outside the lock.
  *   - There is no CPU fallback: without a CUDA device flan_b200_create() fails.
- *   - dft sizes: powers of two from 256 to 8192, window <= dft, hop >= 1. Other sizes return
- *     FLAN_B200_UNSUPPORTED (the reference only guarantees powers of two, Audio.h:151-153).
+ *   - dft sizes: any size from 2 to 2^20 (FFTW plans any size, FFTHelper.cpp:16-26), window <= dft, hop >= 1. Powers of
+ *     two from 256 to 8192 run the register-blocked kernels; every other size a run-time-sized transform (Stockham
+ *     passes for powers of two, Bluestein otherwise) that is correct, not tuned. Sizes outside [2, 2^20] return
+ *     FLAN_B200_UNSUPPORTED. For an odd dft size the bin frequencies and the inverse transform follow
+ *     get_dft_size() = (num_bins - 1) * 2, as in the reference (PVBuffer.cpp:356-359).
  */
 #ifndef FLAN_B200_H
 #define FLAN_B200_H
@@ -248,6 +251,64 @@ int flan_b200_convert_to_pv_host( flan_b200_ctx * ctx, const float * h_audio, in
 int flan_b200_convert_to_audio_host( flan_b200_ctx * ctx, const float * h_pv, int channels, int64_t frames, int bins,
                                      float sample_rate, float analysis_rate, int window_size, int left_right,
                                      float * h_audio_out, const volatile int * cancel, int * nan_or_inf );
+
+/* ---- several GPUs of one box behind one handle (frame-range shards) ------------------------------------
+ * One process, one engine context per device. A signal is cut into contiguous frame ranges at multiples of the segment
+ * length the uncut signal would use, so the result is the single-device result bit for bit. Analysis needs no exchange
+ * (each shard is scattered with its halo of window/2 + hop samples on the left, window/2 on the right); resynthesis
+ * moves the per-bin phase state (32 * channels * bins bytes per shard) and the window - hop overlap-add halo of every
+ * shard boundary device to device (cudaMemcpyPeerAsync over NVLink), the halo behind the interior frames' compute.
+ * Short signals use fewer shards than devices (a shard is at least one segment and 2 * ceil(window / hop) frames).
+ * The structs are plain data owned by the caller; their device blocks come from the per-device contexts. */
+#define FLAN_B200_MAX_DEVICES 16
+typedef struct flan_b200_multi flan_b200_multi;
+typedef struct
+	{
+	int channels; int64_t n;                      /* samples per channel of the whole signal */
+	int shards;
+	int64_t lo[FLAN_B200_MAX_DEVICES], hi[FLAN_B200_MAX_DEVICES];           /* shard i holds samples [lo, hi): float[channels][hi-lo] on device i */
+	int64_t own_lo[FLAN_B200_MAX_DEVICES], own_hi[FLAN_B200_MAX_DEVICES];   /* of those, [own_lo, own_hi) are final (resynthesis output) */
+	float * d[FLAN_B200_MAX_DEVICES];
+	} flan_b200_sharded_audio;
+typedef struct
+	{
+	int channels; int64_t frames; int bins;
+	float sample_rate, analysis_rate; int window_size;
+	int shards;
+	int64_t frame_begin[FLAN_B200_MAX_DEVICES + 1];   /* shard i holds frames [frame_begin[i], frame_begin[i+1]): MF[channels][rows][bins] on device i */
+	float * d[FLAN_B200_MAX_DEVICES];
+	} flan_b200_sharded_pv;
+
+/* devices == NULL: every visible device. A device may be listed more than once (tests on a single GPU). */
+int  flan_b200_multi_create( const int * devices, int n_devices, flan_b200_multi ** out );
+void flan_b200_multi_destroy( flan_b200_multi * m );
+const char * flan_b200_multi_last_error( const flan_b200_multi * m );
+int  flan_b200_multi_device_count( const flan_b200_multi * m );
+flan_b200_ctx * flan_b200_multi_ctx( flan_b200_multi * m, int i );
+int  flan_b200_multi_synchronize( flan_b200_multi * m );
+/* The frame ranges a signal of this shape is cut into: *shards and frame_begin[0 .. *shards]. */
+int  flan_b200_multi_plan( const flan_b200_multi * m, int channels, int64_t n, int window_size, int hop, int dft_size,
+                           int * shards, int64_t * frame_begin );
+/* Host samples float[channels][n] -> every device's frame range with its halos (asynchronous for page-locked memory). */
+int  flan_b200_multi_scatter_audio( flan_b200_multi * m, const float * h_audio, int channels, int64_t n,
+                                    int window_size, int hop, int dft_size, flan_b200_sharded_audio * out );
+/* Audio::convert_to_PV (AudioPV.cpp:12-78) over the shards. */
+int  flan_b200_multi_convert_to_pv( flan_b200_multi * m, const flan_b200_sharded_audio * audio, float sample_rate,
+                                    int window_size, int hop, int dft_size, flan_b200_sharded_pv * pv_out );
+/* PV::convert_to_audio (AudioPV.cpp:86-139) over the shards, with the phase-state and halo exchange. */
+int  flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_sharded_pv * pv, flan_b200_sharded_audio * audio_out );
+/* Final samples of every shard -> host float[channels][n] (returns when the bytes have arrived). */
+int  flan_b200_multi_gather_audio( flan_b200_multi * m, const flan_b200_sharded_audio * audio, float * h_audio );
+/* PV rows of every shard -> host MF[channels][frames][bins] (h_pv, synchronous) and / or one device buffer of that layout
+ * on device `to` of the handle (d_pv, asynchronous on that device's stream). Either pointer may be NULL. */
+int  flan_b200_multi_gather_pv( flan_b200_multi * m, const flan_b200_sharded_pv * pv, float * h_pv, int to, float * d_pv );
+int  flan_b200_multi_free_audio( flan_b200_multi * m, flan_b200_sharded_audio * audio );
+int  flan_b200_multi_free_pv( flan_b200_multi * m, flan_b200_sharded_pv * pv );
+/* What flan::Audio::convert_to_PV / flan::PV::convert_to_audio call for long signals when several GPUs are visible. */
+int  flan_b200_multi_convert_to_pv_host( flan_b200_multi * m, const float * h_audio, int channels, int64_t n, float sample_rate,
+                                         int window_size, int hop, int dft_size, flan_b200_sharded_pv * pv_out );
+/* *nan_or_inf (may be NULL): the is_nan_or_inf() pre-scan of AudioPV.cpp:88 over all shards. */
+int  flan_b200_multi_convert_to_audio_host( flan_b200_multi * m, const flan_b200_sharded_pv * pv, float * h_audio_out, int * nan_or_inf );
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,38 @@ def test_odd_shapes_match_oracle(eng, oracle, W, h, N):
     assert_synthesis_parity(out, oracle.convert_to_audio(ref_pv, sr, ar, W))
 
 
+# Every dft size the reference accepts (FFTW plans any size, FFTHelper.cpp:16-26): the run-time-sized transform of
+# pv_generic.cu serves what the templated kernels do not -- VERDICT r1 item 6 asked for (3000, 100, 3000),
+# (1536, 96, 1536) and (16384, 1024, 16384); plus small powers of two, an odd size (bins and the inverse transform then
+# follow get_dft_size() = (num_bins - 1) * 2, PVBuffer.cpp:356-359), a size whose buffers live in global memory, tiny sizes.
+@pytest.mark.parametrize("W,h,N", [(3000, 100, 3000), (1536, 96, 1536), (16384, 1024, 16384), (128, 8, 128), (64, 16, 64),
+                                   (100, 10, 128), (2048, 128, 32768), (1001, 91, 1001), (250, 25, 375), (5000, 500, 12000),
+                                   (6, 2, 6), (2048, 128, 65536)])
+def test_any_dft_size_matches_oracle(eng, oracle, W, h, N):
+    sr = 32000.0
+    n = 40001 if N >= 16384 else (9001 if N >= 64 else 200)
+    chans = [noise_chirp(n, sr, 31), sine_sweep(n, sr)] + ([np.zeros(n, np.float32)] if N % 2 == 0 else [])
+    x = np.stack(chans)
+    # the oracle's non-power-of-two transform is the O(n^2) definition: bound its work to a window of frames
+    F = n // h + 1
+    f0, f1 = (0, F) if (N & (N - 1)) == 0 or N <= 512 else (max(0, F // 2 - 20), min(F, F // 2 + 20))
+    ref_pv = oracle.convert_to_pv(x, sr, W, h, N, f0, f1)
+    pv = eng.convert_to_pv(dev(x), sr, W, h, N).cpu().numpy()
+    assert pv.shape == (len(chans), F, N // 2 + 1, 2)
+    if N >= 64:
+        assert_analysis_parity(pv[:2, f0:f1], ref_pv[:2], sr, h, N)
+    else:
+        assert np.allclose(pv[:2, f0:f1, :, 0], ref_pv[:2, :, :, 0], rtol=1e-4, atol=1e-5)
+    if N % 2 == 0:      # all-zero channel: deterministic known answer, bit-identical
+        assert np.array_equal(pv[2, f0:f1].view(np.uint32), ref_pv[2].view(np.uint32))
+    if W > (N // 2) * 2:
+        return
+    # resynthesis of (a window of) the oracle's frames, stage-wise on the same PV
+    ar = oracle.analysis_rate(sr, h)
+    out = eng.convert_to_audio(dev(ref_pv), sr, float(ar), W).cpu().numpy()
+    assert_synthesis_parity(out, oracle.convert_to_audio(ref_pv, sr, ar, W))
+
+
 def test_ragged_and_tiny_inputs(eng, oracle):
     sr, W, h, N = 44100.0, 512, 128, 512
     for n in (0, 1, 127, 128, 129, 511, 1000):
@@ -122,7 +154,10 @@ def test_error_behaviour(eng):
     from flan_b200.capi import FlanB200Error, UNSUPPORTED, INVALID
     x = torch.zeros((1, 4096), device="cuda")
     with pytest.raises(FlanB200Error) as e:
-        eng.convert_to_pv(x, 48000.0, 100, 10, 100)          # dft size outside the supported set
+        eng.convert_to_pv(x, 48000.0, 1, 1, 1)               # the smallest dft size is 2
+    assert e.value.code == UNSUPPORTED
+    with pytest.raises(FlanB200Error) as e:
+        eng.convert_to_pv(x, 48000.0, 1024, 64, (1 << 20) + 2)   # ... the largest 2^20
     assert e.value.code == UNSUPPORTED
     with pytest.raises(FlanB200Error) as e:
         eng.convert_to_pv(x, 48000.0, 1024, 64, 512)         # window larger than dft
