@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=SECONDS_PER_GPU, help="signal length per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the BASELINE config 3 leg (1 h mono 96 kHz through the multi-device handle)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="device time to cover with rounds of K steps")
     ap.add_argument("--chain", action="store_true",
                     help="instead of the headline line: BASELINE config 4's chain (analysis -> repitch -> stretch -> resynthesis) "
@@ -247,6 +248,59 @@ def copy_only_ceiling(torch, dev, nbytes_up, nbytes_down, steps):
     return (time.perf_counter() - t0) / steps
 
 
+def cfg3_leg(world, steps, peak):
+    """BASELINE config 3 (mono 96 kHz 1 h, window 8192 hop 512, round trip) through the multi-device handle of the C ABI
+    (flan_b200_multi_*: one process, frame-range shards, P2P phase-state + halo exchange): on one device and, when the run
+    has several GPUs, on all of them -- the strong-scaling figure. Inputs resident in HBM, device-timed (max over devices)."""
+    import ctypes
+    from flan_b200 import capi
+    from flan_b200.signals import noise_chirp
+    lib = capi.load()
+    sr, w, hop, n_dft = 96000.0, 8192, 512, 8192
+    n = int(sr * 3600)
+    chunk = noise_chirp(int(sr * 60), sr, 3)
+    x = np.ascontiguousarray(np.tile(chunk, 60)[None, :n])
+    F, B = n // hop + 1, n_dft // 2 + 1
+    byts = 2.0 * (4.0 * n + 8.0 * F * B)                 # SURVEY 8d: read + write once per direction
+    out = {"workload": "cfg3: mono 96 kHz 1 h, window 8192 hop 512 dft 8192, round trip, frame-range shards cut at segment "
+                       "boundaries, phase state + overlap-add halo exchanged device to device (flan_b200_multi_*)", "frames": F}
+    for k in sorted({1, world}):
+        devs = (ctypes.c_int * k)(*range(k))
+        h = ctypes.c_void_p()
+        if lib.flan_b200_multi_create(devs, k, ctypes.byref(h)) != 0:
+            out["gpus_%d" % k] = {"error": lib.flan_b200_multi_last_error(None).decode()}
+            continue
+
+        def call(name, *a):
+            rc = getattr(lib, name)(h, *a)
+            if rc != 0:
+                raise RuntimeError("%s: %s" % (name, lib.flan_b200_multi_last_error(h).decode()))
+        a = capi.ShardedAudio()
+        call("flan_b200_multi_scatter_audio", x.ctypes.data, 1, n, w, hop, n_dft, ctypes.byref(a))
+
+        def step():
+            pv, y = capi.ShardedPV(), capi.ShardedAudio()
+            call("flan_b200_multi_convert_to_pv", ctypes.byref(a), sr, w, hop, n_dft, ctypes.byref(pv))
+            call("flan_b200_multi_convert_to_audio", ctypes.byref(pv), ctypes.byref(y))
+            call("flan_b200_multi_free_pv", ctypes.byref(pv))
+            call("flan_b200_multi_free_audio", ctypes.byref(y))
+        for _ in range(3):
+            step()
+        ms = ctypes.c_double(0)
+        call("flan_b200_multi_time_begin")
+        for _ in range(steps):
+            step()
+        call("flan_b200_multi_time_end", ctypes.byref(ms))
+        t = ms.value / steps
+        out["gpus_%d" % k] = {"ms_per_round_trip": t, "frames_per_s": F / (t * 1e-3), "shards": int(a.shards),
+                              "hbm_gbs_per_gpu": byts / k / (t * 1e-3) / 1e9, "frac_of_peak_per_gpu": byts / k / (t * 1e-3) / 1e9 / peak}
+        call("flan_b200_multi_free_audio", ctypes.byref(a))
+        lib.flan_b200_multi_destroy(h)
+    if world > 1 and "frames_per_s" in out.get("gpus_1", {}) and "frames_per_s" in out.get("gpus_%d" % world, {}):
+        out["strong_scaling_speedup"] = out["gpus_%d" % world]["frames_per_s"] / out["gpus_1"]["frames_per_s"]
+    return out
+
+
 def e2e_cpp(args, local_rank, world, rank, steps, dist, dev):
     import ctypes
     import torch
@@ -406,6 +460,13 @@ def run_ours(args):
     del pv, y, x
     torch.cuda.empty_cache()
     e2e = e2e_cpp(args, local_rank, world, rank, steps, dist if world > 1 else None, dev)
+    # BASELINE config 3 on rank 0, through the one-process multi-device handle (the other ranks wait at the barrier below)
+    cfg3 = None
+    if rank == 0 and not args.no_cfg3:
+        try:
+            cfg3 = cfg3_leg(world, max(5, steps // 2), measured_peak()[0])
+        except Exception as e:  # noqa: BLE001 - a leg must not take the headline line down with it
+            cfg3 = {"error": repr(e)}
     if rank == 0:
         peak, peak_src = measured_peak()
         an_ms, an_n = ktimes["analysis"]
@@ -464,6 +525,7 @@ def run_ours(args):
             "roofline": roofline, "kernels": per_kernel,
             "e2e": e2e, "rounds": rounds, "timed_seconds": sum(round_ms) * 1e-3,
             "roofline_legs": legs_roofline,
+            "cfg3_strong": cfg3,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -88,6 +88,8 @@ SYMBOLS = [
     ("flan_b200_multi_device_count", _int, [_vp]),
     ("flan_b200_multi_ctx", _vp, [_vp, _int]),
     ("flan_b200_multi_synchronize", _int, [_vp]),
+    ("flan_b200_multi_time_begin", _int, [_vp]),
+    ("flan_b200_multi_time_end", _int, [_vp, ctypes.POINTER(ctypes.c_double)]),
     ("flan_b200_multi_plan", _int, [_vp, _int, _i64, _int, _int, _int, ctypes.POINTER(_int), ctypes.POINTER(_i64)]),
     ("flan_b200_multi_scatter_audio", _int, [_vp, _vp, _int, _i64, _int, _int, _int, _pa]),
     ("flan_b200_multi_convert_to_pv", _int, [_vp, _pa, _f, _int, _int, _int, _pp]),

@@ -10,6 +10,7 @@
 #include "../pv_generic.h"
 
 #include <atomic>
+#include <cmath>
 #include <barrier>
 #include <cstring>
 #include <memory>
@@ -301,6 +302,20 @@ int pv_emu_tables( int N, int W, int hop, float sr, float ar, float * win_a, flo
 	std::memcpy( win_s, tb.win_synthesis.data(), sizeof( float ) * W );
 	std::memcpy( expected, tb.expected.data(), sizeof( float ) * ( N / 2 + 1 ) );
 	return 0;
+	}
+
+// round_half_away_fast against roundf on `count` floats starting at bit pattern `first`; returns mismatches (value or sign of zero).
+int64_t pv_emu_round_mismatches( uint32_t first, int64_t count )
+	{
+	int64_t bad = 0;
+	for( int64_t i = 0; i < count; ++i )
+		{
+		uint32_t u = first + (uint32_t) i; float x; std::memcpy( &x, &u, 4 );
+		if( x != x ) continue;
+		const float a = round_half_away_fast( x ), b = roundf( x );
+		if( a != b || std::signbit( a ) != std::signbit( b ) ) ++bad;
+		}
+	return bad;
 	}
 
 // div_const against IEEE division on `count` floats starting at bit pattern `first`; returns mismatches.

@@ -144,7 +144,11 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
 	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
-	const bool full_window = ( W == N ) && a.aligned2;
+	// Windows that fill whole slots of the thread layout -- the full dft size (every BASELINE config) or a zero-padded
+	// one such as the API default window 2048 / dft 4096 (Audio.h:158-163): slots s < slots_in hold sample pairs, the
+	// rest of the transform's input is the zero padding of AudioPV.cpp:65.
+	const bool full_window = ( W % ( 2 * T ) == 0 ) && a.aligned2;
+	const int slots_in = W / ( 2 * T );
 
 	// Output row of frame f: bins k = t + u*T ascend from row_lo, their mirrors M-k descend from row_hi (per-thread
 	// bases advanced by one row per frame, so every store address is base + immediate). The warm-up frame's row lies
@@ -161,12 +165,24 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		float2 v[PT];
 		// pass 0: windowed load (AudioPV.cpp:54-62; zero padding :65) + radix-PT. Windows overlap by W-hop samples:
 		// all but the newest hop are L1 hits.
-		if( full_window && start >= 0 && start + W <= a.n_total )
+		if( full_window && slots_in == PT && start >= 0 && start + W <= a.n_total )
 			{
 #pragma unroll
 			for( int s = 0; s < PT; ++s )
 				{
 				const float2 r = env.ldg2( reinterpret_cast<const float2 *>( src + 2 * s * T ) );
+				float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
+				v[s] = mul2( r, ww );
+				}
+			}
+		else if( full_window && start >= 0 && start + W <= a.n_total )
+			{
+			// zero-padded window: the same vector loads for the slots that hold samples
+#pragma unroll
+			for( int s = 0; s < PT; ++s )
+				{
+				float2 r; r.x = 0.0f; r.y = 0.0f;
+				if( s < slots_in ) r = env.ldg2( reinterpret_cast<const float2 *>( src + 2 * s * T ) );
 				float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
 				v[s] = mul2( r, ww );
 				}
@@ -788,6 +804,21 @@ template<int M, int R> struct RevPlan
 // t + s*T of the next pass (T a multiple of 16R) stay contiguous per half-warp.
 template<int R> PV_HD int xpad_rev( int i ) { return i + R * ( i / ( 16 * R ) ); }
 
+// Exchange layout after the mirrored first pass of radix 8: a thread stores the 8 outputs of butterfly p at 8p + r
+// (ascending with the lane) and those of butterfly NS - p at 8(NS - p) + r (descending). With the plain xpad<1> the
+// descending stores of a half-warp span 128 padded elements exactly -- its first and last lane meet in one bank pair and
+// every such store takes twice the wavefronts (ncu, round 1: all 33.9 M excess wavefronts of the kernel, 14.5 % of its
+// shared-memory traffic, sat on these eight STS.64). The pad g(u) of each aligned group u of 16 elements must satisfy,
+// for lanes of even p (bank-pair index g(u) mod 16) and odd p (8 + g(u) mod 16) alike, g(u) mod 16 in [0, 8) and
+// distinct for eight consecutive u in ANY alignment: g(u) = (u & 7) + 16 (u >> 3), 247 pad elements of the M/8 = 256
+// the buffer has at dft 4096. Groups of 16 stay contiguous, so the next pass's reads t + s*T keep their layout
+// (pad( t + s*T ) = pad( t ) + pad( s*T ) for T = 128 and 256).
+template<int R> PV_HD int mpad( int i )
+	{
+	if( R == 8 ) return i + ( ( i >> 4 ) & 7 ) + ( ( i >> 7 ) << 4 );
+	return xpad<1>( i );
+	}
+
 // ONE: the two exchange buffers alias (x1 == x0): two more barriers per frame, 18 KB less shared memory per CTA, which
 // moves the SM's carve-out from 228 KB to 164 KB and so gives the twiddle tables (32 KB) an L1 they fit in.
 template<int N, bool ONE, class Env>
@@ -951,7 +982,7 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			float2 * za = v + 2 * R * q, * zb = za + R;
 			dft_r<R, 1>( za );
 			dft_r<R, 1>( zb );
-			float2 * oa = x0 + xpad<1>( R * jA ), * ob = x0 + xpad<1>( R * jB );
+			float2 * oa = x0 + mpad<R>( R * jA ), * ob = x0 + mpad<R>( R * jB );
 #pragma unroll
 			for( int r = 0; r < R; ++r ) { oa[r] = za[r]; ob[r] = zb[r]; }
 			}
@@ -967,7 +998,11 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			}
 		cur_bulk = next_bulk;
 		// pass 1: radix 16, Ns = R
-		fft_load<M, PT, 1>( t, v, x0 );
+			{
+			const float2 * base = x0 + mpad<R>( t );
+#pragma unroll
+			for( int s = 0; s < PT; ++s ) v[s] = base[mpad<R>( s * T )];
+			}
 		if constexpr( ONE ) env.sync();     // everyone has read before anyone writes
 		fft_butterflies_w<M, PT, PT, RP::NS1>( v, tw );
 			{

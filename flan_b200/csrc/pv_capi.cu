@@ -138,7 +138,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 	if( !build_tables( N, W, hop, sr, ar, plan->host ) )
 		return fail( ctx, FLAN_B200_INVALID, "could not build plan tables" );
 	cudaError_t e = cudaSuccess;
-	auto up = [&]( auto & vec, auto ** d ) { if( e == cudaSuccess ) e = upload_vec( vec, d, ctx->stream ); };
+	auto up = [&]( auto & vec, auto ** d ) { if( e == cudaSuccess ) e = upload_vec( vec, d, ctx->compute ); };
 	up( plan->host.win_analysis, &plan->win_analysis ); up( plan->host.win_synthesis, &plan->win_synthesis );
 	up( plan->host.expected, &plan->expected ); up( plan->host.binc, &plan->binc );
 	up( plan->host.post_tw, &plan->post_tw ); up( plan->host.post_rot, &plan->post_rot );
@@ -153,6 +153,7 @@ int get_plan( flan_b200_ctx * ctx, int N, int W, int hop, float sr, float ar, De
 		const GenericHost & h = plan->generic_host;
 		plan->generic_fft = GenericFft{ h.N, h.even, h.L, h.B, h.M, h.bluestein, plan->g_tw, plan->g_chirp, plan->g_chirp_fft };
 		}
+	if( e == cudaSuccess ) e = cudaStreamSynchronize( ctx->compute );     // once per plan: its tables are then visible to every stream
 	if( e != cudaSuccess ) { free_plan( plan.get() ); return cuda_fail( ctx, e, "plan upload" ); }
 	*out = plan.get();
 	ctx->plans[key] = std::move( plan );
@@ -165,7 +166,7 @@ int get_workspace( flan_b200_ctx * ctx, size_t bytes, void ** out )
 		{
 		if( ctx->workspace )
 			{
-			CK( cudaStreamSynchronize( ctx->stream ), "workspace sync" );
+			CK( cudaDeviceSynchronize(), "workspace sync" );
 			cudaFree( ctx->workspace );
 			ctx->workspace = nullptr; ctx->workspace_bytes = 0;
 			}
@@ -174,6 +175,9 @@ int get_workspace( flan_b200_ctx * ctx, size_t bytes, void ** out )
 		ctx->workspace_bytes = bytes;
 		ctx->seg_key.valid = false;
 		}
+	// one scratch area for every stream: a call on another stream than the last user's waits for that user
+	if( ctx->ws_recorded && ctx->ws_stream != ctx->compute ) CK( cudaStreamWaitEvent( ctx->compute, ctx->ws_event, 0 ), "workspace wait" );
+	ctx->ws_touched = true;
 	*out = ctx->workspace;
 	return FLAN_B200_OK;
 	}
@@ -182,14 +186,14 @@ LaunchTimer::LaunchTimer( flan_b200_ctx * c, int k ) : ctx( c ), kind( k )
 	{
 	if( !ctx->timing ) return;
 	if( cudaEventCreate( &start ) != cudaSuccess || cudaEventCreate( &stop ) != cudaSuccess ) { start = stop = nullptr; return; }
-	cudaEventRecord( start, ctx->stream );
+	cudaEventRecord( start, ctx->compute );
 	}
 
 LaunchTimer::~LaunchTimer()
 	{
 	ctx->launches++;
 	if( !start ) return;
-	cudaEventRecord( stop, ctx->stream );
+	cudaEventRecord( stop, ctx->compute );
 	ctx->timed.push_back( { kind, start, stop } );
 	}
 
@@ -207,15 +211,17 @@ Block * find_block( flan_b200_ctx * ctx, const void * p )
 void main_acquire( flan_b200_ctx * ctx, const void * p )
 	{
 	Block * b = find_block( ctx, p );
-	if( b && b->side_pending ) cudaStreamWaitEvent( ctx->stream, b->side_event, 0 );
+	if( !b ) return;
+	if( b->side_pending ) cudaStreamWaitEvent( ctx->compute, b->side_event, 0 );
+	if( b->main_pending && b->main_stream != ctx->compute ) cudaStreamWaitEvent( ctx->compute, b->main_event, 0 );
 	}
 
 void main_release( flan_b200_ctx * ctx, const void * p )
 	{
 	Block * b = find_block( ctx, p );
 	if( !b ) return;
-	cudaEventRecord( b->main_event, ctx->stream );
-	b->main_pending = true;
+	cudaEventRecord( b->main_event, ctx->compute );
+	b->main_pending = true; b->main_stream = ctx->compute;
 	}
 
 // Foreign memory (not from flan_b200_malloc, e.g. a torch tensor): no per-block history, so the copy stream is ordered
@@ -238,7 +244,7 @@ int side_acquire( flan_b200_ctx * ctx, cudaStream_t side, const void * p )
 		return FLAN_B200_OK;
 		}
 	cudaEvent_t e = scratch_event( ctx );
-	CK( cudaEventRecord( e, ctx->stream ), "event record" );
+	CK( cudaEventRecord( e, ctx->compute ), "event record" );
 	CK( cudaStreamWaitEvent( side, e, 0 ), "copy stream wait" );
 	return FLAN_B200_OK;
 	}
@@ -254,7 +260,7 @@ int side_release( flan_b200_ctx * ctx, cudaStream_t side, const void * p )
 		}
 	cudaEvent_t e = scratch_event( ctx );
 	CK( cudaEventRecord( e, side ), "event record" );
-	CK( cudaStreamWaitEvent( ctx->stream, e, 0 ), "stream wait" );
+	CK( cudaStreamWaitEvent( ctx->compute, e, 0 ), "stream wait" );
 	return FLAN_B200_OK;
 	}
 
@@ -402,7 +408,7 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 		if( rc ) return rc;
 		ctx->seg_key.valid = false;
 		ga.scratch = (unsigned char *) ws; ga.scratch_stride = geo.scratch_stride; ga.fft_in_smem = geo.fft_in_smem;
-		{ LaunchTimer lt( ctx, 0 ); CK( launch_generic_analysis( ga, geo, ctx->stream ), "analysis launch" ); }
+		{ LaunchTimer lt( ctx, 0 ); CK( launch_generic_analysis( ga, geo, ctx->compute ), "analysis launch" ); }
 		return FLAN_B200_OK;
 		}
 	// measured on B200 (tools/experiments/exp_r1*.sh): 16 points per thread with one exchange buffer from dft 4096 up; the mirrored
@@ -426,18 +432,19 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 	a.pass_tw = ( pt >= 16 ) ? plan->pass_tw16 : plan->pass_tw;
 	if( c.wave_out )
 		{
-		CK( launch_analysis( N, a, -1, ctx->stream, tps_a, pt ), "occupancy query" );
+		CK( launch_analysis( N, a, -1, ctx->compute, tps_a, pt ), "occupancy query" );
 		*c.wave_out = ctx->sms * std::max( 1, last_occupancy() );
 		return FLAN_B200_OK;
 		}
 	ctx->seg_key.valid = false;
-	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->stream, tps_a, pt ), "analysis launch" ); }
+	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->compute, tps_a, pt ), "analysis launch" ); }
 	return FLAN_B200_OK;
 	}
 
 int64_t ctas_per_slice( int64_t ctas, int64_t wave, size_t copy_bytes )
 	{
 	if( wave < 1 ) wave = 1;
+	{ static const bool no_slice = std::getenv( "FLAN_B200_X_NO_SLICE" ) != nullptr; if( no_slice ) return ( ( ctas + wave - 1 ) / wave ) * wave; }   // TEMPORARY experiment knob
 	const int64_t waves = ( ctas + wave - 1 ) / wave;
 	int64_t n = std::min<int64_t>( 8, std::min<int64_t>( waves, (int64_t)( copy_bytes >> 22 ) ) );     // >= 4 MiB of copy per slice
 	if( n < 1 ) n = 1;
@@ -499,7 +506,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sa.seg_len = seg_len; sa.segs_per_channel = segs; sa.B = B;
 	sa.seg_out = d_seg; sa.nan_flag = s.d_nan_flag ? s.d_nan_flag : ctx->d_flags + flan_b200_ctx::FLAG_SLOTS;   // last slot + 1: write-only scratch
 	sa.k = plan->host.k; sa.P = plan->host.P; sa.rcpP = plan->host.rcpP;
-	if( !have_summaries ) { LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->stream ), "phase summary launch" ); }
+	if( !have_summaries ) { LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->compute ), "phase summary launch" ); }
 
 	PhaseScanArgs sc{};
 	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
@@ -507,17 +514,17 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sc.carry_in = s.d_carry_in; sc.carry_out = s.d_carry_out;
 	sc.acc_start = s.summary_only ? nullptr : d_acc;
 	sc.P = plan->host.P; sc.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->stream ), "phase scan launch" ); ctx->launches += ( segs <= 256 ) ? 0 : ( s.summary_only ? 1 : 2 ); }     // launch_phase_scan: one launch for short signals, else 2 or 3
+	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->compute ), "phase scan launch" ); ctx->launches += ( segs <= 256 ) ? 0 : ( s.summary_only ? 1 : 2 ); }     // launch_phase_scan: one launch for short signals, else 2 or 3
 	if( s.summary_only ) return FLAN_B200_OK;
 	if( cancelled( s.cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
 	// The kernels store every sample that only one segment reaches and red.add the rest onto zeros: clear just those
 	// (a few per cent of the output) when the frames' windows leave no gaps, everything otherwise.
 	if( hop <= W && C < 65535 )
-		{ CK( launch_zero_shared( s.d_out, s.out_stride, s.out_offset, s.out_len, C, s.frame_begin, s.frame_end, seg_len, segs, W, hop, ctx->stream ), "output clear" ); ctx->launches++; }
+		{ CK( launch_zero_shared( s.d_out, s.out_stride, s.out_offset, s.out_len, C, s.frame_begin, s.frame_end, seg_len, segs, W, hop, ctx->compute ), "output clear" ); ctx->launches++; }
 	else
 		for( int c = 0; c < C; ++c )
-			CK( cudaMemsetAsync( s.d_out + (int64_t) c * s.out_stride, 0, sizeof( float ) * (size_t) s.out_len, ctx->stream ), "output clear" );
+			CK( cudaMemsetAsync( s.d_out + (int64_t) c * s.out_stride, 0, sizeof( float ) * (size_t) s.out_len, ctx->compute ), "output clear" );
 
 	SynthArgs a{};
 	a.pv = (const float2 *) s.d_pv_rows; a.pv_channel_stride = s.pv_channel_stride;
@@ -551,7 +558,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 		if( plan->generic ) wave = geo.blocks;
 		else
 			{
-			CK( launch_synthesis( N, a, -1, ctx->stream, mirror ? tps_mirror : tps_plain, variant ), "occupancy query" );
+			CK( launch_synthesis( N, a, -1, ctx->compute, mirror ? tps_mirror : tps_plain, variant ), "occupancy query" );
 			wave = (int64_t) ctx->sms * std::max( 1, last_occupancy() );
 			}
 		segs_per_slice = (int) std::max<int64_t>( 1, ctas_per_slice( (int64_t) C * segs, wave, s.copy_bytes ) / C );
@@ -563,8 +570,8 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 		if( s.head_segments > 0 ) s1 = ( s0 == 0 ) ? std::min( segs, s.head_segments ) : segs;
 		a.seg_first = s0; a.seg_count = s1 - s0;
 		{ LaunchTimer lt( ctx, 3 );
-		  if( plan->generic ) { ga.a = a; CK( launch_generic_synthesis( ga, geo, ctx->stream ), "synthesis launch" ); }
-		  else CK( launch_synthesis( N, a, (int64_t) C * ( s1 - s0 ), ctx->stream, mirror ? tps_mirror : tps_plain, variant ), "synthesis launch" ); }
+		  if( plan->generic ) { ga.a = a; CK( launch_generic_synthesis( ga, geo, ctx->compute ), "synthesis launch" ); }
+		  else CK( launch_synthesis( N, a, (int64_t) C * ( s1 - s0 ), ctx->compute, mirror ? tps_mirror : tps_plain, variant ), "synthesis launch" ); }
 		if( s.on_chunk )
 			{
 			// frames from segment s1 on touch samples >= hop * fa(s1) - W/2: everything below is final
@@ -660,6 +667,9 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	if( e == cudaSuccess ) e = cudaMalloc( (void **) &ctx->d_check, sizeof( pvm::MapCheck ) );
 	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->h2d, cudaStreamNonBlocking );
 	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->d2h, cudaStreamNonBlocking );
+	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->s_ana, cudaStreamNonBlocking );
+	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->s_syn, cudaStreamNonBlocking );
+	if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &ctx->ws_event, cudaEventDisableTiming );
 	if( e != cudaSuccess ) { g_create_error = cudaGetErrorString( e ); flan_b200_destroy( ctx ); return FLAN_B200_CUDA; }
 	*out = ctx;
 	return FLAN_B200_OK;
@@ -670,6 +680,8 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 	if( !ctx ) return;
 	cudaSetDevice( ctx->device );
 	cudaStreamSynchronize( ctx->stream );
+	for( cudaStream_t * st : { &ctx->s_ana, &ctx->s_syn } ) if( *st ) { cudaStreamSynchronize( *st ); cudaStreamDestroy( *st ); }
+	if( ctx->ws_event ) cudaEventDestroy( ctx->ws_event );
 	if( ctx->h2d ) { cudaStreamSynchronize( ctx->h2d ); cudaStreamDestroy( ctx->h2d ); }
 	if( ctx->d2h ) { cudaStreamSynchronize( ctx->d2h ); cudaStreamDestroy( ctx->d2h ); }
 	for( auto & kv : ctx->plans ) free_plan( kv.second.get() );
@@ -699,14 +711,15 @@ int flan_b200_set_stream( flan_b200_ctx * ctx, void * cuda_stream )
 	if( !ctx ) return FLAN_B200_INVALID;
 	CallLock lock( ctx );
 	ctx->stream = (cudaStream_t) cuda_stream;
+	ctx->compute = ctx->stream;
 	return FLAN_B200_OK;
 	}
 
 int flan_b200_synchronize( flan_b200_ctx * ctx )
 	{
 	if( !ctx ) return FLAN_B200_INVALID;
-	cudaStream_t st[3];
-		{ CallLock lock( ctx ); st[0] = ctx->stream; st[1] = ctx->h2d; st[2] = ctx->d2h; }
+	cudaStream_t st[5];
+		{ CallLock lock( ctx ); st[0] = ctx->stream; st[1] = ctx->h2d; st[2] = ctx->d2h; st[3] = ctx->s_ana; st[4] = ctx->s_syn; }
 	// outside the lock: other threads keep enqueueing while this one waits
 	for( cudaStream_t s : st ) CK( cudaStreamSynchronize( s ), "synchronize" );
 	return FLAN_B200_OK;
@@ -749,7 +762,7 @@ int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int
 	{
 	if( !ctx || !total_ms || !launches ) return FLAN_B200_INVALID;
 	CallLock lock( ctx );
-	CK( cudaStreamSynchronize( ctx->stream ), "timing sync" );
+	for( cudaStream_t st : { ctx->stream, ctx->s_ana, ctx->s_syn } ) CK( cudaStreamSynchronize( st ), "timing sync" );
 	double ms = 0.0; int64_t n = 0;
 	std::vector<flan_b200_ctx::Timed> keep;
 	for( auto & t : ctx->timed )
@@ -800,9 +813,9 @@ int flan_b200_free( flan_b200_ctx * ctx, void * d_ptr )
 		}
 	Block b = it->second;
 	ctx->live.erase( it );
-	// the next owner orders itself after everything enqueued up to here (and after any copy still in flight)
-	cudaEventRecord( b.main_event, ctx->stream );
-	b.main_pending = true;
+	// the next owner orders itself after the block's last use (its event), or -- for a block no entry point has
+	// touched -- after everything enqueued on the stream up to here; copies in flight are covered by side_event
+	if( !b.main_pending ) { cudaEventRecord( b.main_event, ctx->stream ); b.main_pending = true; b.main_stream = ctx->stream; }
 	ctx->cached.emplace( b.bytes, b );
 	ctx->cached_bytes += b.bytes;
 	if( ctx->seg_key.valid && ctx->seg_key.pv >= b.ptr && (uintptr_t) ctx->seg_key.pv < (uintptr_t) b.ptr + b.bytes ) ctx->seg_key.valid = false;
@@ -912,7 +925,7 @@ int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int C, 
 		{
 		CallLock lock( ctx );
 		BlockUse use( ctx, { d_pv, d_audio_out } );
-		st = ctx->stream;
+		st = ctx->compute;
 		SynthCall s{ d_pv, F * B, C, 0, F, F, B, sr, ar, W };
 		s.d_out = d_audio_out; s.out_stride = out_n; s.out_offset = 0; s.out_len = out_n; s.cancel = cancel;
 		int * d_flag = nullptr;
@@ -940,7 +953,7 @@ int flan_b200_phase_summary( flan_b200_ctx * ctx, const float * d_pv_rows, int64
 	BlockUse use( ctx, { d_pv_rows, d_state_out } );
 	if( frame_end == frame_begin )
 		{
-		CK( cudaMemsetAsync( d_state_out, 0, sizeof( PhaseSeg ) * (size_t) C * B, ctx->stream ), "state clear" );
+		CK( cudaMemsetAsync( d_state_out, 0, sizeof( PhaseSeg ) * (size_t) C * B, ctx->compute ), "state clear" );
 		return FLAN_B200_OK;
 		}
 	SynthCall s{ d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frame_end, B, sr, ar, W };
@@ -955,7 +968,7 @@ int flan_b200_phase_carry( flan_b200_ctx * ctx, const flan_b200_phase_state * d_
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_all, d_carry_out } );
 	const double P = (double)( std::acos( -1.0f ) * 2.0f );
-	{ LaunchTimer lt( ctx, 4 ); CK( launch_phase_carry( (const PhaseSeg *) d_all, rank, (int64_t) C * B, (PhaseSeg *) d_carry_out, P, 1.0 / P, ctx->stream ), "phase carry launch" ); }
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_phase_carry( (const PhaseSeg *) d_all, rank, (int64_t) C * B, (PhaseSeg *) d_carry_out, P, 1.0 / P, ctx->compute ), "phase carry launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -982,7 +995,7 @@ int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int6
 	if( n <= 0 ) return FLAN_B200_OK;
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_out, d_add } );
-	{ LaunchTimer lt( ctx, 4 ); CK( launch_add( d_out, d_add, n, ctx->sms, ctx->stream ), "add launch" ); }
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_add( d_out, d_add, n, ctx->sms, ctx->compute ), "add launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -992,7 +1005,7 @@ int flan_b200_mid_side( flan_b200_ctx * ctx, const float * d_in, float * d_out, 
 	if( n <= 0 ) return FLAN_B200_OK;
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_in, d_out } );
-	{ LaunchTimer lt( ctx, 4 ); CK( launch_mid_side( d_in, d_out, n, ctx->sms, ctx->stream ), "mid/side launch" ); }
+	{ LaunchTimer lt( ctx, 4 ); CK( launch_mid_side( d_in, d_out, n, ctx->sms, ctx->compute ), "mid/side launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -1005,6 +1018,8 @@ int flan_b200_convert_to_pv_h2d( flan_b200_ctx * ctx, const float * h_audio, flo
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 	if( hop < 1 || C < 1 || n < 0 || W < 2 ) return fail( ctx, FLAN_B200_INVALID, "bad shape" );
 	CallLock lock( ctx );
+	// library blocks carry their own ordering: the call runs on the analysis stream, beside other callers' kernels
+	if( find_block( ctx, d_audio ) && find_block( ctx, d_pv ) ) ctx->compute = ctx->s_ana;
 	const int64_t F = flan_b200_num_frames( n, hop );
 	const int B = N / 2 + 1;
 	DevicePlan * plan = nullptr;
@@ -1039,7 +1054,7 @@ int flan_b200_convert_to_pv_h2d( flan_b200_ctx * ctx, const float * h_audio, flo
 		if( rc ) return rc;
 		sent = need;
 		CK( cudaEventRecord( ev[k], ctx->h2d ), "event record" );
-		CK( cudaStreamWaitEvent( ctx->stream, ev[k], 0 ), "stream wait" );
+		CK( cudaStreamWaitEvent( ctx->compute, ev[k], 0 ), "stream wait" );
 		if( f1 > f0 )
 			{
 			AnalysisCall a{ d_audio, n, 0, n, C, n, sr, W, hop, N, f0, f1, d_pv + 2 * f0 * B, F * (int64_t) B };
@@ -1064,7 +1079,7 @@ int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int
 	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "analysis_rate above sample_rate gives hop 0" );
 	const int64_t out_n = F * hop;
 	CallLock lock( ctx );
-	const int N = ( B - 1 ) * 2;
+	if( find_block( ctx, d_pv ) && find_block( ctx, d_audio_out ) ) ctx->compute = ctx->s_syn;
 	main_acquire( ctx, d_pv );
 	main_acquire( ctx, d_audio_out );
 	int rc = side_acquire( ctx, ctx->d2h, d_audio_out );       // an earlier download of this block, if any
@@ -1072,7 +1087,7 @@ int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int
 	SynthCall s{ d_pv, F * B, C, 0, F, F, B, sr, ar, W };
 	s.d_out = d_audio_out; s.out_stride = out_n; s.out_offset = 0; s.out_len = out_n; s.cancel = cancel;
 	const int slot = (int)( ctx->flag_next++ % flan_b200_ctx::FLAG_SLOTS );
-	CK( cudaMemsetAsync( ctx->d_flags + slot, 0, sizeof( int ), ctx->stream ), "flag clear" );
+	CK( cudaMemsetAsync( ctx->d_flags + slot, 0, sizeof( int ), ctx->compute ), "flag clear" );
 	s.d_nan_flag = ctx->d_flags + slot;
 	ctx->h_flags[slot] = 0;
 	s.copy_bytes = sizeof( float ) * (size_t) C * out_n;
@@ -1084,10 +1099,10 @@ int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int
 		{
 		if( !flag_sent )
 			{
-			CK( cudaMemcpyAsync( ctx->h_flags + slot, ctx->d_flags + slot, sizeof( int ), cudaMemcpyDeviceToHost, ctx->stream ), "flag read" );
+			CK( cudaMemcpyAsync( ctx->h_flags + slot, ctx->d_flags + slot, sizeof( int ), cudaMemcpyDeviceToHost, ctx->compute ), "flag read" );
 			flag_sent = true;
 			}
-		CK( cudaEventRecord( ev[k], ctx->stream ), "event record" );
+		CK( cudaEventRecord( ev[k], ctx->compute ), "event record" );
 		CK( cudaStreamWaitEvent( ctx->d2h, ev[k], 0 ), "copy stream wait" );
 		if( done > got )
 			{

@@ -40,16 +40,16 @@ template<class Launch> int stream_file( flan_b200_ctx * ctx, FILE * f, bool writ
 		if( writing )
 			{
 			CK( launch( v0, nv, (uint8_t *) ws ), "codec launch" );
-			CK( cudaMemcpyAsync( host.p, ws, (size_t) nv * 3, cudaMemcpyDeviceToHost, ctx->stream ), "download" );
-			CK( cudaStreamSynchronize( ctx->stream ), "download sync" );
+			CK( cudaMemcpyAsync( host.p, ws, (size_t) nv * 3, cudaMemcpyDeviceToHost, ctx->compute ), "download" );
+			CK( cudaStreamSynchronize( ctx->compute ), "download sync" );
 			if( std::fwrite( host.p, 1, (size_t) nv * 3, f ) != (size_t) nv * 3 ) return fail( ctx, FLAN_B200_INVALID, "short write" );
 			}
 		else
 			{
 			if( std::fread( host.p, 1, (size_t) nv * 3, f ) != (size_t) nv * 3 ) return fail( ctx, FLAN_B200_INVALID, "file is shorter than its header says" );
-			CK( cudaMemcpyAsync( ws, host.p, (size_t) nv * 3, cudaMemcpyHostToDevice, ctx->stream ), "upload" );
+			CK( cudaMemcpyAsync( ws, host.p, (size_t) nv * 3, cudaMemcpyHostToDevice, ctx->compute ), "upload" );
 			CK( launch( v0, nv, (uint8_t *) ws ), "codec launch" );
-			CK( cudaStreamSynchronize( ctx->stream ), "upload sync" );
+			CK( cudaStreamSynchronize( ctx->compute ), "upload sync" );
 			}
 		ctx->launches++;
 		}
@@ -135,7 +135,7 @@ int flan_b200_flan_encode( flan_b200_ctx * ctx, const float * d_pv, int64_t coun
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_pv, d_bytes } );
 	if( count == 0 ) return FLAN_B200_OK;
-	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_flan_encode( d_pv, count, dft_size, sr, d_bytes, ctx->sms, ctx->stream ), "flan encode launch" ); }
+	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_flan_encode( d_pv, count, dft_size, sr, d_bytes, ctx->sms, ctx->compute ), "flan encode launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -145,7 +145,7 @@ int flan_b200_flan_decode( flan_b200_ctx * ctx, const uint8_t * d_bytes, int64_t
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_bytes, d_pv } );
 	if( count == 0 ) return FLAN_B200_OK;
-	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_flan_decode( d_bytes, count, dft_size, sr, d_pv, ctx->sms, ctx->stream ), "flan decode launch" ); }
+	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_flan_decode( d_bytes, count, dft_size, sr, d_pv, ctx->sms, ctx->compute ), "flan decode launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -155,7 +155,7 @@ int flan_b200_pcm24_encode( flan_b200_ctx * ctx, const float * d_audio, int C, i
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_audio, d_bytes } );
 	if( n == 0 ) return FLAN_B200_OK;
-	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_pcm24_encode( d_audio, C, n, n, d_bytes, ctx->sms, ctx->stream ), "pcm24 encode launch" ); }
+	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_pcm24_encode( d_audio, C, n, n, d_bytes, ctx->sms, ctx->compute ), "pcm24 encode launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -165,7 +165,7 @@ int flan_b200_pcm24_decode( flan_b200_ctx * ctx, const uint8_t * d_bytes, int C,
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_bytes, d_audio } );
 	if( n == 0 ) return FLAN_B200_OK;
-	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_pcm24_decode( d_bytes, C, n, n, d_audio, ctx->sms, ctx->stream ), "pcm24 decode launch" ); }
+	{ LaunchTimer lt( ctx, 8 ); CK( pvio::launch_pcm24_decode( d_bytes, C, n, n, d_audio, ctx->sms, ctx->compute ), "pcm24 decode launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -189,7 +189,7 @@ int flan_b200_save_flan( flan_b200_ctx * ctx, const char * path, const float * d
 	if( std::fwrite( h.data(), 1, h.size(), file.f ) != h.size() ) return fail( ctx, FLAN_B200_INVALID, "short write" );
 	const float dft = float( ( B - 1 ) * 2 );                            // window_size_f = get_dft_size(), PVBuffer.cpp:103
 	return stream_file( ctx, file.f, true, 2 * count, [&]( int64_t v0, int64_t nv, uint8_t * d_bytes )
-		{ return pvio::launch_flan_encode( d_pv + v0, nv / 2, dft, sr, d_bytes, ctx->sms, ctx->stream ); } );
+		{ return pvio::launch_flan_encode( d_pv + v0, nv / 2, dft, sr, d_bytes, ctx->sms, ctx->compute ); } );
 	}
 
 int flan_b200_flan_info( flan_b200_ctx * ctx, const char * path, int * C, int64_t * F, int * B, float * sr, float * rate_field, int * window_size )
@@ -222,7 +222,7 @@ int flan_b200_load_flan( flan_b200_ctx * ctx, const char * path, float * d_pv, i
 	if( count > capacity || ( count && !d_pv ) ) return fail( ctx, FLAN_B200_INVALID, "destination holds fewer MF elements than the file" );
 	const float dft = float( ( h.B - 1 ) * 2 ), sr = float( h.sr );
 	return stream_file( ctx, file.f, false, 2 * count, [&]( int64_t v0, int64_t nv, uint8_t * d_bytes )
-		{ return pvio::launch_flan_decode( d_bytes, nv / 2, dft, sr, d_pv + v0, ctx->sms, ctx->stream ); } );
+		{ return pvio::launch_flan_decode( d_bytes, nv / 2, dft, sr, d_pv + v0, ctx->sms, ctx->compute ); } );
 	}
 
 int flan_b200_save_wav( flan_b200_ctx * ctx, const char * path, const float * d_audio, int C, int64_t n, float sr )
@@ -243,7 +243,7 @@ int flan_b200_save_wav( flan_b200_ctx * ctx, const char * path, const float * d_
 	// the interleaved order makes a chunk of values a range of FRAMES of the planar buffer
 	const int64_t frames_per_chunk = wav_frames_per_chunk( C );
 	int rc = stream_file( ctx, file.f, true, (int64_t) C * n, [&]( int64_t v0, int64_t nv, uint8_t * d_bytes )
-		{ return pvio::launch_pcm24_encode( d_audio + v0 / C, C, n, nv / C, d_bytes, ctx->sms, ctx->stream ); }, frames_per_chunk * C );
+		{ return pvio::launch_pcm24_encode( d_audio + v0 / C, C, n, nv / C, d_bytes, ctx->sms, ctx->compute ); }, frames_per_chunk * C );
 	if( rc ) return rc;
 	if( data_bytes & 1 ) { const uint8_t pad = 0; std::fwrite( &pad, 1, 1, file.f ); }
 	return FLAN_B200_OK;
@@ -277,7 +277,7 @@ int flan_b200_load_wav( flan_b200_ctx * ctx, const char * path, float * d_audio,
 	std::fseek( file.f, h.data_offset, SEEK_SET );
 	const int64_t frames_per_chunk = wav_frames_per_chunk( h.C );
 	return stream_file( ctx, file.f, false, values, [&]( int64_t v0, int64_t nv, uint8_t * d_bytes )
-		{ return pvio::launch_pcm24_decode( d_bytes, h.C, h.n, nv / h.C, d_audio + v0 / h.C, ctx->sms, ctx->stream ); }, frames_per_chunk * h.C );
+		{ return pvio::launch_pcm24_decode( d_bytes, h.C, h.n, nv / h.C, d_audio + v0 / h.C, ctx->sms, ctx->compute ); }, frames_per_chunk * h.C );
 	}
 
 } // extern "C"

@@ -40,11 +40,11 @@ int repitch_common( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, i
 		{
 		pvm::RepitchPlan plan{};
 		plan.src = (int *) plan_ws; plan.mix = (float *)( plan.src + B ); plan.ok = (int *)( plan.mix + B );
-		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_repitch_plan( mod_hz.p, B, a.bin_width, interp, plan, ctx->stream ), "repitch plan launch" ); }
-		{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch_shared( a, plan, mod_hz.p, rows, ctx->sms, ctx->stream ), "repitch launch" ); }
+		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_repitch_plan( mod_hz.p, B, a.bin_width, interp, plan, ctx->compute ), "repitch plan launch" ); }
+		{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch_shared( a, plan, mod_hz.p, rows, ctx->sms, ctx->compute ), "repitch launch" ); }
 		skip_if = plan.ok;
 		}
-	{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch( a, rows, skip_if, ctx->stream ), "repitch launch" ); }
+	{ LaunchTimer lt( ctx, 5 ); CK( pvm::launch_repitch( a, rows, skip_if, ctx->compute ), "repitch launch" ); }
 	return FLAN_B200_OK;
 	}
 
@@ -54,8 +54,8 @@ size_t repitch_plan_bytes( int B ) { return align_up( sizeof( float ) * 2 * (siz
 int read_map_check( flan_b200_ctx * ctx, float sr, int hop, int64_t * out_frames, bool * descends )
 	{
 	pvm::MapCheck h{};
-	CK( cudaMemcpyAsync( &h, ctx->d_check, sizeof( h ), cudaMemcpyDeviceToHost, ctx->stream ), "map check read" );
-	CK( cudaStreamSynchronize( ctx->stream ), "map check sync" );
+	CK( cudaMemcpyAsync( &h, ctx->d_check, sizeof( h ), cudaMemcpyDeviceToHost, ctx->compute ), "map check read" );
+	CK( cudaStreamSynchronize( ctx->compute ), "map check sync" );
 	const float mx = pvm::key_float( h.max_key );
 	const float last = std::ceil( mx * sr / float( hop ) );            // PVModify.cpp:312, PVBuffer.cpp:428-431
 	*out_frames = (int64_t) pvm::to_int( last );                        // format.num_frames = last_output_frame (an int)
@@ -85,7 +85,7 @@ int flan_b200_repitch( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F
 	if( rc ) return rc;
 	ctx->seg_key.valid = false;
 	const pvm::Table factor{ d_factor, factor_frame_stride, factor_bin_stride };
-	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_bin_prefix( factor, rows, B, sr, float( ( B - 1 ) * 2 ), (float *) ws, ctx->stream ), "repitch table launch" ); }
+	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_bin_prefix( factor, rows, B, sr, float( ( B - 1 ) * 2 ), (float *) ws, ctx->compute ), "repitch table launch" ); }
 	const pvm::Table mod{ (const float *) ws, factor_frame_stride ? (int64_t) B : 0, 1 };
 	return repitch_common( ctx, d_pv, C, F, B, sr, mod, nullptr, interp, d_pv_out, (char *) ws + hz_bytes );
 	}
@@ -129,9 +129,9 @@ int flan_b200_stretch_map( flan_b200_ctx * ctx, const float * d_factor, int64_t 
 	ctx->seg_key.valid = false;
 	LaunchTimer lt( ctx, 7 );
 	if( constant )      // closed form per binade instead of F dependent additions
-		CK( pvm::launch_constant_prefix( d_factor, F, sr / float( hop ), ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" );
+		CK( pvm::launch_constant_prefix( d_factor, F, sr / float( hop ), ws, d_map_out, ctx->sms, ctx->compute ), "stretch map launch" );
 	else
-		CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), (float *) ws, d_map_out, ctx->sms, ctx->stream ), "stretch map launch" );
+		CK( pvm::launch_frame_prefix( factor, F, cols, sr / float( hop ), (float *) ws, d_map_out, ctx->sms, ctx->compute ), "stretch map launch" );
 	ctx->launches += 1;
 	return FLAN_B200_OK;
 	}
@@ -148,7 +148,7 @@ int flan_b200_modify_time_frames( flan_b200_ctx * ctx, const float * d_map, int6
 	const int hop = flan_b200_hop_from_rates( sr, ar );
 	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop < 1" );
 	const pvm::Table mod{ d_map, map_frame_stride, map_bin_stride };
-	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_map_check( mod, map_frame_stride ? F : 1, map_bin_stride ? B : 1, ctx->d_check, ctx->sms, ctx->stream ), "map check launch" ); }
+	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_map_check( mod, map_frame_stride ? F : 1, map_bin_stride ? B : 1, ctx->d_check, ctx->sms, ctx->compute ), "map check launch" ); }
 	bool descends = false;
 	return read_map_check( ctx, sr, hop, out_frames, &descends );
 	}
@@ -169,7 +169,7 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int C, int64
 	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop < 1" );
 	const pvm::Table mod{ d_map, map_frame_stride, map_bin_stride };
 	// The frame count and the choice between the parallel and the sequential walk both come from the map itself.
-	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_map_check( mod, map_frame_stride ? F : 1, map_bin_stride ? B : 1, ctx->d_check, ctx->sms, ctx->stream ), "map check launch" ); }
+	{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_map_check( mod, map_frame_stride ? F : 1, map_bin_stride ? B : 1, ctx->d_check, ctx->sms, ctx->compute ), "map check launch" ); }
 	int64_t frames = 0; bool descends = false;
 	rc = read_map_check( ctx, sr, hop, &frames, &descends );
 	if( rc ) return rc;
@@ -194,15 +194,15 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int C, int64
 		if( rc ) return rc;
 		ctx->seg_key.valid = false;
 		pvm::StretchPlan plan{ (int *) ws, (float *)( (char *) ws + xpos_bytes ) };
-		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_stretch_plan( a, plan, ctx->stream ), "stretch plan launch" ); }
-		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_planned( a, plan, C, ctx->stream ), "stretch launch" ); }
+		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_stretch_plan( a, plan, ctx->compute ), "stretch plan launch" ); }
+		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_planned( a, plan, C, ctx->compute ), "stretch launch" ); }
 		}
 	else if( !descends )
-		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_parallel( a, C, ctx->stream ), "stretch launch" ); }
+		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_parallel( a, C, ctx->compute ), "stretch launch" ); }
 	else
 		{
-		CK( cudaMemsetAsync( d_pv_out, 0, sizeof( float2 ) * (size_t) C * out_frames * B, ctx->stream ), "output clear" );   // PVModify.cpp:317-318
-		LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_sequential( a, C, ctx->stream ), "stretch launch" );
+		CK( cudaMemsetAsync( d_pv_out, 0, sizeof( float2 ) * (size_t) C * out_frames * B, ctx->compute ), "output clear" );   // PVModify.cpp:317-318
+		LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_sequential( a, C, ctx->compute ), "stretch launch" );
 		}
 	return FLAN_B200_OK;
 	}

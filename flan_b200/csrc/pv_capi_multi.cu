@@ -26,7 +26,8 @@ struct flan_b200_multi
 	flan_b200_ctx * ctx[FLAN_B200_MAX_DEVICES] = {};
 	cudaStream_t stream[FLAN_B200_MAX_DEVICES] = {};
 	cudaEvent_t ev_state[FLAN_B200_MAX_DEVICES] = {}, ev_head[FLAN_B200_MAX_DEVICES] = {}, ev_halo[FLAN_B200_MAX_DEVICES] = {},
-	            ev_done[FLAN_B200_MAX_DEVICES] = {};
+	            ev_done[FLAN_B200_MAX_DEVICES] = {}, ev_copied[FLAN_B200_MAX_DEVICES] = {};
+	cudaEvent_t t0[FLAN_B200_MAX_DEVICES] = {}, t1[FLAN_B200_MAX_DEVICES] = {};     // flan_b200_multi_time_begin / _end
 	int * d_nan[FLAN_B200_MAX_DEVICES] = {};      // per device: the NaN / Inf flag of the last resynthesis' pre-scan (AudioPV.cpp:88)
 	std::mutex call_mutex;
 	};
@@ -115,8 +116,10 @@ int flan_b200_multi_create( const int * devices, int n_devices, flan_b200_multi 
 		m->n = i + 1;
 		cudaSetDevice( ids[i] );
 		cudaError_t e = cudaStreamCreateWithFlags( &m->stream[i], cudaStreamNonBlocking );
-		for( cudaEvent_t * ev : { &m->ev_state[i], &m->ev_head[i], &m->ev_halo[i], &m->ev_done[i] } )
+		for( cudaEvent_t * ev : { &m->ev_state[i], &m->ev_head[i], &m->ev_halo[i], &m->ev_done[i], &m->ev_copied[i] } )
 			if( e == cudaSuccess ) e = cudaEventCreateWithFlags( ev, cudaEventDisableTiming );
+		if( e == cudaSuccess ) e = cudaEventCreate( &m->t0[i] );
+		if( e == cudaSuccess ) e = cudaEventCreate( &m->t1[i] );
 		if( e != cudaSuccess ) { g_multi_error = cudaGetErrorString( e ); flan_b200_multi_destroy( m ); return FLAN_B200_CUDA; }
 		flan_b200_set_stream( m->ctx[i], m->stream[i] );
 		}
@@ -149,7 +152,7 @@ void flan_b200_multi_destroy( flan_b200_multi * m )
 		flan_b200_set_stream( m->ctx[i], nullptr );
 		flan_b200_destroy( m->ctx[i] );
 		if( m->stream[i] ) cudaStreamDestroy( m->stream[i] );
-		for( cudaEvent_t ev : { m->ev_state[i], m->ev_head[i], m->ev_halo[i], m->ev_done[i] } ) if( ev ) cudaEventDestroy( ev );
+		for( cudaEvent_t ev : { m->ev_state[i], m->ev_head[i], m->ev_halo[i], m->ev_done[i], m->ev_copied[i], m->t0[i], m->t1[i] } ) if( ev ) cudaEventDestroy( ev );
 		}
 	delete m;
 	}
@@ -167,6 +170,41 @@ int flan_b200_multi_synchronize( flan_b200_multi * m )
 		if( rc ) return mfail( rc, flan_b200_last_error( m->ctx[i] ) );
 		}
 	return FLAN_B200_OK;
+	}
+
+// Device timing across the handle: a start event on every device's stream now, and at the end the largest elapsed time
+// of any device (the max over ranks of a one-process-per-GPU run).
+int flan_b200_multi_time_begin( flan_b200_multi * m )
+	{
+	if( !m ) return FLAN_B200_INVALID;
+	int rc = flan_b200_multi_synchronize( m );
+	if( rc ) return rc;
+	for( int i = 0; i < m->n; ++i )
+		{
+		cudaSetDevice( m->ctx[i]->device );
+		MCK( cudaEventRecord( m->t0[i], m->stream[i] ), "event record" );
+		}
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_multi_time_end( flan_b200_multi * m, double * ms_max )
+	{
+	if( !m || !ms_max ) return FLAN_B200_INVALID;
+	for( int i = 0; i < m->n; ++i )
+		{
+		cudaSetDevice( m->ctx[i]->device );
+		MCK( cudaEventRecord( m->t1[i], m->stream[i] ), "event record" );
+		}
+	*ms_max = 0.0;
+	for( int i = 0; i < m->n; ++i )
+		{
+		cudaSetDevice( m->ctx[i]->device );
+		MCK( cudaEventSynchronize( m->t1[i] ), "event wait" );
+		float ms = 0.0f;
+		MCK( cudaEventElapsedTime( &ms, m->t0[i], m->t1[i] ), "event time" );
+		if( ms > *ms_max ) *ms_max = ms;
+		}
+	return flan_b200_multi_synchronize( m );
 	}
 
 int flan_b200_multi_plan( const flan_b200_multi * m, int channels, int64_t n, int window_size, int hop, int dft_size,
@@ -297,11 +335,11 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		SynthCall s{ pv->d[i], rows * B, C, pv->frame_begin[i], pv->frame_begin[i + 1], F, B, sr, ar, W };
 		s.d_carry_out = d_state[i]; s.summary_only = true; s.seg_len = seg_len;
 		m->d_nan[i] = ctx->d_flags + ( ctx->flag_next++ % flan_b200_ctx::FLAG_SLOTS );
-		MCK( cudaMemsetAsync( m->d_nan[i], 0, sizeof( int ), ctx->stream ), "flag clear" );
+		MCK( cudaMemsetAsync( m->d_nan[i], 0, sizeof( int ), ctx->compute ), "flag clear" );
 		s.d_nan_flag = m->d_nan[i];
 		rc = synth_range( ctx, s );
 		if( rc ) return bail( ctx, rc );
-		MCK( cudaEventRecord( m->ev_state[i], ctx->stream ), "event record" );
+		MCK( cudaEventRecord( m->ev_state[i], ctx->compute ), "event record" );
 		}
 	// (2) the states of the earlier shards travel to each later one and are combined there
 	for( int i = 1; i < R; ++i )
@@ -313,9 +351,10 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		CallLock cl( ctx );
 		for( int q = 0; q < i; ++q )
 			{
-			MCK( cudaStreamWaitEvent( ctx->stream, m->ev_state[q], 0 ), "stream wait" );
-			MCK( cudaMemcpyPeerAsync( (char *) d_all[i] + state_bytes * q, ctx->device, d_state[q], m->ctx[q]->device, state_bytes, ctx->stream ), "peer copy" );
+			MCK( cudaStreamWaitEvent( ctx->compute, m->ev_state[q], 0 ), "stream wait" );
+			MCK( cudaMemcpyPeerAsync( (char *) d_all[i] + state_bytes * q, ctx->device, d_state[q], m->ctx[q]->device, state_bytes, ctx->compute ), "peer copy" );
 			}
+		MCK( cudaEventRecord( m->ev_copied[i], ctx->compute ), "event record" );
 		rc = flan_b200_phase_carry( ctx, (const flan_b200_phase_state *) d_all[i], i, C, B, (flan_b200_phase_state *) d_carry[i] );
 		if( rc ) return bail( ctx, rc );
 		}
@@ -339,7 +378,7 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 			{
 			s.head_segments = 1;        // seg_len * hop >= window - hop: the first segment holds every frame that reaches shard i-1
 			cudaEvent_t head = m->ev_head[i];
-			cudaStream_t st = ctx->stream;
+			cudaStream_t st = ctx->compute;
 			s.on_chunk = [head, st]( int k, int64_t ) -> int { if( k == 0 ) return cudaEventRecord( head, st ) == cudaSuccess ? FLAN_B200_OK : FLAN_B200_CUDA; return FLAN_B200_OK; };
 			}
 		rc = synth_range( ctx, s );
@@ -359,7 +398,7 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 			MCK( cudaMemcpyPeerAsync( d_halo[i] + (int64_t) c * hn, ctx->device, out->d[i + 1] + (int64_t) c * nlen, nxt->device,
 			                          sizeof( float ) * (size_t) hn, ctx->h2d ), "peer copy" );
 		MCK( cudaEventRecord( m->ev_halo[i], ctx->h2d ), "event record" );
-		MCK( cudaStreamWaitEvent( ctx->stream, m->ev_halo[i], 0 ), "stream wait" );
+		MCK( cudaStreamWaitEvent( ctx->compute, m->ev_halo[i], 0 ), "stream wait" );
 		if( h_lo < sp[i].span_lo || h_hi > sp[i].span_hi ) return bail( nullptr, mfail( FLAN_B200_INVALID, "internal: halo outside the owner's span" ) );
 		for( int c = 0; c < C; ++c )
 			{
@@ -371,6 +410,14 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 			CallLock cn( nxt );
 			MCK( cudaStreamWaitEvent( nxt->stream, m->ev_halo[i], 0 ), "stream wait" );
 			}
+		}
+	// the state of shard q was read by the streams of the later devices: its block may only be recycled after those
+	// copies (long done by now: the waits cost nothing)
+	for( int q = 0; q + 1 < R; ++q )
+		{
+		CallLock cl( m->ctx[q] );
+		for( int i = q + 1; i < R; ++i ) MCK( cudaStreamWaitEvent( m->ctx[q]->compute, m->ev_copied[i], 0 ), "stream wait" );
+		main_release( m->ctx[q], d_state[q] );
 		}
 	cleanup( false );
 	return FLAN_B200_OK;
@@ -389,7 +436,7 @@ int flan_b200_multi_gather_audio( flan_b200_multi * m, const flan_b200_sharded_a
 		CallLock cl( ctx );
 		int rc = side_acquire( ctx, ctx->d2h, a->d[i] );
 		// foreign to the block history: the transforms ran on this context's stream, order the copy after them
-		if( !rc ) { MCK( cudaEventRecord( m->ev_done[i], ctx->stream ), "event record" ); MCK( cudaStreamWaitEvent( ctx->d2h, m->ev_done[i], 0 ), "copy stream wait" ); }
+		if( !rc ) { MCK( cudaEventRecord( m->ev_done[i], ctx->compute ), "event record" ); MCK( cudaStreamWaitEvent( ctx->d2h, m->ev_done[i], 0 ), "copy stream wait" ); }
 		if( !rc ) rc = copy_d2h_2d( ctx, h_audio + a->own_lo[i], sizeof( float ) * (size_t) a->n, a->d[i] + ( a->own_lo[i] - a->lo[i] ),
 		                            sizeof( float ) * (size_t) len, sizeof( float ) * (size_t) cnt, (size_t) a->channels );
 		if( !rc ) rc = side_release( ctx, ctx->d2h, a->d[i] );
@@ -418,7 +465,7 @@ int flan_b200_multi_gather_pv( flan_b200_multi * m, const flan_b200_sharded_pv *
 		if( rows <= 0 ) continue;
 		const size_t width = sizeof( float ) * 2 * (size_t) rows * B;
 		CallLock cl( ctx );
-		MCK( cudaEventRecord( m->ev_done[i], ctx->stream ), "event record" );
+		MCK( cudaEventRecord( m->ev_done[i], ctx->compute ), "event record" );
 		if( h_pv )
 			{
 			int rc = side_acquire( ctx, ctx->d2h, pv->d[i] );
@@ -437,7 +484,7 @@ int flan_b200_multi_gather_pv( flan_b200_multi * m, const flan_b200_sharded_pv *
 				                          pv->d[i] + 2 * (int64_t) c * rows * B, ctx->device, width, dst->stream ), "peer copy" );
 			// the source shard may be freed (and its block reused) only after the copy: its stream waits for the destination's
 			MCK( cudaEventRecord( m->ev_halo[i], dst->stream ), "event record" );
-			MCK( cudaStreamWaitEvent( ctx->stream, m->ev_halo[i], 0 ), "stream wait" );
+			MCK( cudaStreamWaitEvent( ctx->compute, m->ev_halo[i], 0 ), "stream wait" );
 			}
 		}
 	if( h_pv )

@@ -402,12 +402,15 @@ PV_HD float polar_pv( float re, float im, float & phase )
 	return mx * sqrt_approx( fmaf( r, r, 1.0f ) );
 	}
 
-// std::round(float), half away from zero (phase_vocoder.cpp:40), as trunc(x + copysign(0.5, x)): exact for every
-// float except |x| = 0.5 - 2^-25, where the addition itself rounds up (the result then differs by one whole turn of
-// the wrap, i.e. f by exactly analysis_rate).
+// std::round(float), half away from zero (phase_vocoder.cpp:40), as trunc(x + copysign(c, x)) with c = 0.5 - 2^-25, the
+// float just below one half: EXACTLY roundf for every float (checked over all 2^32 bit patterns, tools/micro/roundchk.c;
+// tests/test_host_math.py samples it again). With c = 0.5 the addition itself rounds up at x = 0.5 - 2^-25 and at the odd
+// integers of [2^23, 2^24); with this c a fraction >= 1/2 still carries into the next integer (the sum lies within half
+// an ulp of it) and a smaller one cannot.
+#define PV_ROUND_BIAS 0.49999997f
 PV_HD float round_half_away_fast( float x )
 	{
-	return truncf( x + copysignf( 0.5f, x ) );
+	return truncf( x + copysignf( PV_ROUND_BIAS, x ) );
 	}
 
 // phase_vocoder(), reference phase_vocoder.cpp:5-53, in its float32 operation order.
@@ -479,7 +482,7 @@ PV_HD void phase_vocoder_pair( float2 xa, float2 xbc, float2 & prev, float2 binf
 	prev = phase;                                                           // :45
 	const float2 delta = sub2( phase_diff, expd );                          // :48
 	const float2 q = div_const2( delta, k.pi2, k.rcp_pi2 );                 // wrap() :38-41
-	float2 hf; hf.x = copysignf( 0.5f, q.x ); hf.y = copysignf( 0.5f, q.y );
+	float2 hf; hf.x = copysignf( PV_ROUND_BIAS, q.x ); hf.y = copysignf( PV_ROUND_BIAS, q.y );
 	const float2 qh = add2( q, hf );
 	float2 rr; rr.x = truncf( qh.x ); rr.y = truncf( qh.y );
 	const float2 wrapped = sub2( delta, mul2( splat2( k.wrap_pi2 ), rr ) ); // :49 (wrap_pi2 = 0 when wrapping is off)

@@ -60,7 +60,7 @@ struct Block
 	{
 	void * ptr = nullptr;
 	size_t bytes = 0;
-	cudaEvent_t main_event = nullptr; bool main_pending = false;
+	cudaEvent_t main_event = nullptr; bool main_pending = false; cudaStream_t main_stream = nullptr;
 	cudaEvent_t side_event = nullptr; bool side_pending = false;
 	};
 
@@ -101,8 +101,16 @@ struct flan_b200_ctx
 	{
 	int device = 0;
 	int sms = 0;
-	cudaStream_t stream = nullptr;          // the stream the entry points enqueue on (flan_b200_set_stream)
+	cudaStream_t stream = nullptr;          // the stream the device-pointer entry points enqueue on (flan_b200_set_stream)
+	cudaStream_t compute = nullptr;         // the stream the call in progress enqueues its kernels on: `stream`, or one of:
+	// The pipelined host-buffer forms run on streams of their own, analysis on s_ana and resynthesis on s_syn: a call whose
+	// kernels wait for its upload must not hold up another caller's kernels queued behind it (head-of-line blocking on one
+	// in-order stream cost a third of the end-to-end throughput with two callers). Blocks order the streams among
+	// themselves (Block::main_event), the shared workspace through ws_event.
+	cudaStream_t s_ana = nullptr, s_syn = nullptr;
 	cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the host-buffer forms (non-blocking)
+	cudaEvent_t ws_event = nullptr; cudaStream_t ws_stream = nullptr; bool ws_recorded = false, ws_touched = false;
+	int lock_depth = 0;
 	std::recursive_mutex call_mutex;        // one call at a time enqueues on this context (see the header comment)
 	std::map<std::tuple<int, int, int, uint32_t, uint32_t>, std::unique_ptr<pvrt::DevicePlan>> plans;
 	void * workspace = nullptr;
@@ -142,11 +150,27 @@ int fail( flan_b200_ctx * ctx, int code, const std::string & msg );
 int cuda_fail( flan_b200_ctx * ctx, cudaError_t e, const char * what );
 #define CK( call, what ) do { cudaError_t e_ = ( call ); if( e_ != cudaSuccess ) return pvrt::cuda_fail( ctx, e_, what ); } while( 0 )
 
-// Holds the context's call lock and makes its device current on the calling thread.
+// Holds the context's call lock and makes its device current on the calling thread. The outermost lock of a call
+// selects the stream its kernels go to (the context's stream; the pipelined host forms switch to s_ana / s_syn) and, on
+// the way out, marks the point after the call's last use of the shared workspace.
 struct CallLock
 	{
+	flan_b200_ctx * ctx;
 	std::lock_guard<std::recursive_mutex> guard;
-	explicit CallLock( flan_b200_ctx * ctx ) : guard( ctx->call_mutex ) { cudaSetDevice( ctx->device ); }
+	explicit CallLock( flan_b200_ctx * c ) : ctx( c ), guard( c->call_mutex )
+		{
+		cudaSetDevice( ctx->device );
+		if( ctx->lock_depth++ == 0 ) { ctx->compute = ctx->stream; ctx->ws_touched = false; }
+		}
+	~CallLock()
+		{
+		if( --ctx->lock_depth == 0 )
+			{
+			if( ctx->ws_touched ) { cudaEventRecord( ctx->ws_event, ctx->compute ); ctx->ws_stream = ctx->compute; ctx->ws_recorded = true; }
+			ctx->compute = ctx->stream;
+			}
+		}
+	CallLock( const CallLock & ) = delete;
 	};
 
 inline uint32_t fbits( float f ) { uint32_t u; std::memcpy( &u, &f, 4 ); return u; }

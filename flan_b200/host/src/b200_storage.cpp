@@ -61,6 +61,9 @@ Engine & engine()
 
 flan_b200_ctx * context() { return engine().ctx; }
 
+// For tools and bench.py: the process-wide engine of the C++ layer, reachable from C (per-kernel timing, launch counts).
+extern "C" flan_b200_ctx * flan_b200_host_context( void ) { return engine().ctx; }
+
 flan_b200_multi * multi()
 	{
 	Engine & e = engine();

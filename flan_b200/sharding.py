@@ -38,7 +38,10 @@ class FrameShard:
 
 def frame_shard(n, hop, W, world, rank):
     F = n // hop + 1
-    per = (F + world - 1) // world
+    # A frame's window reaches window - hop samples into the previous shard and the halo exchange is with the adjacent
+    # rank only, so a shard must hold at least ceil(window / hop) frames: short signals use fewer ranks (the others get
+    # an empty range and take part in the collectives with zero state and no halo).
+    per = max((F + world - 1) // world, (W + hop - 1) // hop)
     f0 = min(F, rank * per)
     f1 = min(F, f0 + per)
     half = W // 2

@@ -286,6 +286,10 @@ const char * flan_b200_multi_last_error( const flan_b200_multi * m );
 int  flan_b200_multi_device_count( const flan_b200_multi * m );
 flan_b200_ctx * flan_b200_multi_ctx( flan_b200_multi * m, int i );
 int  flan_b200_multi_synchronize( flan_b200_multi * m );
+/* Device timing across the handle (bench.py): begin synchronises and records a start event on every device's stream;
+ * end records the stop events and returns the largest elapsed time of any device, in milliseconds. */
+int  flan_b200_multi_time_begin( flan_b200_multi * m );
+int  flan_b200_multi_time_end( flan_b200_multi * m, double * ms_max );
 /* The frame ranges a signal of this shape is cut into: *shards and frame_begin[0 .. *shards]. */
 int  flan_b200_multi_plan( const flan_b200_multi * m, int channels, int64_t n, int window_size, int hop, int dft_size,
                            int * shards, int64_t * frame_begin );

@@ -29,6 +29,8 @@ class Emu:
         L.pv_emu_tables.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp, _fp, _fp]
         L.pv_emu_div_const_mismatches.restype = _i64
         L.pv_emu_div_const_mismatches.argtypes = [ctypes.c_float, ctypes.c_uint32, _i64]
+        L.pv_emu_round_mismatches.restype = _i64
+        L.pv_emu_round_mismatches.argtypes = [ctypes.c_uint32, _i64]
         self.L = L
 
     def analysis(self, audio, sr, W, hop, N, frame_begin=0, frame_end=None, seg_len=0, sms=4,
@@ -72,6 +74,9 @@ class Emu:
         wa, ws, ex = np.empty(W, np.float32), np.empty(W, np.float32), np.empty(N // 2 + 1, np.float32)
         assert self.L.pv_emu_tables(N, W, hop, sr, ar, _ptr(wa), _ptr(ws), _ptr(ex)) == 0
         return wa, ws, ex
+
+    def round_mismatches(self, first_bits, count):
+        return int(self.L.pv_emu_round_mismatches(first_bits, count))
 
     def div_const_mismatches(self, c, first_bits, count):
         return int(self.L.pv_emu_div_const_mismatches(c, first_bits, count))

@@ -14,6 +14,9 @@ only the small test fixtures go there) the 1e-3 Hz term is scaled by analysis_ra
 
 On top of that the gate allows the float32 FFT noise floor itself: 1e-7 * (1/rho_f + 1/rho_{f-1}) rad, rho = m_ref /
 frame peak >= 1e-2, i.e. at most 6e-4 Hz at the gate edge for analysis_rate 187.5 Hz and ~1e-5 Hz for loud bins.
+(fft_noise: 1e-7 for the power-of-two transforms; the Bluestein path of the non-power-of-two sizes runs three float
+FFTs of at least twice the length plus two chirp products per transform; measured on B200 its noise is about ten times
+that of the direct transform, and it is given 1.5e-6 -- magnitudes stay within 1e-5 relative either way.)
 
 Resynthesis, stage-wise on the SAME PV input: max |sample - sample_ref| <= 1e-5.
 """
@@ -25,7 +28,7 @@ def ulp32(x):
     return np.spacing(np.maximum(x, np.float32(1e-30))).astype(np.float64)
 
 
-def analysis_report(pv, pv_ref, sr, hop, N):
+def analysis_report(pv, pv_ref, sr, hop, N, fft_noise=1e-7):
     pv = np.asarray(pv, np.float32)
     pv_ref = np.asarray(pv_ref, np.float32)
     m, f = pv[..., 0].astype(np.float64), pv[..., 1].astype(np.float64)
@@ -33,7 +36,7 @@ def analysis_report(pv, pv_ref, sr, hop, N):
     ar = float(np.float32(sr) / np.float32(hop))
     pi2 = float(np.float32(np.float32(np.arccos(np.float32(-1))) * np.float32(2)))
     B = N // 2 + 1
-    binf = (np.arange(B, dtype=np.float32) * np.float32(sr) / np.float32(N)).astype(np.float32)
+    binf = (np.arange(B, dtype=np.float32) * np.float32(sr) / np.float32((B - 1) * 2)).astype(np.float32)   # PVBuffer.cpp:443-446 over get_dft_size()
     expected = (binf / np.float32(ar) * np.float32(pi2)).astype(np.float32)
     grid = ulp32(expected) * ar / (2 * np.pi)
     peak = mr.max(axis=-1, keepdims=True)
@@ -49,10 +52,20 @@ def analysis_report(pv, pv_ref, sr, hop, N):
     inv_prev = inv.copy()
     inv_prev[..., 1:, :] = inv[..., :-1, :]
     inv_prev[..., 0, :] = 0.0
-    tol_f = tol_f + 1e-7 * (inv + inv_prev) * ar / (2 * np.pi)
+    tol_f = tol_f + fft_noise * (inv + inv_prev) * ar / (2 * np.pi)
     rel_m = np.abs(m - mr) / np.where(mr > 0, mr, 1.0)
     bad_m = gate & (rel_m > 1e-4)
     bad_f = gate & (df > tol_f)
+    # SURVEY 8c's gate as proposed, WITHOUT the three allowances argued above (VERDICT r1 weak #1 asked how many bins
+    # pass only because of them): current-frame level only, 1e-3 Hz unscaled, no noise term. Reported, not asserted:
+    # a float32 FFT other than the oracle's double one cannot meet it on bins near the gate edge.
+    gate0 = (mr >= 1e-2 * peak) & (peak > 0)
+    tol0 = np.maximum(1e-3, 2 * ulp32(pv_ref[..., 1]))
+    strict_fail = gate0 & (df > tol0)
+    tol_scale = np.maximum(1e-3 * max(1.0, ar / 750.0), np.maximum(2 * ulp32(pv_ref[..., 1]), 2 * grid))
+    need_prev = strict_fail & ~gate                                  # excused by the previous frame's level
+    need_scale = strict_fail & gate & (df <= tol_scale)              # excused by the ar/750 scale or the grid term
+    need_noise = strict_fail & gate & (df > tol_scale) & (df <= tol_f)   # excused only by the FFT noise term
     return {
         "gated_bins": int(gate.sum()),
         "max_rel_m": float(rel_m[gate].max()) if gate.any() else 0.0,
@@ -61,16 +74,25 @@ def analysis_report(pv, pv_ref, sr, hop, N):
         "bad_f": int(bad_f.sum()),
         "frac_f_bit_exact": float(np.mean(pv[..., 1] == pv_ref[..., 1])),
         "frac_m_bit_exact": float(np.mean(pv[..., 0] == pv_ref[..., 0])),
+        "frac_f_bit_exact_gated": float(np.mean((pv[..., 1] == pv_ref[..., 1])[gate])) if gate.any() else 1.0,
+        "frac_f_within_1ulp_gated": float(np.mean((df <= ulp32(pv_ref[..., 1]))[gate])) if gate.any() else 1.0,
+        "survey_gate_bins": int(gate0.sum()),
+        "survey_gate_fail": int(strict_fail.sum()),
+        "pass_only_by_prev_frame_gate": int(need_prev.sum()),
+        "pass_only_by_rate_scale_or_grid": int(need_scale.sum()),
+        "pass_only_by_noise_term": int(need_noise.sum()),
         "nan": int(np.isnan(pv).sum()),
     }
 
 
-def assert_analysis_parity(pv, pv_ref, sr, hop, N):
-    r = analysis_report(pv, pv_ref, sr, hop, N)
+def assert_analysis_parity(pv, pv_ref, sr, hop, N, min_f_within_1ulp=None, fft_noise=1e-7):
+    r = analysis_report(pv, pv_ref, sr, hop, N, fft_noise)
     assert r["nan"] == 0, r
     assert r["gated_bins"] > 0, r
     assert r["bad_m"] == 0, r
     assert r["bad_f"] == 0, r
+    if min_f_within_1ulp is not None:       # a floor on the tight statistics: an epilogue regression shows here first
+        assert r["frac_f_within_1ulp_gated"] >= min_f_within_1ulp, r
     return r
 
 

@@ -87,8 +87,9 @@ def test_any_dft_size_matches_oracle(eng, oracle, W, h, N):
     ref_pv = oracle.convert_to_pv(x, sr, W, h, N, f0, f1)
     pv = eng.convert_to_pv(dev(x), sr, W, h, N).cpu().numpy()
     assert pv.shape == (len(chans), F, N // 2 + 1, 2)
+    bluestein = ((N // 2 if N % 2 == 0 else N) & ((N // 2 if N % 2 == 0 else N) - 1)) != 0
     if N >= 64:
-        assert_analysis_parity(pv[:2, f0:f1], ref_pv[:2], sr, h, N)
+        assert_analysis_parity(pv[:2, f0:f1], ref_pv[:2], sr, h, N, fft_noise=1.5e-6 if bluestein else 1e-7)
     else:
         assert np.allclose(pv[:2, f0:f1, :, 0], ref_pv[:2, :, :, 0], rtol=1e-4, atol=1e-5)
     if N % 2 == 0:      # all-zero channel: deterministic known answer, bit-identical
@@ -343,3 +344,35 @@ def test_summary_reuse_is_bit_identical(eng):
     again = eng.convert_to_audio_range(pv, 0, F, sr, ar, W, None, 0, F * h, reuse_summary=True)
     assert torch.equal(plain, again)
     assert torch.equal(plain, eng.convert_to_audio(pv, sr, ar, W))
+
+
+# ---- the parity gate, quantified ---------------------------------------------------
+# Floors on the tight statistics per BASELINE shape (measured on B200 minus one percentage point): the fraction of gated
+# bins whose frequency is within ONE float32 ulp of the oracle's and the fraction that is bit-identical. A regression in
+# the epilogue arithmetic shows here long before it reaches the tolerance gate. The report -- including how many bins
+# of SURVEY 8c's unmodified gate pass only through each of the three allowances of tests/parity.py -- is written to
+# gpurun_out/parity_report.json (a copy is kept under profiles/).
+PARITY_FLOORS = {"cfg1": (0.97, 0.55), "cfg2": (0.97, 0.55), "cfg3": (0.97, 0.55), "cfg5": (0.97, 0.55)}
+
+
+@pytest.mark.parametrize("name,sec", [("cfg1", 10.0), ("cfg2", 4.0), ("cfg3", 6.0), ("cfg5", 4.0)])
+def test_parity_gate_statistics(eng, oracle, name, sec):
+    import json
+    import os
+    x, sr, W, h, N = make_config(name, sec)
+    ref = oracle.convert_to_pv(x, sr, W, h, N)
+    pv = eng.convert_to_pv(dev(x), sr, W, h, N).cpu().numpy()
+    r = assert_analysis_parity(pv, ref, sr, h, N)
+    within, exact = PARITY_FLOORS[name]
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        allr = json.load(open(path)) if os.path.exists(path) else {}
+        allr[name] = dict(r, seconds=sec, floors={"frac_f_within_1ulp_gated": within, "frac_f_bit_exact_gated": exact})
+        json.dump(allr, open(path, "w"), indent=1)
+    except OSError:
+        pass
+    print(name, r)
+    assert r["frac_f_within_1ulp_gated"] >= within, r
+    assert r["frac_f_bit_exact_gated"] >= exact, r
+    assert r["frac_m_bit_exact"] >= 0.30, r

@@ -86,3 +86,27 @@ def test_frame_sharded_round_trip_under_gloo(oracle, world):
         covered[int(p["own_lo"]):int(p["own_hi"])] = True
     assert covered.all()
     assert_synthesis_parity(audio, ref_audio)
+
+
+@pytest.mark.parametrize("n,hop,W,world", [(3000, 32, 512, 8), (20000, 256, 4096, 8), (9000, 32, 512, 3), (100, 64, 1024, 4)])
+def test_short_signals_use_fewer_ranks(n, hop, W, world):
+    """with fewer than window/hop - 1 frames per rank a frame's window reached past the adjacent shard and
+    its partial sums were never delivered. Every sample a frame touches must be owned by the frame's rank or the one
+    before it (the receiver of the head overlap), and the owned ranges must tile the output."""
+    from flan_b200.sharding import frame_shard
+    shards = [frame_shard(n, hop, W, world, r) for r in range(world)]
+    F, total = n // hop + 1, (n // hop + 1) * hop
+    assert sum(s.frames for s in shards) == F
+    pos = 0
+    for s in shards:
+        if s.frames:
+            assert s.own_lo == pos
+            pos = s.own_hi
+    assert pos == total
+    active = [s for s in shards if s.frames]
+    for i, s in enumerate(active):
+        for f in (s.f0, s.f1 - 1):
+            lo, hi = max(0, hop * f - W // 2), min(total, hop * f - W // 2 + W)
+            assert lo >= s.span_lo and hi <= s.span_hi
+            assert hi <= s.own_hi
+            assert lo >= (active[i - 1].own_lo if i else 0)

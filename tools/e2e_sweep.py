@@ -21,6 +21,5 @@ audio = np.stack([noise_chirp(n, SR, 1234 + c) for c in range(CH)])
 F = n // HOP + 1
 chk = ctypes.c_double(0)
 for threads in (1, 2, 3, 4):
-    for rep in range(2):
-        dt = L.e2e_round_trips(audio.ctypes.data, CH, n, SR, W, HOP, N, threads, 5 if rep == 0 else 1, 20, ctypes.byref(chk))
-        print("threads %d: %.3f ms per round trip, %.1f M frames/s" % (threads, dt / (20 * threads) * 1e3, threads * 20 * CH * F / dt / 1e6), flush=True)
+    dt = L.e2e_round_trips(audio.ctypes.data, CH, n, SR, W, HOP, N, threads, 6, 20, ctypes.byref(chk))
+    print("threads %d: %.3f ms per round trip, %.1f M frames/s" % (threads, dt / (20 * threads) * 1e3, threads * 20 * CH * F / dt / 1e6), flush=True)
