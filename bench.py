@@ -44,6 +44,7 @@ SR, W, HOP, N_DFT, CH = 48000.0, 4096, 256, 4096, 2
 SECONDS_PER_GPU = 600
 WORKLOAD = "cfg2: stereo 48 kHz 10 min noise+chirp per GPU, window 4096 hop 256 dft 4096, convert_to_PV + convert_to_audio"
 FALLBACK_HBM_GBS = 6650.0
+E2E_THREADS = 3
 
 
 def parse():
@@ -329,20 +330,23 @@ def e2e_cpp(args, local_rank, world, rank, steps, dist, dev):
         return world * threads * k * CH * F / float(t.item())
 
     k = max(steps, 10)
-    two = run(2, k, 5)          # 5 untimed passes: by then the host vectors are recycled and page-locked
-    one = run(1, k, 5)
+    many = run(E2E_THREADS, k, 6)     # 6 untimed passes: by then the host vectors are recycled and page-locked
+    two = run(2, k, 6)
+    one = run(1, k, 6)
     ceil_s = copy_only_ceiling(torch, dev, 4 * CH * n, 4 * CH * F * HOP, k)
     tc = torch.tensor([ceil_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tc, op=dist.ReduceOp.MAX)
     ceiling = world * CH * F / float(tc.item())
-    return {"value": two, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n), "d2h_bytes_per_step": int(4 * CH * F * HOP),
-            "host_threads": 2, "single_thread_value": one, "steps_per_thread": k,
-            "copy_only_ceiling": ceiling, "frac_of_copy_ceiling": two / ceiling,
+    return {"value": many, "unit": "frames/s", "h2d_bytes_per_step": int(4 * CH * n), "d2h_bytes_per_step": int(4 * CH * F * HOP),
+            "host_threads": E2E_THREADS, "two_thread_value": two, "single_thread_value": one, "steps_per_thread": k,
+            "copy_only_ceiling": ceiling, "frac_of_copy_ceiling": many / ceiling,
             "how": "tools/cpp/e2e_bench.cpp, user code against the reference-facing C++ API: flan::Audio (host std::vector, touched through "
-                   "get_buffer() every step) -> convert_to_PV -> convert_to_audio -> get_buffer() on the result; 2 host threads on independent "
-                   "signals (single_thread_value: one thread); copy_only_ceiling = the same bytes up and down over PCIe from pinned memory, "
-                   "both directions at once, nothing else"
+                   "get_buffer() every step) -> convert_to_PV -> convert_to_audio -> get_buffer() on the result; %d host threads on independent "
+                   "signals, as a program working through a batch of files would (two_thread_value / single_thread_value: fewer threads); "
+                   "copy_only_ceiling = the same bytes up and down over PCIe from cudaHostAlloc'ed memory, both directions at once, nothing "
+                   "else (the API's vectors are page-locked with cudaHostRegister; profiles/r2_e2e_timeline.md shows the copies slowing each "
+                   "other down: a download slice takes 1.0 ms alone and 1.45 ms beside an upload)" % E2E_THREADS
                    + ("; every rank converts its own signal on its own GPU" if world > 1 else "")}
 
 # ------------------------------------------------------------------------------------------------------

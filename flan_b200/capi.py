@@ -51,6 +51,7 @@ SYMBOLS = [
     ("flan_b200_launch_count", _i64, [_vp]),
     ("flan_b200_set_timing", _int, [_vp, _int]),
     ("flan_b200_kernel_time", _int, [_vp, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64)]),
+    ("flan_b200_trace", _int, [_vp, ctypes.POINTER(_int), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), _int, ctypes.POINTER(_int)]),
     ("flan_b200_malloc", _int, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
     ("flan_b200_free", _int, [_vp, _vp]),
     ("flan_b200_upload", _int, [_vp, _vp, _vp, ctypes.c_size_t]),

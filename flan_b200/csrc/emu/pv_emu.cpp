@@ -80,9 +80,15 @@ template<int N, int PT> void analysis_n( const AnalysisArgs & a, int64_t blocks 
 	for( int64_t b = 0; b < blocks; ++b )
 		{
 		if( a.one_buffer && PT == 16 )
-			run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true>( a, b, env, x0, x0 ); } );
+			{
+			// the product's choice: zero-padded windows of whole slots take the vector-load instantiation
+			if( a.W < N && a.W % ( N / PT ) == 0 && a.aligned2 )
+				run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true, true>( a, b, env, x0, x0 ); } );
+			else
+				run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true, false>( a, b, env, x0, x0 ); } );
+			}
 		else
-			run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, false>( a, b, env, x0, x1 ); } );
+			run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, false, false>( a, b, env, x0, x1 ); } );
 		}
 	}
 
@@ -102,7 +108,13 @@ template<int N> void synthesis_mirror_n( const SynthArgs & a, int64_t blocks )
 	{
 	HostEnv::BulkBarrier bar_word = 0;
 	for( int64_t b = 0; b < blocks; ++b )
-		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf ) { if( a.one_buffer ) synthesis_cta_mirror<N, true>( a, b, env, (float2 *) ola, x0, x0, rowbuf, &bar_word ); else synthesis_cta_mirror<N, false>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); } );
+		run_cta<N, 16>( [&]( HostEnv & env, float * ola, float2 * x0, float2 * x1, float2 * rowbuf )
+			{
+			const bool gen = !( a.W == N && a.hop == N / 16 );
+			if( gen ) { if( a.one_buffer ) synthesis_cta_mirror<N, true, true>( a, b, env, (float2 *) ola, x0, x0, rowbuf, &bar_word ); else synthesis_cta_mirror<N, false, true>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word ); }
+			else if( a.one_buffer ) synthesis_cta_mirror<N, true, false>( a, b, env, (float2 *) ola, x0, x0, rowbuf, &bar_word );
+			else synthesis_cta_mirror<N, false, false>( a, b, env, (float2 *) ola, x0, x1, rowbuf, &bar_word );
+			} );
 	}
 
 // The run-time-sized transform (pv_generic_body.cuh): `blocks` persistent CTAs of T threads share the segments, each
@@ -268,9 +280,9 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 			} );
 		return 0;
 		}
-	if( variant == 17 )     // PV_PT_MIRROR; the caller checks the shape conditions (W == N, hop a multiple of N/16)
+	if( variant == 17 )     // PV_PT_MIRROR: the standard shape, or the general form for any aligned window and even hop
 		{
-		if( !( W == N && hop == N / 16 ) ) return 3;
+		if( !( W >= N / 16 && W % ( N / 16 ) == 0 && hop >= 2 && hop % 2 == 0 && hop <= W ) ) return 3;
 		switch( N )
 			{
 			case 1024: synthesis_mirror_n<1024>( a, blocks ); return 0;

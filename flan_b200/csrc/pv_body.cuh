@@ -109,7 +109,10 @@ struct AnalysisArgs
 	PvConsts k;
 	};
 
-template<int N, int PT, bool ONE, class Env>
+// PAD: a zero-padded window that fills whole slots of the thread layout (window a multiple of 2T samples, < dft: the
+// API default window 2048 / dft 4096, Audio.h:158-163) loads its samples as vectors like the full window does; a
+// separate instantiation so that the full-window kernels keep their register budget.
+template<int N, int PT, bool ONE, bool PAD, class Env>
 PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1 )
 	{
 	constexpr int M = N / 2, T = M / PT, H = PT / 2;      // H pairs of bins (k, M-k) per thread
@@ -144,11 +147,9 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
 	const int64_t first = ( fa > 0 ) ? fa - 1 : fa;
-	// Windows that fill whole slots of the thread layout -- the full dft size (every BASELINE config) or a zero-padded
-	// one such as the API default window 2048 / dft 4096 (Audio.h:158-163): slots s < slots_in hold sample pairs, the
-	// rest of the transform's input is the zero padding of AudioPV.cpp:65.
-	const bool full_window = ( W % ( 2 * T ) == 0 ) && a.aligned2;
-	const int slots_in = W / ( 2 * T );
+	// PAD: slots s < slots_in hold sample pairs, the rest of the transform's input is the zero padding of AudioPV.cpp:65
+	const bool full_window = ( PAD ? ( W % ( 2 * T ) == 0 ) : ( W == N ) ) && a.aligned2;
+	const int slots_in = PAD ? W / ( 2 * T ) : PT;
 
 	// Output row of frame f: bins k = t + u*T ascend from row_lo, their mirrors M-k descend from row_hi (per-thread
 	// bases advanced by one row per frame, so every store address is base + immediate). The warm-up frame's row lies
@@ -165,7 +166,7 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 		float2 v[PT];
 		// pass 0: windowed load (AudioPV.cpp:54-62; zero padding :65) + radix-PT. Windows overlap by W-hop samples:
 		// all but the newest hop are L1 hits.
-		if( full_window && slots_in == PT && start >= 0 && start + W <= a.n_total )
+		if( !PAD && full_window && start >= 0 && start + W <= a.n_total )
 			{
 #pragma unroll
 			for( int s = 0; s < PT; ++s )
@@ -175,7 +176,7 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				v[s] = mul2( r, ww );
 				}
 			}
-		else if( full_window && start >= 0 && start + W <= a.n_total )
+		else if( PAD && full_window && start >= 0 && start + W <= a.n_total )
 			{
 			// zero-padded window: the same vector loads for the slots that hold samples
 #pragma unroll
@@ -821,7 +822,13 @@ template<int R> PV_HD int mpad( int i )
 
 // ONE: the two exchange buffers alias (x1 == x0): two more barriers per frame, 18 KB less shared memory per CTA, which
 // moves the SM's carve-out from 228 KB to 164 KB and so gives the twiddle tables (32 KB) an L1 they fit in.
-template<int N, bool ONE, class Env>
+// GEN: any window that fills whole slots of the thread layout (a multiple of dft/16 samples) and any even hop up to the
+// window -- e.g. the API default window 2048 / hop 128 / dft 4096 (Audio.h:158-163). A frame then advances the
+// overlap-add positions by hop/2 pairs, which is no longer a whole slot per thread, so the ring is shared by the CTA (the
+// two exchange barriers of the next frame order one frame's accumulation before the next one's; no barrier is added),
+// and which of a thread's slots start a ring entry, accumulate, or are final depends on the thread: three 16-bit masks,
+// fixed over the walk. !GEN is the standard shape (window == dft, hop == dft/16) with everything resolved at compile time.
+template<int N, bool ONE, bool GEN, class Env>
 PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, float2 * ring, float2 * x0, float2 * x1, float2 * rowbuf,
                                  typename Env::BulkBarrier * bar )
 	{
@@ -837,17 +844,34 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 	const int64_t fb = ( fa + a.seg_len < a.frame_end ) ? fa + a.seg_len : a.frame_end;
 	if( fa >= fb ) return;
 
-	constexpr int hop = 2 * T;                   // == a.hop == N/16; window == N
-	constexpr int half = N / 2;
+	const int hop = GEN ? a.hop : 2 * T;         // !GEN: == a.hop == N/16 and window == N
+	const int half = GEN ? a.W / 2 : N / 2;
+	const int wp = half;                         // window length in sample pairs
+	const int hp = hop / 2;                      // pairs a frame advances by
 	const bool irregular = ( t == 0 );
 	const int khi = irregular ? MP::KHI : 0;
 
 	float w[2 * PT];
+	// GEN: slot s of this thread is pair n = t + s*T of the frame's window: `used` n < wp, `fresh` (the first frame to
+	// reach its absolute pair) n >= wp - hp, `final` (the last one) n < hp
+	unsigned used = 0xffffu, fresh = 1u << ( PT - 1 ), final = 1u;
+	if( GEN ) { used = 0; fresh = 0; final = 0; }
 #pragma unroll
 	for( int s = 0; s < PT; ++s )
 		{
-		w[2 * s]     = env.ldg( a.win + 2 * ( t + s * T ) );
-		w[2 * s + 1] = env.ldg( a.win + 2 * ( t + s * T ) + 1 );
+		const int nn = t + s * T;
+		if( !GEN || nn < wp )
+			{
+			w[2 * s]     = env.ldg( a.win + 2 * nn );
+			w[2 * s + 1] = env.ldg( a.win + 2 * nn + 1 );
+			}
+		else { w[2 * s] = 0.0f; w[2 * s + 1] = 0.0f; }
+		if( GEN )
+			{
+			if( nn < wp ) used |= 1u << s;
+			if( nn < wp && nn >= wp - hp ) fresh |= 1u << s;
+			if( nn < hp ) final |= 1u << s;
+			}
 		}
 	// bin of slot (q, r): k = kbase + r*NS with kbase = p (+ khi for the irregular upper slots); its mirror is M - k
 	double acc[Q][R][2], acc_mid = 0.0;
@@ -1037,10 +1061,12 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			fft_butterflies_w<M, PT, RP::R3, RP::NS3>( v, tw );
 			}
 
-		// windowed overlap-add (AudioPV.cpp:133-134) on the thread's own ring; slot s of this frame is absolute pair
+		// windowed overlap-add (AudioPV.cpp:133-134). !GEN: on the thread's own ring; slot s of this frame is absolute pair
 		// t + T*(f + s - 8) (half/2 == 8T), i.e. ring entry (f + s + 8) & 15
-		// (byte offsets: (t + T*((f + 8 + s) & 15)) * 8 == ((t + T*(f + 8)) * 8 + s*T*8) & (16*T*8 - 1), one add and one mask per slot)
-		const unsigned xb = ( (unsigned) t + (unsigned) T * (unsigned)( ( f + 8 ) & 15 ) ) * 8u;
+		// (byte offsets: (t + T*((f + 8 + s) & 15)) * 8 == ((t + T*(f + 8)) * 8 + s*T*8) & (16*T*8 - 1), one add and one mask per slot).
+		// GEN: absolute pair hp*f - wp/2 + t + s*T, ring entry that modulo 16T (the ring holds dft/2 >= wp pairs).
+		const unsigned xb = GEN ? (unsigned)( ( (int64_t) hp * f - wp / 2 + t + (int64_t) PT * T * 4096 ) & (int64_t)( PT * T - 1 ) ) * 8u
+		                        : ( (unsigned) t + (unsigned) T * (unsigned)( ( f + 8 ) & 15 ) ) * 8u;
 		auto slot = [&]( int s ) { return reinterpret_cast<float2 *>( reinterpret_cast<char *>( ring ) + ( ( xb + (unsigned)( s * T * 8 ) ) & (unsigned)( 16 * T * 8 - 1 ) ) ); };
 		float2 sum[PT];
 #pragma unroll
@@ -1048,19 +1074,53 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			{
 			float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
 			const float2 prod = mul2( swap2( v[s] ), ww );
-			// slot 15 receives its first contribution (its ring entry is simply overwritten)
-			sum[s] = ( s == PT - 1 ) ? prod : add2( *slot( s ), prod );
+			// a fresh slot receives its first contribution (its ring entry is simply overwritten)
+			if( GEN ) { sum[s] = prod; if( ( used >> s & 1u ) && !( fresh >> s & 1u ) ) sum[s] = add2( *slot( s ), prod ); }
+			else sum[s] = ( s == PT - 1 ) ? prod : add2( *slot( s ), prod );
 			}
+		if( GEN )
+			{
 #pragma unroll
-		for( int s = 1; s < PT; ++s ) *slot( s ) = sum[s];
-		// slot 0: no later frame reaches these two samples
-		const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
-		const int64_t pos = start + 2 * t;
-		if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[0] );
-		else { emit( pos, sum[0].x ); emit( pos + 1, sum[0].y ); }
+			for( int s = 0; s < PT; ++s ) if( ( used >> s & 1u ) && !( final >> s & 1u ) ) *slot( s ) = sum[s];
+			// final pairs: no later frame reaches them
+			const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
+#pragma unroll
+			for( int s = 0; s < PT; ++s )
+				if( final >> s & 1u )
+					{
+					const int64_t pos = start + 2 * ( t + s * T );
+					if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[s] );
+					else { emit( pos, sum[s].x ); emit( pos + 1, sum[s].y ); }
+					}
+			}
+		else
+			{
+#pragma unroll
+			for( int s = 1; s < PT; ++s ) *slot( s ) = sum[s];
+			// slot 0: no later frame reaches these two samples
+			const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
+			const int64_t pos = start + 2 * t;
+			if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[0] );
+			else { emit( pos, sum[0].x ); emit( pos + 1, sum[0].y ); }
+			}
 		}
 	// remainder of the last window
 	const int64_t last_start = (int64_t) hop * ( fb - 1 ) - half;
+	if( GEN )
+		{
+		env.sync();                 // the ring entries read here were written by other threads in the last frame
+		const unsigned xl = (unsigned)( ( (int64_t) hp * ( fb - 1 ) - wp / 2 + t + (int64_t) PT * T * 4096 ) & (int64_t)( PT * T - 1 ) );
+#pragma unroll 1
+		for( int s = 0; s < PT; ++s )
+			{
+			const int nn = t + s * T;
+			if( nn < hp || nn >= wp ) continue;
+			const float2 val = ring[( xl + (unsigned)( s * T ) ) & (unsigned)( PT * T - 1 )];
+			const int64_t pos = last_start + 2 * nn;
+			emit( pos, val.x ); emit( pos + 1, val.y );
+			}
+		return;
+		}
 	const int j0 = (int)( ( ( fb - 1 ) + 8 ) & 15 );
 #pragma unroll 1
 	for( int s = 1; s < PT; ++s )

@@ -182,18 +182,18 @@ int get_workspace( flan_b200_ctx * ctx, size_t bytes, void ** out )
 	return FLAN_B200_OK;
 	}
 
-LaunchTimer::LaunchTimer( flan_b200_ctx * c, int k ) : ctx( c ), kind( k )
+LaunchTimer::LaunchTimer( flan_b200_ctx * c, int k, cudaStream_t on ) : ctx( c ), kind( k ), stream( on ? on : c->compute )
 	{
 	if( !ctx->timing ) return;
 	if( cudaEventCreate( &start ) != cudaSuccess || cudaEventCreate( &stop ) != cudaSuccess ) { start = stop = nullptr; return; }
-	cudaEventRecord( start, ctx->compute );
+	cudaEventRecord( start, stream );
 	}
 
 LaunchTimer::~LaunchTimer()
 	{
-	ctx->launches++;
+	if( kind < 9 ) ctx->launches++;
 	if( !start ) return;
-	cudaEventRecord( stop, ctx->compute );
+	cudaEventRecord( stop, stream );
 	ctx->timed.push_back( { kind, start, stop } );
 	}
 
@@ -444,7 +444,6 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 int64_t ctas_per_slice( int64_t ctas, int64_t wave, size_t copy_bytes )
 	{
 	if( wave < 1 ) wave = 1;
-	{ static const bool no_slice = std::getenv( "FLAN_B200_X_NO_SLICE" ) != nullptr; if( no_slice ) return ( ( ctas + wave - 1 ) / wave ) * wave; }   // TEMPORARY experiment knob
 	const int64_t waves = ( ctas + wave - 1 ) / wave;
 	int64_t n = std::min<int64_t>( 8, std::min<int64_t>( waves, (int64_t)( copy_bytes >> 22 ) ) );     // >= 4 MiB of copy per slice
 	if( n < 1 ) n = 1;
@@ -777,6 +776,28 @@ int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int
 	return FLAN_B200_OK;
 	}
 
+// Timeline of everything timed since flan_b200_set_timing( 1 ): (kind, start ms, stop ms) relative to the first entry;
+// kinds as flan_b200_kernel_time, plus 9 = upload slice, 10 = download slice of the pipelined host forms. Synchronises
+// the device; the entries are consumed.
+int flan_b200_trace( flan_b200_ctx * ctx, int * kinds, double * start_ms, double * stop_ms, int capacity, int * count )
+	{
+	if( !ctx || !count ) return FLAN_B200_INVALID;
+	CallLock lock( ctx );
+	CK( cudaDeviceSynchronize(), "trace sync" );
+	int n = 0;
+	cudaEvent_t base = ctx->timed.empty() ? nullptr : ctx->timed.front().start;
+	for( auto & t : ctx->timed )
+		{
+		float a = 0.0f, b = 0.0f;
+		if( n < capacity && cudaEventElapsedTime( &a, base, t.start ) == cudaSuccess && cudaEventElapsedTime( &b, base, t.stop ) == cudaSuccess )
+			{ kinds[n] = t.kind; start_ms[n] = a; stop_ms[n] = b; ++n; }
+		}
+	for( auto & t : ctx->timed ) { cudaEventDestroy( t.start ); cudaEventDestroy( t.stop ); }
+	ctx->timed.clear();
+	*count = n;
+	return FLAN_B200_OK;
+	}
+
 int flan_b200_malloc( flan_b200_ctx * ctx, size_t bytes, void ** d_out )
 	{
 	if( !ctx || !d_out ) return FLAN_B200_INVALID;
@@ -1049,8 +1070,9 @@ int flan_b200_convert_to_pv_h2d( flan_b200_ctx * ctx, const float * h_audio, flo
 		// samples the frames below f1 read: up to hop * (f1 - 1) + W/2 (AudioPV.cpp:52)
 		int64_t need = ( k == slices - 1 ) ? n : std::min<int64_t>( n, (int64_t) hop * ( f1 - 1 ) - W / 2 + W );
 		if( need < sent ) need = sent;
-		rc = copy_h2d_2d( ctx, d_audio + sent, sizeof( float ) * (size_t) n, h_audio + sent, sizeof( float ) * (size_t) n,
-		                  sizeof( float ) * (size_t)( need - sent ), (size_t) C );
+		{ LaunchTimer lt( ctx, 9, ctx->h2d );
+		  rc = copy_h2d_2d( ctx, d_audio + sent, sizeof( float ) * (size_t) n, h_audio + sent, sizeof( float ) * (size_t) n,
+		                    sizeof( float ) * (size_t)( need - sent ), (size_t) C ); }
 		if( rc ) return rc;
 		sent = need;
 		CK( cudaEventRecord( ev[k], ctx->h2d ), "event record" );
@@ -1106,8 +1128,10 @@ int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int
 		CK( cudaStreamWaitEvent( ctx->d2h, ev[k], 0 ), "copy stream wait" );
 		if( done > got )
 			{
-			int rc2 = copy_d2h_2d( ctx, h_audio_out + got, sizeof( float ) * (size_t) out_n, d_audio_out + got, sizeof( float ) * (size_t) out_n,
-			                       sizeof( float ) * (size_t)( done - got ), (size_t) C );
+			int rc2;
+			{ LaunchTimer lt( ctx, 10, ctx->d2h );
+			  rc2 = copy_d2h_2d( ctx, h_audio_out + got, sizeof( float ) * (size_t) out_n, d_audio_out + got, sizeof( float ) * (size_t) out_n,
+			                     sizeof( float ) * (size_t)( done - got ), (size_t) C ); }
 			if( rc2 ) return rc2;
 			got = done;
 			}

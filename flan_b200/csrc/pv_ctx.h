@@ -184,8 +184,8 @@ void free_plan( DevicePlan * p );
 // Brackets one kernel launch with events when timing is on (bench.py's per-kernel roofline).
 struct LaunchTimer
 	{
-	flan_b200_ctx * ctx; int kind; cudaEvent_t start = nullptr, stop = nullptr;
-	LaunchTimer( flan_b200_ctx * c, int k );
+	flan_b200_ctx * ctx; int kind; cudaStream_t stream; cudaEvent_t start = nullptr, stop = nullptr;
+	LaunchTimer( flan_b200_ctx * c, int k, cudaStream_t on = nullptr );     // kinds >= 9: copies on a copy stream (not counted as launches)
 	~LaunchTimer();
 	};
 

@@ -87,14 +87,14 @@ struct DeviceEnv
 constexpr int min_blocks( int threads, int TPS ) { return TPS / threads > 32 ? 32 : ( TPS / threads > 0 ? TPS / threads : 1 ); }
 
 // PT = complex points per thread: 8 (radix-8 passes, N/16 threads per frame) or 16 (radix-16 passes, N/32 threads).
-template<int N, int PT, int TPS, bool ONE>
+template<int N, int PT, int TPS, bool ONE, bool PAD = false>
 __global__ void __launch_bounds__( N / ( 2 * PT ), min_blocks( N / ( 2 * PT ), TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
 	float2 * x1 = ONE ? x0 : x0 + XBuf<N / 2>::size;
 	DeviceEnv env; env.tid = threadIdx.x;
-	analysis_cta<N, PT, ONE>( a, (int64_t) blockIdx.x, env, x0, x1 );
+	analysis_cta<N, PT, ONE, PAD>( a, (int64_t) blockIdx.x, env, x0, x1 );
 	}
 
 // Mirrored last pass (pv_body.cuh: analysis_cta_mirror): 16 points per thread, unpack + phase vocoder on the thread's own registers.
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__( N / 16, min_blocks( N / 16, TPS ) ) pv_synthe
 	}
 
 // Mirrored first pass (pv_body.cuh: synthesis_cta_mirror): 16 points per thread, thread-private row FIFO and overlap-add ring.
-template<int N, int TPS, bool ONE>
+template<int N, int TPS, bool ONE, bool GEN>
 __global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_synthesis_mirror_kernel( const SynthArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__( N / 32, min_blocks( N / 32, TPS ) ) pv_synthe
 	float2 * rowbuf = x1 + XBuf<N / 2>::size;                               // N/2 + 2 pairs
 	__shared__ __align__( 8 ) DeviceEnv::BulkBarrier bar;
 	DeviceEnv env; env.tid = threadIdx.x;
-	synthesis_cta_mirror<N, ONE>( a, (int64_t) blockIdx.x, env, ring, x0, x1, rowbuf, &bar );
+	synthesis_cta_mirror<N, ONE, GEN>( a, (int64_t) blockIdx.x, env, ring, x0, x1, rowbuf, &bar );
 	}
 
 // One thread per (channel, segment, bin): summary of the segment's phase increments.
@@ -349,6 +349,18 @@ template<int N, int PT, int TPS, bool ONE> static cudaError_t launch_analysis_nt
 	cudaError_t e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
 	apply_carveout( pv_analysis_kernel<N, PT, TPS, ONE> );
+	// zero-padded windows that fill whole slots (the API default shape): vector loads, 16 points per thread form only
+	if constexpr( PT == 16 && ONE )
+		{
+		if( a.W < N && a.W % ( N / PT ) == 0 && a.aligned2 )
+			{
+			e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS, ONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+			if( e != cudaSuccess ) return e;
+			if( blocks < 0 ) return report_occupancy( pv_analysis_kernel<N, PT, TPS, ONE, true>, N / ( 2 * PT ), smem );
+			pv_analysis_kernel<N, PT, TPS, ONE, true><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
+			return cudaGetLastError();
+			}
+		}
 	if( blocks < 0 ) return report_occupancy( pv_analysis_kernel<N, PT, TPS, ONE>, N / ( 2 * PT ), smem );
 	pv_analysis_kernel<N, PT, TPS, ONE><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
 	return cudaGetLastError();
@@ -394,7 +406,11 @@ template<int N> static cudaError_t launch_analysis_n( const AnalysisArgs & a, in
 			return launch_analysis_mirror_nt<N, 512>( a, blocks, st );
 			}
 		}
+#ifdef FLAN_B200_DEBUG
 	if constexpr( N >= 512 )
+#else
+	if constexpr( N >= 2048 )       // the policy asks for 16 points per thread from dft 2048 up only
+#endif
 		{
 		if( pt == 16 )
 			{
@@ -421,19 +437,30 @@ template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_nt( const
 	pv_synthesis_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 16, smem, st>>>( a );
 	return cudaGetLastError();
 	}
-template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+template<int N, int TPS, bool ONE, bool GEN> static cudaError_t launch_synthesis_mirror_ntg( const SynthArgs & a, int64_t blocks, cudaStream_t st )
 	{
 	const size_t smem = sizeof( float ) * N + ( ONE ? 1 : 2 ) * sizeof( float2 ) * XBuf<N / 2>::size + sizeof( float2 ) * ( N / 2 + 2 ) + smem_pad();
-	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS, ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
+	cudaError_t e = cudaFuncSetAttribute( pv_synthesis_mirror_kernel<N, TPS, ONE, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem );
 	if( e != cudaSuccess ) return e;
-	apply_carveout( pv_synthesis_mirror_kernel<N, TPS, ONE> );
-	if( blocks < 0 ) return report_occupancy( pv_synthesis_mirror_kernel<N, TPS, ONE>, N / 32, smem );
-	pv_synthesis_mirror_kernel<N, TPS, ONE><<<(unsigned) blocks, N / 32, smem, st>>>( a );
+	apply_carveout( pv_synthesis_mirror_kernel<N, TPS, ONE, GEN> );
+	if( blocks < 0 ) return report_occupancy( pv_synthesis_mirror_kernel<N, TPS, ONE, GEN>, N / 32, smem );
+	pv_synthesis_mirror_kernel<N, TPS, ONE, GEN><<<(unsigned) blocks, N / 32, smem, st>>>( a );
 	return cudaGetLastError();
+	}
+// the standard shape (window == dft, hop == dft/16: every BASELINE config) runs the compile-time form, any other aligned
+// window / hop (the API default 2048 / 128 / 4096 among them) the general one
+template<int N, int TPS, bool ONE> static cudaError_t launch_synthesis_mirror_nt( const SynthArgs & a, int64_t blocks, cudaStream_t st )
+	{
+	if( a.W == N && a.hop == N / 16 ) return launch_synthesis_mirror_ntg<N, TPS, ONE, false>( a, blocks, st );
+	return launch_synthesis_mirror_ntg<N, TPS, ONE, true>( a, blocks, st );
 	}
 bool synthesis_mirror_applies( int N, const SynthArgs & a )
 	{
-	return synth_mirror_supported( N ) && a.W == N && a.hop == N / 16;
+	if( !synth_mirror_supported( N ) ) return false;
+	if( a.W == N && a.hop == N / 16 ) return true;
+	// general form: the window fills whole slots of the thread layout (a multiple of dft/16 samples), the hop is even and
+	// leaves no gaps
+	return a.W >= N / 16 && a.W % ( N / 16 ) == 0 && a.W <= N && a.hop >= 2 && a.hop % 2 == 0 && a.hop <= a.W;
 	}
 template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps, int variant )
 	{

@@ -77,6 +77,10 @@ int64_t flan_b200_launch_count( const flan_b200_ctx * ctx );
  * 5 repitch / modify_frequency, 6 stretch / modify_time, 7 table preparation and checks of the PV-domain chain, 8 file-format sample codecs. */
 int flan_b200_set_timing( flan_b200_ctx * ctx, int enabled );
 int flan_b200_kernel_time( flan_b200_ctx * ctx, int kind, double * total_ms, int64_t * launches );
+/* Timeline of everything timed since timing was enabled: kind, start and stop in milliseconds relative to the first entry
+ * (kinds as above, plus 9 = upload slice and 10 = download slice of the pipelined host-buffer forms). Synchronises the
+ * device and consumes the entries; *count receives how many were written (at most capacity). */
+int flan_b200_trace( flan_b200_ctx * ctx, int * kinds, double * start_ms, double * stop_ms, int capacity, int * count );
 
 /* ---- device buffers (storage behind flan::AudioBuffer / flan::PVBuffer) ----------------------
  * Blocks are cached: flan_b200_free keeps the allocation for the next flan_b200_malloc of a similar size (no cudaMalloc /

@@ -75,20 +75,29 @@ static void fft_run( fft_t * f, int sign )
 	cpx_t * w = f->work;
 	if( !f->pow2 )
 		{
+		/* the angle depends on (k*j) mod n only: one cosl / sinl per residue instead of per term (same values, same bits) */
 		const long double two_pi = 6.283185307179586476925286766559005768L;
+		long double * ct = (long double *) malloc( sizeof( long double ) * 2 * (size_t) n );
+		long double * st = ct + n;
+		for( int r = 0; r < n; ++r )
+			{
+			const long double a = sign * two_pi * (long double) r / n;
+			ct[r] = cosl( a ); st[r] = sinl( a );
+			}
 		for( int k = 0; k < n; ++k )
 			{
 			long double acc_re = 0, acc_im = 0;
 			for( int j = 0; j < n; ++j )
 				{
-				const long double a = sign * two_pi * (long double)( ( (long long) k * j ) % n ) / n;
-				const long double c = cosl( a ), s = sinl( a );
+				const long long r = ( (long long) k * j ) % n;
+				const long double c = ct[r], s = st[r];
 				const long double xr = w[j].re, xi = w[j].im;
 				acc_re += xr * c - xi * s;
 				acc_im += xr * s + xi * c;
 				}
 			f->out[k].re = (double) acc_re; f->out[k].im = (double) acc_im;
 			}
+		free( ct );
 		memcpy( w, f->out, sizeof( cpx_t ) * n );
 		return;
 		}

@@ -70,13 +70,19 @@ struct F64Plan
 			// O(n^2) fallback, exact enough for an oracle.
 			std::vector<std::complex<double>> out( n );
 			const long double two_pi = 6.283185307179586476925286766559005768L;
+			// the angle depends on (k*j) mod n only: one cosl / sinl per residue instead of per term
+			std::vector<std::complex<long double>> root( n );
+			for( int r = 0; r < n; ++r )
+				{
+				const long double a = sign * two_pi * (long double) r / n;
+				root[r] = std::complex<long double>( cosl( a ), sinl( a ) );
+				}
 			for( int k = 0; k < n; ++k )
 				{
 				std::complex<long double> acc = 0;
 				for( int j = 0; j < n; ++j )
+					acc += std::complex<long double>( work[j] ) * root[( (long long) k * j ) % n];
 					{
-					const long double a = sign * two_pi * (long double)( ( (long long) k * j ) % n ) / n;
-					acc += std::complex<long double>( work[j] ) * std::complex<long double>( cosl( a ), sinl( a ) );
 					}
 				out[k] = { (double) acc.real(), (double) acc.imag() };
 				}

@@ -37,7 +37,9 @@ def test_emulated_analysis_matches_oracle(emu, oracle, W, h, N, seg, kind):
 
 
 @pytest.mark.parametrize("W,h,N,seg,pt", [(4096, 256, 4096, 5, 16), (4096, 256, 4096, 0, 116), (8192, 512, 8192, 3, 116),
-                                          (2048, 128, 2048, 7, 116), (1000, 100, 1024, 0, 116), (4096, 256, 4096, 6, 117)])
+                                          (2048, 128, 2048, 7, 116), (1000, 100, 1024, 0, 116), (4096, 256, 4096, 6, 117),
+                                          # zero-padded windows of whole slots (the API default shape): vector-load instantiation
+                                          (2048, 128, 4096, 0, 116), (1024, 64, 2048, 5, 116), (4096, 512, 8192, 0, 116), (768, 96, 4096, 9, 116)])
 def test_emulated_analysis_variants_are_bit_identical(emu, W, h, N, seg, pt):
     # 16 points per thread and the one-buffer exchange (+100) only re-time the same arithmetic
     sr = 48000.0
@@ -93,6 +95,25 @@ def test_emulated_generic_sizes_match_oracle(emu, oracle, W, h, N, seg):
 # thread-private row FIFO / overlap-add ring / sample ring, bulk row copies with their unaligned-row and last-row cases.
 MIRROR_SHAPES = [(4096, 0, 9000), (4096, 17, 9001), (2048, 20, 6000), (2048, 0, 5000), (1024, 16, 6000), (1024, 0, 3001)]
 MIRROR_SYNTH_SHAPES = MIRROR_SHAPES + [(8192, 0, 20000), (8192, 19, 17001)]      # dft 8192: resynthesis only (a fourth, radix-2 pass)
+
+
+# The general form of the mirrored resynthesis: a window of whole slots (a multiple of dft/16), any even hop up to it --
+# the API default window 2048 / hop 128 / dft 4096 among them; the overlap-add ring is then shared by the CTA.
+@pytest.mark.parametrize("W,h,N,seg,n", [(2048, 128, 4096, 0, 9000), (2048, 128, 4096, 17, 9001), (1024, 64, 2048, 20, 6000),
+                                         (512, 32, 1024, 0, 3000), (4096, 512, 4096, 0, 9000), (3072, 96, 4096, 33, 9000),
+                                         (4096, 130, 4096, 40, 9000), (256, 256, 4096, 5, 5000), (4096, 256, 8192, 19, 17001)])
+def test_emulated_general_mirror_synthesis_matches_oracle(emu, oracle, W, h, N, seg, n):
+    sr = 48000.0
+    x = np.stack([noise_chirp(n, sr, 6), sine_sweep(n, sr), noise_chirp(n, sr, 7)])
+    pv = oracle.convert_to_pv(x, sr, W, h, N)
+    ar = oracle.analysis_rate(sr, h)
+    seg_len = max(seg, (W + h - 1) // h) if seg else 0
+    out, _, flag = emu.synthesis(pv, sr, ar, W, seg_len=seg_len, variant=17)
+    assert flag == 0
+    assert_synthesis_parity(out, oracle.convert_to_audio(pv, sr, ar, W))
+    # same bits as the 8-point kernel's accumulation order? (both add contributions in increasing frame order)
+    plain, _, _ = emu.synthesis(pv, sr, ar, W, seg_len=seg_len, variant=8)
+    assert np.abs(out - plain).max() <= 1e-6
 
 
 @pytest.mark.parametrize("N,seg,n", MIRROR_SYNTH_SHAPES)
