@@ -333,6 +333,8 @@ def e2e_cpp(args, local_rank, world, rank, steps, dist, dev):
     many = run(E2E_THREADS, k, 6)     # 6 untimed passes: by then the host vectors are recycled and page-locked
     two = run(2, k, 6)
     one = run(1, k, 6)
+    if dist is not None:
+        dist.barrier()                   # every rank measures its copies at the same time, as they run in the e2e leg
     ceil_s = copy_only_ceiling(torch, dev, 4 * CH * n, 4 * CH * F * HOP, k)
     tc = torch.tensor([ceil_s], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -355,7 +357,7 @@ def run_ours(args):
     import torch.distributed as dist
     from flan_b200.engine import Engine
     from flan_b200.signals import noise_chirp
-    from flan_b200.sharding import frame_shard, sharded_resynthesis
+    from flan_b200.sharding import frame_shard, sharded_resynthesis_overlapped
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -365,6 +367,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # A CPU-side group for the waits during which rank 0 works alone on EVERY GPU (the config 3 leg): an NCCL barrier is a
+    # kernel spinning on the waiting ranks' GPUs, which rank 0's process would then have to time-slice with
+    # (measured: 33.5 ms per round trip on 2 GPUs beside such a barrier, 7.5 ms without it).
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
     eng = Engine(local_rank)
     dev = eng.device
 
@@ -388,6 +394,10 @@ def run_ours(args):
         dist.all_gather_into_tensor(bufs, state.contiguous())
         return bufs
 
+    side_stream = torch.cuda.Stream(device=dev)
+    head_event = torch.cuda.Event()
+    head_event.record()                      # creates the handle the C ABI records on
+
     def step(xin, yout=None):
         if world == 1:
             yout = y if yout is None else yout
@@ -395,8 +405,7 @@ def run_ours(args):
             eng.convert_to_audio(pv, SR, ar, W, out=yout)
             return yout
         eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
-        o, _ = sharded_resynthesis(eng, dist, sh, pv, SR, ar, allgather,
-                                   lambda t, dst: dist.isend(t, dst), lambda t, src: dist.recv(t, src))
+        o, _ = sharded_resynthesis_overlapped(eng, dist, torch, sh, pv, SR, ar, allgather, side_stream, head_event)
         return o
 
     def barrier():
@@ -466,6 +475,9 @@ def run_ours(args):
     e2e = e2e_cpp(args, local_rank, world, rank, steps, dist if world > 1 else None, dev)
     # BASELINE config 3 on rank 0, through the one-process multi-device handle (the other ranks wait at the barrier below)
     cfg3 = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)        # every rank's GPU is idle from here on
     if rank == 0 and not args.no_cfg3:
         try:
             cfg3 = cfg3_leg(world, max(5, steps // 2), measured_peak()[0])
@@ -544,7 +556,7 @@ def run_ours(args):
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
         emit(line)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
 
 

@@ -65,6 +65,7 @@ SYMBOLS = [
     ("flan_b200_phase_summary", _int, [_vp, _vp, _i64, _int, _i64, _i64, _int, _f, _f, _int, _vp]),
     ("flan_b200_phase_carry", _int, [_vp, _vp, _int, _int, _int, _vp]),
     ("flan_b200_convert_to_audio_range", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _int, _vp, _i64, _i64, _i64]),
+    ("flan_b200_convert_to_audio_range_head", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
     ("flan_b200_add", _int, [_vp, _vp, _vp, _i64]),
     ("flan_b200_mid_side", _int, [_vp, _vp, _vp, _i64]),
     ("flan_b200_repitch", _int, [_vp, _vp, _int, _i64, _int, _f, _vp, _i64, _int, _int, _vp]),

@@ -282,7 +282,7 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 		}
 	if( variant == 17 )     // PV_PT_MIRROR: the standard shape, or the general form for any aligned window and even hop
 		{
-		if( !( W >= N / 16 && W % ( N / 16 ) == 0 && hop >= 2 && hop % 2 == 0 && hop <= W ) ) return 3;
+		if( !( W >= N / 16 && W % ( N / 16 ) == 0 && hop >= 2 && hop % 2 == 0 && hop <= W && hop <= N / 16 ) ) return 3;
 		switch( N )
 			{
 			case 1024: synthesis_mirror_n<1024>( a, blocks ); return 0;

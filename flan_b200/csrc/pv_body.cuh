@@ -822,12 +822,12 @@ template<int R> PV_HD int mpad( int i )
 
 // ONE: the two exchange buffers alias (x1 == x0): two more barriers per frame, 18 KB less shared memory per CTA, which
 // moves the SM's carve-out from 228 KB to 164 KB and so gives the twiddle tables (32 KB) an L1 they fit in.
-// GEN: any window that fills whole slots of the thread layout (a multiple of dft/16 samples) and any even hop up to the
-// window -- e.g. the API default window 2048 / hop 128 / dft 4096 (Audio.h:158-163). A frame then advances the
+// GEN: any window that fills whole slots of the thread layout (a multiple of dft/16 samples) and any even hop up to
+// dft/16 -- e.g. the API default window 2048 / hop 128 / dft 4096 (Audio.h:158-163). A frame then advances the
 // overlap-add positions by hop/2 pairs, which is no longer a whole slot per thread, so the ring is shared by the CTA (the
 // two exchange barriers of the next frame order one frame's accumulation before the next one's; no barrier is added),
-// and which of a thread's slots start a ring entry, accumulate, or are final depends on the thread: three 16-bit masks,
-// fixed over the walk. !GEN is the standard shape (window == dft, hop == dft/16) with everything resolved at compile time.
+// and whether a thread's last used slot starts a ring entry and whether its slot 0 is final depends on the thread (two
+// predicates, fixed over the walk). !GEN is the standard shape (window == dft, hop == dft/16) with everything resolved at compile time.
 template<int N, bool ONE, bool GEN, class Env>
 PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, float2 * ring, float2 * x0, float2 * x1, float2 * rowbuf,
                                  typename Env::BulkBarrier * bar )
@@ -852,10 +852,13 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 	const int khi = irregular ? MP::KHI : 0;
 
 	float w[2 * PT];
-	// GEN: slot s of this thread is pair n = t + s*T of the frame's window: `used` n < wp, `fresh` (the first frame to
-	// reach its absolute pair) n >= wp - hp, `final` (the last one) n < hp
-	unsigned used = 0xffffu, fresh = 1u << ( PT - 1 ), final = 1u;
-	if( GEN ) { used = 0; fresh = 0; final = 0; }
+	// GEN (hop <= dft/16, i.e. hp <= T): slot s of this thread is pair n = t + s*T of the frame's window. Slots
+	// s < slots_in are used; of the last used slot the pairs n >= wp - hp are `fresh` (this is the first frame to reach
+	// their absolute pair: the ring entry is overwritten), of slot 0 the pairs n < hp are `final` (no later frame reaches
+	// them: they go straight to global memory). Both are ranges of t, uniform per warp when hp is a multiple of 32.
+	const int slots_in = GEN ? wp / T : PT;
+	const bool is_final = GEN ? ( t < hp ) : true;
+	const bool is_fresh = GEN ? ( t >= T - hp ) : true;
 #pragma unroll
 	for( int s = 0; s < PT; ++s )
 		{
@@ -866,12 +869,6 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			w[2 * s + 1] = env.ldg( a.win + 2 * nn + 1 );
 			}
 		else { w[2 * s] = 0.0f; w[2 * s + 1] = 0.0f; }
-		if( GEN )
-			{
-			if( nn < wp ) used |= 1u << s;
-			if( nn < wp && nn >= wp - hp ) fresh |= 1u << s;
-			if( nn < hp ) final |= 1u << s;
-			}
 		}
 	// bin of slot (q, r): k = kbase + r*NS with kbase = p (+ khi for the irregular upper slots); its mirror is M - k
 	double acc[Q][R][2], acc_mid = 0.0;
@@ -1075,23 +1072,27 @@ PV_HD void synthesis_cta_mirror( const SynthArgs & a, int64_t block, Env & env, 
 			float2 ww; ww.x = w[2 * s]; ww.y = w[2 * s + 1];
 			const float2 prod = mul2( swap2( v[s] ), ww );
 			// a fresh slot receives its first contribution (its ring entry is simply overwritten)
-			if( GEN ) { sum[s] = prod; if( ( used >> s & 1u ) && !( fresh >> s & 1u ) ) sum[s] = add2( *slot( s ), prod ); }
+			if( GEN )
+				{
+				float2 cur; cur.x = 0.0f; cur.y = 0.0f;
+				if( s < slots_in ) cur = *slot( s );                       // uniform over the CTA
+				sum[s] = ( s == slots_in - 1 && is_fresh ) ? prod : add2( cur, prod );
+				}
 			else sum[s] = ( s == PT - 1 ) ? prod : add2( *slot( s ), prod );
 			}
 		if( GEN )
 			{
 #pragma unroll
-			for( int s = 0; s < PT; ++s ) if( ( used >> s & 1u ) && !( final >> s & 1u ) ) *slot( s ) = sum[s];
-			// final pairs: no later frame reaches them
-			const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
-#pragma unroll
-			for( int s = 0; s < PT; ++s )
-				if( final >> s & 1u )
-					{
-					const int64_t pos = start + 2 * ( t + s * T );
-					if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[s] );
-					else { emit( pos, sum[s].x ); emit( pos + 1, sum[s].y ); }
-					}
+			for( int s = 1; s < PT; ++s ) if( s < slots_in ) *slot( s ) = sum[s];
+			if( !is_final ) *slot( 0 ) = sum[0];
+			else
+				{
+				// final pairs: no later frame reaches them
+				const bool fast = start >= interior_lo && start + hop <= interior_hi && start >= a.out_lo && start + hop <= a.out_hi && a.out_aligned2;
+				const int64_t pos = start + 2 * t;
+				if( fast ) env.st_stream2( reinterpret_cast<float2 *>( och + ( pos - a.out_offset ) ), sum[0] );
+				else { emit( pos, sum[0].x ); emit( pos + 1, sum[0].y ); }
+				}
 			}
 		else
 			{

@@ -1010,6 +1010,35 @@ int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_ro
 	return synth_range( ctx, s );
 	}
 
+// The same, with the frames whose windows reach into the previous shard launched FIRST: `head_event` (a cudaEvent_t of the
+// caller) is recorded on the stream right after them, so the caller can send the window - hop partial sums at the head of
+// d_out_local to the previous rank on another stream while the rest of the frames compute.
+int flan_b200_convert_to_audio_range_head( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                                           int C, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
+                                           int B, float sr, float ar, int W,
+                                           const flan_b200_phase_state * d_carry_in, int reuse_summary,
+                                           float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len,
+                                           void * head_event )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	if( !( ar > 0.0f ) || !( sr > 0.0f ) || flan_b200_hop_from_rates( sr, ar ) < 1 )
+		return fail( ctx, FLAN_B200_INVALID, "bad rates" );
+	CallLock lock( ctx );
+	BlockUse use( ctx, { d_pv_rows, d_carry_in, d_out_local } );
+	SynthCall s{ d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frames_total, B, sr, ar, W };
+	s.d_carry_in = (const PhaseSeg *) d_carry_in; s.reuse_summary = reuse_summary != 0;
+	s.d_out = d_out_local; s.out_stride = out_stride; s.out_offset = out_offset; s.out_len = out_len;
+	if( head_event )
+		{
+		// the first segment holds every frame that reaches the previous shard (a segment is at least window / hop frames)
+		s.head_segments = 1;
+		cudaEvent_t ev = (cudaEvent_t) head_event;
+		cudaStream_t st = ctx->compute;
+		s.on_chunk = [ev, st]( int k, int64_t ) -> int { return ( k == 0 && cudaEventRecord( ev, st ) != cudaSuccess ) ? FLAN_B200_CUDA : FLAN_B200_OK; };
+		}
+	return synth_range( ctx, s );
+	}
+
 int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n )
 	{
 	if( !ctx ) return FLAN_B200_INVALID;

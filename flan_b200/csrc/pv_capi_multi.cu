@@ -483,8 +483,9 @@ int flan_b200_multi_gather_pv( flan_b200_multi * m, const flan_b200_sharded_pv *
 				MCK( cudaMemcpyPeerAsync( d_pv + 2 * ( (int64_t) c * F + pv->frame_begin[i] ) * B, dst->device,
 				                          pv->d[i] + 2 * (int64_t) c * rows * B, ctx->device, width, dst->stream ), "peer copy" );
 			// the source shard may be freed (and its block reused) only after the copy: its stream waits for the destination's
-			MCK( cudaEventRecord( m->ev_halo[i], dst->stream ), "event record" );
-			MCK( cudaStreamWaitEvent( ctx->compute, m->ev_halo[i], 0 ), "stream wait" );
+			// (an event is recorded on a stream of its own device: the destination's)
+			MCK( cudaEventRecord( m->ev_copied[to], dst->stream ), "event record" );
+			MCK( cudaStreamWaitEvent( ctx->compute, m->ev_copied[to], 0 ), "stream wait" );
 			}
 		}
 	if( h_pv )

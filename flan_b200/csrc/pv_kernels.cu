@@ -459,8 +459,8 @@ bool synthesis_mirror_applies( int N, const SynthArgs & a )
 	if( !synth_mirror_supported( N ) ) return false;
 	if( a.W == N && a.hop == N / 16 ) return true;
 	// general form: the window fills whole slots of the thread layout (a multiple of dft/16 samples), the hop is even and
-	// leaves no gaps
-	return a.W >= N / 16 && a.W % ( N / 16 ) == 0 && a.W <= N && a.hop >= 2 && a.hop % 2 == 0 && a.hop <= a.W;
+	// at most one slot (dft/16 samples) and leaves no gaps
+	return a.W >= N / 16 && a.W % ( N / 16 ) == 0 && a.W <= N && a.hop >= 2 && a.hop % 2 == 0 && a.hop <= a.W && a.hop <= N / 16;
 	}
 template<int N> static cudaError_t launch_synthesis_n( const SynthArgs & a, int64_t blocks, cudaStream_t st, int tps, int variant )
 	{

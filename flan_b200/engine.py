@@ -118,6 +118,20 @@ class Engine:
                       int(reuse_summary), self._chk(out), out_len, out_offset, out_len)
         return out
 
+    def convert_to_audio_range_head(self, pv_rows, frame_begin, frames_total, sr, ar, W, carry, out_offset, out_len, head_event,
+                                    out=None, reuse_summary=False):
+        """convert_to_audio_range with the frames that reach into the previous shard launched first; head_event (a
+        torch.cuda.Event that has been recorded once, so that its handle exists) is recorded right after them."""
+        C, rows, B, _ = pv_rows.shape
+        if out is None:
+            out = torch.empty((C, out_len), dtype=torch.float32, device=self.device)
+        self._bind_stream()
+        self.ctx.call("flan_b200_convert_to_audio_range_head", self._chk(pv_rows), rows * B, C, frame_begin, frame_begin + rows,
+                      frames_total, B, sr, ar, W, None if carry is None else self._chk(carry, torch.float64),
+                      int(reuse_summary), self._chk(out), out_len, out_offset, out_len,
+                      ctypes.c_void_p(head_event.cuda_event) if head_event is not None else None)
+        return out
+
     def add(self, dst, src):
         assert dst.numel() == src.numel()
         self._bind_stream()

@@ -97,3 +97,42 @@ def sharded_resynthesis(engine, dist, shard, pv_rows, sr, ar, allgather, send, r
         if r is not None:
             r.wait()
     return out, lo
+
+
+def sharded_resynthesis_overlapped(engine, dist, torch, shard, pv_rows, sr, ar, allgather, side_stream, head_event):
+    """sharded_resynthesis with the halo exchange off the critical path (GPU ranks; SURVEY 8e: "boundary tiles first,
+    then exchange on a side stream"): the frames whose windows reach into the previous rank are launched first
+    (flan_b200_convert_to_audio_range_head records head_event after them), their partial sums leave on side_stream in
+    one batched NCCL send / recv with the right neighbour's while the remaining frames compute, and the owner adds what
+    it received after its own frames (lower-frame contributions first, AudioPV.cpp:133-134).
+    head_event: a torch.cuda.Event that has been recorded once (its handle must exist)."""
+    state = engine.phase_summary(pv_rows, shard.f0, sr, ar, shard.W)
+    carry = engine.phase_carry(allgather(state), shard.rank)
+    lo, hi = shard.span_lo, shard.span_hi
+    h_lo, h_hi = head_overlap(shard)
+    sends = h_hi > h_lo and shard.rank > 0
+    out = engine.convert_to_audio_range_head(pv_rows, shard.f0, shard.frames_total, sr, ar, shard.W, carry, lo, hi - lo,
+                                             head_event if sends else None, reuse_summary=True)
+    main = torch.cuda.current_stream()
+    n_lo = n_hi = 0
+    if shard.rank + 1 < shard.world:
+        n_lo, n_hi = head_overlap(frame_shard(shard.n, shard.hop, shard.W, shard.world, shard.rank + 1))
+    buf = None
+    with torch.cuda.stream(side_stream):
+        ops = []
+        if sends:
+            side_stream.wait_event(head_event)
+            head = out[:, h_lo - lo:h_hi - lo].contiguous()
+            ops.append(dist.P2POp(dist.isend, head, shard.rank - 1))
+        if n_hi > n_lo:
+            buf = torch.empty((out.shape[0], n_hi - n_lo), dtype=out.dtype, device=out.device)
+            ops.append(dist.P2POp(dist.irecv, buf, shard.rank + 1))
+        for r in (dist.batch_isend_irecv(ops) if ops else []):
+            r.wait()
+    if buf is not None:
+        main.wait_stream(side_stream)
+        buf.record_stream(main)
+        engine.add_into(out[:, n_lo - lo:n_hi - lo], buf)
+    elif sends:
+        main.wait_stream(side_stream)      # `out` must outlive the send that reads it
+    return out, lo

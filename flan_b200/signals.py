@@ -58,4 +58,8 @@ def make_config(name, seconds=None):
         sr, W, h, N, C = 48000, 1024, 64, 1024, 1
         n = int(sr * (60 if seconds is None else seconds))
         return np.stack([noise_chirp(n, sr, 5000)]), sr, W, h, N
+    if name == "apidefault":    # Audio::convert_to_PV() with no arguments (Audio.h:158-163): window 2048, hop 128, dft 4096; one cfg4 channel
+        sr, W, h, N, C = 48000, 2048, 128, 4096, 1
+        n = int(sr * (600 if seconds is None else seconds))
+        return np.stack([noise_chirp(n, sr, 40)]), sr, W, h, N
     raise KeyError(name)

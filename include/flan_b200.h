@@ -157,6 +157,15 @@ int flan_b200_convert_to_audio_range( flan_b200_ctx * ctx, const float * d_pv_ro
                                       int bins, float sample_rate, float analysis_rate, int window_size,
                                       const flan_b200_phase_state * d_carry_in, int reuse_summary,
                                       float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len );
+/* The same with the frames whose windows reach into the previous shard launched first: head_event (a cudaEvent_t of the
+ * caller, may be NULL) is recorded on the stream right after them, so that the window - hop partial sums at the head of
+ * d_out_local can travel to the previous rank on another stream while the remaining frames compute. */
+int flan_b200_convert_to_audio_range_head( flan_b200_ctx * ctx, const float * d_pv_rows, int64_t pv_channel_stride,
+                                           int channels, int64_t frame_begin, int64_t frame_end, int64_t frames_total,
+                                           int bins, float sample_rate, float analysis_rate, int window_size,
+                                           const flan_b200_phase_state * d_carry_in, int reuse_summary,
+                                           float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len,
+                                           void * head_event );
 /* d_out[i] += d_add[i], i < n (overlap-add halo received from a neighbour). */
 int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n );
 

@@ -14,9 +14,8 @@ only the small test fixtures go there) the 1e-3 Hz term is scaled by analysis_ra
 
 On top of that the gate allows the float32 FFT noise floor itself: 1e-7 * (1/rho_f + 1/rho_{f-1}) rad, rho = m_ref /
 frame peak >= 1e-2, i.e. at most 6e-4 Hz at the gate edge for analysis_rate 187.5 Hz and ~1e-5 Hz for loud bins.
-(fft_noise: 1e-7 for the power-of-two transforms; the Bluestein path of the non-power-of-two sizes runs three float
-FFTs of at least twice the length plus two chirp products per transform; measured on B200 its noise is about ten times
-that of the direct transform, and it is given 1.5e-6 -- magnitudes stay within 1e-5 relative either way.)
+(The Bluestein path of the non-power-of-two sizes meets the same gate: magnitudes within 1.2e-5, no bin needs the noise
+term in the shapes tested.)
 
 Resynthesis, stage-wise on the SAME PV input: max |sample - sample_ref| <= 1e-5.
 """
@@ -28,7 +27,7 @@ def ulp32(x):
     return np.spacing(np.maximum(x, np.float32(1e-30))).astype(np.float64)
 
 
-def analysis_report(pv, pv_ref, sr, hop, N, fft_noise=1e-7):
+def analysis_report(pv, pv_ref, sr, hop, N, fft_noise=1e-7, first_frame_has_history=False):
     pv = np.asarray(pv, np.float32)
     pv_ref = np.asarray(pv_ref, np.float32)
     m, f = pv[..., 0].astype(np.float64), pv[..., 1].astype(np.float64)
@@ -43,6 +42,10 @@ def analysis_report(pv, pv_ref, sr, hop, N, fft_noise=1e-7):
     gate = (mr >= 1e-2 * peak) & (peak > 0)
     # f is built from this frame's AND the previous frame's phase (phase_vocoder.cpp:44): both must be above the floor
     gate[..., 1:, :] &= gate[..., :-1, :].copy()
+    if first_frame_has_history:
+        # the arrays are a window of frames out of a longer signal: the first frame's phase difference involves a frame
+        # that is not here, whose level cannot be checked -- it is left out
+        gate[..., 0, :] = False
     df = np.abs(f - fr)
     df = np.minimum(df, np.abs(df - ar))            # +-pi wrap ambiguity: f is defined mod analysis_rate
     tol_f = np.maximum(1e-3 * max(1.0, ar / 750.0), np.maximum(2 * ulp32(pv_ref[..., 1]), 2 * grid))
@@ -85,8 +88,8 @@ def analysis_report(pv, pv_ref, sr, hop, N, fft_noise=1e-7):
     }
 
 
-def assert_analysis_parity(pv, pv_ref, sr, hop, N, min_f_within_1ulp=None, fft_noise=1e-7):
-    r = analysis_report(pv, pv_ref, sr, hop, N, fft_noise)
+def assert_analysis_parity(pv, pv_ref, sr, hop, N, min_f_within_1ulp=None, fft_noise=1e-7, first_frame_has_history=False):
+    r = analysis_report(pv, pv_ref, sr, hop, N, fft_noise, first_frame_has_history)
     assert r["nan"] == 0, r
     assert r["gated_bins"] > 0, r
     assert r["bad_m"] == 0, r

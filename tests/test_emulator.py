@@ -100,8 +100,9 @@ MIRROR_SYNTH_SHAPES = MIRROR_SHAPES + [(8192, 0, 20000), (8192, 19, 17001)]     
 # The general form of the mirrored resynthesis: a window of whole slots (a multiple of dft/16), any even hop up to it --
 # the API default window 2048 / hop 128 / dft 4096 among them; the overlap-add ring is then shared by the CTA.
 @pytest.mark.parametrize("W,h,N,seg,n", [(2048, 128, 4096, 0, 9000), (2048, 128, 4096, 17, 9001), (1024, 64, 2048, 20, 6000),
-                                         (512, 32, 1024, 0, 3000), (4096, 512, 4096, 0, 9000), (3072, 96, 4096, 33, 9000),
-                                         (4096, 130, 4096, 40, 9000), (256, 256, 4096, 5, 5000), (4096, 256, 8192, 19, 17001)])
+                                         (512, 32, 1024, 0, 3000), (4096, 128, 4096, 0, 9000), (3072, 96, 4096, 33, 9000),
+                                         (4096, 130, 4096, 40, 9000), (256, 256, 4096, 5, 5000), (4096, 256, 8192, 19, 17001),
+                                         (256, 2, 4096, 130, 2000)])
 def test_emulated_general_mirror_synthesis_matches_oracle(emu, oracle, W, h, N, seg, n):
     sr = 48000.0
     x = np.stack([noise_chirp(n, sr, 6), sine_sweep(n, sr), noise_chirp(n, sr, 7)])

@@ -89,9 +89,10 @@ def test_any_dft_size_matches_oracle(eng, oracle, W, h, N):
     ref_pv = oracle.convert_to_pv(x, sr, W, h, N, f0, f1)
     pv = eng.convert_to_pv(dev(x), sr, W, h, N).cpu().numpy()
     assert pv.shape == (len(chans), F, N // 2 + 1, 2)
-    bluestein = ((N // 2 if N % 2 == 0 else N) & ((N // 2 if N % 2 == 0 else N) - 1)) != 0
     if N >= 64:
-        assert_analysis_parity(pv[:2, f0:f1], ref_pv[:2], sr, h, N, fft_noise=1.5e-6 if bluestein else 1e-7)
+        # the gate needs the PREVIOUS frame's level too (its phase enters the difference): the first frame of a window
+        # that does not start at frame 0 has none to look at and is left out
+        assert_analysis_parity(pv[:2, f0:f1], ref_pv[:2], sr, h, N, first_frame_has_history=f0 > 0)
     else:
         assert np.allclose(pv[:2, f0:f1, :, 0], ref_pv[:2, :, :, 0], rtol=1e-4, atol=1e-5)
     if len(chans) == 3:      # all-zero channel: deterministic known answer, bit-identical
@@ -354,7 +355,7 @@ def test_summary_reuse_is_bit_identical(eng):
 # the epilogue arithmetic shows here long before it reaches the tolerance gate. The report -- including how many bins
 # of SURVEY 8c's unmodified gate pass only through each of the three allowances of tests/parity.py -- is written to
 # gpurun_out/parity_report.json (a copy is kept under profiles/).
-PARITY_FLOORS = {"cfg1": (0.97, 0.55), "cfg2": (0.97, 0.55), "cfg3": (0.97, 0.55), "cfg5": (0.97, 0.55)}
+PARITY_FLOORS = {"cfg1": (0.985, 0.97), "cfg2": (0.95, 0.90), "cfg3": (0.95, 0.90), "cfg5": (0.95, 0.90)}
 
 
 @pytest.mark.parametrize("name,sec", [("cfg1", 10.0), ("cfg2", 4.0), ("cfg3", 6.0), ("cfg5", 4.0)])
@@ -376,5 +377,4 @@ def test_parity_gate_statistics(eng, oracle, name, sec):
         pass
     print(name, r)
     assert r["frac_f_within_1ulp_gated"] >= within, r
-    assert r["frac_f_bit_exact_gated"] >= exact, r
-    assert r["frac_m_bit_exact"] >= 0.30, r
+    assert r["frac_f_bit_exact_gated"] >= exact, r      # (magnitudes: |z| is max * sqrt(1 + r^2), a few ulp from hypotf: tolerance only)

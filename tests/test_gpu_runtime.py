@@ -186,3 +186,32 @@ def test_repeated_round_trips_recycle_and_prefetch(api, oracle):
         xr = (x * np.float32(1.0 + 0.125 * r)).astype(np.float32)
         assert api.api_round_trip(_ptr(xr), C, n, sr, W, h, N, 0, 0, _ptr(single)) == F * h
         assert np.array_equal(out[r], single), "pass %d" % r
+
+
+def test_head_first_range_resynthesis_is_bit_identical(eng, oracle):
+    """flan_b200_convert_to_audio_range_head launches the frames that reach into the previous shard first and records the
+    caller's event after them (the torchrun path sends its halo from there); the samples are those of the plain call."""
+    import torch
+    from flan_b200.sharding import frame_shard, head_overlap
+    sr, W, h, N = 48000.0, 2048, 128, 2048
+    n = 500000
+    x = np.stack([noise_chirp(n, sr, 61), sine_sweep(n, sr)])
+    pv = eng.convert_to_pv(torch.from_numpy(x).cuda(), sr, W, h, N)
+    ar = eng.analysis_rate(sr, h)
+    sh = frame_shard(n, h, W, 3, 1)                               # the middle one of three shards
+    rows = pv[:, sh.f0:sh.f1].contiguous()
+    state = eng.phase_summary(pv[:, :sh.f0].contiguous(), 0, sr, ar, W)
+    carry = eng.phase_carry(state.unsqueeze(0), 1)
+    lo, hi = sh.span_lo, sh.span_hi
+    plain = eng.convert_to_audio_range(rows, sh.f0, sh.frames_total, sr, ar, W, carry, lo, hi - lo)
+    ev = torch.cuda.Event()
+    ev.record()
+    head_first = eng.convert_to_audio_range_head(rows, sh.f0, sh.frames_total, sr, ar, W, carry, lo, hi - lo, ev)
+    side = torch.cuda.Stream()
+    side.wait_event(ev)
+    h_lo, h_hi = head_overlap(sh)
+    with torch.cuda.stream(side):
+        head = head_first[:, h_lo - lo:h_hi - lo].clone()        # readable as soon as the event has fired
+    torch.cuda.synchronize()
+    assert torch.equal(plain, head_first)
+    assert torch.equal(head, plain[:, h_lo - lo:h_hi - lo])

@@ -1,6 +1,6 @@
 """Kernel-level timing of the two transforms on one BASELINE shape (development aid; bench.py is the judged line).
 
-    python tools/kbench.py [cfg2|cfg1|cfg3|cfg5] [seconds]
+    python tools/kbench.py [cfg2|cfg1|cfg3|cfg5|cfg4|apidefault] [seconds]
 Prints ms per launch of each kernel kind and the HBM fraction, for the current FLAN_B200_TPS_* environment."""
 import json
 import os
@@ -16,7 +16,7 @@ from flan_b200.signals import make_config  # noqa: E402
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-    seconds = float(sys.argv[2]) if len(sys.argv) > 2 else {"cfg2": 600, "cfg1": 10, "cfg3": 600, "cfg5": 60, "cfg4": 120}[name]
+    seconds = float(sys.argv[2]) if len(sys.argv) > 2 else {"cfg2": 600, "cfg1": 10, "cfg3": 600, "cfg5": 60, "cfg4": 120, "apidefault": 600}[name]
     x, sr, W, h, N = make_config(name, seconds)
     if name == "cfg5":
         x = np.repeat(x, 32, axis=0)          # 32 clips per GPU
@@ -44,8 +44,7 @@ def main():
     seg = res["phase_seg"][0] / reps
     scan = res["phase_scan"][0] / reps
     byts = 4.0 * C * n + 8.0 * C * F * B
-    out = {"cfg": name, "N": N, "frames": C * F, "tps_a": os.environ.get("FLAN_B200_TPS_ANALYSIS", "768"),
-           "tps_s": os.environ.get("FLAN_B200_TPS_SYNTHESIS", "768"),
+    out = {"cfg": name, "N": N, "W": W, "hop": h, "frames": C * F,
            "analysis_ms": round(an, 4), "analysis_frac": round(byts / an / 1e6 / peak, 4),
            "synthesis_ms": round(sy, 4), "synthesis_frac": round(byts / sy / 1e6 / peak, 4),
            "phase_seg_ms": round(seg, 4), "phase_scan_ms": round(scan, 4),
