@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seconds", type=float, default=SECONDS_PER_GPU, help="signal length per GPU (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how the phase state and the overlap-add halo travel between the ranks")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the BASELINE config 3 leg (1 h mono 96 kHz through the multi-device handle)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="device time to cover with rounds of K steps")
     ap.add_argument("--chain", action="store_true",
@@ -357,7 +359,7 @@ def run_ours(args):
     import torch.distributed as dist
     from flan_b200.engine import Engine
     from flan_b200.signals import noise_chirp
-    from flan_b200.sharding import frame_shard, sharded_resynthesis_overlapped
+    from flan_b200.sharding import PeerExchange, frame_shard, sharded_resynthesis_overlapped, sharded_resynthesis_peer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -397,6 +399,12 @@ def run_ours(args):
     side_stream = torch.cuda.Stream(device=dev)
     head_event = torch.cuda.Event()
     head_event.record()                      # creates the handle the C ABI records on
+    # The two exchanges of sharded resynthesis (phase state, overlap-add halo) go through flan_b200_exchange_*: peer copies
+    # into CUDA-IPC mailboxes ordered by sequence flags (no NCCL kernel beside the transforms). --exchange nccl keeps the
+    # torch.distributed form (all_gather + batched send / recv on a side stream).
+    exchange = None
+    if world > 1 and args.exchange == "peer":
+        exchange = PeerExchange(eng, dist, rank, world, CH, B, max(0, W - HOP))
 
     def step(xin, yout=None):
         if world == 1:
@@ -405,7 +413,10 @@ def run_ours(args):
             eng.convert_to_audio(pv, SR, ar, W, out=yout)
             return yout
         eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
-        o, _ = sharded_resynthesis_overlapped(eng, dist, torch, sh, pv, SR, ar, allgather, side_stream, head_event)
+        if exchange is not None:
+            o, _ = sharded_resynthesis_peer(eng, exchange, torch, sh, pv, SR, ar, head_event)
+        else:
+            o, _ = sharded_resynthesis_overlapped(eng, dist, torch, sh, pv, SR, ar, allgather, side_stream, head_event)
         return o
 
     def barrier():
@@ -532,7 +543,8 @@ def run_ours(args):
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "channels": CH, "frames_per_gpu": sh.frames, "bins": B,
-                       "seconds_per_gpu": args.seconds, "sharding": "none" if world == 1 else "contiguous frame ranges, dp%d" % world,
+                       "seconds_per_gpu": args.seconds, "sharding": "none" if world == 1 else "contiguous frame ranges, dp%d; phase state + halo exchange: %s" % (
+                           world, "peer copies into CUDA-IPC mailboxes (flan_b200_exchange_*)" if exchange is not None else "NCCL all_gather + send/recv"),
                        "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush"},
             "legs": {"analysis_frames_per_s": frames_rank / (an_ms / an_n * 1e-3) if an_n else None,
                      "resynthesis_frames_per_s": frames_rank / ((sy_ms + seg_ms + scan_ms) / sy_n * 1e-3) if sy_n else None,

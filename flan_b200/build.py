@@ -51,7 +51,7 @@ def build_library(force=False, verbose=False, debug=False):
     units = [("pv_kernels.cu", []), ("pv_capi.cu", []), ("pv_capi_modify.cu", []), ("pv_capi_io.cu", []),
              ("pv_modify.cu", ["-fmad=false"]), ("pv_io.cu", ["-fmad=false"])]
     units = [u for u in units if os.path.exists(os.path.join(CSRC, u[0]))]
-    for extra_unit in ("pv_generic.cu", "pv_capi_multi.cu"):
+    for extra_unit in ("pv_generic.cu", "pv_capi_multi.cu", "pv_capi_exchange.cu"):
         if os.path.exists(os.path.join(CSRC, extra_unit)):
             units.append((extra_unit, []))
     srcs = _sources(*[u for u, _ in units])

@@ -66,6 +66,16 @@ SYMBOLS = [
     ("flan_b200_phase_carry", _int, [_vp, _vp, _int, _int, _int, _vp]),
     ("flan_b200_convert_to_audio_range", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _int, _vp, _i64, _i64, _i64]),
     ("flan_b200_convert_to_audio_range_head", _int, [_vp, _vp, _i64, _int, _i64, _i64, _i64, _int, _f, _f, _int, _vp, _int, _vp, _i64, _i64, _i64, _vp]),
+    ("flan_b200_exchange_create", _int, [_vp, _int, _int, _int, _int, _i64, ctypes.POINTER(_vp)]),
+    ("flan_b200_exchange_destroy", None, [_vp]),
+    ("flan_b200_exchange_handle", _int, [_vp, _vp]),
+    ("flan_b200_exchange_connect", _int, [_vp, _vp]),
+    ("flan_b200_exchange_state_slot", _int, [_vp, ctypes.POINTER(_vp)]),
+    ("flan_b200_exchange_put_state", _int, [_vp, _vp]),
+    ("flan_b200_exchange_get_states", _int, [_vp, ctypes.POINTER(_vp)]),
+    ("flan_b200_exchange_release_states", _int, [_vp]),
+    ("flan_b200_exchange_put_halo", _int, [_vp, _vp, _i64, _int, _i64, _vp]),
+    ("flan_b200_exchange_add_halo", _int, [_vp, _vp, _i64, _int, _i64]),
     ("flan_b200_add", _int, [_vp, _vp, _vp, _i64]),
     ("flan_b200_mid_side", _int, [_vp, _vp, _vp, _i64]),
     ("flan_b200_repitch", _int, [_vp, _vp, _int, _i64, _int, _f, _vp, _i64, _int, _int, _vp]),

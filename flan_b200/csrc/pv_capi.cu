@@ -497,6 +497,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	const flan_b200_ctx::SegKey & old = ctx->seg_key;
 	const bool have_summaries = s.reuse_summary && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
 	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.seg_len == key.seg_len && old.sr == key.sr && old.ar == key.ar;
+	const bool old_group_prefix = old.group_prefix;
 	ctx->seg_key = key;
 
 	PhaseSegArgs sa{};
@@ -513,7 +514,15 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sc.carry_in = s.d_carry_in; sc.carry_out = s.d_carry_out;
 	sc.acc_start = s.summary_only ? nullptr : d_acc;
 	sc.P = plan->host.P; sc.rcpP = plan->host.rcpP;
-	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->compute ), "phase scan launch" ); ctx->launches += ( segs <= 256 ) ? 0 : ( s.summary_only ? 1 : 2 ); }     // launch_phase_scan: one launch for short signals, else 2 or 3
+	// A summary-only call without a carry (flan_b200_phase_summary: the shard's own state, before the states of the
+	// earlier shards are known) leaves the carry-free group prefixes behind; the range call that follows on the same
+	// data then only re-walks the groups, entering each through carry (+) prefix.
+	const bool three_launches = segs > 256 || C > 65535;
+	sc.expand_only = ( have_summaries && old_group_prefix && three_launches && !s.summary_only && !s.d_carry_out ) ? 1 : 0;
+	sc.expand_carry = sc.expand_only ? s.d_carry_in : nullptr;
+	ctx->seg_key.group_prefix = s.summary_only && !s.d_carry_in && three_launches;
+	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->compute ), "phase scan launch" );
+	  ctx->launches += three_launches ? ( sc.expand_only ? 0 : ( s.summary_only ? 1 : 2 ) ) : 0; }     // launch_phase_scan: one launch for short signals, else 1 to 3
 	if( s.summary_only ) return FLAN_B200_OK;
 	if( cancelled( s.cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
@@ -562,15 +571,38 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 			}
 		segs_per_slice = (int) std::max<int64_t>( 1, ctas_per_slice( (int64_t) C * segs, wave, s.copy_bytes ) / C );
 		}
+	auto launch_segments = [&]( int s0, int s1, cudaStream_t st, bool timed ) -> int
+		{
+		a.seg_first = s0; a.seg_count = s1 - s0;
+		std::unique_ptr<LaunchTimer> lt;
+		if( timed ) lt.reset( new LaunchTimer( ctx, 3 ) ); else ctx->launches++;
+		if( plan->generic ) { ga.a = a; CK( launch_generic_synthesis( ga, geo, st ), "synthesis launch" ); }
+		else CK( launch_synthesis( N, a, (int64_t) C * ( s1 - s0 ), st, mirror ? tps_mirror : tps_plain, variant ), "synthesis launch" );
+		return FLAN_B200_OK;
+		};
+	if( s.head_segments > 0 && !plan->generic )
+		{
+		// the head of the shard beside its interior (the generic kernels share per-CTA slabs of scratch between launches:
+		// they take the sliced form below)
+		const int sh = std::min( segs, s.head_segments );
+		CK( cudaEventRecord( ctx->head_fork, ctx->compute ), "event record" );
+		CK( cudaStreamWaitEvent( ctx->s_head, ctx->head_fork, 0 ), "stream wait" );
+		rc = launch_segments( 0, sh, ctx->s_head, false );
+		if( rc ) return rc;
+		if( s.head_event ) CK( cudaEventRecord( s.head_event, ctx->s_head ), "event record" );
+		CK( cudaEventRecord( ctx->head_join, ctx->s_head ), "event record" );
+		if( sh < segs ) { rc = launch_segments( sh, segs, ctx->compute, true ); if( rc ) return rc; }
+		CK( cudaStreamWaitEvent( ctx->compute, ctx->head_join, 0 ), "stream wait" );
+		return FLAN_B200_OK;
+		}
 	int k = 0;
 	for( int s0 = 0; s0 < segs; ++k )
 		{
 		int s1 = std::min( segs, s0 + segs_per_slice );
 		if( s.head_segments > 0 ) s1 = ( s0 == 0 ) ? std::min( segs, s.head_segments ) : segs;
-		a.seg_first = s0; a.seg_count = s1 - s0;
-		{ LaunchTimer lt( ctx, 3 );
-		  if( plan->generic ) { ga.a = a; CK( launch_generic_synthesis( ga, geo, ctx->compute ), "synthesis launch" ); }
-		  else CK( launch_synthesis( N, a, (int64_t) C * ( s1 - s0 ), ctx->compute, mirror ? tps_mirror : tps_plain, variant ), "synthesis launch" ); }
+		rc = launch_segments( s0, s1, ctx->compute, true );
+		if( rc ) return rc;
+		if( s.head_segments > 0 && k == 0 && s.head_event ) CK( cudaEventRecord( s.head_event, ctx->compute ), "event record" );
 		if( s.on_chunk )
 			{
 			// frames from segment s1 on touch samples >= hop * fa(s1) - W/2: everything below is final
@@ -669,6 +701,13 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->s_ana, cudaStreamNonBlocking );
 	if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &ctx->s_syn, cudaStreamNonBlocking );
 	if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &ctx->ws_event, cudaEventDisableTiming );
+		{
+		int lo = 0, hi = 0;                                             // numerically lower = higher priority
+		if( e == cudaSuccess ) e = cudaDeviceGetStreamPriorityRange( &lo, &hi );
+		if( e == cudaSuccess ) e = cudaStreamCreateWithPriority( &ctx->s_head, cudaStreamNonBlocking, hi );
+		}
+	if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &ctx->head_fork, cudaEventDisableTiming );
+	if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &ctx->head_join, cudaEventDisableTiming );
 	if( e != cudaSuccess ) { g_create_error = cudaGetErrorString( e ); flan_b200_destroy( ctx ); return FLAN_B200_CUDA; }
 	*out = ctx;
 	return FLAN_B200_OK;
@@ -679,8 +718,8 @@ void flan_b200_destroy( flan_b200_ctx * ctx )
 	if( !ctx ) return;
 	cudaSetDevice( ctx->device );
 	cudaStreamSynchronize( ctx->stream );
-	for( cudaStream_t * st : { &ctx->s_ana, &ctx->s_syn } ) if( *st ) { cudaStreamSynchronize( *st ); cudaStreamDestroy( *st ); }
-	if( ctx->ws_event ) cudaEventDestroy( ctx->ws_event );
+	for( cudaStream_t * st : { &ctx->s_ana, &ctx->s_syn, &ctx->s_head } ) if( *st ) { cudaStreamSynchronize( *st ); cudaStreamDestroy( *st ); }
+	for( cudaEvent_t ev : { ctx->ws_event, ctx->head_fork, ctx->head_join } ) if( ev ) cudaEventDestroy( ev );
 	if( ctx->h2d ) { cudaStreamSynchronize( ctx->h2d ); cudaStreamDestroy( ctx->h2d ); }
 	if( ctx->d2h ) { cudaStreamSynchronize( ctx->d2h ); cudaStreamDestroy( ctx->d2h ); }
 	for( auto & kv : ctx->plans ) free_plan( kv.second.get() );
@@ -1032,9 +1071,7 @@ int flan_b200_convert_to_audio_range_head( flan_b200_ctx * ctx, const float * d_
 		{
 		// the first segment holds every frame that reaches the previous shard (a segment is at least window / hop frames)
 		s.head_segments = 1;
-		cudaEvent_t ev = (cudaEvent_t) head_event;
-		cudaStream_t st = ctx->compute;
-		s.on_chunk = [ev, st]( int k, int64_t ) -> int { return ( k == 0 && cudaEventRecord( ev, st ) != cudaSuccess ) ? FLAN_B200_CUDA : FLAN_B200_OK; };
+		s.head_event = (cudaEvent_t) head_event;
 		}
 	return synth_range( ctx, s );
 	}

@@ -377,9 +377,7 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		if( i > 0 )
 			{
 			s.head_segments = 1;        // seg_len * hop >= window - hop: the first segment holds every frame that reaches shard i-1
-			cudaEvent_t head = m->ev_head[i];
-			cudaStream_t st = ctx->compute;
-			s.on_chunk = [head, st]( int k, int64_t ) -> int { if( k == 0 ) return cudaEventRecord( head, st ) == cudaSuccess ? FLAN_B200_OK : FLAN_B200_CUDA; return FLAN_B200_OK; };
+			s.head_event = m->ev_head[i];
 			}
 		rc = synth_range( ctx, s );
 		if( rc ) return bail( ctx, rc );

@@ -109,6 +109,8 @@ struct flan_b200_ctx
 	// themselves (Block::main_event), the shared workspace through ws_event.
 	cudaStream_t s_ana = nullptr, s_syn = nullptr;
 	cudaStream_t h2d = nullptr, d2h = nullptr;   // copy streams of the host-buffer forms (non-blocking)
+	// the first segment of a frame-range shard runs here, beside the rest of the shard on the calling stream (SynthCall::head_segments)
+	cudaStream_t s_head = nullptr; cudaEvent_t head_fork = nullptr, head_join = nullptr;
 	cudaEvent_t ws_event = nullptr; cudaStream_t ws_stream = nullptr; bool ws_recorded = false, ws_touched = false;
 	int lock_depth = 0;
 	std::recursive_mutex call_mutex;        // one call at a time enqueues on this context (see the header comment)
@@ -124,7 +126,9 @@ struct flan_b200_ctx
 	int64_t launches = 0;
 	bool timing = false;
 	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
-	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0, seg_len = 0; uint32_t sr = 0, ar = 0; bool valid = false; } seg_key;
+	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0, seg_len = 0; uint32_t sr = 0, ar = 0; bool valid = false;
+	                bool group_prefix = false;   // the scan scratch holds the carry-free group prefixes of these summaries
+	              } seg_key;
 	int max_seg_len = 0;                    // frames per CTA at most; 0 = by size (FLAN_B200_DEBUG builds: FLAN_B200_SEG_LEN)
 #ifdef FLAN_B200_DEBUG
 	// experiment knobs of development builds only (tools/experiments); release builds carry the measured policy
@@ -239,10 +243,13 @@ struct SynthCall
 	// sample up to which the local span is final (every contribution enqueued)
 	size_t copy_bytes = 0;
 	std::function<int( int, int64_t )> on_chunk;
-	// head_segments > 0 (multi-device forms): the first slice is exactly the first head_segments segments -- the frames
-	// whose windows reach into the previous shard -- and the rest follows as one launch, so the halo can travel while
-	// the interior computes
+	// head_segments > 0 (multi-device forms): the first head_segments segments -- the frames whose windows reach into the
+	// previous shard -- run as a launch of their own on the context's head stream, BESIDE the launch of all the other
+	// segments (segments only meet in red.add's on pre-zeroed samples, so the two launches commute); head_event is
+	// recorded on the head stream right after it, so the halo can travel while the interior computes. The calling
+	// stream joins the head stream before synth_range returns.
 	int head_segments = 0;
+	cudaEvent_t head_event = nullptr;
 	};
 int synth_range( flan_b200_ctx * ctx, const SynthCall & s );
 // Slices of whole waves: CTAs per slice for `ctas` CTAs of a kernel with `wave` resident CTAs on the device.

@@ -193,6 +193,12 @@ __global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanAr
 		return;
 		}
 	st = grp[(int64_t) g * a.B];
+	if( a.expand_only && a.expand_carry )
+		{
+		PhaseSeg cin = a.expand_carry[(int64_t) c * a.B + b];
+		phase_state_combine( cin, st, a.P, a.rcpP );
+		st = cin;
+		}
 	double * dst = a.acc_start + (int64_t) c * a.segs_per_channel * a.B + b;
 	for( int s = s0; s < s1; ++s )
 		{
@@ -538,13 +544,16 @@ cudaError_t launch_phase_seg( const PhaseSegArgs & a, int C, cudaStream_t st )
 cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 	{
 	const dim3 wide( ( a.B + 127 ) / 128, a.groups, C ), narrow( ( a.B + 127 ) / 128, 1, C );
-	if( a.segs_per_channel <= 256 && C <= 65535 )     // latency-bound sizes: one launch instead of three
+	if( a.segs_per_channel <= 256 && C <= 65535 && !a.expand_only )     // latency-bound sizes: one launch instead of three
 		{
 		pv_phase_scan_small_kernel<<<dim3( ( a.B + 31 ) / 32, C ), dim3( 32, 16 ), 0, st>>>( a );
 		return cudaGetLastError();
 		}
-	pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
-	pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
+	if( !a.expand_only )
+		{
+		pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
+		pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
+		}
 	if( a.acc_start ) pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 2 );
 	return cudaGetLastError();
 	}

@@ -28,6 +28,11 @@ struct PhaseScanArgs
 	PhaseSeg * carry_out;       // [C][B] or null (state after the last local frame)
 	double * acc_start;         // [C][segs_per_channel][B] or null
 	double P, rcpP;
+	// expand_only: `group` already holds the exclusive prefixes of a scan that ran WITHOUT a carry (a summary-only call on
+	// the same data); only the re-walk runs, entering every group through expand_carry (+) prefix (the combine is exact
+	// and associative, DESIGN.md 4.2, so the result has the bits of the scan with carry_in == expand_carry)
+	int expand_only;
+	const PhaseSeg * expand_carry;   // [C][B] or null
 	};
 
 // points_per_thread values of launch_analysis: 8, 16, or PV_PT_MIRROR (16 points per thread with the mirrored last

@@ -136,3 +136,65 @@ def sharded_resynthesis_overlapped(engine, dist, torch, shard, pv_rows, sr, ar, 
     elif sends:
         main.wait_stream(side_stream)      # `out` must outlive the send that reads it
     return out, lo
+
+
+class PeerExchange:
+    """flan_b200_exchange_* (include/flan_b200.h): the phase states and overlap-add halos of frame-range shards travel
+    between the per-GPU processes as device-to-device copies into CUDA-IPC mailboxes, ordered by sequence flags; no
+    exchange kernel runs on an SM. `dist` is only used once, to all-gather the 64-byte mailbox handles."""
+
+    def __init__(self, engine, dist, rank, world, channels, bins, halo_samples):
+        import ctypes
+        self.engine, self.rank, self.world, self.channels, self.bins = engine, rank, world, channels, bins
+        self.lib, self.ctx = engine.lib, engine.ctx
+        h = ctypes.c_void_p()
+        self.ctx.check(self.lib.flan_b200_exchange_create(self.ctx.h, rank, world, channels, bins, halo_samples, ctypes.byref(h)))
+        self.h = h
+        mine = ctypes.create_string_buffer(64)
+        self._call("flan_b200_exchange_handle", mine)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine.raw))
+        self._call("flan_b200_exchange_connect", ctypes.create_string_buffer(b"".join(handles), 64 * world))
+
+    def _call(self, name, *args):
+        self.ctx.check(getattr(self.lib, name)(self.h, *args))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.flan_b200_exchange_destroy(self.h)
+            self.h = None
+
+
+def sharded_resynthesis_peer(engine, ex, torch, shard, pv_rows, sr, ar, head_event):
+    """sharded_resynthesis with both exchanges as peer copies (PeerExchange), the halo off the critical path: the frames
+    whose windows reach into the previous rank run beside the rest of the shard (flan_b200_convert_to_audio_range_head
+    records head_event after them), their partial sums are pushed into the previous rank's mailbox while both ranks
+    compute, and the owner adds what it received after its own frames (lower-frame contributions first, AudioPV.cpp:133-134).
+    head_event: a torch.cuda.Event that has been recorded once (its handle must exist)."""
+    import ctypes
+    C, rows, B, _ = pv_rows.shape
+    engine._bind_stream()
+    d_state = ctypes.c_void_p()
+    ex._call("flan_b200_exchange_state_slot", ctypes.byref(d_state))
+    engine.ctx.call("flan_b200_phase_summary", engine._chk(pv_rows), rows * B, C, shard.f0, shard.f0 + rows, B, sr, ar, shard.W, d_state)
+    ex._call("flan_b200_exchange_put_state", d_state)
+    carry = None
+    if shard.rank > 0:
+        d_all = ctypes.c_void_p()
+        ex._call("flan_b200_exchange_get_states", ctypes.byref(d_all))
+        carry = torch.empty((C, B, 4), dtype=torch.float64, device=pv_rows.device)
+        engine.ctx.call("flan_b200_phase_carry", d_all, shard.rank, C, B, engine._chk(carry, torch.float64))
+        ex._call("flan_b200_exchange_release_states")
+    lo, hi = shard.span_lo, shard.span_hi
+    h_lo, h_hi = head_overlap(shard)
+    sends = h_hi > h_lo and shard.rank > 0
+    out = engine.convert_to_audio_range_head(pv_rows, shard.f0, shard.frames_total, sr, ar, shard.W, carry, lo, hi - lo,
+                                             head_event if sends else None, reuse_summary=True)
+    if sends:
+        ex._call("flan_b200_exchange_put_halo", ctypes.c_void_p(out.data_ptr() + 4 * (h_lo - lo)), hi - lo, C, h_hi - h_lo,
+                 ctypes.c_void_p(head_event.cuda_event))
+    if shard.rank + 1 < shard.world:
+        n_lo, n_hi = head_overlap(frame_shard(shard.n, shard.hop, shard.W, shard.world, shard.rank + 1))
+        if n_hi > n_lo:
+            ex._call("flan_b200_exchange_add_halo", ctypes.c_void_p(out.data_ptr() + 4 * (n_lo - lo)), hi - lo, C, n_hi - n_lo)
+    return out, lo

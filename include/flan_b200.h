@@ -166,6 +166,28 @@ int flan_b200_convert_to_audio_range_head( flan_b200_ctx * ctx, const float * d_
                                            const flan_b200_phase_state * d_carry_in, int reuse_summary,
                                            float * d_out_local, int64_t out_stride, int64_t out_offset, int64_t out_len,
                                            void * head_event );
+/* ---- the two exchanges of sharded resynthesis between PROCESSES (one process per GPU) ----------------------
+ * Phase states and overlap-add halos travel as device-to-device copies over NVLink into mailboxes the peers opened through
+ * CUDA IPC, ordered by sequence flags the receiving stream waits on (cuStreamWaitValue32): no kernel of the exchange
+ * occupies an SM and nothing synchronises on the host. Every rank makes the same calls in the same order:
+ *   create -> handle -> (all-gather the 64-byte handles by any means) -> connect, then per step
+ *   state_slot -> flan_b200_phase_summary into it -> put_state -> get_states -> flan_b200_phase_carry -> release_states ->
+ *   flan_b200_convert_to_audio_range_head -> put_halo (ranks > 0) -> add_halo (ranks < world - 1).
+ * halo_samples: samples per channel of the largest halo (window - hop). Single-process callers use flan_b200_multi_*. */
+#define FLAN_B200_IPC_HANDLE_BYTES 64
+typedef struct flan_b200_exchange flan_b200_exchange;
+int flan_b200_exchange_create( flan_b200_ctx * ctx, int rank, int world, int channels, int bins, int64_t halo_samples, flan_b200_exchange ** out );
+void flan_b200_exchange_destroy( flan_b200_exchange * ex );
+int flan_b200_exchange_handle( flan_b200_exchange * ex, void * handle64 );
+int flan_b200_exchange_connect( flan_b200_exchange * ex, const void * handles /* world x 64 bytes, by rank */ );
+/* where the next step's flan_b200_phase_summary should write this rank's state (pushed from there without a staging copy) */
+int flan_b200_exchange_state_slot( flan_b200_exchange * ex, flan_b200_phase_state ** d_slot );
+int flan_b200_exchange_put_state( flan_b200_exchange * ex, const flan_b200_phase_state * d_state );
+int flan_b200_exchange_get_states( flan_b200_exchange * ex, const flan_b200_phase_state ** d_states /* [rank][channels][bins] */ );
+int flan_b200_exchange_release_states( flan_b200_exchange * ex );
+int flan_b200_exchange_put_halo( flan_b200_exchange * ex, const float * d_head, int64_t pitch, int channels, int64_t n, void * after_event );
+int flan_b200_exchange_add_halo( flan_b200_exchange * ex, float * d_out, int64_t pitch, int channels, int64_t n );
+
 /* d_out[i] += d_add[i], i < n (overlap-add halo received from a neighbour). */
 int flan_b200_add( flan_b200_ctx * ctx, float * d_out, const float * d_add, int64_t n );
 

@@ -215,3 +215,39 @@ def test_head_first_range_resynthesis_is_bit_identical(eng, oracle):
     torch.cuda.synchronize()
     assert torch.equal(plain, head_first)
     assert torch.equal(head, plain[:, h_lo - lo:h_hi - lo])
+
+
+def test_range_after_summary_only_rewalks_the_scan_bit_identical(eng):
+    """A range call that follows flan_b200_phase_summary on the same rows (reuse_summary) skips the phase summary AND the
+    first two scan phases: the carry enters at the re-walk (carry (+) carry-free prefix; exact and associative). More
+    than 256 segments per shard so that the three-launch scan is the one that runs; head-first form included."""
+    import torch
+    from flan_b200.sharding import frame_shard
+    sr, W, h, N = 48000.0, 1024, 64, 1024
+    n = int(sr * 75)
+    x = np.stack([noise_chirp(n, sr, 77)])
+    xd = torch.from_numpy(x).cuda()
+    pv = eng.convert_to_pv(xd, sr, W, h, N)
+    ar = eng.analysis_rate(sr, h)
+    full = eng.convert_to_audio(pv, sr, ar, W)
+    shards = [frame_shard(n, h, W, 3, r) for r in range(3)]
+    rows = [pv[:, s.f0:s.f1].contiguous() for s in shards]
+    states = torch.stack([eng.phase_summary(r, s.f0, sr, ar, W) for r, s in zip(rows, shards)])
+    total = torch.zeros_like(full)
+    ev = torch.cuda.Event()
+    ev.record()
+    for s, r in zip(shards, rows):
+        carry = eng.phase_carry(states, s.rank)
+        plain = eng.convert_to_audio_range(r, s.f0, s.frames_total, sr, ar, W, carry, s.span_lo, s.span_hi - s.span_lo)
+        eng.phase_summary(r, s.f0, sr, ar, W)
+        launches = eng.launch_count()
+        reused = eng.convert_to_audio_range(r, s.f0, s.frames_total, sr, ar, W, carry, s.span_lo, s.span_hi - s.span_lo,
+                                            reuse_summary=True)
+        assert eng.launch_count() - launches == 3, "re-walk, output clear, transform"
+        assert torch.equal(plain, reused)
+        eng.phase_summary(r, s.f0, sr, ar, W)
+        head = eng.convert_to_audio_range_head(r, s.f0, s.frames_total, sr, ar, W, carry, s.span_lo, s.span_hi - s.span_lo, ev,
+                                               reuse_summary=True)
+        assert torch.equal(plain, head)
+        total[:, s.span_lo:s.span_hi] += plain
+    assert (total - full).abs().max().item() <= 2e-6
