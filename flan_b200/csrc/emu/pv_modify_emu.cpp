@@ -136,12 +136,17 @@ int64_t pv_emu_stretch( const float * pv, int C, int64_t F, int B, float sr, flo
 	if( a.chunks < 1 ) a.chunks = 1;
 	if( !descends && !force_sequential && bs == 0 )
 		{
-		std::vector<int> xpos( F ); std::vector<float> mix( out_frames );
-		StretchPlan plan{ xpos.data(), mix.data() };
+		// as on the device: plan, then the gather by segments of output frames (`chunk` doubles as the segment length here,
+		// so the tests cut segments inside pairs, at pair boundaries and beyond the covered range)
+		std::vector<int> xpos( F ); std::vector<float> mix( out_frames ); std::vector<int> src( out_frames, -1 );
+		StretchPlan plan{ xpos.data(), mix.data(), src.data() };
 		for( int64_t f = F - 1; f >= 0; --f ) stretch_plan_frame( a, plan, f );
+		const int seg_len = chunk;
+		const int64_t segs = ( out_frames + seg_len - 1 ) / seg_len;
+		pvk::PvConsts k{};
 		for( int c = C - 1; c >= 0; --c )
-			for( int64_t k = a.chunks - 1; k >= 0; --k )
-				for( int b = B - 1; b >= 0; --b ) stretch_chunk_planned( a, plan, c, k, b );
+			for( int64_t sgm = segs - 1; sgm >= 0; --sgm )
+				for( int b = B - 1; b >= 0; --b ) stretch_segment_planned<false>( a, plan, c, sgm, seg_len, b, nullptr, k );
 		}
 	else if( !descends && !force_sequential )
 		{

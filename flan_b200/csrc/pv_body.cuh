@@ -485,14 +485,7 @@ template<class Ld>
 PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, int64_t rows, const PvConsts & k,
                                       double P, double rcpP, int & flag, Ld && ld )
 	{
-	double sum = 0.0, mx = 0.0;
-	bool bad = false;
-	auto step = [&]( float2 mf )
-		{
-		bad = bad || !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f );
-		sum += (double) phase_increment( mf.y, k );
-		mx = ( sum > mx ) ? sum : mx;
-		};
+	PhaseSegAcc acc;
 	int64_t i = 0;
 	for( ; i + 8 <= rows; i += 8 )          // eight independent row loads in flight per thread
 		{
@@ -500,14 +493,11 @@ PV_HD PhaseSeg phase_segment_summary( const float2 * col, int64_t row_stride, in
 #pragma unroll
 		for( int j = 0; j < 8; ++j ) mf[j] = ld( col + ( i + j ) * row_stride );
 #pragma unroll
-		for( int j = 0; j < 8; ++j ) step( mf[j] );
+		for( int j = 0; j < 8; ++j ) acc.step( mf[j], k );
 		}
-	for( ; i < rows; ++i ) step( ld( col + i * row_stride ) );
-	if( bad ) flag = 1;
-	PhaseSeg s;
-	phase_sum_from_double( sum, P, rcpP, s.sum.q, s.sum.r );
-	phase_sum_from_double( mx, P, rcpP, s.mx.q, s.mx.r );
-	return s;
+	for( ; i < rows; ++i ) acc.step( ld( col + i * row_stride ), k );
+	if( acc.bad ) flag = 1;
+	return acc.finish( P, rcpP );
 	}
 
 // state <- state (+) seg : running (sum, max prefix) over segments in frame order.

@@ -450,6 +450,35 @@ int64_t ctas_per_slice( int64_t ctas, int64_t wave, size_t copy_bytes )
 	return ( ( waves + n - 1 ) / n ) * wave;
 	}
 
+PhaseLayout phase_layout( const flan_b200_ctx * ctx, int C, int64_t frames, int B, int W, int hop, int seg_len_given )
+	{
+	PhaseLayout l{};
+	const int N = ( B - 1 ) * 2;
+	int seg_len = seg_len_given ? seg_len_given : choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ) );
+	if( seg_len > frames ) seg_len = (int) frames;
+	if( seg_len < 1 ) seg_len = 1;
+	l.seg_len = seg_len;
+	l.segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	l.seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * l.segs * B, 256 );
+	l.acc_bytes = align_up( sizeof( double ) * (size_t) C * l.segs * B, 256 );
+	l.group_len = 32;
+	while( ( l.segs + l.group_len - 1 ) / l.group_len > 65535 ) l.group_len *= 2;
+	l.groups = ( l.segs + l.group_len - 1 ) / l.group_len;
+	l.grp_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * l.groups * B, 256 );
+	return l;
+	}
+
+// The promise of flan_b200_promise_unchanged, per calling thread: the next whole-signal resynthesis of exactly this
+// buffer may use the phase summaries its producer left in the workspace.
+static thread_local const void * g_promised_pv = nullptr;
+void promise_unchanged( const void * d_pv ) { g_promised_pv = d_pv; }
+bool take_promise( const void * d_pv )
+	{
+	const bool hit = d_pv && g_promised_pv == d_pv;
+	g_promised_pv = nullptr;
+	return hit;
+	}
+
 int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	{
 	const int C = s.C, B = s.B, W = s.W;
@@ -466,15 +495,9 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 
 	// s.seg_len: the multi-device forms pass the segment length of the WHOLE signal and cut their shards at multiples of
 	// it, so that a shard walks exactly the segments the uncut signal would and gives the same bits
-	int seg_len = s.seg_len ? s.seg_len : choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ) );
-	if( seg_len > frames ) seg_len = (int) frames;
-	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
-	const size_t seg_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * segs * B, 256 );
-	const size_t acc_bytes = align_up( sizeof( double ) * (size_t) C * segs * B, 256 );
-	int group_len = 32;
-	while( ( segs + group_len - 1 ) / group_len > 65535 ) group_len *= 2;
-	const int groups = ( segs + group_len - 1 ) / group_len;
-	const size_t grp_bytes = align_up( sizeof( PhaseSeg ) * (size_t) C * groups * B, 256 );
+	const PhaseLayout lay = phase_layout( ctx, C, frames, B, W, hop, s.seg_len );
+	const int seg_len = lay.seg_len, segs = lay.segs, group_len = lay.group_len, groups = lay.groups;
+	const size_t seg_bytes = lay.seg_bytes, acc_bytes = lay.acc_bytes, grp_bytes = lay.grp_bytes;
 	GenericSynthArgs ga{};
 	GenericGeometry geo{};
 	if( plan->generic )       // the per-CTA slabs of the run-time-sized transform go behind the phase scratch
@@ -495,9 +518,10 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	key.pv = s.d_pv_rows; key.stride = s.pv_channel_stride; key.fb = s.frame_begin; key.fe = s.frame_end;
 	key.C = C; key.B = B; key.W = W; key.seg_len = seg_len; key.sr = fbits( s.sr ); key.ar = fbits( s.ar ); key.valid = true;
 	const flan_b200_ctx::SegKey & old = ctx->seg_key;
-	const bool have_summaries = s.reuse_summary && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
+	// summaries whose NaN / Inf flag is gone cannot serve a caller that asks for the flag
+	const bool have_summaries = s.reuse_summary && ( !s.d_nan_flag || old.nan_known ) && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
 	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.seg_len == key.seg_len && old.sr == key.sr && old.ar == key.ar;
-	const bool old_group_prefix = old.group_prefix;
+	const bool old_group_prefix = old.group_prefix, old_nan_known = old.nan_known;
 	ctx->seg_key = key;
 
 	PhaseSegArgs sa{};
@@ -507,6 +531,11 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sa.seg_out = d_seg; sa.nan_flag = s.d_nan_flag ? s.d_nan_flag : ctx->d_flags + flan_b200_ctx::FLAG_SLOTS;   // last slot + 1: write-only scratch
 	sa.k = plan->host.k; sa.P = plan->host.P; sa.rcpP = plan->host.rcpP;
 	if( !have_summaries ) { LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->compute ), "phase summary launch" ); }
+	else
+		{
+		ctx->seg_key.nan_known = old_nan_known;
+		if( s.d_nan_flag ) CK( cudaMemcpyAsync( s.d_nan_flag, ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1, sizeof( int ), cudaMemcpyDeviceToDevice, ctx->compute ), "flag copy" );
+		}
 
 	PhaseScanArgs sc{};
 	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
@@ -691,8 +720,8 @@ int flan_b200_create( int device, flan_b200_ctx ** out )
 	if( const char * v = std::getenv( "FLAN_B200_SYNTH_VARIANT" ) ) ctx->synth_variant = std::atoi( v );
 #endif
 	ctx->sms = prop.multiProcessorCount;
-	e = cudaMalloc( (void **) &ctx->d_flags, sizeof( int ) * ( flan_b200_ctx::FLAG_SLOTS + 1 ) );
-	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flags, 0, sizeof( int ) * ( flan_b200_ctx::FLAG_SLOTS + 1 ) );
+	e = cudaMalloc( (void **) &ctx->d_flags, sizeof( int ) * ( flan_b200_ctx::FLAG_SLOTS + 2 ) );
+	if( e == cudaSuccess ) e = cudaMemset( ctx->d_flags, 0, sizeof( int ) * ( flan_b200_ctx::FLAG_SLOTS + 2 ) );
 	if( e == cudaSuccess ) e = cudaMallocHost( (void **) &ctx->h_flags, sizeof( int ) * flan_b200_ctx::FLAG_SLOTS );
 	if( e == cudaSuccess ) std::memset( ctx->h_flags, 0, sizeof( int ) * flan_b200_ctx::FLAG_SLOTS );
 	if( e == cudaSuccess ) e = cudaMalloc( (void **) &ctx->d_check, sizeof( pvm::MapCheck ) );
@@ -988,6 +1017,7 @@ int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int C, 
 		st = ctx->compute;
 		SynthCall s{ d_pv, F * B, C, 0, F, F, B, sr, ar, W };
 		s.d_out = d_audio_out; s.out_stride = out_n; s.out_offset = 0; s.out_len = out_n; s.cancel = cancel;
+		s.reuse_summary = take_promise( d_pv );
 		int * d_flag = nullptr;
 		if( nan_or_inf )
 			{
@@ -1001,6 +1031,13 @@ int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int C, 
 		}
 	if( nan_or_inf ) CK( cudaStreamSynchronize( st ), "flag sync" );
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_promise_unchanged( flan_b200_ctx * ctx, const float * d_pv )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	promise_unchanged( d_pv );
 	return FLAN_B200_OK;
 	}
 
@@ -1174,6 +1211,7 @@ int flan_b200_convert_to_audio_d2h( flan_b200_ctx * ctx, const float * d_pv, int
 	if( rc ) return rc;
 	SynthCall s{ d_pv, F * B, C, 0, F, F, B, sr, ar, W };
 	s.d_out = d_audio_out; s.out_stride = out_n; s.out_offset = 0; s.out_len = out_n; s.cancel = cancel;
+	s.reuse_summary = take_promise( d_pv );
 	const int slot = (int)( ctx->flag_next++ % flan_b200_ctx::FLAG_SLOTS );
 	CK( cudaMemsetAsync( ctx->d_flags + slot, 0, sizeof( int ), ctx->compute ), "flag clear" );
 	s.d_nan_flag = ctx->d_flags + slot;

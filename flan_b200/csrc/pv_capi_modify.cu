@@ -155,7 +155,7 @@ int flan_b200_modify_time_frames( flan_b200_ctx * ctx, const float * d_map, int6
 
 int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int C, int64_t F, int B, float sr, float ar,
                            const float * d_map, int64_t map_frame_stride, int map_bin_stride,
-                           int interp, int64_t out_frames, float * d_pv_out )
+                           int interp, int64_t out_frames, float * d_pv_out, int summary_window )
 	{
 	if( !ctx || !d_pv || !d_map ) return FLAN_B200_INVALID;
 	CallLock lock( ctx );
@@ -187,15 +187,39 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int C, int64
 	if( a.chunks < 1 ) a.chunks = 1;
 	if( !descends && map_bin_stride == 0 && F < 0x7fffffff && out_frames < 0x7fffffff )
 		{
-		// one geometry for every bin: plan it once, then only the per-bin arithmetic remains
+		// one geometry for every bin: plan it once, then only the per-bin arithmetic remains -- as a gather by segments of
+		// output frames, in the order resynthesis accumulates phase, so that with summary_window > 0 the kernel also leaves
+		// the phase summaries of its output where flan_b200_convert_to_audio looks for them (flan_b200_promise_unchanged)
+		const int W = summary_window > 0 ? summary_window : ( B - 1 ) * 2;
+		const PhaseLayout lay = phase_layout( ctx, C, out_frames, B, W, hop, 0 );
+		DevicePlan * dp = nullptr;
+		if( summary_window > 0 ) { rc = get_plan( ctx, ( B - 1 ) * 2, W, hop, sr, ar, &dp ); if( rc ) return rc; }
 		void * ws = nullptr;
-		const size_t xpos_bytes = align_up( sizeof( int ) * (size_t) F, 256 );
-		rc = get_workspace( ctx, xpos_bytes + sizeof( float ) * (size_t) out_frames, &ws );
+		const size_t xpos_bytes = align_up( sizeof( int ) * (size_t) F, 256 ), mix_bytes = align_up( sizeof( float ) * (size_t) out_frames, 256 );
+		const size_t phase_bytes = summary_window > 0 ? lay.bytes() : 0;
+		rc = get_workspace( ctx, phase_bytes + xpos_bytes + mix_bytes + sizeof( int ) * (size_t) out_frames, &ws );
 		if( rc ) return rc;
 		ctx->seg_key.valid = false;
-		pvm::StretchPlan plan{ (int *) ws, (float *)( (char *) ws + xpos_bytes ) };
-		{ LaunchTimer lt( ctx, 7 ); CK( pvm::launch_stretch_plan( a, plan, ctx->compute ), "stretch plan launch" ); }
-		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_planned( a, plan, C, ctx->compute ), "stretch launch" ); }
+		char * base = (char *) ws + phase_bytes;
+		pvm::StretchPlan plan{ (int *) base, (float *)( base + xpos_bytes ), (int *)( base + xpos_bytes + mix_bytes ) };
+		pvm::StretchSummary summ{};
+		summ.seg_len = lay.seg_len; summ.segs_per_channel = lay.segs;
+		if( summary_window > 0 )
+			{
+			summ.seg_out = (pvk::PhaseSeg *) ws;
+			summ.nan_flag = ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1;
+			summ.k = dp->host.k; summ.P = dp->host.P; summ.rcpP = dp->host.rcpP;
+			CK( cudaMemsetAsync( summ.nan_flag, 0, sizeof( int ), ctx->compute ), "flag clear" );
+			}
+		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_planned( a, plan, summ, C, ctx->compute ), "stretch launch" ); ctx->launches++; }
+		if( summary_window > 0 )
+			{
+			flan_b200_ctx::SegKey key;
+			key.pv = d_pv_out; key.stride = out_frames * B; key.fb = 0; key.fe = out_frames;
+			key.C = C; key.B = B; key.W = W; key.seg_len = lay.seg_len; key.sr = fbits( sr ); key.ar = fbits( ar );
+			key.valid = true; key.nan_known = true;
+			ctx->seg_key = key;
+			}
 		}
 	else if( !descends )
 		{ LaunchTimer lt( ctx, 6 ); CK( pvm::launch_stretch_parallel( a, C, ctx->compute ), "stretch launch" ); }

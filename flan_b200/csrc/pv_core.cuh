@@ -631,4 +631,50 @@ PV_HD bool phase_sum_less( const PhaseSum & a, const PhaseSum & b )
 
 struct PhaseSeg { PhaseSum sum, mx; };   // total and max prefix (the empty prefix counts as 0)
 
+// Summary of one bin over the frames of a segment, fed in frame order: total phase increment and its max prefix. Within
+// a segment (a few thousand radians at most) the running sum is a plain double -- absolute error ~1e-12 rad -- and only
+// the two results are converted to the split form. `bad` is the is_nan_or_inf() pre-scan of AudioPV.cpp:88. Used by
+// pv_phase_seg_kernel and by every kernel that PRODUCES PV rows in frame order per bin and leaves their summary behind
+// (pv_stretch_planned_kernel), so that both give the same bits.
+// (double) x, exactly. On the device the conversion instruction runs on the 16-lane XU pipe, which the kernels that
+// produce PV rows already keep busy (IEEE division, MUFU): normal numbers are widened with integer operations instead
+// (exponent rebias + mantissa shift); zero, denormals, Inf and NaN take the instruction.
+PV_HD double float_to_double( float x )
+	{
+#if defined(__CUDA_ARCH__)
+	const unsigned u = __float_as_uint( x );
+	const unsigned a = u & 0x7fffffffu;
+	if( a - 0x00800000u < 0x7f000000u )
+		return __hiloint2double( (int)( ( u & 0x80000000u ) | ( ( a >> 3 ) + 0x38000000u ) ), (int)( a << 29 ) );
+	return (double) x;
+#else
+	return (double) x;
+#endif
+	}
+
+struct PhaseSegAcc
+	{
+	double sum = 0.0, mx = 0.0;
+	bool bad = false;
+	// The running maximum only has to be taken where a non-decreasing run of prefix sums ends: right before an increment
+	// that is not >= 0 (negative or NaN) and at the end. ALU: widen the increment with integer operations (kernels whose XU
+	// pipe is the busy one); pv_phase_seg_kernel, which waits for HBM, keeps the conversion instruction.
+	template<bool ALU = false>
+	PV_HD void step( float2 mf, const PvConsts & k )
+		{
+		bad = bad || !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f );
+		const float inc = phase_increment( mf.y, k );
+		if( !( inc >= 0.0f ) ) mx = ( sum > mx ) ? sum : mx;
+		sum += ALU ? float_to_double( inc ) : (double) inc;
+		}
+	PV_HD PhaseSeg finish( double P, double rcpP ) const
+		{
+		const double m = ( sum > mx ) ? sum : mx;
+		PhaseSeg s;
+		phase_sum_from_double( sum, P, rcpP, s.sum.q, s.sum.r );
+		phase_sum_from_double( m, P, rcpP, s.mx.q, s.mx.r );
+		return s;
+		}
+	};
+
 } // namespace pvk

@@ -128,6 +128,7 @@ struct flan_b200_ctx
 	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
 	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0, seg_len = 0; uint32_t sr = 0, ar = 0; bool valid = false;
 	                bool group_prefix = false;   // the scan scratch holds the carry-free group prefixes of these summaries
+	                bool nan_known = false;      // d_flags[FLAG_SLOTS + 1] holds the NaN / Inf pre-scan result of these rows (a producing kernel left it)
 	              } seg_key;
 	int max_seg_len = 0;                    // frames per CTA at most; 0 = by size (FLAN_B200_DEBUG builds: FLAN_B200_SEG_LEN)
 #ifdef FLAN_B200_DEBUG
@@ -252,6 +253,13 @@ struct SynthCall
 	cudaEvent_t head_event = nullptr;
 	};
 int synth_range( flan_b200_ctx * ctx, const SynthCall & s );
+// Where synth_range keeps the phase scratch of a signal in the workspace: summaries [C][segs][B] at offset 0, then the
+// accumulators entering each segment, then the scan's group states. A kernel that produces PV rows and leaves their
+// summaries behind (flan_b200_modify_time) writes them there and sets ctx->seg_key.
+struct PhaseLayout { int seg_len, segs, group_len, groups; size_t seg_bytes, acc_bytes, grp_bytes; size_t bytes() const { return seg_bytes + acc_bytes + grp_bytes; } };
+PhaseLayout phase_layout( const flan_b200_ctx * ctx, int C, int64_t frames, int B, int W, int hop, int seg_len_given );
+void promise_unchanged( const void * d_pv );
+bool take_promise( const void * d_pv );
 // Slices of whole waves: CTAs per slice for `ctas` CTAs of a kernel with `wave` resident CTAs on the device.
 int64_t ctas_per_slice( int64_t ctas, int64_t wave, size_t copy_bytes );
 

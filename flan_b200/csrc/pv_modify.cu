@@ -200,13 +200,22 @@ __global__ void pv_stretch_plan_kernel( const StretchArgs a, const StretchPlan p
 	if( f < a.F ) stretch_plan_frame( a, plan, f );
 	}
 
-__global__ void __launch_bounds__( 128 ) pv_stretch_planned_kernel( const StretchArgs a, const StretchPlan plan, int bin_tiles )
+// thread = (channel, segment of seg_len OUTPUT frames, bin); summ.seg_out != null: also the segment's phase summary, laid
+// out like pv_phase_seg_kernel's ([C][segs][B]), and the NaN / Inf flag of AudioPV.cpp:88
+template<bool SUMM>
+__global__ void __launch_bounds__( 128 ) pv_stretch_planned_kernel( const StretchArgs a, const StretchPlan plan, const StretchSummary summ, int bin_tiles )
 	{
 	const int64_t blk = blockIdx.x;
 	const int bin = (int)( blk % bin_tiles ) * 128 + threadIdx.x;
-	const int64_t chunk_index = blk / bin_tiles;
+	const int64_t seg = blk / bin_tiles;
 	if( bin >= a.B ) return;
-	stretch_chunk_planned( a, plan, blockIdx.y, chunk_index, bin );
+	pvk::PhaseSegAcc acc;
+	stretch_segment_planned<SUMM>( a, plan, blockIdx.y, seg, summ.seg_len, bin, &acc, summ.k );
+	if( SUMM )
+		{
+		summ.seg_out[( (int64_t) blockIdx.y * summ.segs_per_channel + seg ) * a.B + bin] = acc.finish( summ.P, summ.rcpP );
+		if( acc.bad ) *summ.nan_flag = 1;
+		}
 	}
 
 bool repitch_shared_supported( int B ) { return B <= REPITCH_J * 1024; }
@@ -239,18 +248,16 @@ cudaError_t launch_repitch_shared( const RepitchArgs & a, const RepitchPlan & pl
 	return launch_repitch_shared_t<1024>( a, plan, hz, rows, sms, st );
 	}
 
-cudaError_t launch_stretch_plan( const StretchArgs & a, const StretchPlan & plan, cudaStream_t st )
-	{
-	pv_stretch_plan_kernel<<<(unsigned)( ( a.F + 127 ) / 128 ), 128, 0, st>>>( a, plan );
-	return cudaGetLastError();
-	}
-
-cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, int C, cudaStream_t st )
+cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, const StretchSummary & summ, int C, cudaStream_t st )
 	{
 	const int bin_tiles = ( a.B + 127 ) / 128;
-	const int64_t blocks = a.chunks * bin_tiles;
-	if( blocks > 0x7fffffff ) return cudaErrorInvalidValue;
-	pv_stretch_planned_kernel<<<dim3( (unsigned) blocks, C ), 128, 0, st>>>( a, plan, bin_tiles );
+	const int64_t blocks = (int64_t) summ.segs_per_channel * bin_tiles;
+	if( blocks > 0x7fffffff || summ.seg_len < 1 ) return cudaErrorInvalidValue;
+	cudaError_t e = cudaMemsetAsync( plan.src, 0xff, sizeof( int ) * (size_t) a.out_frames, st );      // -1: no pair covers the frame
+	if( e != cudaSuccess ) return e;
+	pv_stretch_plan_kernel<<<(unsigned)( ( a.F + 127 ) / 128 ), 128, 0, st>>>( a, plan );
+	if( summ.seg_out ) pv_stretch_planned_kernel<true><<<dim3( (unsigned) blocks, C ), 128, 0, st>>>( a, plan, summ, bin_tiles );
+	else pv_stretch_planned_kernel<false><<<dim3( (unsigned) blocks, C ), 128, 0, st>>>( a, plan, summ, bin_tiles );
 	return cudaGetLastError();
 	}
 

@@ -21,8 +21,16 @@ cudaError_t launch_repitch( const RepitchArgs & a, int64_t rows, const int * ski
 bool repitch_shared_supported( int B );
 cudaError_t launch_repitch_plan( const float * hz, int B, float bin_width, int interp, const RepitchPlan & plan, cudaStream_t st );
 cudaError_t launch_repitch_shared( const RepitchArgs & a, const RepitchPlan & plan, const float * hz, int64_t rows, int sms, cudaStream_t st );
-cudaError_t launch_stretch_plan( const StretchArgs & a, const StretchPlan & plan, cudaStream_t st );
-cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, int C, cudaStream_t st );
+// Bin-shared time map: plan (src preset, xpos, mix) + the gather by output segments of summ.seg_len frames. With
+// summ.seg_out set the kernel also leaves the phase summaries of its output rows (what pv_phase_seg_kernel would compute).
+struct StretchSummary
+	{
+	int seg_len; int segs_per_channel;      // output frames per thread, ceil( out_frames / seg_len )
+	pvk::PhaseSeg * seg_out;                // [C][segs_per_channel][B] or null
+	int * nan_flag;
+	pvk::PvConsts k; double P, rcpP;
+	};
+cudaError_t launch_stretch_planned( const StretchArgs & a, const StretchPlan & plan, const StretchSummary & summ, int C, cudaStream_t st );
 cudaError_t launch_stretch_parallel( const StretchArgs & a, int C, cudaStream_t st );
 cudaError_t launch_stretch_sequential( const StretchArgs & a, int C, cudaStream_t st );
 

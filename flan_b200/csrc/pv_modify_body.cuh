@@ -23,6 +23,8 @@
 #include <cstdint>
 #include <cmath>
 
+#include "pv_core.cuh"      // PhaseSegAcc: the phase summary a producing kernel leaves behind for PV::convert_to_audio
+
 #if defined( __CUDACC__ )
 #include <cuda_runtime.h>
 #define PVM_HD __host__ __device__ __forceinline__
@@ -535,6 +537,7 @@ struct StretchPlan
 	{
 	int * xpos;                 // [F]
 	float * mix;                // [out_frames]
+	int * src;                  // [out_frames] the frame f whose pair (f-1, f) covers the output frame; -1 (preset) where none does
 	};
 
 PVM_HD void stretch_plan_frame( const StretchArgs & a, const StretchPlan & plan, int64_t f )
@@ -549,7 +552,95 @@ PVM_HD void stretch_plan_frame( const StretchArgs & a, const StretchPlan & plan,
 	int64_t xs = to_int( ceilf( lFrame ) );
 	xs = xs < 0 ? 0 : xs;
 	const float den = pos - lFrame;
-	for( ; xs < x; ++xs ) plan.mix[xs] = interp_eval( a.interp, ( (float) xs - lFrame ) / den );
+	for( ; xs < x; ++xs ) { plan.mix[xs] = interp_eval( a.interp, ( (float) xs - lFrame ) / den ); plan.src[xs] = (int) f; }
+	}
+
+// The same arithmetic by OUTPUT segments: thread = (channel, run of seg_len output frames, bin) gathers its frames in
+// increasing order -- the order in which PV::convert_to_audio accumulates the phase of a bin (phase_vocoder.cpp:57-59)
+// -- so it can leave the segment's phase summary behind (summary != null) and resynthesis need not read the rows again.
+// A segment that begins inside a pair first re-evaluates whether an earlier frame of the pair ended it
+// (`return` at PVModify.cpp:351-352).
+template<bool SUMM>
+PVM_HD void stretch_segment_planned( const StretchArgs & a, const StretchPlan & plan, int c, int64_t seg, int seg_len, int bin,
+                                     pvk::PhaseSegAcc * summary, const pvk::PvConsts & k )
+	{
+	const float2 * in = a.pv + (int64_t) c * a.F * a.B + bin;
+	const int64_t B = a.B;
+	int x = (int)( seg * seg_len );                                     // the planned form runs below 2^31 frames
+	int x1 = x + seg_len;
+	if( (int64_t) x1 > a.out_frames ) x1 = (int) a.out_frames;
+	float2 * o = a.out + ( (int64_t) c * a.out_frames + x ) * B + bin;  // the output cell of frame x
+	const float2 zero = make_float2( 0.0f, 0.0f );
+	// The pairs cover [xpos[0], xpos[F-1]) without gaps (the map never descends): zeros below, pairs f_lo .. f_hi, zeros above.
+	int c0 = plan.xpos[0], c1 = plan.xpos[a.F - 1];
+	if( c0 > x1 ) c0 = x1;
+	if( c1 > x1 ) c1 = x1;
+	if( c1 < x ) c1 = x;
+	for( ; x < c0; ++x, o += B ) { *o = zero; if( SUMM ) summary->step<true>( zero, k ); }
+	if( x < c1 )
+		{
+		const int f_lo = plan.src[x], f_hi = plan.src[c1 - 1];
+		const float2 * row = in + (int64_t) f_lo * B;                   // right frame of the current pair
+		float2 l = *( row - B );
+		bool live = true;
+		// a segment that begins inside a pair: did an earlier frame of the pair end it (PVModify.cpp:351-352)?
+		const int z0 = plan.xpos[f_lo - 1];
+		if( z0 < x )
+			{
+			const float2 r = *row;
+			for( int z = z0; z < x && live; ++z )
+				{
+				const float mix = plan.mix[z];
+				const float w0 = ( 1.0f - mix ) * l.x;
+				const float w1 = mix * r.x;
+				if( w0 + w1 == 0.0f ) live = false;
+				}
+			}
+		constexpr int BATCH = SUMM ? 4 : 8;
+		const int * xp = plan.xpos + f_lo;
+		const float * mixp = plan.mix + x;
+		for( int f = f_lo; f <= f_hi; f += BATCH, xp += BATCH )
+			{
+			float2 r[BATCH]; int xe[BATCH];
+#pragma unroll
+			for( int j = 0; j < BATCH; ++j )
+				if( f + j <= f_hi )
+					{
+					r[j] = row[(int64_t) j * B];
+					xe[j] = xp[j];
+					}
+			row += (int64_t) BATCH * B;
+#pragma unroll
+			for( int j = 0; j < BATCH; ++j )
+				if( f + j <= f_hi )
+					{
+					const int xend = xe[j] < c1 ? xe[j] : c1;
+					for( ; x < xend; ++x, o += B, ++mixp )
+						{
+						float2 nw = zero;
+						if( live )
+							{
+							const float mix = *mixp;
+							const float w0 = ( 1.0f - mix ) * l.x;
+							const float w1 = mix * r[j].x;
+							const float totalWeight = w0 + w1;
+							const float weightedFreqSum = w0 * l.y + w1 * r[j].y;
+							if( totalWeight == 0.0f ) live = false;
+							else
+								{
+								nw.y = ( 0.0f * 0.0f + weightedFreqSum ) / ( 0.0f + totalWeight );
+								nw.x = 0.0f + totalWeight;
+								}
+							}
+						*o = nw;
+						if( SUMM ) summary->step<true>( nw, k );
+						}
+					l = r[j];
+					live = true;
+					}
+			}
+		}
+	for( ; x < x1; ++x, o += B ) { *o = zero; if( SUMM ) summary->step<true>( zero, k ); }
 	}
 
 PVM_HD void stretch_chunk_planned( const StretchArgs & a, const StretchPlan & plan, int c, int64_t chunk_index, int bin )

@@ -81,13 +81,17 @@ class Engine:
         return out
 
     # -- PV::convert_to_audio --------------------------------------------------------------------
-    def convert_to_audio(self, pv, sr, ar, W, out=None, check_nan=False):
+    def convert_to_audio(self, pv, sr, ar, W, out=None, check_nan=False, unchanged=False):
+        """unchanged: pv has not been written since the call that produced it (flan_b200_promise_unchanged): phase
+        summaries that call left behind, if any, are used instead of a second read of the rows."""
         C, F, B, _ = pv.shape
         hop = self.hop_from_rates(sr, ar)
         if out is None:
             out = torch.empty((C, F * hop), dtype=torch.float32, device=self.device)
         flag = ctypes.c_int(0)
         self._bind_stream()
+        if unchanged:
+            self.ctx.call("flan_b200_promise_unchanged", self._chk(pv))
         self.ctx.call("flan_b200_convert_to_audio", self._chk(pv), C, F, B, sr, ar, W, self._chk(out), None,
                       ctypes.byref(flag) if check_nan else None)
         return (out, bool(flag.value)) if check_nan else out
@@ -198,7 +202,7 @@ class Engine:
         self.ctx.call("flan_b200_stretch_map", tp, fs, bs, F, B, sr, ar, self._chk(out))
         return out
 
-    def modify_time(self, pv, sr, ar, seconds, interp=0):
+    def modify_time(self, pv, sr, ar, seconds, interp=0, summary_window=0):
         C, F, B, _ = pv.shape
         t, tp, fs, bs = self._table(seconds, F, B)
         frames = ctypes.c_int64(0)
@@ -207,12 +211,14 @@ class Engine:
         n = max(int(frames.value), 0)
         out = torch.empty((C, n, B, 2), dtype=torch.float32, device=self.device)
         self.ctx.call("flan_b200_modify_time", self._chk(pv), C, F, B, sr, ar, tp, fs, bs, interp, frames.value,
-                      self._chk(out) if n else None)
+                      self._chk(out) if n else None, summary_window)
         return out
 
-    def stretch(self, pv, sr, ar, factor, interp=0):
+    def stretch(self, pv, sr, ar, factor, interp=0, summary_window=0):
+        """summary_window: the PV's window size; the kernel then also leaves the phase summaries of its output behind, and
+        convert_to_audio(..., unchanged=True) right after it skips the second read of the rows."""
         C, F, B, _ = pv.shape
-        return self.modify_time(pv, sr, ar, self.stretch_map(F, B, sr, ar, factor), interp)
+        return self.modify_time(pv, sr, ar, self.stretch_map(F, B, sr, ar, factor), interp, summary_window)
 
     # -- file formats either side of the path (PVBuffer::save / load, AudioBuffer::save / load) -----------------
     def flan_encode(self, pv, sr):

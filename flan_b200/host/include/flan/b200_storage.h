@@ -92,6 +92,10 @@ public:
 	bool host_is_current() const { return host_valid_.load( std::memory_order_acquire ); }
 	const T * host_data_if_current() const { return host_is_current() ? host_.data() : nullptr; }
 
+	// The device copy is still exactly what the call that produced it wrote (never re-uploaded from the host): phase
+	// summaries that call left in the engine (flan_b200_modify_time) describe it (flan_b200_promise_unchanged).
+	bool device_untouched() const { return produced_on_device_ && uploads_ == 0 && device_valid_.load( std::memory_order_acquire ); }
+
 	Mirror deep_copy() const;
 
 private:
@@ -113,6 +117,7 @@ private:
 	mutable bool download_in_flight_ = false;  // the producer started an asynchronous copy into host_
 	mutable bool upload_in_flight_ = false;    // an asynchronous copy out of (page-locked) host_ may still be running
 	mutable int uploads_ = 0;
+	bool produced_on_device_ = false;
 	mutable const volatile int * nan_flag_ = nullptr;
 	};
 

@@ -192,6 +192,8 @@ Audio PV::convert_to_audio( flan_CANCEL_ARG_CPP ) const
 	// When a recycled page-locked vector is at hand, the engine also copies the samples to the host slice by slice behind
 	// the transform, so a later get_buffer() only waits for the tail of that copy.
 	int rc;
+	// rows that are still exactly what their producer wrote: phase summaries it left behind (PV::stretch) are used
+	if( storage().device_untouched() ) flan_b200_promise_unchanged( ctx, reinterpret_cast<const float *>( d_pv ) );
 	if( h_audio )
 		{
 		const volatile int * flag = nullptr;

@@ -103,7 +103,8 @@ PV modify_time_on_device( const PV & me, const char * what, const float * d_map,
 	b200::Mirror<MF> data = b200::Mirror<MF>::device_result( size_t( format.num_channels ) * size_t( format.num_frames ) * size_t( format.num_bins ), &d_out );
 	if( !d_out ) return PV();
 	if( report( ctx, what, flan_b200_modify_time( ctx, as_floats( d_pv ), me.get_num_channels(), me.get_num_frames(), me.get_num_bins(),
-			me.get_sample_rate(), me.get_analysis_rate(), d_map, fs, bs, interp, out_frames, reinterpret_cast<float *>( d_out ) ) ) ) return PV();
+			me.get_sample_rate(), me.get_analysis_rate(), d_map, fs, bs, interp, out_frames, reinterpret_cast<float *>( d_out ),
+			int( me.get_window_size() ) ) ) ) return PV();      // also leaves the phase summaries PV::convert_to_audio needs
 	return PV( PVBuffer::from_device_result( format, std::move( data ) ) );
 	}
 

@@ -193,7 +193,7 @@ void Mirror<T>::take( Mirror & o )
 	host_valid_ = o.host_valid_.load(); device_valid_ = o.device_valid_.load();
 	host_pinned_ = o.host_pinned_; pinned_ptr_ = o.pinned_ptr_;
 	download_in_flight_ = o.download_in_flight_; upload_in_flight_ = o.upload_in_flight_;
-	uploads_ = o.uploads_; nan_flag_ = o.nan_flag_;
+	uploads_ = o.uploads_; nan_flag_ = o.nan_flag_; produced_on_device_ = o.produced_on_device_; o.produced_on_device_ = false;
 	o.host_.clear(); o.count_ = 0; o.host_valid_ = true; o.device_valid_ = false;
 	o.host_pinned_ = false; o.pinned_ptr_ = nullptr; o.download_in_flight_ = o.upload_in_flight_ = false; o.uploads_ = 0; o.nan_flag_ = nullptr;
 	}
@@ -213,7 +213,7 @@ void Mirror<T>::release()
 	host_pinned_ = false; pinned_ptr_ = nullptr;
 	dev_.reset();
 	shards_.reset();
-	count_ = 0; host_valid_ = true; device_valid_ = false; uploads_ = 0; nan_flag_ = nullptr;
+	count_ = 0; host_valid_ = true; device_valid_ = false; uploads_ = 0; nan_flag_ = nullptr; produced_on_device_ = false;
 	}
 
 template<typename T>
@@ -310,6 +310,7 @@ Mirror<T> Mirror<T>::device_result( size_t count, T ** d_out, T ** h_prefetch )
 	m.count_ = count;
 	m.host_valid_ = false;
 	m.device_valid_ = true;
+	m.produced_on_device_ = true;
 	*d_out = static_cast<T *>( mem->ptr );
 	if( h_prefetch && count )
 		{

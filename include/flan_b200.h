@@ -234,7 +234,13 @@ int flan_b200_modify_time_frames( flan_b200_ctx * ctx, const float * d_map, int6
 int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int channels, int64_t frames, int bins,
                            float sample_rate, float analysis_rate,
                            const float * d_map, int64_t map_frame_stride, int map_bin_stride,
-                           int interp, int64_t out_frames, float * d_pv_out );
+                           int interp, int64_t out_frames, float * d_pv_out, int summary_window );
+/* summary_window > 0 (the PV's window size): when the time map is shared by all bins and never descends (PV::stretch with
+ * a constant or time-only factor) the kernel walks its output frames in order and ALSO leaves behind the per-segment
+ * phase summaries that flan_b200_convert_to_audio would otherwise compute with a second read of the rows. They stay
+ * valid until the next call on this context that uses its scratch space or writes the buffer. A caller that knows d_pv is
+ * unchanged since the call that produced it says so right before resynthesis (same host thread): */
+int flan_b200_promise_unchanged( flan_b200_ctx * ctx, const float * d_pv );
 
 /* ---- file formats either side of the path ---------------------------------------------------------
  * .flan RIFF-PV (PVBuffer::save / load, src/flan/PV/PVBuffer.cpp:99-140, 216-273; format described at

@@ -183,3 +183,44 @@ def test_chain_properties_at_scale(eng):
     assert st.shape[1] == 2 * F
     assert torch.equal(st[0, 2:2 * F:2, :, 0], pv[0, 0:F - 1, :, 0])
     assert not st[0, :2].any()
+
+
+@pytest.mark.parametrize("factor,frames", [(2.0, 3000), (0.7, 3000), (3.3, 300), (1.0, 40)])
+def test_stretch_leaves_the_phase_summaries_resynthesis_needs(eng, factor, frames):
+    """With summary_window set, the bin-shared stretch kernel also leaves the per-segment phase summaries of its output;
+    convert_to_audio(unchanged=True) then skips pv_phase_seg_kernel (one launch fewer) and gives the same bits, the
+    NaN / Inf pre-scan flag included. Summaries are dropped by anything that writes the rows or uses the scratch space."""
+    import torch
+    sr, W, hop, B = 48000.0, 2048, 128, 1025
+    ar = eng.analysis_rate(sr, hop)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pv = torch.rand((2, frames, B, 2), generator=g, device="cuda", dtype=torch.float32)
+    pv[..., 1] = (pv[..., 1] - 0.02) * 20000.0          # a few negative frequencies: the max-prefix part of the summaries
+    pv[0, frames // 3, 5, 0] = 0.0
+    pv[0, frames // 3 + 1, 5, 0] = 0.0                  # a pair of zero magnitudes: the pair ends early (PVModify.cpp:351-352)
+    plain_st = eng.stretch(pv, sr, ar, factor, 0)
+    plain, plain_flag = eng.convert_to_audio(plain_st, sr, ar, W, check_nan=True)
+    st = eng.stretch(pv, sr, ar, factor, 0, summary_window=W)
+    assert torch.equal(st, plain_st)
+    n0 = eng.launch_count()
+    reused, flag = eng.convert_to_audio(st, sr, ar, W, check_nan=True, unchanged=True)
+    n_reused = eng.launch_count() - n0
+    assert torch.equal(reused, plain) and flag == plain_flag and not flag
+    n0 = eng.launch_count()
+    eng.convert_to_audio(st, sr, ar, W)
+    assert eng.launch_count() - n0 == n_reused + 1, "the reuse saves exactly the phase summary launch"
+    # a NaN in the input reaches the output rows and the flag travels with the summaries
+    bad = pv.clone()
+    bad[1, frames // 2, 7, 1] = float("nan")
+    st_bad = eng.stretch(bad, sr, ar, factor, 0, summary_window=W)
+    _, flag_bad = eng.convert_to_audio(st_bad, sr, ar, W, check_nan=True, unchanged=True)
+    _, flag_ref = eng.convert_to_audio(st_bad, sr, ar, W, check_nan=True)
+    assert flag_bad == flag_ref
+    # an unrelated call in between uses the scratch space: the promise finds nothing to reuse and the rows are read again
+    st2 = eng.stretch(pv, sr, ar, factor, 0, summary_window=W)
+    eng.convert_to_audio(plain_st, sr, ar, W)
+    assert torch.equal(eng.convert_to_audio(st2, sr, ar, W, unchanged=True), plain)
+    # a promise for rows that were overwritten since is the caller's lie; one for OTHER rows is simply ignored
+    st3 = eng.stretch(pv, sr, ar, factor, 0, summary_window=W)
+    assert torch.equal(eng.convert_to_audio(plain_st, sr, ar, W, unchanged=True), plain)
+    del st3

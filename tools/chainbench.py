@@ -15,6 +15,11 @@ from flan_b200.engine import Engine  # noqa: E402
 from flan_b200.signals import noise_chirp  # noqa: E402
 
 
+PLAIN = "--plain" in sys.argv      # the round-1 form: phase summaries from a second read of the stretched rows
+if PLAIN:
+    sys.argv.remove("--plain")
+
+
 def main():
     seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
     C = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -31,8 +36,9 @@ def main():
     def chain():
         eng.convert_to_pv(xd, sr, W, h, N, out=pv)
         eng.repitch(pv, sr, 1.5, 0, out=rp)
-        st = eng.stretch(rp, sr, ar, 2.0, 0)
-        y = eng.convert_to_audio(st, sr, ar, W)
+        # the stretch kernel leaves the phase summaries of its rows; resynthesis does not read the rows a second time
+        st = eng.stretch(rp, sr, ar, 2.0, 0, summary_window=0 if PLAIN else W)
+        y = eng.convert_to_audio(st, sr, ar, W, unchanged=not PLAIN)
         return st, y
 
     for _ in range(2):
