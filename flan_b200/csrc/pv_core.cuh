@@ -636,36 +636,26 @@ struct PhaseSeg { PhaseSum sum, mx; };   // total and max prefix (the empty pref
 // the two results are converted to the split form. `bad` is the is_nan_or_inf() pre-scan of AudioPV.cpp:88. Used by
 // pv_phase_seg_kernel and by every kernel that PRODUCES PV rows in frame order per bin and leaves their summary behind
 // (pv_stretch_planned_kernel), so that both give the same bits.
-// (double) x, exactly. On the device the conversion instruction runs on the 16-lane XU pipe, which the kernels that
-// produce PV rows already keep busy (IEEE division, MUFU): normal numbers are widened with integer operations instead
-// (exponent rebias + mantissa shift); zero, denormals, Inf and NaN take the instruction.
-PV_HD double float_to_double( float x )
-	{
-#if defined(__CUDA_ARCH__)
-	const unsigned u = __float_as_uint( x );
-	const unsigned a = u & 0x7fffffffu;
-	if( a - 0x00800000u < 0x7f000000u )
-		return __hiloint2double( (int)( ( u & 0x80000000u ) | ( ( a >> 3 ) + 0x38000000u ) ), (int)( a << 29 ) );
-	return (double) x;
-#else
-	return (double) x;
-#endif
-	}
-
 struct PhaseSegAcc
 	{
 	double sum = 0.0, mx = 0.0;
 	bool bad = false;
 	// The running maximum only has to be taken where a non-decreasing run of prefix sums ends: right before an increment
-	// that is not >= 0 (negative or NaN) and at the end. ALU: widen the increment with integer operations (kernels whose XU
-	// pipe is the busy one); pv_phase_seg_kernel, which waits for HBM, keeps the conversion instruction.
-	template<bool ALU = false>
+	// that is not >= 0 (negative or NaN) and at the end. RARE_DIP: that update sits behind a real branch (a call), for
+	// kernels that are short of issue slots (pv_stretch_planned_kernel: frequencies are almost never negative);
+	// pv_phase_seg_kernel, which waits for HBM, lets the compiler predicate it.
+#if defined(__CUDACC__)
+	__host__ __device__ __noinline__
+#endif
+	static double dip( double sum_, double mx_ ) { return ( sum_ > mx_ ) ? sum_ : mx_; }      // by value: the accumulator stays in registers
+	template<bool RARE_DIP = false>
 	PV_HD void step( float2 mf, const PvConsts & k )
 		{
 		bad = bad || !( fabsf( mf.x ) <= 3.402823466e38f ) || !( fabsf( mf.y ) <= 3.402823466e38f );
 		const float inc = phase_increment( mf.y, k );
-		if( !( inc >= 0.0f ) ) mx = ( sum > mx ) ? sum : mx;
-		sum += ALU ? float_to_double( inc ) : (double) inc;
+		if( RARE_DIP ) { if( !( inc >= 0.0f ) ) mx = dip( sum, mx ); }
+		else if( !( inc >= 0.0f ) ) mx = ( sum > mx ) ? sum : mx;
+		sum += (double) inc;
 		}
 	PV_HD PhaseSeg finish( double P, double rcpP ) const
 		{

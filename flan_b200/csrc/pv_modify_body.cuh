@@ -576,7 +576,7 @@ PVM_HD void stretch_segment_planned( const StretchArgs & a, const StretchPlan & 
 	if( c0 > x1 ) c0 = x1;
 	if( c1 > x1 ) c1 = x1;
 	if( c1 < x ) c1 = x;
-	for( ; x < c0; ++x, o += B ) { *o = zero; if( SUMM ) summary->step<true>( zero, k ); }
+	for( ; x < c0; ++x, o += B ) *o = zero;                              // a zero row adds nothing to the phase summary
 	if( x < c1 )
 		{
 		const int f_lo = plan.src[x], f_hi = plan.src[c1 - 1];
@@ -615,32 +615,29 @@ PVM_HD void stretch_segment_planned( const StretchArgs & a, const StretchPlan & 
 				if( f + j <= f_hi )
 					{
 					const int xend = xe[j] < c1 ? xe[j] : c1;
-					for( ; x < xend; ++x, o += B, ++mixp )
-						{
-						float2 nw = zero;
-						if( live )
+					if( live )
+						for( ; x < xend; ++x, o += B, ++mixp )
 							{
 							const float mix = *mixp;
 							const float w0 = ( 1.0f - mix ) * l.x;
 							const float w1 = mix * r[j].x;
 							const float totalWeight = w0 + w1;
 							const float weightedFreqSum = w0 * l.y + w1 * r[j].y;
-							if( totalWeight == 0.0f ) live = false;
-							else
-								{
-								nw.y = ( 0.0f * 0.0f + weightedFreqSum ) / ( 0.0f + totalWeight );
-								nw.x = 0.0f + totalWeight;
-								}
+							if( totalWeight == 0.0f ) break;                        // leaves this frame pair (PVModify.cpp:351-352)
+							float2 nw;
+							nw.y = ( 0.0f * 0.0f + weightedFreqSum ) / ( 0.0f + totalWeight );
+							nw.x = 0.0f + totalWeight;
+							*o = nw;
+							if( SUMM ) summary->step<true>( nw, k );
 							}
-						*o = nw;
-						if( SUMM ) summary->step<true>( nw, k );
-						}
+					// what is left of a pair that ended early stays zero (a zero row adds nothing to the phase summary)
+					for( ; x < xend; ++x, o += B, ++mixp ) *o = zero;
 					l = r[j];
 					live = true;
 					}
 			}
 		}
-	for( ; x < x1; ++x, o += B ) { *o = zero; if( SUMM ) summary->step<true>( zero, k ); }
+	for( ; x < x1; ++x, o += B ) *o = zero;
 	}
 
 PVM_HD void stretch_chunk_planned( const StretchArgs & a, const StretchPlan & plan, int c, int64_t chunk_index, int bin )
