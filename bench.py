@@ -464,7 +464,12 @@ def run_ours(args):
     ktimes = {k: eng.kernel_time(k) for k in eng.KERNEL_KINDS}
     eng.set_timing(False)
     t = torch.tensor(round_ms, dtype=torch.float64, device=dev)
+    rank_ms = [float(t.mean().item()) / steps]           # every rank's own mean step (diagnostic: which rank is the slowest)
     if world > 1:
+        mine = torch.tensor(rank_ms, dtype=torch.float64, device=dev)
+        every = torch.empty((world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        rank_ms = [float(v) for v in every.tolist()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)         # per round: the slowest rank
     ms_max = float(t.mean().item())                      # mean round, K steps each
     ms = ms_max
@@ -553,7 +558,7 @@ def run_ours(args):
             "roofline": roofline, "kernels": per_kernel,
             "e2e": e2e, "rounds": rounds, "timed_seconds": sum(round_ms) * 1e-3,
             "roofline_legs": legs_roofline,
-            "cfg3_strong": cfg3,
+            "cfg3_strong": cfg3, "ms_per_step_by_rank": rank_ms,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -384,8 +384,8 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 	if( need_hi > need_lo && ( c.audio_offset > need_lo || c.audio_offset + c.audio_len < need_hi ) )
 		return fail( ctx, FLAN_B200_INVALID, "local audio does not cover the halo of the requested frame range" );
 
-	const int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ), true );
-	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	int seg_len = choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ), true );
+	int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
 	AnalysisArgs a{};
 	a.audio = c.d_audio_local; a.audio_stride = c.audio_stride; a.audio_offset = c.audio_offset; a.n_total = c.n_total;
 	a.pv = (float2 *) c.d_pv_rows; a.pv_channel_stride = c.pv_channel_stride;
@@ -437,6 +437,22 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 		return FLAN_B200_OK;
 		}
 	ctx->seg_key.valid = false;
+	// Whole waves: with a few waves of CTAs the last, partly filled one is a large share of the launch (a 1/8 shard of cfg3:
+	// 660 CTAs = 2.23 waves of 296). Segments are shortened until the CTAs just fill the waves they need anyway. Analysis
+	// results do not depend on where segments are cut (the warm-up frame recomputes the previous phase exactly).
+	if( (int64_t) C * segs > 2 * (int64_t) ctx->sms )
+		{
+		CK( launch_analysis( N, a, -1, ctx->compute, tps_a, pt ), "occupancy query" );
+		const int64_t wave = (int64_t) ctx->sms * std::max( 1, last_occupancy() );
+		const int64_t ctas = (int64_t) C * segs;
+		const int64_t per_channel = ( ( ctas + wave - 1 ) / wave * wave ) / C;
+		const int64_t shorter = per_channel > 0 ? ( frames + per_channel - 1 ) / per_channel : seg_len;
+		if( ctas > wave && shorter >= 8 && shorter < seg_len )
+			{
+			seg_len = (int) shorter; segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+			a.seg_len = seg_len; a.segs_per_channel = segs;
+			}
+		}
 	{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->compute, tps_a, pt ), "analysis launch" ); }
 	return FLAN_B200_OK;
 	}
@@ -454,7 +470,7 @@ PhaseLayout phase_layout( const flan_b200_ctx * ctx, int C, int64_t frames, int 
 	{
 	PhaseLayout l{};
 	const int N = ( B - 1 ) * 2;
-	int seg_len = seg_len_given ? seg_len_given : choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ) );
+	int seg_len = seg_len_given ? seg_len_given : choose_seg_len( frames, C, ctx->sms, W, hop, seg_len_cap( ctx, N ), false, synth_ctas_per_sm( N ) );
 	if( seg_len > frames ) seg_len = (int) frames;
 	if( seg_len < 1 ) seg_len = 1;
 	l.seg_len = seg_len;

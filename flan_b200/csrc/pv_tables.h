@@ -160,7 +160,15 @@ inline bool build_tables( int N, int W, int hop, float sample_rate, float analys
 // amortised; short enough that the grid covers the SMs several times over.
 // `analysis_only`: the overlap constraint does not apply; short signals then get segments down to 8 frames (one
 // warm-up FFT per 8) so that the grid still covers the SMs.
-inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len = 64, bool analysis_only = false )
+// Resident CTAs per SM of the resynthesis kernels under the launch policy of pv_capi.cu (0: not known).
+inline int synth_ctas_per_sm( int dft ) { return dft == 8192 ? 2 : ( ( dft == 1024 || dft == 2048 || dft == 4096 ) ? 3 : 0 ); }
+
+// `ctas_per_sm` > 0 (resynthesis of long signals): the length is shortened (never below ~2/3 of max_len) so that the
+// CTA count is just under a multiple of EIGHT waves of the kernel -- a whole number of waves on 1, 2, 4 or 8 devices.
+// cfg3 (675 001 frames, 296 CTAs per wave at dft 8192): 128 frames per CTA gave 5 274 CTAs = 2.23 waves on each of
+// eight devices, of which the third is a quarter full; 96 frames give 879 CTAs = 2.97 waves. The choice is a function of
+// the WHOLE signal only, so every shard of a signal -- and the unsharded call -- walks the same segments (same bits).
+inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len = 64, bool analysis_only = false, int ctas_per_sm = 0 )
 	{
 	int64_t min_len = ( W + hop - 1 ) / hop;                 // >= W/hop
 	if( analysis_only && min_len > 8 ) min_len = 8;
@@ -170,6 +178,18 @@ inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop
 	if( len < min_len ) len = min_len;
 	if( len < 4 ) len = 4;
 	if( len > frames ) len = frames > 0 ? frames : 1;
+	if( ctas_per_sm > 0 && !analysis_only && channels > 0 )
+		{
+		const int64_t wave = (int64_t) sms * ctas_per_sm;
+		const int64_t ctas = channels * ( ( frames + len - 1 ) / len );
+		if( ctas >= 16 * wave )
+			{
+			const int64_t k = ( ctas + 8 * wave - 1 ) / ( 8 * wave );
+			const int64_t per_channel = ( 8 * wave * k ) / channels;
+			const int64_t shorter = per_channel > 0 ? ( frames + per_channel - 1 ) / per_channel : len;
+			if( shorter >= min_len && shorter >= 4 && shorter < len ) len = shorter;
+			}
+		}
 	return (int) len;
 	}
 
