@@ -8,7 +8,8 @@
 // Protocol. Every rank owns one mailbox allocation:
 //     state slots   [2 parities][world]   the phase state (flan_b200_phase_state[C * B]) pushed by each EARLIER rank
 //     halo slots    [2 parities]          the window - hop partial sums pushed by the NEXT rank
-//     flags         state_flag[2][world], halo_flag[2]     sequence number of the data in the slot (written by the pusher
+//     flags         state_count[2] (arrivals per parity: every pusher adds one per step), halo_flag[2] (sequence number of the
+//                                                         data in the slot), both written by the pusher
 //                                                         AFTER the data, in stream order: a copy completes before the next starts)
 //     acks          state_ack[world], halo_ack             last sequence number the receiver has consumed (written by the
 //                                                         receiver into the PUSHER's mailbox): a pusher overwrites the slot
@@ -45,6 +46,29 @@ WaitValue32Fn wait_value32()
 	}
 
 constexpr int SEQ_RING = 4096;
+
+// One launch pushes this rank's state to EVERY later rank: CTA b copies the slot to destination b with 16-byte peer
+// stores and then increments that destination's arrival counter of the step's parity (release at system scope). Fourteen DMA operations in a row -- a copy
+// and a flag per destination -- took ~14 us per destination, and rank r's step grew by that much per earlier rank
+// (bench.py, 8 GPUs: 3.95 ... 4.05 ms from rank 0 to rank 7). The SMs are between the phase scan and the transform here.
+struct StatePush
+	{
+	const uint4 * src; unsigned n16;                 // the own slot, in 16-byte units
+	uint4 * dst[FLAN_B200_MAX_DEVICES]; unsigned * count[FLAN_B200_MAX_DEVICES];
+	};
+
+__global__ void __launch_bounds__( 1024 ) pv_state_push_kernel( const StatePush p )
+	{
+	uint4 * dst = p.dst[blockIdx.x];
+	for( unsigned i = threadIdx.x; i < p.n16; i += blockDim.x ) dst[i] = p.src[i];
+	__threadfence_system();
+	__syncthreads();
+	if( threadIdx.x == 0 )
+		{
+		__threadfence_system();
+		atomicAdd_system( p.count[blockIdx.x], 1u );      // the destination waits for ONE value: (its rank) x (steps of this parity)
+		}
+	}
 
 } // namespace
 
@@ -203,14 +227,19 @@ int flan_b200_exchange_put_state( flan_b200_exchange * ex, const flan_b200_phase
 		}
 	CK( cudaEventRecord( ex->ev, ctx->compute ), "event record" );
 	CK( cudaStreamWaitEvent( ex->copy, ex->ev, 0 ), "stream wait" );
-	for( int dst = ex->rank + 1; dst < ex->world; ++dst )
+	StatePush push{};
+	push.src = (const uint4 *) own; push.n16 = (unsigned)( ex->state_bytes / 16 );      // 32-byte elements: a whole number of 16-byte units
+	int n = 0;
+	for( int dst = ex->rank + 1; dst < ex->world; ++dst, ++n )
 		{
 		if( !ex->peer[dst] ) return fail( ctx, FLAN_B200_INVALID, "exchange is not connected" );
 		if( s > 2 ) { int rc = wait_geq( ex, ex->copy, ex->word( ex->box, ex->w_state_ack( dst ) ), s - 2 ); if( rc ) return rc; }
-		CK( cudaMemcpyAsync( ex->peer[dst] + ex->off_state( parity, ex->rank ), own, ex->state_bytes, cudaMemcpyDeviceToDevice, ex->copy ), "state push" );
-		int rc = put_word( ex, ex->copy, ex->word( ex->peer[dst], ex->w_state_flag( parity, ex->rank ) ), s );
-		if( rc ) return rc;
+		push.dst[n] = (uint4 *)( ex->peer[dst] + ex->off_state( parity, ex->rank ) );
+		push.count[n] = ex->word( ex->peer[dst], ex->w_state_flag( parity, 0 ) );
 		}
+	pv_state_push_kernel<<<n, 1024, 0, ex->copy>>>( push );
+	CK( cudaGetLastError(), "state push launch" );
+	ctx->launches++;
 	CK( cudaEventRecord( ex->ev_pushed[parity], ex->copy ), "event record" );
 	ex->pushed_recorded[parity] = true;
 	return FLAN_B200_OK;
@@ -225,9 +254,11 @@ int flan_b200_exchange_get_states( flan_b200_exchange * ex, const flan_b200_phas
 	CallLock lock( ctx );
 	const uint32_t s = ex->seq;
 	const int parity = (int)( s & 1 );
-	for( int src = 0; src < ex->rank; ++src )
+	// every earlier rank has incremented the counter of this parity once per step of this parity; none can be a step ahead
+	// on it (a pusher overwrites a slot only after the acknowledgement of the step two before)
+	if( ex->rank > 0 )
 		{
-		int rc = wait_geq( ex, ctx->compute, ex->word( ex->box, ex->w_state_flag( parity, src ) ), s );
+		int rc = wait_geq( ex, ctx->compute, ex->word( ex->box, ex->w_state_flag( parity, 0 ) ), (uint32_t) ex->rank * ( ( s + 1 ) / 2 ) );
 		if( rc ) return rc;
 		}
 	*d_states = (const flan_b200_phase_state *)( ex->box + ex->off_state( parity, 0 ) );
@@ -240,9 +271,13 @@ int flan_b200_exchange_release_states( flan_b200_exchange * ex )
 	if( !ex ) return FLAN_B200_INVALID;
 	flan_b200_ctx * ctx = ex->ctx;
 	CallLock lock( ctx );
+	if( ex->rank == 0 ) return FLAN_B200_OK;
+	// off the critical path: the acknowledgements leave on the copy stream, behind the kernel that read the states
+	CK( cudaEventRecord( ex->ev, ctx->compute ), "event record" );
+	CK( cudaStreamWaitEvent( ex->copy, ex->ev, 0 ), "stream wait" );
 	for( int src = 0; src < ex->rank; ++src )
 		{
-		int rc = put_word( ex, ctx->compute, ex->word( ex->peer[src], ex->w_state_ack( ex->rank ) ), ex->seq );
+		int rc = put_word( ex, ex->copy, ex->word( ex->peer[src], ex->w_state_ack( ex->rank ) ), ex->seq );
 		if( rc ) return rc;
 		}
 	return FLAN_B200_OK;
@@ -290,7 +325,9 @@ int flan_b200_exchange_add_halo( flan_b200_exchange * ex, float * d_out, int64_t
 		rc = flan_b200_add( ctx, d_out + (int64_t) c * pitch, halo + (int64_t) c * n, n );
 		if( rc ) return rc;
 		}
-	return put_word( ex, ctx->compute, ex->word( ex->peer[src], ex->w_halo_ack() ), s );
+	CK( cudaEventRecord( ex->ev, ctx->compute ), "event record" );
+	CK( cudaStreamWaitEvent( ex->copy, ex->ev, 0 ), "stream wait" );
+	return put_word( ex, ex->copy, ex->word( ex->peer[src], ex->w_halo_ack() ), s );
 	}
 
 } // extern "C"
