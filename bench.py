@@ -402,9 +402,14 @@ def run_ours(args):
     # The two exchanges of sharded resynthesis (phase state, overlap-add halo) go through flan_b200_exchange_*: peer copies
     # into CUDA-IPC mailboxes ordered by sequence flags (no NCCL kernel beside the transforms). --exchange nccl keeps the
     # torch.distributed form (all_gather + batched send / recv on a side stream).
-    exchange = None
+    exchange, exchange_note = None, None
     if world > 1 and args.exchange == "peer":
-        exchange = PeerExchange(eng, dist, rank, world, CH, B, max(0, W - HOP))
+        try:
+            exchange = PeerExchange(eng, dist, rank, world, CH, B, max(0, W - HOP))
+        except RuntimeError as e:      # raised on every rank together: the NCCL form takes over
+            exchange_note = str(e)
+            if rank == 0:
+                print("bench.py: %s; falling back to --exchange nccl" % e, file=sys.stderr)
 
     def step(xin, yout=None):
         if world == 1:
@@ -549,7 +554,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "channels": CH, "frames_per_gpu": sh.frames, "bins": B,
                        "seconds_per_gpu": args.seconds, "sharding": "none" if world == 1 else "contiguous frame ranges, dp%d; phase state + halo exchange: %s" % (
-                           world, "peer copies into CUDA-IPC mailboxes (flan_b200_exchange_*)" if exchange is not None else "NCCL all_gather + send/recv"),
+                           world, "peer copies into CUDA-IPC mailboxes (flan_b200_exchange_*)" if exchange is not None else "NCCL all_gather + send/recv" + (
+                               " (%s)" % exchange_note if exchange_note else "")),
                        "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush"},
             "legs": {"analysis_frames_per_s": frames_rank / (an_ms / an_n * 1e-3) if an_n else None,
                      "resynthesis_frames_per_s": frames_rank / ((sy_ms + seg_ms + scan_ms) / sy_n * 1e-3) if sy_n else None,

@@ -144,17 +144,36 @@ class PeerExchange:
     exchange kernel runs on an SM. `dist` is only used once, to all-gather the 64-byte mailbox handles."""
 
     def __init__(self, engine, dist, rank, world, channels, bins, halo_samples):
+        """Collective: every rank calls it. If the mailbox cannot be set up on ANY rank (no peer access, CUDA IPC or
+        cuStreamWaitValue32 unavailable) every rank raises RuntimeError, so that callers can fall back together."""
         import ctypes
         self.engine, self.rank, self.world, self.channels, self.bins = engine, rank, world, channels, bins
         self.lib, self.ctx = engine.lib, engine.ctx
-        h = ctypes.c_void_p()
-        self.ctx.check(self.lib.flan_b200_exchange_create(self.ctx.h, rank, world, channels, bins, halo_samples, ctypes.byref(h)))
-        self.h = h
-        mine = ctypes.create_string_buffer(64)
-        self._call("flan_b200_exchange_handle", mine)
+        self.h = None
+        mine, error = None, None
+        try:
+            h = ctypes.c_void_p()
+            self.ctx.check(self.lib.flan_b200_exchange_create(self.ctx.h, rank, world, channels, bins, halo_samples, ctypes.byref(h)))
+            self.h = h
+            buf = ctypes.create_string_buffer(64)
+            self._call("flan_b200_exchange_handle", buf)
+            mine = bytes(buf.raw)
+        except Exception as e:  # noqa: BLE001 - reported to every rank below
+            error = "rank %d: %r" % (rank, e)
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(mine.raw))
-        self._call("flan_b200_exchange_connect", ctypes.create_string_buffer(b"".join(handles), 64 * world))
+        dist.all_gather_object(handles, (mine, error))
+        errors = [e for _, e in handles if e]
+        if not errors:
+            try:
+                self._call("flan_b200_exchange_connect", ctypes.create_string_buffer(b"".join(h for h, _ in handles), 64 * world))
+            except Exception as e:  # noqa: BLE001
+                error = "rank %d: %r" % (rank, e)
+            connected = [None] * world
+            dist.all_gather_object(connected, error)
+            errors = [e for e in connected if e]
+        if errors:
+            self.close()
+            raise RuntimeError("peer exchange unavailable (%s)" % "; ".join(errors))
 
     def _call(self, name, *args):
         self.ctx.check(getattr(self.lib, name)(self.h, *args))
