@@ -182,10 +182,13 @@ inline int choose_seg_len( int64_t frames, int channels, int sms, int W, int hop
 		{
 		const int64_t wave = (int64_t) sms * ctas_per_sm;
 		const int64_t ctas = channels * ( ( frames + len - 1 ) / len );
-		if( ctas >= 16 * wave )
+		// long signals: a multiple of eight waves (see above); a few waves: just the waves the launch needs anyway (a 1/8
+		// shard of cfg3 handed to a per-GPU process: 660 CTAs = 2.23 waves -> 879 = 2.97)
+		const int64_t unit = ( ctas >= 16 * wave ) ? 8 * wave : wave;
+		if( ctas > wave )
 			{
-			const int64_t k = ( ctas + 8 * wave - 1 ) / ( 8 * wave );
-			const int64_t per_channel = ( 8 * wave * k ) / channels;
+			const int64_t k = ( ctas + unit - 1 ) / unit;
+			const int64_t per_channel = ( unit * k ) / channels;
 			const int64_t shorter = per_channel > 0 ? ( frames + per_channel - 1 ) / per_channel : len;
 			if( shorter >= min_len && shorter >= 4 && shorter < len ) len = shorter;
 			}

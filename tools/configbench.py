@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flan_b200.engine import Engine  # noqa: E402
-from flan_b200.sharding import frame_shard, sharded_resynthesis  # noqa: E402
+from flan_b200.sharding import PeerExchange, frame_shard, sharded_resynthesis, sharded_resynthesis_peer  # noqa: E402
 
 
 def signal(n, sr, seed, dev, offset=0, n_total=None):
@@ -80,10 +80,25 @@ def main():
             dist.all_gather_into_tensor(bufs, state.contiguous())
             return bufs
 
+        # phase state + halo between the ranks: peer copies into CUDA-IPC mailboxes (flan_b200_exchange_*), NCCL if that
+        # cannot be set up
+        exchange = None
+        if world > 1:
+            try:
+                exchange = PeerExchange(eng, dist, rank, world, 1, B, max(0, W - hop))
+            except RuntimeError as e:
+                if rank == 0:
+                    print("configbench: %s; using NCCL" % e, file=sys.stderr)
+        head_event = torch.cuda.Event()
+        head_event.record()
+
         def step():
             eng.convert_to_pv_range(x, sh.audio_lo, n_total, sr, W, hop, N, sh.f0, sh.f1, out=pv)
             if world == 1:
                 return eng.convert_to_audio(pv, sr, ar, W)
+            if exchange is not None:
+                o, _ = sharded_resynthesis_peer(eng, exchange, torch, sh, pv, sr, ar, head_event)
+                return o
             o, _ = sharded_resynthesis(eng, dist, sh, pv, sr, ar, allgather,
                                        lambda t, dst: dist.isend(t, dst), lambda t, src: dist.recv(t, src))
             return o
@@ -107,9 +122,9 @@ def main():
             for x in xs:
                 eng.convert_to_pv(x, sr, W, hop, N, out=pv)
                 eng.repitch(pv, sr, 1.5, 0, out=rp)
-                st = eng.stretch(rp, sr, ar, 2.0, 0)
+                st = eng.stretch(rp, sr, ar, 2.0, 0, summary_window=W)      # leaves the phase summaries of its rows
                 out_frames[0] = st.shape[1]
-                y = eng.convert_to_audio(st, sr, ar, W)
+                y = eng.convert_to_audio(st, sr, ar, W, unchanged=True)
                 del st
             return y
         frames_rank = F * len(chans)
