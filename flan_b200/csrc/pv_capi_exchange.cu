@@ -126,7 +126,7 @@ extern "C" {
 
 int flan_b200_exchange_create( flan_b200_ctx * ctx, int rank, int world, int channels, int bins, int64_t halo_samples, flan_b200_exchange ** out )
 	{
-	if( !ctx || !out || world < 1 || rank < 0 || rank >= world || channels < 1 || bins < 2 || halo_samples < 0 ) return FLAN_B200_INVALID;
+	if( !ctx || !out || world < 1 || world > FLAN_B200_MAX_DEVICES || rank < 0 || rank >= world || channels < 1 || bins < 2 || halo_samples < 0 ) return FLAN_B200_INVALID;
 	*out = nullptr;
 	CallLock lock( ctx );
 	if( !wait_value32() ) return fail( ctx, FLAN_B200_UNSUPPORTED, "cuStreamWaitValue32 is not available" );

@@ -640,59 +640,6 @@ PVM_HD void stretch_segment_planned( const StretchArgs & a, const StretchPlan & 
 	for( ; x < x1; ++x, o += B ) *o = zero;
 	}
 
-PVM_HD void stretch_chunk_planned( const StretchArgs & a, const StretchPlan & plan, int c, int64_t chunk_index, int bin )
-	{
-	const float2 * in = a.pv + (int64_t) c * a.F * a.B + bin;
-	float2 * out_col = a.out + (int64_t) c * a.out_frames * a.B + bin;
-	const int64_t f0 = chunk_index * a.chunk;
-	int64_t f1 = f0 + a.chunk;
-	if( f1 > a.F - 1 ) f1 = a.F - 1;
-	float2 l = in[f0 * a.B];
-	int x = plan.xpos[f0];
-	if( chunk_index == 0 )
-		for( int64_t z = 0; z < x; ++z ) out_col[z * a.B] = make_float2( 0.0f, 0.0f );
-	constexpr int BATCH = 8;
-	for( int64_t f = f0; f < f1; f += BATCH )
-		{
-		float2 r[BATCH]; int xe[BATCH];
-#pragma unroll
-		for( int j = 0; j < BATCH; ++j )
-			if( f + 1 + j <= f1 )
-				{
-				r[j] = in[( f + 1 + j ) * a.B];
-				xe[j] = plan.xpos[f + 1 + j];
-				}
-#pragma unroll
-		for( int j = 0; j < BATCH; ++j )
-			if( f + 1 + j <= f1 )
-				{
-				bool live = true;
-				for( ; x < xe[j]; ++x )
-					{
-					float2 nw = make_float2( 0.0f, 0.0f );
-					if( live )
-						{
-						const float mix = plan.mix[x];
-						const float w0 = ( 1.0f - mix ) * l.x;
-						const float w1 = mix * r[j].x;
-						const float totalWeight = w0 + w1;
-						const float weightedFreqSum = w0 * l.y + w1 * r[j].y;
-						if( totalWeight == 0.0f ) live = false;
-						else
-							{
-							nw.y = ( 0.0f * 0.0f + weightedFreqSum ) / ( 0.0f + totalWeight );
-							nw.x = 0.0f + totalWeight;
-							}
-						}
-					out_col[(int64_t) x * a.B] = nw;
-					}
-				l = r[j];
-				}
-		}
-	if( chunk_index == a.chunks - 1 )
-		for( int64_t z = x; z < a.out_frames; ++z ) out_col[z * a.B] = make_float2( 0.0f, 0.0f );
-	}
-
 // Sequential form (the reference's walk): thread = (channel, bin); the output was cleared beforehand.
 PVM_HD void stretch_column( const StretchArgs & a, int c, int bin )
 	{
