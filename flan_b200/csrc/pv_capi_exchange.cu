@@ -47,29 +47,6 @@ WaitValue32Fn wait_value32()
 
 constexpr int SEQ_RING = 4096;
 
-// One launch pushes this rank's state to EVERY later rank: CTA b copies the slot to destination b with 16-byte peer
-// stores and then increments that destination's arrival counter of the step's parity (release at system scope). Fourteen DMA operations in a row -- a copy
-// and a flag per destination -- took ~14 us per destination, and rank r's step grew by that much per earlier rank
-// (bench.py, 8 GPUs: 3.95 ... 4.05 ms from rank 0 to rank 7). The SMs are between the phase scan and the transform here.
-struct StatePush
-	{
-	const uint4 * src; unsigned n16;                 // the own slot, in 16-byte units
-	uint4 * dst[FLAN_B200_MAX_DEVICES]; unsigned * count[FLAN_B200_MAX_DEVICES];
-	};
-
-__global__ void __launch_bounds__( 1024 ) pv_state_push_kernel( const StatePush p )
-	{
-	uint4 * dst = p.dst[blockIdx.x];
-	for( unsigned i = threadIdx.x; i < p.n16; i += blockDim.x ) dst[i] = p.src[i];
-	__threadfence_system();
-	__syncthreads();
-	if( threadIdx.x == 0 )
-		{
-		__threadfence_system();
-		atomicAdd_system( p.count[blockIdx.x], 1u );      // the destination waits for ONE value: (its rank) x (steps of this parity)
-		}
-	}
-
 } // namespace
 
 struct flan_b200_exchange
@@ -227,7 +204,7 @@ int flan_b200_exchange_put_state( flan_b200_exchange * ex, const flan_b200_phase
 		}
 	CK( cudaEventRecord( ex->ev, ctx->compute ), "event record" );
 	CK( cudaStreamWaitEvent( ex->copy, ex->ev, 0 ), "stream wait" );
-	StatePush push{};
+	pvk::StatePush push{};
 	push.src = (const uint4 *) own; push.n16 = (unsigned)( ex->state_bytes / 16 );      // 32-byte elements: a whole number of 16-byte units
 	int n = 0;
 	for( int dst = ex->rank + 1; dst < ex->world; ++dst, ++n )
@@ -237,8 +214,7 @@ int flan_b200_exchange_put_state( flan_b200_exchange * ex, const flan_b200_phase
 		push.dst[n] = (uint4 *)( ex->peer[dst] + ex->off_state( parity, ex->rank ) );
 		push.count[n] = ex->word( ex->peer[dst], ex->w_state_flag( parity, 0 ) );
 		}
-	pv_state_push_kernel<<<n, 1024, 0, ex->copy>>>( push );
-	CK( cudaGetLastError(), "state push launch" );
+	CK( pvk::launch_state_push( push, n, ex->copy ), "state push launch" );
 	ctx->launches++;
 	CK( cudaEventRecord( ex->ev_pushed[parity], ex->copy ), "event record" );
 	ex->pushed_recorded[parity] = true;

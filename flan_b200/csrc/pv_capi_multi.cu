@@ -29,6 +29,7 @@ struct flan_b200_multi
 	            ev_done[FLAN_B200_MAX_DEVICES] = {}, ev_copied[FLAN_B200_MAX_DEVICES] = {};
 	cudaEvent_t t0[FLAN_B200_MAX_DEVICES] = {}, t1[FLAN_B200_MAX_DEVICES] = {};     // flan_b200_multi_time_begin / _end
 	int * d_nan[FLAN_B200_MAX_DEVICES] = {};      // per device: the NaN / Inf flag of the last resynthesis' pre-scan (AudioPV.cpp:88)
+	bool all_peers = true;        // every pair of distinct devices has direct peer access: kernels may store into each other's memory
 	std::mutex call_mutex;
 	};
 
@@ -134,8 +135,9 @@ int flan_b200_multi_create( const int * devices, int n_devices, flan_b200_multi 
 				{
 				cudaSetDevice( ids[i] );
 				const cudaError_t e = cudaDeviceEnablePeerAccess( ids[j], 0 );
-				if( e != cudaSuccess ) cudaGetLastError();      // already enabled
+				if( e != cudaSuccess ) { cudaGetLastError(); if( e != cudaErrorPeerAccessAlreadyEnabled ) m->all_peers = false; }
 				}
+			else m->all_peers = false;
 			}
 	*out = m;
 	return FLAN_B200_OK;
@@ -322,7 +324,18 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		};
 	auto bail = [&]( flan_b200_ctx * ctx, int code ) { const std::string e = ctx ? flan_b200_last_error( ctx ) : thread_error(); cleanup( true ); return mfail( code, e ); };
 
-	// (1) phase state of every shard, on its device
+	// (0) where the states of the earlier shards will land on each later device
+	for( int i = 1; i < R; ++i )
+		{
+		flan_b200_ctx * ctx = m->ctx[i];
+		rc = flan_b200_malloc( ctx, state_bytes * i, (void **) &d_all[i] );
+		if( !rc ) rc = flan_b200_malloc( ctx, state_bytes, (void **) &d_carry[i] );
+		if( rc ) return bail( ctx, rc );
+		CallLock cl( ctx );
+		BlockUse use( ctx, { d_all[i] } );                  // earlier users of the recycled block are ahead of this point on the stream
+		MCK( cudaEventRecord( m->ev_copied[i], ctx->compute ), "event record" );
+		}
+	// (1) phase state of every shard, on its device; one kernel then pushes it to every later device (peer stores)
 	for( int i = 0; i < R; ++i )
 		{
 		flan_b200_ctx * ctx = m->ctx[i];
@@ -339,22 +352,33 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		s.d_nan_flag = m->d_nan[i];
 		rc = synth_range( ctx, s );
 		if( rc ) return bail( ctx, rc );
+		if( i + 1 < R && m->all_peers )
+			{
+			pvk::StatePush push{};
+			push.src = (const uint4 *) d_state[i]; push.n16 = (unsigned)( state_bytes / 16 );
+			int n = 0;
+			for( int j = i + 1; j < R; ++j, ++n )
+				{
+				MCK( cudaStreamWaitEvent( ctx->compute, m->ev_copied[j], 0 ), "stream wait" );
+				push.dst[n] = (uint4 *)( (char *) d_all[j] + state_bytes * i );
+				}
+			MCK( pvk::launch_state_push( push, n, ctx->compute ), "state push launch" );
+			ctx->launches++;
+			}
 		MCK( cudaEventRecord( m->ev_state[i], ctx->compute ), "event record" );
 		}
-	// (2) the states of the earlier shards travel to each later one and are combined there
+	// (2) ... and are combined there
 	for( int i = 1; i < R; ++i )
 		{
 		flan_b200_ctx * ctx = m->ctx[i];
-		rc = flan_b200_malloc( ctx, state_bytes * i, (void **) &d_all[i] );
-		if( !rc ) rc = flan_b200_malloc( ctx, state_bytes, (void **) &d_carry[i] );
-		if( rc ) return bail( ctx, rc );
 		CallLock cl( ctx );
 		for( int q = 0; q < i; ++q )
 			{
 			MCK( cudaStreamWaitEvent( ctx->compute, m->ev_state[q], 0 ), "stream wait" );
-			MCK( cudaMemcpyPeerAsync( (char *) d_all[i] + state_bytes * q, ctx->device, d_state[q], m->ctx[q]->device, state_bytes, ctx->compute ), "peer copy" );
+			// without peer access everywhere the runtime stages the copies
+			if( !m->all_peers ) MCK( cudaMemcpyPeerAsync( (char *) d_all[i] + state_bytes * q, ctx->device, d_state[q], m->ctx[q]->device, state_bytes, ctx->compute ), "peer copy" );
 			}
-		MCK( cudaEventRecord( m->ev_copied[i], ctx->compute ), "event record" );
+		if( !m->all_peers ) MCK( cudaEventRecord( m->ev_done[i], ctx->compute ), "event record" );
 		rc = flan_b200_phase_carry( ctx, (const flan_b200_phase_state *) d_all[i], i, C, B, (flan_b200_phase_state *) d_carry[i] );
 		if( rc ) return bail( ctx, rc );
 		}
@@ -409,14 +433,15 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 			MCK( cudaStreamWaitEvent( nxt->stream, m->ev_halo[i], 0 ), "stream wait" );
 			}
 		}
-	// the state of shard q was read by the streams of the later devices: its block may only be recycled after those
-	// copies (long done by now: the waits cost nothing)
-	for( int q = 0; q + 1 < R; ++q )
-		{
-		CallLock cl( m->ctx[q] );
-		for( int i = q + 1; i < R; ++i ) MCK( cudaStreamWaitEvent( m->ctx[q]->compute, m->ev_copied[i], 0 ), "stream wait" );
-		main_release( m->ctx[q], d_state[q] );
-		}
+	// (staged copies only) the state of shard q was read by the streams of the later devices: its block may only be
+	// recycled after those copies
+	if( !m->all_peers )
+		for( int q = 0; q + 1 < R; ++q )
+			{
+			CallLock cl( m->ctx[q] );
+			for( int i = q + 1; i < R; ++i ) MCK( cudaStreamWaitEvent( m->ctx[q]->compute, m->ev_done[i], 0 ), "stream wait" );
+			main_release( m->ctx[q], d_state[q] );
+			}
 	cleanup( false );
 	return FLAN_B200_OK;
 	}

@@ -582,4 +582,26 @@ cudaError_t launch_add( float * out, const float * add, int64_t n, int sms, cuda
 	return cudaGetLastError();
 	}
 
+
+__global__ void __launch_bounds__( 1024 ) pv_state_push_kernel( const StatePush p )
+	{
+	uint4 * dst = p.dst[blockIdx.x];
+	for( unsigned i = threadIdx.x; i < p.n16; i += blockDim.x ) dst[i] = p.src[i];
+	__threadfence_system();
+	__syncthreads();
+	if( threadIdx.x == 0 && p.count[blockIdx.x] )
+		{
+		__threadfence_system();
+		atomicAdd_system( p.count[blockIdx.x], 1u );      // the destination waits for ONE value: (its rank) x (steps of this parity)
+		}
+	}
+
+cudaError_t launch_state_push( const StatePush & p, int destinations, cudaStream_t st )
+	{
+	if( destinations < 1 ) return cudaSuccess;
+	if( destinations > 16 ) return cudaErrorInvalidValue;
+	pv_state_push_kernel<<<destinations, 1024, 0, st>>>( p );
+	return cudaGetLastError();
+	}
+
 } // namespace pvk

@@ -58,4 +58,15 @@ cudaError_t launch_zero_shared( float * out, int64_t out_stride, int64_t out_off
                                 int64_t frame_begin, int64_t frame_end, int seg_len, int segs, int W, int hop, cudaStream_t st );
 cudaError_t launch_add( float * out, const float * add, int64_t n, int sms, cudaStream_t st );
 
+
+// One launch pushes a phase state to several peers: CTA b copies `n16` 16-byte units from src to dst[b] (peer memory over
+// NVLink: P2P access enabled or an IPC mapping) and then, when count[b] is set, increments that peer's arrival counter at
+// system scope. Fourteen DMA operations in a row -- a copy and a flag per destination -- took ~14 us per destination.
+struct StatePush
+	{
+	const uint4 * src; unsigned n16;
+	uint4 * dst[16]; unsigned * count[16];
+	};
+cudaError_t launch_state_push( const StatePush & p, int destinations, cudaStream_t st );
+
 } // namespace pvk
