@@ -305,6 +305,12 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 	return 0;
 	}
 
+// Frames per CTA as the launch policy chooses them (pv_tables.h), for the whole-wave tests.
+int pv_emu_choose_seg_len( int64_t frames, int channels, int sms, int W, int hop, int max_len, int analysis_only, int dft )
+	{
+	return choose_seg_len( frames, channels, sms, W, hop, max_len, analysis_only != 0, synth_ctas_per_sm( dft ) );
+	}
+
 // Host tables, for tests of the plan arithmetic.
 int pv_emu_tables( int N, int W, int hop, float sr, float ar, float * win_a, float * win_s, float * expected )
 	{

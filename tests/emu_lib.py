@@ -70,6 +70,9 @@ class Emu:
         assert rc == 0, rc
         return out, carry_out, flag.value
 
+    def choose_seg_len(self, frames, channels, sms, W, hop, max_len, dft, analysis_only=False):
+        return int(self.L.pv_emu_choose_seg_len(ctypes.c_int64(frames), channels, sms, W, hop, max_len, int(analysis_only), dft))
+
     def tables(self, N, W, hop, sr, ar):
         wa, ws, ex = np.empty(W, np.float32), np.empty(W, np.float32), np.empty(N // 2 + 1, np.float32)
         assert self.L.pv_emu_tables(N, W, hop, sr, ar, _ptr(wa), _ptr(ws), _ptr(ex)) == 0

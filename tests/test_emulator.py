@@ -271,3 +271,63 @@ def test_round_half_away_is_exactly_roundf(emu):
     assert emu.round_mismatches(bits(0.25), 40_000_000) == 0          # every float of [0.25, 4)
     assert emu.round_mismatches(bits(-0.25), 40_000_000) == 0
     assert emu.round_mismatches(bits(8388608.0) - 100, 9_000_000) == 0  # across 2^23 and up through 2^24
+
+
+# ---- phase state against the reference recurrence, negative frequencies included (round 2: the running maximum of a
+# segment is only taken where a non-decreasing run of prefix sums ends) ---------------------------------------------
+@pytest.mark.parametrize("seg_len", [5, 64, 300])
+def test_phase_state_equals_the_reference_accumulator(emu, seg_len):
+    """phase_vocoder.cpp:57-59: acc += float(f / ar * pi2); if (acc > P) acc = fmod(acc, P), P = double(pi2_float). The
+    scan form keeps (sum, max prefix) per segment and combines them; its value S - P * floor(max prefix / P) must be the
+    accumulator the serial loop ends with -- also where frequencies are negative for long stretches (accumulators
+    below zero are never wrapped), which is where the maximum matters."""
+    rng = np.random.default_rng(17)
+    sr, hop, N = 48000.0, 32, 256
+    B, F = N // 2 + 1, 300
+    ar = np.float32(sr) / np.float32(hop)
+    f = rng.uniform(-3000.0, 9000.0, (1, F, B)).astype(np.float32)
+    f[0, 40:90, :20] = rng.uniform(-20000.0, -10.0, (50, 20)).astype(np.float32)      # long negative runs
+    f[0, :, 100] = np.float32(-1.0)                                                   # never positive
+    f[0, :, 101] = np.float32(0.0)
+    pv = np.stack([np.ones_like(f), f], axis=-1)
+    _, state, flag = emu.synthesis(pv, sr, float(ar), N, seg_len=seg_len, want_carry=True, synth=False)
+    assert flag == 0
+    pi2 = np.float32(np.arccos(np.float32(-1.0))) * np.float32(2.0)
+    P = float(pi2)
+    inc = ((f[0] / ar).astype(np.float32) * pi2).astype(np.float32).astype(np.float64)       # [F][B]
+    acc = np.zeros(B)
+    for j in range(F):
+        acc = acc + inc[j]
+        wrap = acc > P
+        acc[wrap] = np.fmod(acc[wrap], P)
+    sum_q, sum_r, max_q, max_r = (state[0, :, i] for i in range(4))
+    value = (sum_q - max_q) * P + sum_r
+    assert np.all(max_q >= 0) and np.all((0 <= sum_r) & (sum_r < P)) and np.all((0 <= max_r) & (max_r < P))
+    assert np.abs(value - acc).max() < 1e-7, np.abs(value - acc).max()
+    assert value[100] < 0 and max_q[100] == 0 and max_r[100] == 0                            # the empty prefix is the maximum
+
+
+# ---- frames per CTA: whole waves (round 2) ---------------------------------------------------------------------------
+def test_segment_lengths_fill_whole_waves(emu):
+    """pv_tables.h: choose_seg_len. Long signals: the CTA count of resynthesis is just under a multiple of eight waves, so
+    1, 2, 4 or 8 devices each run a whole number of waves on shards cut at multiples of that length; the choice depends on
+    the whole signal only. cfg3 is the measured case (675 001 frames, 2 CTAs per SM at dft 8192: 96 frames per CTA)."""
+    sms = 148
+    assert emu.choose_seg_len(675001, 1, sms, 8192, 512, 128, 8192) == 96
+    for frames, C, W, hop, dft, occ in [(675001, 1, 8192, 512, 8192, 2), (1350002, 1, 2048, 128, 2048, 3), (112501, 2, 4096, 256, 4096, 3),
+                                        (84375, 1, 8192, 512, 8192, 2), (5000001, 3, 1024, 64, 1024, 3)]:
+        cap = 128 if dft >= 2048 else 64
+        L = emu.choose_seg_len(frames, C, sms, W, hop, cap, dft)
+        assert W // hop <= L <= cap
+        wave = sms * occ
+        ctas = C * -(-frames // L)
+        if ctas >= 16 * wave:
+            assert ctas <= -(-ctas // (8 * wave)) * 8 * wave and ctas > (-(-ctas // (8 * wave)) * 8 - 1) * wave, (frames, L, ctas)
+            for devices in (2, 4, 8):                    # shards of ceil(segs / devices) segments
+                per = -(-(-(-frames // L)) // devices)
+                assert C * per <= -(-ctas // (8 * wave)) * (8 // devices) * wave + C, (frames, devices)
+        elif ctas > wave:
+            assert ctas / wave > -(-ctas // wave) - 0.15, (frames, L, ctas)     # the last wave is nearly full
+    # short signals and analysis are untouched by the wave rule
+    assert emu.choose_seg_len(3446, 1, sms, 2048, 128, 128, 2048) == 16
+    assert emu.choose_seg_len(3446, 1, sms, 2048, 128, 128, 2048, analysis_only=True) == 8
