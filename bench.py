@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N > 1: how the phase state and the overlap-add halo travel between the ranks")
+    ap.add_argument("--no-summary-hint", action="store_true",
+                    help="N = 1: analysis without flan_b200_hint_resynthesis (resynthesis then reads the rows twice, as in round 1)")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the BASELINE config 3 leg (1 h mono 96 kHz through the multi-device handle)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="device time to cover with rounds of K steps")
     ap.add_argument("--chain", action="store_true",
@@ -396,6 +398,7 @@ def run_ours(args):
         dist.all_gather_into_tensor(bufs, state.contiguous())
         return bufs
 
+    hint = not args.no_summary_hint
     side_stream = torch.cuda.Stream(device=dev)
     head_event = torch.cuda.Event()
     head_event.record()                      # creates the handle the C ABI records on
@@ -413,9 +416,11 @@ def run_ours(args):
 
     def step(xin, yout=None):
         if world == 1:
+            # the round trip resynthesises the rows as analysis wrote them: with the hint the analysis kernel also leaves their
+            # phase summaries (flan_b200_hint_resynthesis) and resynthesis does not read the rows a second time
             yout = y if yout is None else yout
-            eng.convert_to_pv(xin, SR, W, HOP, N_DFT, out=pv)
-            eng.convert_to_audio(pv, SR, ar, W, out=yout)
+            eng.convert_to_pv(xin, SR, W, HOP, N_DFT, out=pv, for_resynthesis=hint)
+            eng.convert_to_audio(pv, SR, ar, W, out=yout, unchanged=hint)
             return yout
         eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
         if exchange is not None:
@@ -468,6 +473,22 @@ def run_ours(args):
     launches = (eng.launch_count() - launches0) // rounds
     ktimes = {k: eng.kernel_time(k) for k in eng.KERNEL_KINDS}
     eng.set_timing(False)
+    # for comparison (N = 1): the same round trip without the hint -- analysis as a caller who keeps the PV for something
+    # else runs it, resynthesis with its own pass over the rows for the phase summaries (round 1's form)
+    plain_ms = None
+    if world == 1 and hint:
+        hint = False
+        for _ in range(3):
+            step(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(x)
+        e1.record()
+        torch.cuda.synchronize()
+        plain_ms = e0.elapsed_time(e1) / steps
+        hint = True
     t = torch.tensor(round_ms, dtype=torch.float64, device=dev)
     rank_ms = [float(t.mean().item()) / steps]           # every rank's own mean step (diagnostic: which rank is the slowest)
     if world > 1:
@@ -556,7 +577,9 @@ def run_ours(args):
                        "seconds_per_gpu": args.seconds, "sharding": "none" if world == 1 else "contiguous frame ranges, dp%d; phase state + halo exchange: %s" % (
                            world, "peer copies into CUDA-IPC mailboxes (flan_b200_exchange_*)" if exchange is not None else "NCCL all_gather + send/recv" + (
                                " (%s)" % exchange_note if exchange_note else "")),
-                       "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush"},
+                       "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush",
+                       "phase_summaries": ("left by the analysis kernel (flan_b200_hint_resynthesis): the round trip resynthesises the rows unchanged"
+                                           if (world == 1 and hint) else "second pass over the rows (pv_phase_seg_kernel)")},
             "legs": {"analysis_frames_per_s": frames_rank / (an_ms / an_n * 1e-3) if an_n else None,
                      "resynthesis_frames_per_s": frames_rank / ((sy_ms + seg_ms + scan_ms) / sy_n * 1e-3) if sy_n else None,
                      "audio_samples_per_s": value * HOP,
@@ -564,7 +587,7 @@ def run_ours(args):
             "roofline": roofline, "kernels": per_kernel,
             "e2e": e2e, "rounds": rounds, "timed_seconds": sum(round_ms) * 1e-3,
             "roofline_legs": legs_roofline,
-            "cfg3_strong": cfg3, "ms_per_step_by_rank": rank_ms,
+            "cfg3_strong": cfg3, "ms_per_step_by_rank": rank_ms, "ms_per_step_without_summary_hint": plain_ms,
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -84,6 +84,7 @@ SYMBOLS = [
     ("flan_b200_modify_time_frames", _int, [_vp, _vp, _i64, _int, _i64, _int, _f, _f, ctypes.POINTER(_i64)]),
     ("flan_b200_modify_time", _int, [_vp, _vp, _int, _i64, _int, _f, _f, _vp, _i64, _int, _int, _i64, _vp, _int]),
     ("flan_b200_promise_unchanged", _int, [_vp, _vp]),
+    ("flan_b200_hint_resynthesis", _int, [_vp]),
     ("flan_b200_flan_encode", _int, [_vp, _vp, _i64, _f, _f, _vp]),
     ("flan_b200_flan_decode", _int, [_vp, _vp, _i64, _f, _f, _vp]),
     ("flan_b200_save_flan", _int, [_vp, ctypes.c_char_p, _vp, _int, _i64, _int, _f, _f, _int]),

@@ -38,6 +38,7 @@ struct HostEnv
 	void st_stream( float * p, float v ) { *p = v; }
 	void red_add( float * p, float v ) { std::atomic_ref<float>( *p ).fetch_add( v ); }
 	void prefetch( const void * ) {}
+	void shared_add( int * p, int v ) { *p += v; }
 	void cp_async8( float2 * dst, const float2 * src ) { *dst = *src; }
 	void cp_async_commit() {}
 	void cp_async_wait_all() {}
@@ -84,6 +85,8 @@ template<int N, int PT> void analysis_n( const AnalysisArgs & a, int64_t blocks 
 			// the product's choice: zero-padded windows of whole slots take the vector-load instantiation
 			if( a.W < N && a.W % ( N / PT ) == 0 && a.aligned2 )
 				run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true, true>( a, b, env, x0, x0 ); } );
+			else if( a.seg_out )      // the instantiation that also leaves the phase summaries (ring: N floats = room for the N/2 + 1 ints)
+				run_cta<N, PT>( [&]( HostEnv & env, float * ring, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true, false, true>( a, b, env, x0, x0, (int *) ring ); } );
 			else
 				run_cta<N, PT>( [&]( HostEnv & env, float *, float2 * x0, float2 * x1, float2 * ) { analysis_cta<N, PT, true, false>( a, b, env, x0, x0 ); } );
 			}
@@ -149,7 +152,7 @@ extern "C" {
 // Same contract as flan_b200_convert_to_pv_range, on host memory. seg_len <= 0 picks the product's choice for `sms` SMs.
 int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_offset, int C, int64_t n_total,
                      float sr, int W, int hop, int N, int64_t frame_begin, int64_t frame_end, int seg_len, int sms,
-                     float * pv_rows, int64_t pv_channel_stride, int points_per_thread )
+                     float * pv_rows, int64_t pv_channel_stride, int points_per_thread, PhaseSeg * seg_out )
 	{
 	const bool one_buffer = points_per_thread >= 100;      // +100: the exchange buffers alias
 	points_per_thread %= 100;
@@ -169,6 +172,8 @@ int pv_emu_analysis( const float * audio, int64_t audio_stride, int64_t audio_of
 	a.pass_tw = pt16 ? tb.pass_tw16.data() : tb.pass_tw.data();
 	a.one_buffer = one_buffer;
 	a.k = tb.k;
+	a.seg_out = seg_out; a.P = tb.P; a.rcpP = tb.rcpP;
+	if( seg_out && !( pt16 && one_buffer && W == N && points_per_thread == 16 ) ) return 5;
 	const int64_t blocks = (int64_t) C * segs;
 	if( !dft_size_is_templated( N ) )
 		{
@@ -302,6 +307,26 @@ int pv_emu_synthesis( const float * pv_rows, int64_t pv_channel_stride, int C, i
 		case 8192: synthesis_n<8192>( a, blocks ); break;
 		default: return 2;
 		}
+	return 0;
+	}
+
+// What pv_phase_seg_kernel computes: the summaries of the segments of seg_len frames, [C][segs][B].
+int pv_emu_phase_segments( const float * pv_rows, int C, int64_t frames, int B, float sr, float ar, int W, int seg_len, PhaseSeg * out, int * nan_flag )
+	{
+	const int N = ( B - 1 ) * 2;
+	HostTables tb;
+	if( !build_tables( N, W, (int)( sr / ar ), sr, ar, tb ) ) return 1;
+	const int segs = (int)( ( frames + seg_len - 1 ) / seg_len );
+	int flag = 0;
+	for( int c = 0; c < C; ++c )
+		for( int s = 0; s < segs; ++s )
+			for( int b = 0; b < B; ++b )
+				{
+				const int64_t fa = (int64_t) s * seg_len, fb = fa + seg_len < frames ? fa + seg_len : frames;
+				const float2 * col = (const float2 *) pv_rows + ( (int64_t) c * frames + fa ) * B + b;
+				out[( (size_t) c * segs + s ) * B + b] = phase_segment_summary( col, (int64_t) B, fb - fa, tb.k, tb.P, tb.rcpP, flag, []( const float2 * p ) { return *p; } );
+				}
+	if( nan_flag ) *nan_flag = flag;
 	return 0;
 	}
 

@@ -107,13 +107,26 @@ struct AnalysisArgs
 	const float2 * pass_tw;     // concatenated per-pass twiddles
 	int one_buffer;             // the two exchange buffers alias (half the shared memory, two more barriers per frame)
 	PvConsts k;
+	// EMIT instantiations only: the phase summaries PV::convert_to_audio needs of the rows this launch writes
+	// ([C][segs_per_channel][B], the layout of pv_phase_seg_kernel's output; entries the fast form cannot produce carry a
+	// NaN in sum.q and are recomputed from the rows by the scan), P = double( pi2 ), rcpP = 1 / P
+	PhaseSeg * seg_out;
+	double P, rcpP;
 	};
 
 // PAD: a zero-padded window that fills whole slots of the thread layout (window a multiple of 2T samples, < dft: the
 // API default window 2048 / dft 4096, Audio.h:158-163) loads its samples as vectors like the full window does; a
 // separate instantiation so that the full-window kernels keep their register budget.
-template<int N, int PT, bool ONE, bool PAD, class Env>
-PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1 )
+// EMIT: the CTA also leaves the phase summary of its segment -- what pv_phase_seg_kernel would compute
+// from a second read of the rows. A bin's increment inc = float( f / ar * pi2 ) lies within pi of its expected phase
+// advance c (the table value the phase vocoder subtracts); from c >= 2 and inc >= 2 on both are multiples of 2^-22, so
+// d = inc - c is exact, |d| < 4, and the segment's sum of up to 128 such d fits an int32 in units of 2^-22: ONE shared-
+// memory word per bin, private to the thread that owns the bin (`ssum`, M + 1 ints), no registers. The total
+// frames * c + 2^-22 * sum is exact in double and equals the plain double running sum of pv_phase_seg_kernel bit for
+// bit (that sum is exact too: multiples of 2^-22 below 2^18); increments are positive, so the running maximum is the
+// total. A bin that ever leaves those conditions (the lowest bins, NaN / Inf) is marked and gets the NaN entry.
+template<int N, int PT, bool ONE, bool PAD, bool EMIT = false, class Env>
+PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float2 * x0, float2 * x1, int * ssum = nullptr )
 	{
 	constexpr int M = N / 2, T = M / PT, H = PT / 2;      // H pairs of bins (k, M-k) per thread
 	const int t = env.tid;
@@ -143,6 +156,19 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 	float prev_mid = 0.0f;
 #pragma unroll
 	for( int u = 0; u < H; ++u ) { prev[u].x = 0.0f; prev[u].y = 0.0f; }
+
+	unsigned dirty = 0;             // EMIT: bit 2u / 2u+1 = bin k / M-k of slot u left the fast form, bit 2H = bin M/2
+	if( EMIT )
+		{
+#pragma unroll
+		for( int u = 0; u < H; ++u )
+			{
+			ssum[t + u * T] = 0; ssum[M - t - u * T] = 0;
+			const float4 cc = env.ldg4( a.binc4 + ( t + u * T ) );
+			dirty |= ( cc.z >= 6.0f ? 0u : 1u << ( 2 * u ) ) | ( -cc.w >= 6.0f ? 0u : 2u << ( 2 * u ) );
+			}
+		if( t == T / 2 ) { ssum[M / 2] = 0; dirty |= env.ldg2( a.binc + M / 2 ).y >= 6.0f ? 0u : 1u << ( 2 * H ); }
+		}
 
 	// The serial reference loop carries frame f-1's phase into frame f (phase_vocoder.cpp:44-45); a segment
 	// that does not start at frame 0 recomputes it with one warm-up FFT.
@@ -252,6 +278,24 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 				{
 				env.st_stream2( row_lo + u * T, mk );
 				env.st_stream2( row_hi - u * T, mm );
+				if( EMIT )
+					{
+					// both bins at once; a bin whose expected advance is below 6 rad was marked before the walk, for the others
+					// |d| < 4 implies inc > 2 (a NaN fails the comparison); sums of marked bins are never read
+					float2 Fq; Fq.x = mk.y; Fq.y = mm.y;
+					// phase_increment of both bins. The product is rounded on its own (scalar __fmul_rn): nvcc contracts the packed
+					// multiply with the packed subtraction that follows into one FFMA2, i.e. inc * pi2 - c with a single rounding.
+					const float2 qq = div_const2( Fq, a.k.analysis_rate, a.k.rcp_analysis_rate );
+					float2 inc; inc.x = mul_rn( qq.x, a.k.pi2 ); inc.y = mul_rn( qq.y, a.k.pi2 );
+					float2 cen; cen.x = expd.x; cen.y = -expd.y;
+					float2 dd; dd.x = sub_rn( inc.x, cen.x ); dd.y = sub_rn( inc.y, cen.y );
+					const float2 sc = mul2( dd, splat2( 4194304.0f ) );                     // (inc - c) * 2^22: exact, an integer
+					const bool ok_k = fabsf( sc.x ) < 16777216.0f && fabsf( mk.x ) <= 3.402823466e38f;
+					const bool ok_m = fabsf( sc.y ) < 16777216.0f && fabsf( mm.x ) <= 3.402823466e38f;
+					env.shared_add( ssum + k, (int) sc.x );
+					env.shared_add( ssum + ( M - k ), (int) sc.y );
+					dirty |= ( ok_k ? 0u : 1u << ( 2 * u ) ) | ( ok_m ? 0u : 2u << ( 2 * u ) );
+					}
 				}
 			}
 		if( t == T / 2 )
@@ -260,9 +304,39 @@ PV_HD void analysis_cta( const AnalysisArgs & a, int64_t block, Env & env, float
 			const float2 ch = env.ldg2( a.binc + M / 2 );
 			const float2 mh = phase_vocoder_bin( 2.0f * zh.x, -2.0f * zh.y, prev_mid, ch.x, ch.y, a.k );
 			if( emit ) env.st_stream2( row_mid, mh );
+			if( EMIT && emit )
+				{
+				const float sc = mul_rn( sub_rn( phase_increment( mh.y, a.k ), ch.y ), 4194304.0f );
+				const bool ok = fabsf( sc ) < 16777216.0f && fabsf( mh.x ) <= 3.402823466e38f;
+				env.shared_add( ssum + M / 2, (int) sc );
+				dirty |= ok ? 0u : 1u << ( 2 * H );
+				}
 			}
 		// the next frame's pass 0 writes x0, last read two barriers ago; its pass 1 writes x1 after one more barrier
 		if( ONE || ( FftPlan<M, PT>::num_passes - 1 ) % 2 == 0 ) env.sync();
+		}
+	if( EMIT )
+		{
+		PhaseSeg * out = a.seg_out + ( (int64_t) c * a.segs_per_channel + seg ) * (int64_t)( M + 1 );
+		const double frames = (double)( fb - fa );
+		auto put = [&]( int bin, float center, bool bad )
+			{
+			PhaseSeg s;
+			const double total = frames * (double) center + (double) ssum[bin] * 2.384185791015625e-07;    // 2^-22; exact
+			phase_sum_from_double( total, a.P, a.rcpP, s.sum.q, s.sum.r );
+			s.mx = s.sum;                                                 // every increment was positive
+			if( bad ) s.sum.q = nan_marker();
+			out[bin] = s;
+			};
+#pragma unroll
+		for( int u = 0; u < H; ++u )
+			{
+			const int k = t + u * T;
+			const float4 cc = env.ldg4( a.binc4 + k );
+			put( k, cc.z, ( dirty >> ( 2 * u ) ) & 1u );
+			put( M - k, -cc.w, ( dirty >> ( 2 * u + 1 ) ) & 1u );           // slot (0, 0): DC in lane x, Nyquist (bin M) in lane y
+			}
+		if( t == T / 2 ) put( M / 2, env.ldg2( a.binc + M / 2 ).y, ( dirty >> ( 2 * H ) ) & 1u );
 		}
 	}
 

@@ -437,6 +437,31 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 		return FLAN_B200_OK;
 		}
 	ctx->seg_key.valid = false;
+	// Summaries for a resynthesis of these rows as they are (flan_b200_hint_resynthesis): the 16-point full-window kernel
+	// leaves them in the workspace, in the segments resynthesis will use; anything else ignores the hint.
+	if( c.emit_summary && pt == 16 && a.one_buffer && tps_a == 512 && N >= 2048 && W == N && c.frame_begin == 0 && c.frame_end == F
+	    && c.pv_channel_stride == F * (int64_t)( N / 2 + 1 ) )
+		{
+		const int B = N / 2 + 1;
+		const PhaseLayout lay = phase_layout( ctx, C, F, B, W, hop, 0 );
+		if( lay.segs > 256 && lay.seg_len <= 128 )           // the three-launch scan is the one that repairs marked entries
+			{
+			void * ws = nullptr;
+			rc = get_workspace( ctx, lay.bytes(), &ws );
+			if( rc ) return rc;
+			seg_len = lay.seg_len; segs = lay.segs;
+			a.seg_len = seg_len; a.segs_per_channel = segs;
+			a.seg_out = (PhaseSeg *) ws; a.P = plan->host.P; a.rcpP = plan->host.rcpP;
+			CK( cudaMemsetAsync( ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1, 0, sizeof( int ), ctx->compute ), "flag clear" );
+			{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->compute, tps_a, pt ), "analysis launch" ); }
+			flan_b200_ctx::SegKey key;
+			key.pv = c.d_pv_rows; key.stride = c.pv_channel_stride; key.fb = 0; key.fe = F;
+			key.C = C; key.B = B; key.W = W; key.seg_len = seg_len; key.sr = fbits( c.sr ); key.ar = fbits( flan_b200_analysis_rate( c.sr, hop ) );
+			key.valid = true; key.nan_known = true; key.needs_fix = true;
+			ctx->seg_key = key;
+			return FLAN_B200_OK;
+			}
+		}
 	// Whole waves: with a few waves of CTAs the last, partly filled one is a large share of the launch (a 1/8 shard of cfg3:
 	// 660 CTAs = 2.23 waves of 296). Segments are shortened until the CTAs just fill the waves they need anyway. Analysis
 	// results do not depend on where segments are cut (the warm-up frame recomputes the previous phase exactly).
@@ -488,6 +513,10 @@ PhaseLayout phase_layout( const flan_b200_ctx * ctx, int C, int64_t frames, int 
 // buffer may use the phase summaries its producer left in the workspace.
 static thread_local const void * g_promised_pv = nullptr;
 void promise_unchanged( const void * d_pv ) { g_promised_pv = d_pv; }
+// flan_b200_hint_resynthesis, per calling thread: consumed by the next flan_b200_convert_to_pv.
+static thread_local bool g_resynthesis_hint = false;
+bool take_resynthesis_hint() { const bool h = g_resynthesis_hint; g_resynthesis_hint = false; return h; }
+void set_resynthesis_hint() { g_resynthesis_hint = true; }
 bool take_promise( const void * d_pv )
 	{
 	const bool hit = d_pv && g_promised_pv == d_pv;
@@ -537,7 +566,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	// summaries whose NaN / Inf flag is gone cannot serve a caller that asks for the flag
 	const bool have_summaries = s.reuse_summary && ( !s.d_nan_flag || old.nan_known ) && old.valid && old.pv == key.pv && old.stride == key.stride && old.fb == key.fb
 	                         && old.fe == key.fe && old.C == key.C && old.B == key.B && old.W == key.W && old.seg_len == key.seg_len && old.sr == key.sr && old.ar == key.ar;
-	const bool old_group_prefix = old.group_prefix, old_nan_known = old.nan_known;
+	const bool old_group_prefix = old.group_prefix, old_nan_known = old.nan_known, old_needs_fix = old.needs_fix;
 	ctx->seg_key = key;
 
 	PhaseSegArgs sa{};
@@ -547,11 +576,7 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sa.seg_out = d_seg; sa.nan_flag = s.d_nan_flag ? s.d_nan_flag : ctx->d_flags + flan_b200_ctx::FLAG_SLOTS;   // last slot + 1: write-only scratch
 	sa.k = plan->host.k; sa.P = plan->host.P; sa.rcpP = plan->host.rcpP;
 	if( !have_summaries ) { LaunchTimer lt( ctx, 1 ); CK( launch_phase_seg( sa, C, ctx->compute ), "phase summary launch" ); }
-	else
-		{
-		ctx->seg_key.nan_known = old_nan_known;
-		if( s.d_nan_flag ) CK( cudaMemcpyAsync( s.d_nan_flag, ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1, sizeof( int ), cudaMemcpyDeviceToDevice, ctx->compute ), "flag copy" );
-		}
+	else ctx->seg_key.nan_known = old_nan_known;
 
 	PhaseScanArgs sc{};
 	sc.seg = d_seg; sc.segs_per_channel = segs; sc.B = B;
@@ -566,8 +591,18 @@ int synth_range( flan_b200_ctx * ctx, const SynthCall & s )
 	sc.expand_only = ( have_summaries && old_group_prefix && three_launches && !s.summary_only && !s.d_carry_out ) ? 1 : 0;
 	sc.expand_carry = sc.expand_only ? s.d_carry_in : nullptr;
 	ctx->seg_key.group_prefix = s.summary_only && !s.d_carry_in && three_launches;
+	if( have_summaries && old_needs_fix )
+		{
+		// summaries of the analysis kernel: the group reduction recomputes the entries it marked (the lowest bins, NaN / Inf)
+		if( !three_launches || sc.expand_only ) return fail( ctx, FLAN_B200_INVALID, "internal: marked summaries need the three-launch scan" );
+		sc.fix_pv = (const float2 *) s.d_pv_rows; sc.fix_channel_stride = s.pv_channel_stride;
+		sc.fix_frame_begin = s.frame_begin; sc.fix_frame_end = s.frame_end; sc.fix_seg_len = seg_len;
+		sc.fix_k = plan->host.k; sc.fix_nan_flag = ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1;
+		}
 	{ LaunchTimer lt( ctx, 2 ); CK( launch_phase_scan( sc, C, ctx->compute ), "phase scan launch" );
 	  ctx->launches += three_launches ? ( sc.expand_only ? 0 : ( s.summary_only ? 1 : 2 ) ) : 0; }     // launch_phase_scan: one launch for short signals, else 1 to 3
+	if( have_summaries && s.d_nan_flag )
+		CK( cudaMemcpyAsync( s.d_nan_flag, ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1, sizeof( int ), cudaMemcpyDeviceToDevice, ctx->compute ), "flag copy" );
 	if( s.summary_only ) return FLAN_B200_OK;
 	if( cancelled( s.cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 
@@ -1011,7 +1046,14 @@ int flan_b200_convert_to_pv( flan_b200_ctx * ctx, const float * d_audio, int C, 
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 	if( hop < 1 ) return fail( ctx, FLAN_B200_INVALID, "hop must be >= 1" );
 	const int64_t F = flan_b200_num_frames( n, hop );
-	int rc = flan_b200_convert_to_pv_range( ctx, d_audio, n, 0, n, C, n, sr, W, hop, N, 0, F, d_pv, F * ( N / 2 + 1 ) );
+	int rc;
+		{
+		CallLock lock( ctx );
+		BlockUse use( ctx, { d_audio, d_pv } );
+		AnalysisCall a{ d_audio, n, 0, n, C, n, sr, W, hop, N, 0, F, d_pv, F * ( N / 2 + 1 ) };
+		a.emit_summary = take_resynthesis_hint();
+		rc = analysis_range( ctx, a );
+		}
 	if( rc ) return rc;
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
 	return FLAN_B200_OK;
@@ -1047,6 +1089,13 @@ int flan_b200_convert_to_audio( flan_b200_ctx * ctx, const float * d_pv, int C, 
 		}
 	if( nan_or_inf ) CK( cudaStreamSynchronize( st ), "flag sync" );
 	if( cancelled( cancel ) ) return fail( ctx, FLAN_B200_CANCELLED, "cancelled" );
+	return FLAN_B200_OK;
+	}
+
+int flan_b200_hint_resynthesis( flan_b200_ctx * ctx )
+	{
+	if( !ctx ) return FLAN_B200_INVALID;
+	pvrt::set_resynthesis_hint();
 	return FLAN_B200_OK;
 	}
 

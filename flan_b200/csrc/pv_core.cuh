@@ -631,6 +631,17 @@ PV_HD bool phase_sum_less( const PhaseSum & a, const PhaseSum & b )
 
 struct PhaseSeg { PhaseSum sum, mx; };   // total and max prefix (the empty prefix counts as 0)
 
+// sum.q of a summary its producer could not compute (analysis_cta<EMIT>): the scan recomputes the entry from the rows.
+PV_HD double nan_marker()
+	{
+#if defined(__CUDA_ARCH__)
+	return __longlong_as_double( 0x7ff8000000000000ll );
+#else
+	return (double) NAN;
+#endif
+	}
+PV_HD bool is_nan_marker( const PhaseSeg & s ) { return s.sum.q != s.sum.q; }
+
 // Summary of one bin over the frames of a segment, fed in frame order: total phase increment and its max prefix. Within
 // a segment (a few thousand radians at most) the running sum is a plain double -- absolute error ~1e-12 rad -- and only
 // the two results are converted to the split form. `bad` is the is_nan_or_inf() pre-scan of AudioPV.cpp:88. Used by

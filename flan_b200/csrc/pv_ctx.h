@@ -128,6 +128,7 @@ struct flan_b200_ctx
 	// identity of the phase-segment summaries currently held in the workspace (flan_b200_phase_summary -> _range reuse)
 	struct SegKey { const void * pv = nullptr; int64_t stride = 0, fb = 0, fe = 0; int C = 0, B = 0, W = 0, seg_len = 0; uint32_t sr = 0, ar = 0; bool valid = false;
 	                bool group_prefix = false;   // the scan scratch holds the carry-free group prefixes of these summaries
+	                bool needs_fix = false;      // the summaries come from the analysis kernel: entries with the NaN marker are recomputed by the next scan
 	                bool nan_known = false;      // d_flags[FLAG_SLOTS + 1] holds the NaN / Inf pre-scan result of these rows (a producing kernel left it)
 	              } seg_key;
 	int max_seg_len = 0;                    // frames per CTA at most; 0 = by size (FLAN_B200_DEBUG builds: FLAN_B200_SEG_LEN)
@@ -260,6 +261,8 @@ struct PhaseLayout { int seg_len, segs, group_len, groups; size_t seg_bytes, acc
 PhaseLayout phase_layout( const flan_b200_ctx * ctx, int C, int64_t frames, int B, int W, int hop, int seg_len_given );
 void promise_unchanged( const void * d_pv );
 bool take_promise( const void * d_pv );
+bool take_resynthesis_hint();
+void set_resynthesis_hint();
 // Slices of whole waves: CTAs per slice for `ctas` CTAs of a kernel with `wave` resident CTAs on the device.
 int64_t ctas_per_slice( int64_t ctas, int64_t wave, size_t copy_bytes );
 
@@ -270,6 +273,7 @@ struct AnalysisCall
 	int64_t frame_begin, frame_end;
 	float * d_pv_rows; int64_t pv_channel_stride;
 	int * wave_out = nullptr;       // query only: CTAs of one full wave of the kernel this call would launch; nothing is launched
+	bool emit_summary = false;      // whole-signal call whose rows will be resynthesised unchanged: also leave their phase summaries
 	};
 int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & a );
 

@@ -38,6 +38,8 @@ struct DeviceEnv
 		{ asm volatile( "st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" :: "l"( p ), "f"( v.x ), "f"( v.y ) : "memory" ); }
 	__device__ __forceinline__ void st_stream( float * p, float v ) { __stcs( p, v ); }
 	__device__ __forceinline__ void red_add( float * p, float v ) { atomicAdd( p, v ); }
+	// shared-memory word += v without a round trip through registers (the word is private to the calling thread)
+	__device__ __forceinline__ void shared_add( int * p, int v ) { asm volatile( "red.shared.add.s32 [%0], %1;" :: "r"( (unsigned) __cvta_generic_to_shared( p ) ), "r"( v ) : "memory" ); }
 	// 8-byte asynchronous global->shared copy (LDGSTS), completion tracked per thread by commit / wait groups
 	__device__ __forceinline__ void cp_async8( float2 * dst, const float2 * src )
 		{
@@ -87,14 +89,15 @@ struct DeviceEnv
 constexpr int min_blocks( int threads, int TPS ) { return TPS / threads > 32 ? 32 : ( TPS / threads > 0 ? TPS / threads : 1 ); }
 
 // PT = complex points per thread: 8 (radix-8 passes, N/16 threads per frame) or 16 (radix-16 passes, N/32 threads).
-template<int N, int PT, int TPS, bool ONE, bool PAD = false>
+template<int N, int PT, int TPS, bool ONE, bool PAD = false, bool EMIT = false>
 __global__ void __launch_bounds__( N / ( 2 * PT ), min_blocks( N / ( 2 * PT ), TPS ) ) pv_analysis_kernel( const AnalysisArgs a )
 	{
 	extern __shared__ __align__( 16 ) unsigned char smem_raw[];
 	float2 * x0 = reinterpret_cast<float2 *>( smem_raw );
 	float2 * x1 = ONE ? x0 : x0 + XBuf<N / 2>::size;
+	int * ssum = EMIT ? reinterpret_cast<int *>( x1 + XBuf<N / 2>::size ) : nullptr;      // N/2 + 1 per-bin sums (EMIT only)
 	DeviceEnv env; env.tid = threadIdx.x;
-	analysis_cta<N, PT, ONE, PAD>( a, (int64_t) blockIdx.x, env, x0, x1 );
+	analysis_cta<N, PT, ONE, PAD, EMIT>( a, (int64_t) blockIdx.x, env, x0, x1, ssum );
 	}
 
 // Mirrored last pass (pv_body.cuh: analysis_cta_mirror): 16 points per thread, unpack + phase vocoder on the thread's own registers.
@@ -156,6 +159,24 @@ __global__ void __launch_bounds__( 256 ) pv_phase_seg_kernel( const PhaseSegArgs
 	if( flag ) *a.nan_flag = 1;
 	}
 
+// Summaries left by the analysis kernel (analysis_cta<EMIT>): the entries it marked -- the lowest bins, whose expected
+// phase advance is too small for the 32-bit form -- are recomputed from the rows, one thread per (channel, segment,
+// bin < bins), all at once. (Marked entries elsewhere, NaN / Inf, are repaired by the scan's group reduction.)
+__global__ void __launch_bounds__( 64 ) pv_phase_fix_kernel( const PhaseScanArgs a, int bins )
+	{
+	const int b = threadIdx.x + blockIdx.z * 64;
+	const int s = blockIdx.x, c = blockIdx.y;
+	if( b >= bins || b >= a.B ) return;
+	PhaseSeg * e = const_cast<PhaseSeg *>( a.seg ) + ( (int64_t) c * a.segs_per_channel + s ) * a.B + b;
+	if( !( e->sum.q != e->sum.q ) ) return;
+	const int64_t fa = a.fix_frame_begin + (int64_t) s * a.fix_seg_len;
+	const int64_t fb = ( fa + a.fix_seg_len < a.fix_frame_end ) ? fa + a.fix_seg_len : a.fix_frame_end;
+	const float2 * col = a.fix_pv + (int64_t) c * a.fix_channel_stride + ( fa - a.fix_frame_begin ) * (int64_t) a.B + b;
+	int flag = 0;
+	*e = phase_segment_summary( col, (int64_t) a.B, fb - fa, a.fix_k, a.P, a.rcpP, flag, []( const float2 * p ) { return __ldg( p ); } );
+	if( flag ) *a.fix_nan_flag = 1;
+	}
+
 // One thread per (channel, bin): serial walk over the segments (a few thousand at most), writing the
 // accumulator value that enters each segment. carry_in/carry_out chain frame-range shards across GPUs.
 // The scan over segments runs in three short phases so that its serial depth is group_len + groups + group_len
@@ -188,7 +209,21 @@ __global__ void __launch_bounds__( 128 ) pv_phase_scan_kernel( const PhaseScanAr
 	const PhaseSeg * src = a.seg + (int64_t) c * a.segs_per_channel * a.B + b;
 	if( mode == 0 )
 		{
-		for( int s = s0; s < s1; ++s ) phase_state_combine( st, src[(int64_t) s * a.B], a.P, a.rcpP );
+		for( int s = s0; s < s1; ++s )
+			{
+			PhaseSeg v = src[(int64_t) s * a.B];
+			if( a.fix_pv && is_nan_marker( v ) )
+				{
+				const int64_t fa = a.fix_frame_begin + (int64_t) s * a.fix_seg_len;
+				const int64_t fb = ( fa + a.fix_seg_len < a.fix_frame_end ) ? fa + a.fix_seg_len : a.fix_frame_end;
+				const float2 * col = a.fix_pv + (int64_t) c * a.fix_channel_stride + ( fa - a.fix_frame_begin ) * (int64_t) a.B + b;
+				int flag = 0;
+				v = phase_segment_summary( col, (int64_t) a.B, fb - fa, a.fix_k, a.P, a.rcpP, flag, []( const float2 * p ) { return __ldg( p ); } );
+				if( flag ) *a.fix_nan_flag = 1;
+				const_cast<PhaseSeg *>( src )[(int64_t) s * a.B] = v;
+				}
+			phase_state_combine( st, v, a.P, a.rcpP );
+			}
 		grp[(int64_t) g * a.B] = st;
 		return;
 		}
@@ -367,6 +402,22 @@ template<int N, int PT, int TPS, bool ONE> static cudaError_t launch_analysis_nt
 			return cudaGetLastError();
 			}
 		}
+	// the full-window launch that also leaves the phase summaries of its rows (16 points per thread, one buffer, TPS 512: the
+	// policy's variant from dft 2048 up)
+	if constexpr( PT == 16 && ONE && TPS == 512 && N >= 2048 )
+		{
+		if( a.seg_out )
+			{
+			const size_t smem_emit = smem + sizeof( int ) * ( N / 2 + 4 );
+			e = cudaFuncSetAttribute( pv_analysis_kernel<N, PT, TPS, ONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_emit );
+			if( e != cudaSuccess ) return e;
+			apply_carveout( pv_analysis_kernel<N, PT, TPS, ONE, false, true> );
+			if( blocks < 0 ) return report_occupancy( pv_analysis_kernel<N, PT, TPS, ONE, false, true>, N / ( 2 * PT ), smem_emit );
+			pv_analysis_kernel<N, PT, TPS, ONE, false, true><<<(unsigned) blocks, N / ( 2 * PT ), smem_emit, st>>>( a );
+			return cudaGetLastError();
+			}
+		}
+	if( a.seg_out ) return cudaErrorInvalidValue;          // the caller asks for summaries only where this form exists
 	if( blocks < 0 ) return report_occupancy( pv_analysis_kernel<N, PT, TPS, ONE>, N / ( 2 * PT ), smem );
 	pv_analysis_kernel<N, PT, TPS, ONE><<<(unsigned) blocks, N / ( 2 * PT ), smem, st>>>( a );
 	return cudaGetLastError();
@@ -551,6 +602,8 @@ cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 		}
 	if( !a.expand_only )
 		{
+		if( a.fix_pv && a.segs_per_channel <= 65535 * 32 && C <= 65535 )
+			pv_phase_fix_kernel<<<dim3( a.segs_per_channel, C, 1 ), 64, 0, st>>>( a, 64 );
 		pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
 		pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
 		}

@@ -33,6 +33,10 @@ struct PhaseScanArgs
 	// and associative, DESIGN.md 4.2, so the result has the bits of the scan with carry_in == expand_carry)
 	int expand_only;
 	const PhaseSeg * expand_carry;   // [C][B] or null
+	// fix_pv != null: summaries left by the analysis kernel (analysis_cta<EMIT>); entries it could not produce carry a NaN
+	// marker and are recomputed here, in the group reduction, from the rows -- and written back for the re-walk
+	const float2 * fix_pv; int64_t fix_channel_stride, fix_frame_begin, fix_frame_end; int fix_seg_len;
+	PvConsts fix_k; int * fix_nan_flag;
 	};
 
 // points_per_thread values of launch_analysis: 8, 16, or PV_PT_MIRROR (16 points per thread with the mirrored last

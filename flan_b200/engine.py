@@ -59,13 +59,17 @@ class Engine:
         self.ctx.call("flan_b200_synchronize")
 
     # -- Audio::convert_to_PV --------------------------------------------------------------------
-    def convert_to_pv(self, audio, sr, W, hop, N, out=None):
-        """audio: cuda float32 [C, n] -> pv: cuda float32 [C, F, N/2+1, 2] of (m, f)."""
+    def convert_to_pv(self, audio, sr, W, hop, N, out=None, for_resynthesis=False):
+        """audio: cuda float32 [C, n] -> pv: cuda float32 [C, F, N/2+1, 2] of (m, f).
+        for_resynthesis: the rows will be resynthesised as they are (flan_b200_hint_resynthesis): the kernel also leaves
+        their phase summaries, and convert_to_audio(..., unchanged=True) does not read the rows a second time."""
         C, n = audio.shape
         F = self.num_frames(n, hop)
         if out is None:
             out = torch.empty((C, F, N // 2 + 1, 2), dtype=torch.float32, device=self.device)
         self._bind_stream()
+        if for_resynthesis:
+            self.ctx.call("flan_b200_hint_resynthesis")
         self.ctx.call("flan_b200_convert_to_pv", self._chk(audio), C, n, sr, W, hop, N, self._chk(out), None)
         return out
 

@@ -241,6 +241,13 @@ int flan_b200_modify_time( flan_b200_ctx * ctx, const float * d_pv, int channels
  * valid until the next call on this context that uses its scratch space or writes the buffer. A caller that knows d_pv is
  * unchanged since the call that produced it says so right before resynthesis (same host thread): */
 int flan_b200_promise_unchanged( flan_b200_ctx * ctx, const float * d_pv );
+/* The producer can also be the analysis itself: after this hint (same host thread) the next flan_b200_convert_to_pv also
+ * leaves the phase summaries of the rows it writes, for a caller that will resynthesise them as they are -- the round trip
+ * of BASELINE configs 1-3. Full-window transforms of dft 2048 / 4096 / 8192 on long signals have that form (one
+ * shared-memory word per bin: the increments of a bin lie within pi of its expected phase advance, and their differences
+ * to it sum exactly in 32 bits); every other call ignores the hint. Costs ~10 % of the analysis kernel, saves the second
+ * read of the rows (0.56 of 3.9 ms on cfg2). */
+int flan_b200_hint_resynthesis( flan_b200_ctx * ctx );
 
 /* ---- file formats either side of the path ---------------------------------------------------------
  * .flan RIFF-PV (PVBuffer::save / load, src/flan/PV/PVBuffer.cpp:99-140, 216-273; format described at

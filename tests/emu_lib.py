@@ -22,10 +22,12 @@ class Emu:
             build.build_emulator()
         L = ctypes.CDLL(path)
         L.pv_emu_analysis.argtypes = [_fp, _i64, _i64, ctypes.c_int, _i64, ctypes.c_float, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, _i64, _i64, ctypes.c_int, ctypes.c_int, _fp, _i64, ctypes.c_int]
+                                      ctypes.c_int, _i64, _i64, ctypes.c_int, ctypes.c_int, _fp, _i64, ctypes.c_int, ctypes.c_void_p]
         L.pv_emu_synthesis.argtypes = [_fp, _i64, ctypes.c_int, _i64, _i64, _i64, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, _fp, _i64, _i64, _i64, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.pv_emu_phase_segments.argtypes = [_fp, ctypes.c_int, _i64, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_int)]
         L.pv_emu_tables.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, _fp, _fp, _fp]
         L.pv_emu_div_const_mismatches.restype = _i64
         L.pv_emu_div_const_mismatches.argtypes = [ctypes.c_float, ctypes.c_uint32, _i64]
@@ -34,7 +36,9 @@ class Emu:
         self.L = L
 
     def analysis(self, audio, sr, W, hop, N, frame_begin=0, frame_end=None, seg_len=0, sms=4,
-                 audio_offset=0, n_total=None, points_per_thread=8):
+                 audio_offset=0, n_total=None, points_per_thread=8, emit_summary=False):
+        """emit_summary (116: 16 points per thread, one buffer; needs seg_len): also returns the phase summaries the kernel
+        leaves, float64 [C, segs, B, 4] = (sum.q, sum.r, max.q, max.r); a NaN in sum.q marks an entry left to the scan."""
         audio = np.ascontiguousarray(audio, np.float32)
         C, n_local = audio.shape
         if n_total is None:
@@ -45,10 +49,25 @@ class Emu:
         rows = frame_end - frame_begin
         B = N // 2 + 1
         pv = np.full((C, rows, B, 2), np.nan, np.float32)
+        seg = None
+        if emit_summary:
+            assert seg_len > 0
+            seg = np.full((C, -(-rows // seg_len), B, 4), 7.0, np.float64)
         rc = self.L.pv_emu_analysis(_ptr(audio), n_local, audio_offset, C, n_total, sr, W, hop, N, frame_begin,
-                                    frame_end, seg_len, sms, _ptr(pv), rows * B, points_per_thread)
+                                    frame_end, seg_len, sms, _ptr(pv), rows * B, points_per_thread,
+                                    None if seg is None else seg.ctypes.data)
         assert rc == 0, rc
-        return pv
+        return (pv, seg) if emit_summary else pv
+
+    def phase_segments(self, pv, sr, ar, W, seg_len):
+        """The summaries pv_phase_seg_kernel computes from the rows: float64 [C, segs, B, 4], and the NaN / Inf flag."""
+        pv = np.ascontiguousarray(pv, np.float32)
+        C, F, B, _ = pv.shape
+        out = np.zeros((C, -(-F // seg_len), B, 4), np.float64)
+        flag = ctypes.c_int(0)
+        assert self.L.pv_emu_phase_segments(_ptr(pv), C, ctypes.c_int64(F), B, ctypes.c_float(sr), ctypes.c_float(ar), W, seg_len,
+                                            out.ctypes.data, ctypes.byref(flag)) == 0
+        return out, flag.value
 
     def synthesis(self, pv, sr, ar, W, frame_begin=0, frames_total=None, seg_len=0, sms=4, carry_in=None,
                   want_carry=False, out_offset=None, out_len=None, synth=True, variant=8):

@@ -331,3 +331,34 @@ def test_segment_lengths_fill_whole_waves(emu):
     # short signals and analysis are untouched by the wave rule
     assert emu.choose_seg_len(3446, 1, sms, 2048, 128, 128, 2048) == 16
     assert emu.choose_seg_len(3446, 1, sms, 2048, 128, 128, 2048, analysis_only=True) == 8
+
+
+# ---- analysis that also leaves the phase summaries of its rows (round 2: flan_b200_hint_resynthesis) ----------------
+@pytest.mark.parametrize("N,hop,seg_len,n", [(2048, 128, 37, 30000), (4096, 256, 23, 40000), (8192, 512, 17, 70000)])
+def test_emulated_analysis_leaves_the_segment_summaries(emu, N, hop, seg_len, n):
+    """analysis_cta<EMIT>: per bin one shared-memory int32 holds the segment's sum of (increment - expected advance) in
+    units of 2^-22. Every entry it writes without the NaN marker must be the summary pv_phase_seg_kernel computes from the
+    rows, bit for bit; the rows themselves are those of the plain kernel; marked entries are few (the lowest bins)."""
+    sr = 48000.0
+    x = np.stack([noise_chirp(n, sr, 9), sine_sweep(n, sr) * np.float32(0.7)])
+    plain = emu.analysis(x, sr, N, hop, N, seg_len=seg_len, points_per_thread=116)
+    pv, seg = emu.analysis(x, sr, N, hop, N, seg_len=seg_len, points_per_thread=116, emit_summary=True)
+    assert np.array_equal(pv.view(np.uint32), plain.view(np.uint32))
+    ar = float(np.float32(sr) / np.float32(hop))
+    want, flag = emu.phase_segments(pv, sr, ar, N, seg_len)
+    assert flag == 0 and seg.shape == want.shape
+    marked = np.isnan(seg[..., 0])
+    assert not np.isnan(seg[..., 1:]).any()
+    assert np.array_equal(seg[~marked].view(np.uint64), want[~marked].view(np.uint64))
+    B = N // 2 + 1
+    per_bin = marked.reshape(-1, B).mean(axis=0)
+    assert per_bin[:6].min() == 1.0, "bins whose expected advance is below 2 rad are always left to the scan"
+    assert marked.mean() < 0.03 and per_bin[64:].max() == 0.0, (marked.mean(), np.nonzero(per_bin)[0][-5:])
+    # a NaN sample poisons the frames it reaches: every entry of those segments is marked, nothing is silently wrong
+    x[0, n // 2] = np.nan
+    pv, seg = emu.analysis(x, sr, N, hop, N, seg_len=seg_len, points_per_thread=116, emit_summary=True)
+    want, flag = emu.phase_segments(pv, sr, ar, N, seg_len)
+    marked = np.isnan(seg[..., 0])
+    assert flag == 1 and np.array_equal(seg[~marked].view(np.uint64), want[~marked].view(np.uint64))
+    hit = (n // 2) // hop // seg_len
+    assert marked[0, hit].all()

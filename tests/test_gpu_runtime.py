@@ -251,3 +251,51 @@ def test_range_after_summary_only_rewalks_the_scan_bit_identical(eng):
         assert torch.equal(plain, head)
         total[:, s.span_lo:s.span_hi] += plain
     assert (total - full).abs().max().item() <= 2e-6
+
+
+@pytest.mark.parametrize("N,hop,seconds", [(4096, 256, 200), (8192, 512, 420), (2048, 128, 100)])
+def test_analysis_hint_leaves_the_phase_summaries(eng, N, hop, seconds):
+    """flan_b200_hint_resynthesis: the next convert_to_pv also leaves the phase summaries of its rows (one shared-memory word
+    per bin; entries it cannot produce are marked and recomputed by the scan), and convert_to_audio(unchanged=True) skips
+    pv_phase_seg_kernel. Rows, samples and the NaN / Inf flag are those of the plain calls, bit for bit."""
+    import torch
+    sr = 48000.0
+    n = int(sr * seconds)
+    x = np.stack([noise_chirp(n, sr, 3), sine_sweep(n, sr) * np.float32(0.5)])
+    xd = torch.from_numpy(x).cuda()
+    ar = eng.analysis_rate(sr, hop)
+    pv = eng.convert_to_pv(xd, sr, N, hop, N)
+    y, flag = eng.convert_to_audio(pv, sr, ar, N, check_nan=True)
+    pv_h = eng.convert_to_pv(xd, sr, N, hop, N, for_resynthesis=True)
+    assert torch.equal(pv_h, pv)
+    n0 = eng.launch_count()
+    y_h, flag_h = eng.convert_to_audio(pv_h, sr, ar, N, check_nan=True, unchanged=True)
+    used = eng.launch_count() - n0
+    assert torch.equal(y_h, y) and flag_h == flag and not flag
+    n0 = eng.launch_count()
+    eng.convert_to_audio(pv, sr, ar, N)
+    assert eng.launch_count() - n0 == used + 1, "the hint saves exactly the phase summary launch"
+    # the scan repaired the marked entries in place: a second resynthesis of the same rows reuses them as they are
+    pv_h = eng.convert_to_pv(xd, sr, N, hop, N, for_resynthesis=True)
+    a = eng.convert_to_audio(pv_h, sr, ar, N, unchanged=True)
+    b = eng.convert_to_audio(pv_h, sr, ar, N, unchanged=True)
+    assert torch.equal(a, y) and torch.equal(b, y)
+    # NaN in the signal: the frames it reaches are marked, recomputed, and raise the flag like the plain path
+    xd[1, n // 3] = float("nan")
+    pv = eng.convert_to_pv(xd, sr, N, hop, N)
+    y, flag = eng.convert_to_audio(pv, sr, ar, N, check_nan=True)
+    pv_h = eng.convert_to_pv(xd, sr, N, hop, N, for_resynthesis=True)
+    y_h, flag_h = eng.convert_to_audio(pv_h, sr, ar, N, check_nan=True, unchanged=True)
+    assert flag and flag_h
+    assert torch.equal(y_h.view(torch.int32), y.view(torch.int32))
+
+
+def test_analysis_hint_is_ignored_where_the_form_does_not_exist(eng):
+    import torch
+    for (N, W, hop, n) in [(1024, 1024, 64, 48000 * 30), (4096, 2048, 128, 48000 * 60), (4096, 4096, 256, 48000 * 4), (3000, 3000, 100, 200000)]:
+        x = torch.from_numpy(np.stack([noise_chirp(n, 48000.0, 8)])).cuda()
+        ar = eng.analysis_rate(48000.0, hop)
+        pv = eng.convert_to_pv(x, 48000.0, W, hop, N)
+        pv_h = eng.convert_to_pv(x, 48000.0, W, hop, N, for_resynthesis=True)
+        assert torch.equal(pv, pv_h)
+        assert torch.equal(eng.convert_to_audio(pv_h, 48000.0, ar, W, unchanged=True), eng.convert_to_audio(pv, 48000.0, ar, W))
