@@ -475,12 +475,15 @@ def run_ours(args):
     eng.set_timing(False)
     # for comparison (N = 1): the same round trip without the hint -- analysis as a caller who keeps the PV for something
     # else runs it, resynthesis with its own pass over the rows for the phase summaries (round 1's form)
-    plain_ms = None
+    plain_ms, plain_kernels = None, None
     if world == 1 and hint:
         hint = False
         for _ in range(3):
             step(x)
         torch.cuda.synchronize()
+        eng.set_timing(True)
+        for k in eng.KERNEL_KINDS:
+            eng.kernel_time(k)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -488,6 +491,9 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         plain_ms = e0.elapsed_time(e1) / steps
+        pk = {k: eng.kernel_time(k) for k in ("analysis", "phase_seg", "phase_scan", "synthesis")}
+        plain_kernels = {k: (v[0] / v[1] if v[1] else None) for k, v in pk.items()}
+        eng.set_timing(False)
         hint = True
     t = torch.tensor(round_ms, dtype=torch.float64, device=dev)
     rank_ms = [float(t.mean().item()) / steps]           # every rank's own mean step (diagnostic: which rank is the slowest)
@@ -534,7 +540,11 @@ def run_ours(args):
         an_bytes = 4.0 * CH * n_local + 8.0 * CH * sh.frames * B          # per launch: audio read + PV written
         sy_bytes = 8.0 * CH * sh.frames * B + 4.0 * CH * out_len          # per launch: PV read + audio written
         kern = []
-        if an_n:
+        if an_n and world == 1 and hint:
+            # the instantiation that also writes the phase summaries of its rows (32 bytes per bin and segment of <= 128 frames)
+            segs = -(-sh.frames // 127)
+            kern.append(("pv_analysis_kernel<4096> +summaries", an_bytes + 32.0 * CH * segs * B, an_ms / an_n))
+        elif an_n:
             kern.append(("pv_analysis_kernel<4096>", an_bytes, an_ms / an_n))
         if sy_n:
             kern.append(("pv_synthesis_mirror_kernel<4096>", sy_bytes, sy_ms / sy_n))
@@ -587,7 +597,10 @@ def run_ours(args):
             "roofline": roofline, "kernels": per_kernel,
             "e2e": e2e, "rounds": rounds, "timed_seconds": sum(round_ms) * 1e-3,
             "roofline_legs": legs_roofline,
-            "cfg3_strong": cfg3, "ms_per_step_by_rank": rank_ms, "ms_per_step_without_summary_hint": plain_ms,
+            "cfg3_strong": cfg3, "ms_per_step_by_rank": rank_ms, "without_summary_hint": None if plain_ms is None else {
+                "ms_per_step": plain_ms, "value": frames_all / (plain_ms * 1e-3), "ms_per_launch": plain_kernels,
+                "note": "the same round trip when the analysis does not know that its rows will be resynthesised unchanged: "
+                        "the plain analysis kernel, and pv_phase_seg_kernel reads the rows a second time"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }

@@ -78,6 +78,8 @@ def main():
             tm, tu = kernels[k]["gpu__time_duration.sum"]
             rd, wr = float(rd.replace(",", "")) * TO_BYTES[ru], float(wr.replace(",", "")) * TO_BYTES[wu]
             key = re.sub(r"<(\d+),.*>", r"<\1>", k)
+            if k.startswith("pv_analysis_kernel<") and k.count(",") == 5 and re.search(r",\s*1>$", k):
+                key += " +summaries"        # the instantiation that also leaves the phase summaries (last template argument)
             traffic["kernels"][key] = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "capture": tag,
                                        "time_ms": float(tm.replace(",", "")) * TO_MS[tu]}
         except Exception as e:
