@@ -285,7 +285,9 @@ def cfg3_leg(world, steps, peak):
 
         def step():
             pv, y = capi.ShardedPV(), capi.ShardedAudio()
+            call("flan_b200_multi_hint_resynthesis")          # a round trip: the shards' analysis leaves their phase summaries
             call("flan_b200_multi_convert_to_pv", ctypes.byref(a), sr, w, hop, n_dft, ctypes.byref(pv))
+            call("flan_b200_multi_promise_unchanged", ctypes.byref(pv))
             call("flan_b200_multi_convert_to_audio", ctypes.byref(pv), ctypes.byref(y))
             call("flan_b200_multi_free_pv", ctypes.byref(pv))
             call("flan_b200_multi_free_audio", ctypes.byref(y))

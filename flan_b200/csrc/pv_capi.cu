@@ -439,11 +439,12 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 	ctx->seg_key.valid = false;
 	// Summaries for a resynthesis of these rows as they are (flan_b200_hint_resynthesis): the 16-point full-window kernel
 	// leaves them in the workspace, in the segments resynthesis will use; anything else ignores the hint.
-	if( c.emit_summary && pt == 16 && a.one_buffer && tps_a == 512 && N >= 2048 && W == N && c.frame_begin == 0 && c.frame_end == F
-	    && c.pv_channel_stride == F * (int64_t)( N / 2 + 1 ) )
+	if( c.emit_summary && pt == 16 && a.one_buffer && tps_a == 512 && N >= 2048 && W == N
+	    && ( c.emit_seg_len > 0 || ( c.frame_begin == 0 && c.frame_end == F ) )
+	    && c.pv_channel_stride == frames * (int64_t)( N / 2 + 1 ) )
 		{
 		const int B = N / 2 + 1;
-		const PhaseLayout lay = phase_layout( ctx, C, F, B, W, hop, 0 );
+		const PhaseLayout lay = phase_layout( ctx, C, frames, B, W, hop, c.emit_seg_len );
 		if( lay.segs > 256 && lay.seg_len <= 128 )           // the three-launch scan is the one that repairs marked entries
 			{
 			void * ws = nullptr;
@@ -455,7 +456,7 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 			CK( cudaMemsetAsync( ctx->d_flags + flan_b200_ctx::FLAG_SLOTS + 1, 0, sizeof( int ), ctx->compute ), "flag clear" );
 			{ LaunchTimer lt( ctx, 0 ); CK( launch_analysis( N, a, (int64_t) C * segs, ctx->compute, tps_a, pt ), "analysis launch" ); }
 			flan_b200_ctx::SegKey key;
-			key.pv = c.d_pv_rows; key.stride = c.pv_channel_stride; key.fb = 0; key.fe = F;
+			key.pv = c.d_pv_rows; key.stride = c.pv_channel_stride; key.fb = c.frame_begin; key.fe = c.frame_end;
 			key.C = C; key.B = B; key.W = W; key.seg_len = seg_len; key.sr = fbits( c.sr ); key.ar = fbits( flan_b200_analysis_rate( c.sr, hop ) );
 			key.valid = true; key.nan_known = true; key.needs_fix = true;
 			ctx->seg_key = key;

@@ -277,15 +277,41 @@ int flan_b200_multi_convert_to_pv( flan_b200_multi * m, const flan_b200_sharded_
 	pv->channels = C; pv->frames = p.F; pv->bins = B; pv->sample_rate = sample_rate;
 	pv->analysis_rate = flan_b200_analysis_rate( sample_rate, hop ); pv->window_size = window_size; pv->shards = p.shards;
 	for( int i = 0; i <= p.shards; ++i ) pv->frame_begin[i] = p.fb[i];
+	// flan_b200_hint_resynthesis (this thread): every shard's analysis also leaves the phase summaries of its rows, in the
+	// segments of the whole signal
+	const bool hint = take_resynthesis_hint();
 	for( int i = 0; i < p.shards; ++i )
 		{
 		flan_b200_ctx * ctx = m->ctx[i];
 		const int64_t rows = p.fb[i + 1] - p.fb[i];
 		int rc = flan_b200_malloc( ctx, sizeof( float ) * 2 * (size_t) C * (size_t) rows * B, (void **) &pv->d[i] );
-		if( !rc ) rc = flan_b200_convert_to_pv_range( ctx, a->d[i], a->hi[i] - a->lo[i], a->lo[i], a->hi[i] - a->lo[i], C, a->n,
-		                                              sample_rate, window_size, hop, dft_size, p.fb[i], p.fb[i + 1], pv->d[i], rows * B );
+		if( !rc )
+			{
+			CallLock lock( ctx );
+			BlockUse use( ctx, { a->d[i], pv->d[i] } );
+			AnalysisCall call{ a->d[i], a->hi[i] - a->lo[i], a->lo[i], a->hi[i] - a->lo[i], C, a->n, sample_rate, window_size, hop, dft_size,
+			                   p.fb[i], p.fb[i + 1], pv->d[i], rows * B };
+			call.emit_summary = hint; call.emit_seg_len = p.seg_len;
+			rc = analysis_range( ctx, call );
+			}
 		if( rc ) { const std::string e = flan_b200_last_error( ctx ); flan_b200_multi_free_pv( m, pv ); return mfail( rc, e ); }
 		}
+	return FLAN_B200_OK;
+	}
+
+// The two statements of a caller that resynthesises what it has just analysed (flan_b200_hint_resynthesis /
+// flan_b200_promise_unchanged), for the sharded forms: per calling thread, consumed by the next
+// flan_b200_multi_convert_to_pv / flan_b200_multi_convert_to_audio.
+int flan_b200_multi_hint_resynthesis( flan_b200_multi * m )
+	{
+	if( !m ) return FLAN_B200_INVALID;
+	set_resynthesis_hint();
+	return FLAN_B200_OK;
+	}
+int flan_b200_multi_promise_unchanged( flan_b200_multi * m, const flan_b200_sharded_pv * pv )
+	{
+	if( !m || !pv || pv->shards < 1 ) return FLAN_B200_INVALID;
+	promise_unchanged( pv->d[0] );
 	return FLAN_B200_OK;
 	}
 
@@ -324,6 +350,7 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		};
 	auto bail = [&]( flan_b200_ctx * ctx, int code ) { const std::string e = ctx ? flan_b200_last_error( ctx ) : thread_error(); cleanup( true ); return mfail( code, e ); };
 
+	const bool unchanged = take_promise( pv->d[0] );       // flan_b200_promise_unchanged( ., pv->d[0] ) by this thread
 	// (0) where the states of the earlier shards will land on each later device
 	for( int i = 1; i < R; ++i )
 		{
@@ -347,6 +374,7 @@ int flan_b200_multi_convert_to_audio( flan_b200_multi * m, const flan_b200_shard
 		const int64_t rows = pv->frame_begin[i + 1] - pv->frame_begin[i];
 		SynthCall s{ pv->d[i], rows * B, C, pv->frame_begin[i], pv->frame_begin[i + 1], F, B, sr, ar, W };
 		s.d_carry_out = d_state[i]; s.summary_only = true; s.seg_len = seg_len;
+		s.reuse_summary = unchanged;      // summaries the shard's analysis left (flan_b200_hint_resynthesis), if they are still this buffer's
 		m->d_nan[i] = ctx->d_flags + ( ctx->flag_next++ % flan_b200_ctx::FLAG_SLOTS );
 		MCK( cudaMemsetAsync( m->d_nan[i], 0, sizeof( int ), ctx->compute ), "flag clear" );
 		s.d_nan_flag = m->d_nan[i];

@@ -273,7 +273,8 @@ struct AnalysisCall
 	int64_t frame_begin, frame_end;
 	float * d_pv_rows; int64_t pv_channel_stride;
 	int * wave_out = nullptr;       // query only: CTAs of one full wave of the kernel this call would launch; nothing is launched
-	bool emit_summary = false;      // whole-signal call whose rows will be resynthesised unchanged: also leave their phase summaries
+	bool emit_summary = false;      // the rows will be resynthesised unchanged: also leave their phase summaries
+	int emit_seg_len = 0;           // frame-range shards: the segment length of the WHOLE signal (0: this call is the whole signal)
 	};
 int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & a );
 

@@ -46,6 +46,7 @@ def _devices(k):
     (44100.0, 2048, 128, 2048, 1, 1_500_000, 4),
     (48000.0, 2048, 128, 4096, 2, 900_000, 2),         # the API-default shape (zero-padded)
     (96000.0, 8192, 512, 8192, 1, 4_000_000, 4),       # cfg3's shape
+    (48000.0, 4096, 256, 4096, 1, 48000 * 500, 2),     # > 256 segments per shard: the analysis can leave the phase summaries
     (32000.0, 3000, 100, 3000, 1, 300_000, 3),         # the run-time-sized transform
     (48000.0, 512, 32, 512, 2, 9_000, 8),              # short signal: fewer shards than devices
 ])
@@ -76,6 +77,21 @@ def test_sharded_round_trip_is_bit_identical_to_one_device(eng, sr, W, h, N, C, 
     y = np.empty((C, F * h), np.float32)
     m.call("flan_b200_multi_gather_audio", ctypes.byref(out), y.ctypes.data)
     assert np.array_equal(y.view(np.uint32), y_ref.view(np.uint32))
+    # the round trip of a caller that says so (flan_b200_multi_hint_resynthesis / _promise_unchanged): the shards' analysis
+    # leaves their phase summaries where that form exists (full window, dft 2048 ... 8192, > 256 segments per shard), the
+    # statements are ignored elsewhere; rows and samples keep their bits
+    pv3, out3 = capi.ShardedPV(), capi.ShardedAudio()
+    m.call("flan_b200_multi_hint_resynthesis")
+    m.call("flan_b200_multi_convert_to_pv", ctypes.byref(a), sr, W, h, N, ctypes.byref(pv3))
+    m.call("flan_b200_multi_gather_pv", ctypes.byref(pv3), pv_h.ctypes.data, 0, None)
+    assert np.array_equal(pv_h.view(np.uint32), pv_ref.view(np.uint32))
+    m.call("flan_b200_multi_promise_unchanged", ctypes.byref(pv3))
+    m.call("flan_b200_multi_convert_to_audio", ctypes.byref(pv3), ctypes.byref(out3))
+    y3 = np.empty_like(y)
+    m.call("flan_b200_multi_gather_audio", ctypes.byref(out3), y3.ctypes.data)
+    assert np.array_equal(y3.view(np.uint32), y_ref.view(np.uint32))
+    m.call("flan_b200_multi_free_audio", ctypes.byref(out3))
+    m.call("flan_b200_multi_free_pv", ctypes.byref(pv3))
     # the host-buffer forms, twice (device blocks and scratch come back from the caches)
     for _ in range(2):
         pv2 = capi.ShardedPV()

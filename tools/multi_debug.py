@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flan_b200 import capi  # noqa: E402
 from flan_b200.signals import noise_chirp  # noqa: E402
 
+HINT = "--hint" in sys.argv
+if HINT:
+    sys.argv.remove("--hint")
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 1800.0
 lib = capi.load()
@@ -31,6 +34,8 @@ for kk in sorted({1, k}):
 
     def analysis():
         pv = capi.ShardedPV()
+        if HINT:
+            call("flan_b200_multi_hint_resynthesis")
         call("flan_b200_multi_convert_to_pv", ctypes.byref(a), sr, w, hop, n_dft, ctypes.byref(pv))
         return pv
 
@@ -62,6 +67,8 @@ for kk in sorted({1, k}):
     def both():
         only_analysis_pv = analysis()
         y = capi.ShardedAudio()
+        if HINT:
+            call("flan_b200_multi_promise_unchanged", ctypes.byref(only_analysis_pv))
         call("flan_b200_multi_convert_to_audio", ctypes.byref(only_analysis_pv), ctypes.byref(y))
         call("flan_b200_multi_free_pv", ctypes.byref(only_analysis_pv))
         call("flan_b200_multi_free_audio", ctypes.byref(y))
