@@ -424,9 +424,9 @@ def run_ours(args):
             eng.convert_to_pv(xin, SR, W, HOP, N_DFT, out=pv, for_resynthesis=hint)
             eng.convert_to_audio(pv, SR, ar, W, out=yout, unchanged=hint)
             return yout
-        eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv)
+        eng.convert_to_pv_range(xin, sh.audio_lo, n_total, SR, W, HOP, N_DFT, sh.f0, sh.f1, out=pv, for_resynthesis=hint and exchange is not None)
         if exchange is not None:
-            o, _ = sharded_resynthesis_peer(eng, exchange, torch, sh, pv, SR, ar, head_event)
+            o, _ = sharded_resynthesis_peer(eng, exchange, torch, sh, pv, SR, ar, head_event, unchanged=hint)
         else:
             o, _ = sharded_resynthesis_overlapped(eng, dist, torch, sh, pv, SR, ar, allgather, side_stream, head_event)
         return o
@@ -542,7 +542,7 @@ def run_ours(args):
         an_bytes = 4.0 * CH * n_local + 8.0 * CH * sh.frames * B          # per launch: audio read + PV written
         sy_bytes = 8.0 * CH * sh.frames * B + 4.0 * CH * out_len          # per launch: PV read + audio written
         kern = []
-        if an_n and world == 1 and hint:
+        if an_n and hint and (world == 1 or exchange is not None):
             # the instantiation that also writes the phase summaries of its rows (32 bytes per bin and segment of <= 128 frames)
             segs = -(-sh.frames // 127)
             kern.append(("pv_analysis_kernel<4096> +summaries", an_bytes + 32.0 * CH * segs * B, an_ms / an_n))
@@ -591,7 +591,7 @@ def run_ours(args):
                                " (%s)" % exchange_note if exchange_note else "")),
                        "l2": "inputs larger than L2 (3.69 GB PV per GPU), no flush",
                        "phase_summaries": ("left by the analysis kernel (flan_b200_hint_resynthesis): the round trip resynthesises the rows unchanged"
-                                           if (world == 1 and hint) else "second pass over the rows (pv_phase_seg_kernel)")},
+                                           if (hint and (world == 1 or exchange is not None)) else "second pass over the rows (pv_phase_seg_kernel)")},
             "legs": {"analysis_frames_per_s": frames_rank / (an_ms / an_n * 1e-3) if an_n else None,
                      "resynthesis_frames_per_s": frames_rank / ((sy_ms + seg_ms + scan_ms) / sy_n * 1e-3) if sy_n else None,
                      "audio_samples_per_s": value * HOP,

@@ -439,8 +439,9 @@ int analysis_range( flan_b200_ctx * ctx, const AnalysisCall & c )
 	ctx->seg_key.valid = false;
 	// Summaries for a resynthesis of these rows as they are (flan_b200_hint_resynthesis): the 16-point full-window kernel
 	// leaves them in the workspace, in the segments resynthesis will use; anything else ignores the hint.
+	// (a frame range without emit_seg_len is a shard of a per-GPU process: its resynthesis chooses the segments from the
+	// local frame count, and so does this)
 	if( c.emit_summary && pt == 16 && a.one_buffer && tps_a == 512 && N >= 2048 && W == N
-	    && ( c.emit_seg_len > 0 || ( c.frame_begin == 0 && c.frame_end == F ) )
 	    && c.pv_channel_stride == frames * (int64_t)( N / 2 + 1 ) )
 		{
 		const int B = N / 2 + 1;
@@ -1037,6 +1038,7 @@ int flan_b200_convert_to_pv_range( flan_b200_ctx * ctx, const float * d_audio_lo
 	CallLock lock( ctx );
 	BlockUse use( ctx, { d_audio_local, d_pv_rows } );
 	AnalysisCall a{ d_audio_local, audio_stride, audio_offset, audio_len, C, n_total, sr, W, hop, N, frame_begin, frame_end, d_pv_rows, pv_channel_stride };
+	a.emit_summary = take_resynthesis_hint();
 	return analysis_range( ctx, a );
 	}
 
@@ -1121,6 +1123,7 @@ int flan_b200_phase_summary( flan_b200_ctx * ctx, const float * d_pv_rows, int64
 		}
 	SynthCall s{ d_pv_rows, pv_channel_stride, C, frame_begin, frame_end, frame_end, B, sr, ar, W };
 	s.d_carry_out = (PhaseSeg *) d_state_out; s.summary_only = true;
+	s.reuse_summary = take_promise( d_pv_rows );      // summaries the shard's analysis left (flan_b200_hint_resynthesis)
 	return synth_range( ctx, s );
 	}
 

@@ -73,13 +73,16 @@ class Engine:
         self.ctx.call("flan_b200_convert_to_pv", self._chk(audio), C, n, sr, W, hop, N, self._chk(out), None)
         return out
 
-    def convert_to_pv_range(self, audio_local, audio_offset, n_total, sr, W, hop, N, frame_begin, frame_end, out=None):
+    def convert_to_pv_range(self, audio_local, audio_offset, n_total, sr, W, hop, N, frame_begin, frame_end, out=None,
+                            for_resynthesis=False):
         C, n_local = audio_local.shape
         rows = frame_end - frame_begin
         B = N // 2 + 1
         if out is None:
             out = torch.empty((C, rows, B, 2), dtype=torch.float32, device=self.device)
         self._bind_stream()
+        if for_resynthesis:
+            self.ctx.call("flan_b200_hint_resynthesis")
         self.ctx.call("flan_b200_convert_to_pv_range", self._chk(audio_local), n_local, audio_offset, n_local, C, n_total,
                       sr, W, hop, N, frame_begin, frame_end, self._chk(out), rows * B)
         return out
@@ -100,10 +103,12 @@ class Engine:
                       ctypes.byref(flag) if check_nan else None)
         return (out, bool(flag.value)) if check_nan else out
 
-    def phase_summary(self, pv_rows, frame_begin, sr, ar, W):
+    def phase_summary(self, pv_rows, frame_begin, sr, ar, W, unchanged=False):
         C, rows, B, _ = pv_rows.shape
         state = torch.empty((C, B, 4), dtype=torch.float64, device=self.device)
         self._bind_stream()
+        if unchanged:
+            self.ctx.call("flan_b200_promise_unchanged", self._chk(pv_rows))
         self.ctx.call("flan_b200_phase_summary", self._chk(pv_rows), rows * B, C, frame_begin, frame_begin + rows, B,
                       sr, ar, W, self._chk(state, torch.float64))
         return state

@@ -184,17 +184,21 @@ class PeerExchange:
             self.h = None
 
 
-def sharded_resynthesis_peer(engine, ex, torch, shard, pv_rows, sr, ar, head_event):
+def sharded_resynthesis_peer(engine, ex, torch, shard, pv_rows, sr, ar, head_event, unchanged=False):
     """sharded_resynthesis with both exchanges as peer copies (PeerExchange), the halo off the critical path: the frames
     whose windows reach into the previous rank run beside the rest of the shard (flan_b200_convert_to_audio_range_head
     records head_event after them), their partial sums are pushed into the previous rank's mailbox while both ranks
     compute, and the owner adds what it received after its own frames (lower-frame contributions first, AudioPV.cpp:133-134).
-    head_event: a torch.cuda.Event that has been recorded once (its handle must exist)."""
+    head_event: a torch.cuda.Event that has been recorded once (its handle must exist).
+    unchanged: pv_rows are exactly what convert_to_pv_range(..., for_resynthesis=True) wrote: the phase summaries it left
+    are used (flan_b200_promise_unchanged) instead of a second read of the rows."""
     import ctypes
     C, rows, B, _ = pv_rows.shape
     engine._bind_stream()
     d_state = ctypes.c_void_p()
     ex._call("flan_b200_exchange_state_slot", ctypes.byref(d_state))
+    if unchanged:
+        engine.ctx.call("flan_b200_promise_unchanged", engine._chk(pv_rows))
     engine.ctx.call("flan_b200_phase_summary", engine._chk(pv_rows), rows * B, C, shard.f0, shard.f0 + rows, B, sr, ar, shard.W, d_state)
     ex._call("flan_b200_exchange_put_state", d_state)
     carry = None

@@ -246,7 +246,8 @@ int flan_b200_promise_unchanged( flan_b200_ctx * ctx, const float * d_pv );
  * of BASELINE configs 1-3. Full-window transforms of dft 2048 / 4096 / 8192 on long signals have that form (one
  * shared-memory word per bin: the increments of a bin lie within pi of its expected phase advance, and their differences
  * to it sum exactly in 32 bits); every other call ignores the hint. Costs ~10 % of the analysis kernel, saves the second
- * read of the rows (0.56 of 3.9 ms on cfg2). */
+ * read of the rows (0.56 of 3.9 ms on cfg2). flan_b200_convert_to_pv_range consumes the hint too (a shard of a per-GPU
+ * process: flan_b200_promise_unchanged before flan_b200_phase_summary then uses what it left). */
 int flan_b200_hint_resynthesis( flan_b200_ctx * ctx );
 
 /* ---- file formats either side of the path ---------------------------------------------------------
