@@ -362,3 +362,23 @@ def test_emulated_analysis_leaves_the_segment_summaries(emu, N, hop, seg_len, n)
     assert flag == 1 and np.array_equal(seg[~marked].view(np.uint64), want[~marked].view(np.uint64))
     hit = (n // 2) // hop // seg_len
     assert marked[0, hit].all()
+
+
+def test_emulated_analysis_summaries_of_a_frame_range(emu):
+    """The same for a frame-range shard (a warm-up frame before its first one, local audio with halos): the summaries are
+    those of the shard's rows, segment 0 beginning at the shard's first frame."""
+    sr, N, hop, seg_len = 48000.0, 2048, 128, 19
+    n = 40000
+    x = np.stack([noise_chirp(n, sr, 31)])
+    F = n // hop + 1
+    f0, f1 = 97, 251
+    lo, hi = max(0, hop * (f0 - 1) - N // 2), min(n, hop * (f1 - 1) + N // 2)
+    full = emu.analysis(x, sr, N, hop, N, seg_len=seg_len, points_per_thread=116)
+    pv, seg = emu.analysis(x[:, lo:hi], sr, N, hop, N, frame_begin=f0, frame_end=f1, seg_len=seg_len, audio_offset=lo, n_total=n,
+                           points_per_thread=116, emit_summary=True)
+    assert np.array_equal(pv.view(np.uint32), full[:, f0:f1].view(np.uint32))
+    ar = float(np.float32(sr) / np.float32(hop))
+    want, _ = emu.phase_segments(pv, sr, ar, N, seg_len)
+    marked = np.isnan(seg[..., 0])
+    assert seg.shape == want.shape and marked.mean() < 0.03
+    assert np.array_equal(seg[~marked].view(np.uint64), want[~marked].view(np.uint64))
