@@ -159,9 +159,11 @@ __global__ void __launch_bounds__( 256 ) pv_phase_seg_kernel( const PhaseSegArgs
 	if( flag ) *a.nan_flag = 1;
 	}
 
-// Summaries left by the analysis kernel (analysis_cta<EMIT>): the entries it marked -- the lowest bins, whose expected
-// phase advance is too small for the 32-bit form -- are recomputed from the rows, one thread per (channel, segment,
-// bin < bins), all at once. (Marked entries elsewhere, NaN / Inf, are repaired by the scan's group reduction.)
+// Summaries left by the analysis kernel (analysis_cta<EMIT>): the entries it marked -- always the lowest bins, whose
+// expected phase advance is too small for the 32-bit form; every bin of a segment of digital silence, whose frequencies
+// are nowhere near their bins' centres; NaN / Inf -- are recomputed from the rows, one thread per (channel, segment, bin),
+// all at once: unmarked entries cost a 8-byte read, a fully marked buffer what pv_phase_seg_kernel costs. (The scan's
+// group reduction repairs what a caller-limited launch leaves.)
 __global__ void __launch_bounds__( 64 ) pv_phase_fix_kernel( const PhaseScanArgs a, int bins )
 	{
 	const int b = threadIdx.x + blockIdx.z * 64;
@@ -602,8 +604,8 @@ cudaError_t launch_phase_scan( const PhaseScanArgs & a, int C, cudaStream_t st )
 		}
 	if( !a.expand_only )
 		{
-		if( a.fix_pv && a.segs_per_channel <= 65535 * 32 && C <= 65535 )
-			pv_phase_fix_kernel<<<dim3( a.segs_per_channel, C, 1 ), 64, 0, st>>>( a, 64 );
+		if( a.fix_pv && C <= 65535 && ( a.B + 63 ) / 64 <= 65535 )
+			pv_phase_fix_kernel<<<dim3( a.segs_per_channel, C, ( a.B + 63 ) / 64 ), 64, 0, st>>>( a, a.B );
 		pv_phase_scan_kernel<<<wide, 128, 0, st>>>( a, 0 );
 		pv_phase_scan_kernel<<<narrow, 128, 0, st>>>( a, 1 );
 		}
