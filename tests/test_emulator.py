@@ -382,3 +382,32 @@ def test_emulated_analysis_summaries_of_a_frame_range(emu):
     marked = np.isnan(seg[..., 0])
     assert seg.shape == want.shape and marked.mean() < 0.03
     assert np.array_equal(seg[~marked].view(np.uint64), want[~marked].view(np.uint64))
+
+
+def test_the_exactness_claims_behind_the_32_bit_segment_sums():
+    """DESIGN.md 4.1c, checked in exact rational arithmetic: for an expected advance c >= 6 (a float) and increments inc
+    (floats) with |inc - c| < 4, (i) the float subtraction inc - c is exact and a multiple of 2^-22, (ii) the plain double
+    running sum of the increments -- what pv_phase_seg_kernel computes -- is exact, and (iii) it equals
+    frames * c + 2^-22 * (the int32 sum of (inc - c) * 2^22), evaluated in double."""
+    from fractions import Fraction
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        c = np.float32(rng.uniform(6.0, 1700.0))
+        frames = int(rng.integers(1, 129))
+        inc = (np.float64(c) + rng.uniform(-3.999, 3.999, frames)).astype(np.float32)
+        inc = inc[np.abs(inc.astype(np.float64) - np.float64(c)) < 4.0]
+        if inc.size == 0:
+            continue
+        d = (inc - c).astype(np.float32)                                        # float32 subtraction
+        assert all(Fraction(float(a)) - Fraction(float(c)) == Fraction(float(b)) for a, b in zip(inc, d))
+        scaled = d.astype(np.float64) * 4194304.0
+        assert np.array_equal(scaled, np.trunc(scaled)) and np.abs(scaled).max() < 2 ** 24
+        ints = scaled.astype(np.int64)
+        assert abs(int(ints.sum())) < 2 ** 31
+        running = 0.0
+        for a in inc:
+            running += float(a)                                                 # double running sum, frame order
+        exact = sum(Fraction(float(a)) for a in inc)
+        assert Fraction(running) == exact
+        closed = float(len(inc)) * float(c) + float(int(ints.sum())) * 2.0 ** -22
+        assert closed == running
